@@ -1,0 +1,351 @@
+// attention_tc.cu — flash-attention forward (non-causal) on tcgen05 for sm_100a.
+//
+//   O[b, s, h, :] = softmax(Q[b, s, h, :] . K[b, :, h, :]^T * scale) . V[b, :, h, :]
+//
+// Covers the UNet's self-attention (S = 4096/1024/256/64, d = 40/80/160) and cross-attention (77 context
+// tokens) — upstream ldm CrossAttention (SURVEY.md §8 a-ext x6, x7; not in /root/reference).
+//
+// Layout: Q/K/V rows are tokens; every head owns d_pad (multiple of 64) consecutive halfs, the first d of
+// which are data and the rest zero (the projection GEMM produces this directly from zero-padded weight
+// rows), so each 64-half chunk of a tile is exactly one TMA SWIZZLE_128B box.  O is written unpadded
+// ([b, s, h*d]) because it feeds the out-projection GEMM as a plain K-major A operand.
+//
+// One CTA = one 128-row Q tile of one (batch, head).  192 threads:
+//   warp 0   TMA producer (Q once; K ring, V ring)
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer:  S = Q K^T  (M128 x N<=128 x K=d),
+//            O (+)= P V  (M128 x N=d16 x K<=128, V consumed MN-major straight from its TMA tile)
+//   warps 2-5 softmax: thread == query row (TMEM lane); online max/sum in fp32, P written as fp16 into a
+//            K-major SWIZZLE_128B smem tile, O rescaled in TMEM when the running max moves.
+// For d <= 64 the CTA needs 96 KB smem and 256 TMEM columns, so two CTAs share an SM and one's softmax
+// overlaps the other's MMAs.
+#include "tc_common.cuh"
+#include "b200sd_internal.h"
+
+namespace b200sd {
+
+constexpr int kAttnThreads = 192;
+constexpr int kQTile = 128;
+constexpr int kKvTile = 128;
+constexpr int kMaxRing = 2;
+
+struct AttnParams {
+  int B, heads, Sq, Skv, d, d_pad;
+  int d16;           // d rounded up to 16 (MMA K of Q.K^T; O columns that carry data)
+  int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
+  int chunks;        // d_pad / 64
+  int k_stages, v_stages;
+  int tmem_cols;
+  float scale_log2;  // softmax scale * log2(e)
+  void* O;
+  long long ldo;
+  int is_bf16;
+};
+
+struct __align__(8) AttnBarriers {
+  uint64_t q_full;
+  uint64_t k_full[kMaxRing], k_empty[kMaxRing];
+  uint64_t v_full[kMaxRing], v_empty[kMaxRing];
+  uint64_t s_full, p_full, o_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b, bool bf16) {
+  if (bf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t tile_bytes = static_cast<uint32_t>(p.chunks) * 16384u;  // one 128-row x d_pad operand tile
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + tile_bytes;  // 2 x 16 KB (kv columns 0-63, 64-127)
+  uint8_t* sK = sP + 32768;
+  uint8_t* sV = sK + static_cast<size_t>(p.k_stages) * tile_bytes;
+  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(sV + static_cast<size_t>(p.v_stages) * tile_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQTile;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = (p.Skv + kKvTile - 1) / kKvTile;
+  const int col0 = head * p.d_pad;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(&bars->k_full[s], 1);
+      mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1);
+      mbar_init(&bars->v_empty[s], 1);
+    }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
+  const uint32_t tmem_O = tmem_base + 128;  // dpv fp32 columns (first d16 carry data)
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->q_full, tile_bytes);
+      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &bars->q_full, col0 + c * 64, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int ks = j % p.k_stages;
+        const uint32_t kph = (j / p.k_stages) & 1;
+        mbar_wait(&bars->k_empty[ks], kph ^ 1u, 11);
+        mbar_arrive_expect_tx(&bars->k_full[ks], tile_bytes);
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_3d(sK + static_cast<size_t>(ks) * tile_bytes + c * 16384, &tmK, &bars->k_full[ks], col0 + c * 64,
+                      j * kKvTile, b);
+        const int vs = j % p.v_stages;
+        const uint32_t vph = (j / p.v_stages) & 1;
+        mbar_wait(&bars->v_empty[vs], vph ^ 1u, 12);
+        mbar_arrive_expect_tx(&bars->v_full[vs], tile_bytes);
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_3d(sV + static_cast<size_t>(vs) * tile_bytes + c * 16384, &tmV, &bars->v_full[vs], col0 + c * 64,
+                      j * kKvTile, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ---------------------------------------
+    if (lane == 0) {
+      const bool bf = p.is_bf16 != 0;
+      const int ksteps_qk = p.d16 / 16;
+      mbar_wait(&bars->q_full, 0, 13);
+      for (int j = 0; j < nkv; ++j) {
+        const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
+        const int n16 = (nvalid + 15) & ~15;
+        const int ks = j % p.k_stages;
+        const uint32_t kph = (j / p.k_stages) & 1;
+        const int vs = j % p.v_stages;
+        const uint32_t vph = (j / p.v_stages) & 1;
+        // ---- S = Q K^T ----  (S is free: softmax(j-1) finished reading it before arriving on p_full(j-1))
+        mbar_wait(&bars->k_full[ks], kph, 14);
+        tc_fence_after();
+        {
+          const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
+          const uint32_t aQ = smem_u32(sQ);
+          const uint32_t aK = smem_u32(sK + static_cast<size_t>(ks) * tile_bytes);
+          for (int k = 0; k < ksteps_qk; ++k) {
+            const uint32_t off = static_cast<uint32_t>(k >> 2) * 16384u + static_cast<uint32_t>(k & 3) * 32u;
+            umma_f16_ss(tmem_S, make_sdesc_sw128(aQ + off, 16, 1024), make_sdesc_sw128(aK + off, 16, 1024), idesc,
+                        k != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->k_empty[ks]);
+          umma_commit(&bars->s_full);
+        }
+        // ---- O (+)= P V ----
+        mbar_wait(&bars->p_full, j & 1, 15);
+        mbar_wait(&bars->v_full[vs], vph, 16);
+        tc_fence_after();
+        {
+          const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
+          const uint32_t aP = smem_u32(sP);
+          const uint32_t aV = smem_u32(sV + static_cast<size_t>(vs) * tile_bytes);
+          const int ksteps_pv = n16 / 16;
+          for (int k = 0; k < ksteps_pv; ++k) {
+            const uint32_t offP = static_cast<uint32_t>(k >> 2) * 16384u + static_cast<uint32_t>(k & 3) * 32u;
+            const uint32_t offV = static_cast<uint32_t>(k) * 2048u;  // 16 kv rows x 128 B
+            umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, 16384, 1024),
+                        idesc, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->v_empty[vs]);
+          umma_commit(&bars->o_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------ softmax warps ------------------------------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool bf = p.is_bf16 != 0;
+    float m_scaled = -INFINITY;  // running max, already multiplied by scale_log2
+    float l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
+      mbar_wait(&bars->s_full, j & 1, 17);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if (c * 32 >= nvalid) break;
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_scaled, mx * p.scale_log2);
+      const float alpha = fast_exp2(m_scaled - m_new);
+      if (j > 0) {
+        // P and O are still owned by P.V of the previous block until it retires
+        mbar_wait(&bars->o_full, (j - 1) & 1, 18);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          for (int c = 0; c < p.d16 / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_x16(tmem_O + lane_base + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(tmem_O + lane_base + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      l *= alpha;
+      m_scaled = m_new;
+      // pass 2: P = exp2(S * scale - m), row sum, fp16 -> swizzled smem
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (c * 32 < nvalid) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+            e[i] = (c * 32 + i < nvalid) ? t : 0.f;
+            l += e[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1], bf);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        }
+        uint8_t* atom = sP + (c >> 1) * 16384;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk16 = static_cast<uint32_t>((c & 1) * 4 + q);
+          *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk16)) =
+              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full);
+    }
+    // ---- epilogue: O / l -> global ----
+    mbar_wait(&bars->o_full, (nkv - 1) & 1, 19);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int srow = q0 + r;
+    const bool valid = srow < p.Sq;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
+                    ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
+    for (int c = 0; c < p.d16 / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld_x16(tmem_O + lane_base + c * 16, o);
+      tmem_ld_wait();
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        h[i] = pack_h2(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l, bf);
+      if (valid) {
+        if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int g_attn_max_smem = 0;
+
+int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                 long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int is_bf16,
+                 cudaStream_t stream) {
+  if (B <= 0 || heads <= 0 || Sq <= 0) return B200SD_OK;
+  if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 64 != 0 || d_pad < d || d > 240) return B200SD_ERR_INVALID;
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return B200SD_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
+       reinterpret_cast<uintptr_t>(O)) & 15)
+    return B200SD_ERR_INVALID;
+  if (ldq < static_cast<long long>(heads) * d_pad || ldk < static_cast<long long>(heads) * d_pad ||
+      ldv < static_cast<long long>(heads) * d_pad || ldo < static_cast<long long>(heads) * d)
+    return B200SD_ERR_INVALID;
+  if (g_attn_max_smem == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return B200SD_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&g_attn_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+      return B200SD_ERR_CUDA;
+    if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem) !=
+        cudaSuccess)
+      return B200SD_ERR_CUDA;
+  }
+  AttnParams p{};
+  p.B = B; p.heads = heads; p.Sq = Sq; p.Skv = Skv; p.d = d; p.d_pad = d_pad;
+  p.d16 = (d + 15) & ~15;
+  p.chunks = d_pad / 64;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
+  p.dpv = d_pad;
+  if (p.dpv > 256) return B200SD_ERR_UNSUPPORTED;
+  p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
+  const size_t tile = static_cast<size_t>(p.chunks) * 16384;
+  const size_t fixed = 1024 + tile /*Q*/ + 32768 /*P*/ + sizeof(AttnBarriers) + 64;
+  const size_t budget = static_cast<size_t>(g_attn_max_smem);
+  // K ring first (its prefetch hides the next block's load), then V
+  if (fixed + 4 * tile <= budget && p.chunks > 1) { p.k_stages = 2; p.v_stages = 2; }
+  else if (fixed + 3 * tile <= budget) { p.k_stages = 2; p.v_stages = 1; }
+  else if (fixed + 2 * tile <= budget) { p.k_stages = 1; p.v_stages = 1; }
+  else return B200SD_ERR_UNSUPPORTED;
+  const size_t smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * tile;
+
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t es[3] = {1, 1, 1};
+  int rc;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Sq), static_cast<uint64_t>(B)};
+    const uint64_t st[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * Sq};
+    if ((rc = make_tmap_sw128(&tmQ, Q, 3, dims, st, box, es)) != B200SD_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Skv), static_cast<uint64_t>(B)};
+    const uint64_t st[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(ldk) * 2 * Skv};
+    if ((rc = make_tmap_sw128(&tmK, K, 3, dims, st, box, es)) != B200SD_OK) return rc;
+  }
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Skv), static_cast<uint64_t>(B)};
+    const uint64_t st[2] = {static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
+    if ((rc = make_tmap_sw128(&tmV, V, 3, dims, st, box, es)) != B200SD_OK) return rc;
+  }
+  dim3 grid((Sq + kQTile - 1) / kQTile, heads, B);
+  attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}
+
+}  // namespace b200sd

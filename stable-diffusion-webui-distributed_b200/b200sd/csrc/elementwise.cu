@@ -1,0 +1,344 @@
+// elementwise.cu — small HBM/latency-bound kernels around the tensor-core ops: nearest 2x upsample,
+// row softmax (VAE mid attention), SiLU, sinusoidal timestep embedding, per-step bias folding/selection,
+// CFG + DDIM / Euler-ancestral latent update fused with re-packing the next UNet input, and the final
+// [-1,1] -> uint8 quantisation.
+//
+// Upstream: ldm Upsample, timestep_embedding, ResBlock.emb_layers; sdwui CFGDenoiser,
+// sd_samplers_timesteps_impl.ddim, k-diffusion sample_euler_ancestral, process_images_inner's
+// clamp/255/uint8 (SURVEY.md §8 a-ext x2, x4, x10, x11 and App. C; not in /root/reference).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../../include/b200sd.h"
+
+namespace b200sd {
+
+template <bool kBf16>
+__device__ __forceinline__ float load1(const void* p, long long i) {
+  if constexpr (kBf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  else return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+template <bool kBf16>
+__device__ __forceinline__ void store1(void* p, long long i, float v) {
+  if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ X, long long pitch_x_v, uint4* __restrict__ Y,
+                                  long long pitch_y_v, int NB, int H, int W, int cvec) {
+  // one thread per (output pixel, 16-byte channel vector)
+  const long long total = static_cast<long long>(NB) * (2 * H) * (2 * W) * cvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cvec);
+    const long long pix = i / cvec;
+    const int x = static_cast<int>(pix % (2 * W));
+    const int y = static_cast<int>((pix / (2 * W)) % (2 * H));
+    const int n = static_cast<int>(pix / (static_cast<long long>(2 * W) * (2 * H)));
+    const long long src = (static_cast<long long>(n) * H + (y >> 1)) * W + (x >> 1);
+    Y[pix * pitch_y_v + v] = __ldg(&X[src * pitch_x_v + v]);
+  }
+}
+
+// one CTA per row; in place; cols <= 16384
+template <bool kBf16>
+__global__ void softmax_rows_kernel(void* S, long long lds, int cols, float scale_log2) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  uint8_t* base = reinterpret_cast<uint8_t*>(S) + row * lds * 2;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, load1<kBf16>(base, c));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += exp2f((load1<kBf16>(base, c) - mx) * scale_log2);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    store1<kBf16>(base, c, exp2f((load1<kBf16>(base, c) - mx) * scale_log2) * inv);
+}
+
+template <bool kBf16>
+__global__ void silu_kernel(const void* X, void* Y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = load1<kBf16>(X, i);
+    store1<kBf16>(Y, i, v / (1.0f + __expf(-v)));
+  }
+}
+
+// emb[t][0:half] = cos(t * f_k), emb[t][half:] = sin(t * f_k), f_k = exp(-ln(10000) * k / half)
+template <bool kBf16>
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int T, int dim, void* out, long long ldo) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * half) return;
+  const int row = i / half, k = i % half;
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+  const float a = t[row] * freq;
+  store1<kBf16>(out, row * ldo + k, cosf(a));
+  store1<kBf16>(out, row * ldo + half + k, sinf(a));
+}
+
+template <bool kBf16>
+__global__ void fold_bias_kernel(const void* emb, long long lde, const float* __restrict__ bias, float* table, int T,
+                                 int C) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(T) * C) return;
+  const int row = static_cast<int>(i / C), c = static_cast<int>(i % C);
+  table[i] = bias[c] + load1<kBf16>(emb, row * lde + c);
+}
+
+__global__ void select_step_kernel(const float* __restrict__ table, long long row_len, const int* step, float* cur) {
+  const float* src = table + static_cast<long long>(*step) * row_len;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < row_len;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    cur[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// latents: x fp32 [B][HW][4]; UNet input xin [2B][HW][pitch] (channels 0..3 written, rest stay zero)
+template <bool kBf16>
+__device__ __forceinline__ void write_xin(void* xin, long long pitch, int B, int HW, int b, int pix, float4 v) {
+  uint2 pk;
+  if constexpr (kBf16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), c = __floats2bfloat162_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&c);
+  } else {
+    __half2 a = __floats2half2_rn(v.x, v.y), c = __floats2half2_rn(v.z, v.w);
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&c);
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>(xin);
+  *reinterpret_cast<uint2*>(base + ((static_cast<long long>(b) * HW + pix) * pitch) * 2) = pk;
+  *reinterpret_cast<uint2*>(base + ((static_cast<long long>(b + B) * HW + pix) * pitch) * 2) = pk;
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float4 read_eps4(const void* eps, long long pitch, long long row) {
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(eps) + row * pitch * 2);
+  float2 a, c;
+  if constexpr (kBf16) {
+    a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  } else {
+    a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  }
+  return make_float4(a.x, a.y, c.x, c.y);
+}
+
+template <bool kBf16>
+__global__ void pack_unet_input_kernel(const float4* __restrict__ x, void* xin, long long pitch, int B, int HW,
+                                       float in_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  float4 v = x[i];
+  v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+  write_xin<kBf16>(xin, pitch, B, HW, i / HW, i % HW, v);
+}
+
+template <bool kBf16>
+__global__ void cfg_ddim_step_kernel(const void* eps, long long pitch_e, float4* x, void* xin, long long pitch_x, int B,
+                                     int HW, float cfg, const float* __restrict__ coef, int* step_counter) {
+  const int step = *step_counter;
+  const float sa = coef[step * 4 + 0], s1a = coef[step * 4 + 1], sap = coef[step * 4 + 2], s1ap = coef[step * 4 + 3];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * HW) {
+    const int b = i / HW, pix = i % HW;
+    const float4 ec = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b) * HW + pix);
+    const float4 eu = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b + B) * HW + pix);
+    float4 xv = x[i];
+    float e[4] = {eu.x + cfg * (ec.x - eu.x), eu.y + cfg * (ec.y - eu.y), eu.z + cfg * (ec.z - eu.z),
+                  eu.w + cfg * (ec.w - eu.w)};
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = (xs[k] - s1a * e[k]) / sa;
+      xs[k] = sap * x0 + s1ap * e[k];
+    }
+    xv = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    x[i] = xv;
+    write_xin<kBf16>(xin, pitch_x, B, HW, b, pix, xv);
+  }
+}
+
+// coef[step] = {sigma, sigma_down, sigma_up, in_scale_next}; x lives in sigma space (x = latent * sqrt(1+sigma^2));
+// the UNet input of the NEXT step is x_next * in_scale_next with in_scale_next = 1/sqrt(sigma_next^2 + 1).
+template <bool kBf16>
+__global__ void cfg_euler_a_step_kernel(const void* eps, long long pitch_e, float4* x, const float4* __restrict__ noise,
+                                        void* xin, long long pitch_x, int B, int HW, float cfg,
+                                        const float* __restrict__ coef, int* step_counter) {
+  const int step = *step_counter;
+  const float sigma = coef[step * 4 + 0], sdown = coef[step * 4 + 1], sup = coef[step * 4 + 2],
+              in_next = coef[step * 4 + 3];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * HW) {
+    const int b = i / HW, pix = i % HW;
+    const float4 ec = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b) * HW + pix);
+    const float4 eu = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b + B) * HW + pix);
+    float4 xv = x[i];
+    float e[4] = {eu.x + cfg * (ec.x - eu.x), eu.y + cfg * (ec.y - eu.y), eu.z + cfg * (ec.z - eu.z),
+                  eu.w + cfg * (ec.w - eu.w)};
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise != nullptr && sup > 0.f) {
+      const float4 nv = noise[static_cast<long long>(step) * B * HW + i];
+      nz[0] = nv.x; nz[1] = nv.y; nz[2] = nv.z; nz[3] = nv.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // denoised = x - sigma * eps; d = (x - denoised) / sigma = eps; x += d * (sigma_down - sigma)
+      xs[k] = xs[k] + e[k] * (sdown - sigma) + nz[k] * sup;
+    }
+    xv = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    x[i] = xv;
+    write_xin<kBf16>(xin, pitch_x, B, HW, b, pix,
+                     make_float4(xs[0] * in_next, xs[1] * in_next, xs[2] * in_next, xs[3] * in_next));
+  }
+}
+
+__global__ void bump_step_kernel(int* step_counter) { *step_counter += 1; }
+
+template <bool kBf16>
+__global__ void quantize_u8_kernel(const void* img, long long pitch, unsigned char* out, long long npix) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = load1<kBf16>(img, i * pitch + c);
+    v = fminf(fmaxf((v + 1.0f) * 0.5f, 0.f), 1.f);
+    out[i * 3 + c] = static_cast<unsigned char>(255.0f * v);  // truncation, as numpy astype(uint8)
+  }
+}
+
+}  // namespace b200sd
+
+using namespace b200sd;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define RET_LAUNCH() return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA
+
+extern "C" int b200sd_upsample2x(const void* X, long long pitch_x, void* Y, long long pitch_y, int NB, int H, int W,
+                                 int C, int dtype, void* stream) {
+  (void)dtype;
+  if (NB <= 0) return B200SD_OK;
+  if (C % 8 || pitch_x % 8 || pitch_y % 8 || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15))
+    return B200SD_ERR_INVALID;
+  const long long total = static_cast<long long>(NB) * 4 * H * W * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(
+      static_cast<const uint4*>(X), pitch_x / 8, static_cast<uint4*>(Y), pitch_y / 8, NB, H, W, C / 8);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_softmax_rows(void* S, long long lds, int rows, int cols, float scale, int dtype, void* stream) {
+  if (rows <= 0) return B200SD_OK;
+  if (cols <= 0) return B200SD_ERR_INVALID;
+  const float sl2 = scale * 1.4426950408889634f;
+  if (dtype == B200SD_BF16) softmax_rows_kernel<true><<<rows, 256, 0, ST(stream)>>>(S, lds, cols, sl2);
+  else softmax_rows_kernel<false><<<rows, 256, 0, ST(stream)>>>(S, lds, cols, sl2);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_silu(const void* X, void* Y, long long n, int dtype, void* stream) {
+  if (n <= 0) return B200SD_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype == B200SD_BF16) silu_kernel<true><<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(X, Y, n);
+  else silu_kernel<false><<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(X, Y, n);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_timestep_embedding(const float* t, int T, int dim, void* out, long long ldo, int dtype,
+                                         void* stream) {
+  if (T <= 0) return B200SD_OK;
+  if (dim % 2) return B200SD_ERR_INVALID;
+  const int n = T * (dim / 2);
+  if (dtype == B200SD_BF16) timestep_embedding_kernel<true><<<(n + 127) / 128, 128, 0, ST(stream)>>>(t, T, dim, out, ldo);
+  else timestep_embedding_kernel<false><<<(n + 127) / 128, 128, 0, ST(stream)>>>(t, T, dim, out, ldo);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_fold_bias(const void* emb, long long lde, const float* bias, float* table, int T, int C,
+                                int dtype, void* stream) {
+  if (T <= 0 || C <= 0) return B200SD_OK;
+  const long long n = static_cast<long long>(T) * C;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (dtype == B200SD_BF16) fold_bias_kernel<true><<<blocks, 256, 0, ST(stream)>>>(emb, lde, bias, table, T, C);
+  else fold_bias_kernel<false><<<blocks, 256, 0, ST(stream)>>>(emb, lde, bias, table, T, C);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_select_step(const float* table, long long row_len, const int* step_counter, float* cur,
+                                  void* stream) {
+  if (row_len <= 0) return B200SD_OK;
+  long long blocks = (row_len + 255) / 256;
+  if (blocks > 148) blocks = 148;
+  select_step_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(table, row_len, step_counter, cur);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_pack_unet_input(const float* x, void* xin, long long pitch, int B, int HW, float in_scale,
+                                      int dtype, void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (pitch % 4) return B200SD_ERR_INVALID;
+  const int n = B * HW;
+  if (dtype == B200SD_BF16)
+    pack_unet_input_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
+  else
+    pack_unet_input_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_cfg_ddim_step(const void* eps, long long pitch_e, float* x, void* xin, long long pitch_x, int B,
+                                    int HW, float cfg_scale, const float* coef, int* step_counter, int dtype,
+                                    void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (pitch_e % 4 || pitch_x % 4) return B200SD_ERR_INVALID;
+  const int n = B * HW;
+  if (dtype == B200SD_BF16)
+    cfg_ddim_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  else
+    cfg_ddim_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float* x, const float* noise, void* xin,
+                                       long long pitch_x, int B, int HW, float cfg_scale, const float* coef,
+                                       int* step_counter, int dtype, void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (pitch_e % 4 || pitch_x % 4) return B200SD_ERR_INVALID;
+  const int n = B * HW;
+  if (dtype == B200SD_BF16)
+    cfg_euler_a_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  else
+    cfg_euler_a_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_quantize_u8(const void* img, long long pitch, unsigned char* out, int B, int HW, int dtype,
+                                  void* stream) {
+  if (B <= 0) return B200SD_OK;
+  const long long n = static_cast<long long>(B) * HW;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (dtype == B200SD_BF16) quantize_u8_kernel<true><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
+  else quantize_u8_kernel<false><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
+  RET_LAUNCH();
+}

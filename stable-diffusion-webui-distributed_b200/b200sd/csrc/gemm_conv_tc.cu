@@ -1,0 +1,446 @@
+// gemm_conv_tc.cu — persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M, N] = epilogue( A[M, K] * Wt[N, K]^T )          fp16 or bf16 operands, fp32 accumulation in TMEM
+//
+// mode GEMM : A is a row-major [M, K] matrix (row pitch lda), loaded by 2-D TMA tiles {64 x 128}.
+//             Covers every Linear layer and every 1x1 convolution of the UNet / VAE (NHWC activations).
+// mode CONV : A is never materialised.  The activation is an NHWC tensor seen through a 4-D tensor map
+//             {C, W, H, N}; one M-tile is a box of bw x bh x bn output pixels (bw*bh*bn <= 128) and the
+//             K loop runs over (tap, 64-channel block): tap (dy, dx) is the same box shifted by
+//             (dx - pad, dy - pad) — TMA's out-of-bounds zero fill is the convolution padding, and
+//             elementStrides = 2 gives the stride-2 Downsample.  Weights are packed [Cout][tap][Cin].
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias / per-image bias / residual / GEGLU -> global).
+// Two TMEM accumulators (columns 0 and 256) let tile i's epilogue overlap tile i+1's MMAs.
+//
+// Upstream ops this kernel stands in for (not in /root/reference; reached from world.py:196 / worker.py:432):
+// ldm ResBlock conv3x3 / skip 1x1, Up/Downsample conv, SpatialTransformer proj_in/out, CrossAttention
+// to_q/k/v/out, FeedForward GEGLU + out, AutoencoderKL decoder convs (SURVEY.md §8 a-ext x1,x2,x5,x7,x8,x9,x11).
+#include "tc_common.cuh"
+#include "b200sd_internal.h"
+
+namespace b200sd {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 halfs = 128 B = one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int block_n;
+  int num_m_tiles, num_n_tiles, num_k_blocks, num_stages;
+  uint32_t a_bytes, b_bytes;
+  int mode;                        // 0 = GEMM, 1 = CONV
+  int H, W, NB;                    // CONV: output height / width / images
+  int bw, bh, bn;                  // CONV: output-pixel box
+  int tiles_x, tiles_y;            // CONV: boxes per row / column
+  int taps, cblocks, stride, pad;  // CONV
+  const float* bias;               // [groups][N] fp32 or nullptr
+  int bias_group_rows;             // rows (output pixels) sharing one bias row; <= 0 -> single row
+  const void* residual;            // [M][N-ish] same dtype as D, row pitch ldr, or nullptr
+  long long ldr;
+  void* D;
+  long long ldd;
+  int flags;                       // B200SD_EPI_*
+  int is_bf16;
+};
+
+struct __align__(8) GemmBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (kBf16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t tmem_acc, int m_tile, int n_tile,
+                                              int quarter, int lane) {
+  const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+  long long row;
+  bool valid;
+  if (p.mode == 0) {
+    row = static_cast<long long>(m_tile) * kBlockM + r;
+    valid = row < p.M;
+  } else {
+    const int tx = m_tile % p.tiles_x;
+    const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+    const int tn = m_tile / (p.tiles_x * p.tiles_y);
+    const int x = tx * p.bw + r % p.bw;
+    const int y = ty * p.bh + (r / p.bw) % p.bh;
+    const int n = tn * p.bn + r / (p.bw * p.bh);
+    valid = (r < p.bw * p.bh * p.bn) && x < p.W && y < p.H && n < p.NB;
+    row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+  }
+  const float* bias_row = nullptr;
+  if (p.bias != nullptr) {
+    const long long g = (p.bias_group_rows > 0 && valid) ? row / p.bias_group_rows : 0;
+    bias_row = p.bias + g * p.N;
+  }
+  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  const bool geglu = (p.flags & B200SD_EPI_GEGLU) != 0;
+  const int out_bn = geglu ? p.block_n / 2 : p.block_n;
+  const int nchunks = out_bn / 32;
+  uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) + (valid ? row : 0) * p.ldd * 2;
+  const uint8_t* rrow =
+      p.residual ? reinterpret_cast<const uint8_t*>(p.residual) + (valid ? row : 0) * p.ldr * 2 : nullptr;
+
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t v[32];
+    tmem_ld_x32(taddr_row + c * 32, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    const int col_in = n_tile * p.block_n + c * 32;  // column in the [N] space of the GEMM (bias index)
+    if (bias_row) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + col_in + j));
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    }
+    if (geglu) {
+      uint32_t g[32];
+      tmem_ld_x32(taddr_row + out_bn + c * 32, g);
+      tmem_ld_wait();
+      const int gcol = col_in + out_bn;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + j));
+        f[j] *= gelu_erf(__uint_as_float(g[j]) + b.x);
+        f[j + 1] *= gelu_erf(__uint_as_float(g[j + 1]) + b.y);
+        f[j + 2] *= gelu_erf(__uint_as_float(g[j + 2]) + b.z);
+        f[j + 3] *= gelu_erf(__uint_as_float(g[j + 3]) + b.w);
+      }
+    }
+    const int col_out = n_tile * out_bn + c * 32;
+    if (valid) {
+      if (rrow) {
+        const uint4* rp = reinterpret_cast<const uint4*>(rrow + static_cast<long long>(col_out) * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 rv = __ldg(rp + q);
+          const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = unpack2<kBf16>(w[e]);
+            f[q * 8 + e * 2] += t.x;
+            f[q * 8 + e * 2 + 1] += t.y;
+          }
+        }
+      }
+      if (p.flags & B200SD_EPI_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+      }
+      uint4* dp = reinterpret_cast<uint4*>(drow + static_cast<long long>(col_out) * 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack2<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
+        o.y = pack2<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
+        o.z = pack2<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
+        o.w = pack2<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
+        dp[q] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + static_cast<size_t>(p.num_stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        int cx = 0, cy = 0, cn = 0;
+        if (p.mode == 1) {
+          const int tx = m_tile % p.tiles_x;
+          const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+          cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn;
+          cx = tx * p.bw * p.stride - p.pad;
+          cy = ty * p.bh * p.stride - p.pad;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
+          uint8_t* sA = smem + static_cast<size_t>(stage) * stage_bytes;
+          uint8_t* sB = sA + 16384;
+          mbar_arrive_expect_tx(&bars->full[stage], p.a_bytes + p.b_bytes);
+          if (p.mode == 0) {
+            tma_load_2d(sA, &tmA, &bars->full[stage], kb * kBlockK, m_tile * kBlockM);
+          } else {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int dy = (p.taps == 9) ? tap / 3 : 0;
+            const int dx = (p.taps == 9) ? tap - dy * 3 : 0;
+            tma_load_4d(sA, &tmA, &bars->full[stage], cb * kBlockK, cx + dx, cy + dy, cn);
+          }
+          tma_load_2d(sB, &tmB, &bars->full[stage], kb * kBlockK, n_tile * p.block_n);
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, p.is_bf16 != 0, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sB = sA + 16384u;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_sdesc_sw128(sA + k * (kUmmaK * 2), 16, 1024);
+            const uint64_t db = make_sdesc_sw128(sB + k * (kUmmaK * 2), 16, 1024);
+            umma_f16_ss(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);  // smem slot free once these MMAs retire
+          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -----------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      mbar_wait(&bars->tmem_full[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * kAccStride;
+      if (p.is_bf16) epilogue_tile<true>(p, tmem_acc, m_tile, n_tile, quarter, lane);
+      else           epilogue_tile<false>(p, tmem_acc, m_tile, n_tile, quarter, lane);
+      tc_fence_before();
+      mbar_arrive(&bars->tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+static int device_props() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return B200SD_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200SD_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+      return B200SD_ERR_CUDA;
+    if (cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) !=
+        cudaSuccess)
+      return B200SD_ERR_CUDA;
+  }
+  return B200SD_OK;
+}
+
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams& p, int max_ctas,
+                  cudaStream_t stream) {
+  int rc = device_props();
+  if (rc != B200SD_OK) return rc;
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
+  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(GemmBarriers)) - 64;
+  int stages = budget / static_cast<int>(stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return B200SD_ERR_UNSUPPORTED;
+  p.num_stages = stages;
+  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + sizeof(GemmBarriers) + 64;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the kernel owns all 512 TMEM columns
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid <= 0) return B200SD_OK;
+  gemm_conv_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}
+
+static int fill_common(GemmKernelParams& p, int M, int N, int K, int block_n, const b200sd_epilogue* epi, void* D,
+                       long long ldd, int is_bf16) {
+  if (block_n < 32 || block_n > 256 || block_n % 32 != 0 || N % block_n != 0 || K % kBlockK != 0) return B200SD_ERR_INVALID;
+  p.M = M; p.N = N; p.K = K; p.block_n = block_n;
+  p.num_n_tiles = N / block_n;
+  p.num_k_blocks = K / kBlockK;
+  p.b_bytes = static_cast<uint32_t>(block_n) * 128u;
+  p.bias = epi ? epi->bias : nullptr;
+  p.bias_group_rows = epi ? epi->bias_group_rows : 0;
+  p.residual = epi ? epi->residual : nullptr;
+  p.ldr = epi ? epi->ldr : 0;
+  p.flags = epi ? epi->flags : 0;
+  p.D = D; p.ldd = ldd; p.is_bf16 = is_bf16;
+  if ((p.flags & B200SD_EPI_GEGLU) && block_n % 64 != 0) return B200SD_ERR_INVALID;
+  if (ldd % 8 != 0 || (reinterpret_cast<uintptr_t>(D) & 15) != 0) return B200SD_ERR_INVALID;
+  if (p.residual && (p.ldr % 8 != 0 || (reinterpret_cast<uintptr_t>(p.residual) & 15) != 0)) return B200SD_ERR_INVALID;
+  if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return B200SD_ERR_INVALID;
+  return B200SD_OK;
+}
+
+int gemm_tc(const void* A, long long lda, const void* Wt, void* D, long long ldd, int M, int N, int K, int block_n,
+            const b200sd_epilogue* epi, int is_bf16, int max_ctas, cudaStream_t stream) {
+  if (M <= 0) return B200SD_OK;
+  GemmKernelParams p{};
+  int rc = fill_common(p, M, N, K, block_n, epi, D, ldd, is_bf16);
+  if (rc != B200SD_OK) return rc;
+  if (lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(Wt) & 15) != 0)
+    return B200SD_ERR_INVALID;
+  p.mode = 0;
+  p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.a_bytes = 16384u;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {kBlockK, kBlockM};
+    const uint32_t es[2] = {1, 1};
+    rc = make_tmap_sw128(&tmA, A, 2, dims, strides, box, es);
+    if (rc != B200SD_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    const uint32_t es[2] = {1, 1};
+    rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
+    if (rc != B200SD_OK) return rc;
+  }
+  return launch(tmA, tmB, p, max_ctas, stream);
+}
+
+int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, const void* Wt, int ksize, int stride,
+            int pad, int pad_end, void* D, long long ldd, int Cout, int block_n, const b200sd_epilogue* epi,
+            int is_bf16, int max_ctas, cudaStream_t stream) {
+  if (NB <= 0) return B200SD_OK;
+  if ((ksize != 3 && ksize != 1) || (stride != 1 && stride != 2) || C % kBlockK != 0) return B200SD_ERR_INVALID;
+  if (pitch_c % 8 != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0 || (reinterpret_cast<uintptr_t>(Wt) & 15) != 0)
+    return B200SD_ERR_INVALID;
+  const int taps = ksize * ksize;
+  // pad = zeros before the first row/column, pad_end = zeros after the last (the VAE encoder pads (0,1,0,1))
+  const int Ho = (Hin + pad + pad_end - ksize) / stride + 1;
+  const int Wo = (Win + pad + pad_end - ksize) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return B200SD_ERR_INVALID;
+  GemmKernelParams p{};
+  int rc = fill_common(p, NB * Ho * Wo, Cout, taps * C, block_n, epi, D, ldd, is_bf16);
+  if (rc != B200SD_OK) return rc;
+  p.mode = 1;
+  p.H = Ho; p.W = Wo; p.NB = NB;
+  p.taps = taps; p.cblocks = C / kBlockK; p.stride = stride; p.pad = pad;
+  // output-pixel box: as much of a row as fits, then rows, then images (all <= 128 pixels)
+  p.bw = Wo < kBlockM ? Wo : kBlockM;
+  p.bh = kBlockM / p.bw; if (p.bh > Ho) p.bh = Ho; if (p.bh < 1) p.bh = 1;
+  p.bn = kBlockM / (p.bw * p.bh); if (p.bn > NB) p.bn = NB; if (p.bn < 1) p.bn = 1;
+  p.tiles_x = (Wo + p.bw - 1) / p.bw;
+  p.tiles_y = (Ho + p.bh - 1) / p.bh;
+  const int tiles_n = (NB + p.bn - 1) / p.bn;
+  p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
+  p.a_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bn) * 128u;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                              static_cast<uint64_t>(NB)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(pitch_c) * 2, static_cast<uint64_t>(pitch_c) * 2 * Win,
+                                 static_cast<uint64_t>(pitch_c) * 2 * Win * Hin};
+    // with elementStrides s the box extent is given in input elements: s * (#loaded elements)
+    const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(p.bw * stride), static_cast<uint32_t>(p.bh * stride),
+                             static_cast<uint32_t>(p.bn)};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    if (box[1] > 256 || box[2] > 256) return B200SD_ERR_UNSUPPORTED;
+    rc = make_tmap_sw128(&tmA, X, 4, dims, strides, box, es);
+    if (rc != B200SD_OK) return rc;
+  }
+  {
+    const uint64_t K = static_cast<uint64_t>(taps) * C;
+    const uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    const uint32_t es[2] = {1, 1};
+    rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
+    if (rc != B200SD_OK) return rc;
+  }
+  return launch(tmA, tmB, p, max_ctas, stream);
+}
+
+}  // namespace b200sd

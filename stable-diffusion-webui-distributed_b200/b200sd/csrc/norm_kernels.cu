@@ -1,0 +1,259 @@
+// norm_kernels.cu — HBM-bound normalisation kernels (NHWC, 16-byte vector loads, fp32 statistics).
+//
+//   groupnorm_stats  : per-(image, group) sum / sum-of-squares            1 read
+//   groupnorm_apply  : y = (x - mean) * rstd * gamma + beta [, SiLU]       1 read + 1 write
+//   layernorm        : one warp per token row, two passes in registers     1 read + 1 write
+//
+// Upstream: ldm GroupNorm32 (ResBlock.in_layers/out_layers, out), Normalize (SpatialTransformer.norm, VAE),
+// BasicTransformerBlock.norm1/2/3 (SURVEY.md §8 a-ext x3, x9; not in /root/reference).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../../include/b200sd.h"
+
+namespace b200sd {
+
+template <bool kBf16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t;
+    if constexpr (kBf16) t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    else t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (kBf16) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&v);
+    } else {
+      __half2 v = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&v);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// block = (C/8, PY): thread (v, py) owns channels [8v, 8v+8) for pixels py, py+PY, ... of its pixel range.
+template <bool kBf16>
+__global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long pitch, int HW, int C, int G,
+                                       int pix_per_cta, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [2][C]
+  const int n = blockIdx.y;
+  const int v = threadIdx.x;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) sh[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const uint8_t* base = X + (static_cast<long long>(n) * HW) * pitch * 2 + static_cast<long long>(v) * 16;
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * pitch * 2));
+    float f[8];
+    unpack8<kBf16>(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&sh[v * 8 + i], s[i]);
+    atomicAdd(&sh[C + v * 8 + i], q[i]);
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < G; g += blockDim.x * blockDim.y) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sh[c]; b += sh[C + c]; }
+    atomicAdd(&stats[(static_cast<long long>(n) * G + g) * 2], a);
+    atomicAdd(&stats[(static_cast<long long>(n) * G + g) * 2 + 1], b);
+  }
+}
+
+template <bool kBf16>
+__global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long pitch_x, uint8_t* __restrict__ Y,
+                                       long long pitch_y, int HW, int C, int G, int pix_per_cta,
+                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int silu) {
+  const int n = blockIdx.y;
+  const int v = threadIdx.x;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const int cpg = C / G;
+  const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(HW));
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    const int g = c / cpg;
+    const float sum = stats[(static_cast<long long>(n) * G + g) * 2];
+    const float sq = stats[(static_cast<long long>(n) * G + g) * 2 + 1];
+    const float mean = sum * inv_cnt;
+    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    a[i] = rstd * gamma[c];
+    b[i] = beta[c] - mean * a[i];
+  }
+  const uint8_t* xb = X + (static_cast<long long>(n) * HW) * pitch_x * 2 + static_cast<long long>(v) * 16;
+  uint8_t* yb = Y + (static_cast<long long>(n) * HW) * pitch_y * 2 + static_cast<long long>(v) * 16;
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(p) * pitch_x * 2));
+    float f[8];
+    unpack8<kBf16>(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = fmaf(f[i], a[i], b[i]);
+      if (silu) t = t / (1.0f + __expf(-t));
+      f[i] = t;
+    }
+    *reinterpret_cast<uint4*>(yb + static_cast<long long>(p) * pitch_y * 2) = pack8<kBf16>(f);
+  }
+}
+
+// one warp per row; C <= 2048, C % 8 == 0
+template <bool kBf16>
+__global__ void layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy,
+                                 int rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C / 8;
+  const uint8_t* xr = X + static_cast<long long>(warp) * ldx * 2;
+  uint8_t* yr = Y + static_cast<long long>(warp) * ldy * 2;
+  constexpr int kMaxIter = 8;  // 8 * 32 * 8 = 2048 channels
+  float f[kMaxIter][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int vec = it * 32 + lane;
+    if (vec < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long long>(vec) * 16));
+      unpack8<kBf16>(u, f[it]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += f[it][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / static_cast<float>(C);
+  float var = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int vec = it * 32 + lane;
+    if (vec < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[it][i] - mean; var += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int it = 0; it < kMaxIter; ++it) {
+    const int vec = it * 32 + lane;
+    if (vec < nvec) {
+      float o8[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o8[i] = (f[it][i] - mean) * rstd * gg[i] + bb[i];
+      *reinterpret_cast<uint4*>(yr + static_cast<long long>(vec) * 16) = pack8<kBf16>(o8);
+    }
+  }
+}
+
+static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_per_cta) {
+  if (C % 8 != 0 || C / 8 > 1024) return B200SD_ERR_INVALID;
+  const int vx = C / 8;
+  int py = 512 / vx;
+  if (py < 1) py = 1;
+  if (py > HW) py = HW;
+  block = dim3(vx, py, 1);
+  // aim for ~4 CTAs per SM over the whole grid; every CTA gets a whole multiple of py pixels
+  int want = (148 * 4 + NB - 1) / NB;
+  int ppc = (HW + want - 1) / want;
+  ppc = ((ppc + py - 1) / py) * py;
+  if (ppc < py) ppc = py;
+  pix_per_cta = ppc;
+  grid = dim3((HW + ppc - 1) / ppc, NB, 1);
+  return B200SD_OK;
+}
+
+}  // namespace b200sd
+
+using namespace b200sd;
+
+extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, int HW, int C, int G, float* stats,
+                                      int dtype, void* stream) {
+  if (NB <= 0 || HW <= 0) return B200SD_OK;
+  if (G <= 0 || C % G != 0 || pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(X) & 15)) return B200SD_ERR_INVALID;
+  dim3 block, grid;
+  int ppc;
+  int rc = gn_geometry(NB, HW, C, block, grid, ppc);
+  if (rc != B200SD_OK) return rc;
+  const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200SD_BF16)
+    groupnorm_stats_kernel<true><<<grid, block, sh, st>>>(static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+  else
+    groupnorm_stats_kernel<false><<<grid, block, sh, st>>>(static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}
+
+extern "C" int b200sd_groupnorm_apply(const void* X, long long pitch_x, void* Y, long long pitch_y, int NB, int HW,
+                                      int C, int G, const float* stats, const float* gamma, const float* beta,
+                                      float eps, int silu, int dtype, void* stream) {
+  if (NB <= 0 || HW <= 0) return B200SD_OK;
+  if (G <= 0 || C % G != 0 || pitch_x % 8 != 0 || pitch_y % 8 != 0 ||
+      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15))
+    return B200SD_ERR_INVALID;
+  dim3 block, grid;
+  int ppc;
+  int rc = gn_geometry(NB, HW, C, block, grid, ppc);
+  if (rc != B200SD_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200SD_BF16)
+    groupnorm_apply_kernel<true><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(X), pitch_x,
+                                                         static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats, gamma,
+                                                         beta, eps, silu);
+  else
+    groupnorm_apply_kernel<false><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(X), pitch_x,
+                                                          static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats,
+                                                          gamma, beta, eps, silu);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}
+
+extern "C" int b200sd_layernorm(const void* X, long long ldx, void* Y, long long ldy, int rows, int C,
+                                const float* gamma, const float* beta, float eps, int dtype, void* stream) {
+  if (rows <= 0) return B200SD_OK;
+  if (C % 8 != 0 || C > 2048 || ldx % 8 != 0 || ldy % 8 != 0 ||
+      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(gamma) |
+        reinterpret_cast<uintptr_t>(beta)) & 15))
+    return B200SD_ERR_INVALID;
+  const int warps_per_block = 8;
+  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200SD_BF16)
+    layernorm_kernel<true><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const uint8_t*>(X), ldx,
+                                                                    static_cast<uint8_t*>(Y), ldy, rows, C, gamma, beta,
+                                                                    eps);
+  else
+    layernorm_kernel<false><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const uint8_t*>(X), ldx,
+                                                                     static_cast<uint8_t*>(Y), ldy, rows, C, gamma,
+                                                                     beta, eps);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}

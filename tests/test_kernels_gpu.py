@@ -1,0 +1,351 @@
+"""GPU parity tests of every C-ABI op against a plain PyTorch fp32 reference of the same op.
+
+Tolerances (fp16 operands, fp32 accumulation): outputs are fp16, so one rounding of the result (rel 2^-11)
+plus accumulation-order differences; atol scales with sqrt(K) * |a| * |w|.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from kutil import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from b200sd import ops as _ops
+    return _ops
+
+
+def _rand(shape, gen, scale=1.0, dtype=torch.float16):
+    return (torch.randn(shape, generator=gen, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _gen(seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return g
+
+
+# ----------------------------------------------------------------------------------------------- linear
+@pytest.mark.parametrize("m,n,k,bn", [
+    (128, 64, 64, 64), (256, 128, 128, 128), (300, 256, 192, 256), (77, 320, 768, 160), (4096, 320, 320, 160),
+    (2048, 1280, 1280, 256), (1000, 960, 320, 192), (512, 96, 64, 32), (20, 1280, 320, 256),
+])
+def test_linear_plain(ops, m, n, k, bn):
+    g = _gen(m * 7 + n)
+    a = _rand((m, k), g)
+    w = _rand((n, k), g, 1.0 / math.sqrt(k))
+    out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.float16)
+    ops.linear(a, w, out, block_n=bn)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    assert_close(f"linear_plain m{m} n{n} k{k} bn{bn}", out, ref, atol=2e-2, rtol=2e-3)
+
+
+def test_linear_bias_residual_pitched(ops):
+    g = _gen(1)
+    m, n, k = 1024, 640, 640
+    abuf = _rand((m, k + 64), g)
+    a = abuf[:, 64:]  # pitched A (lda = k + 64), 128-byte aligned column offset
+    w = _rand((n, k), g, 1.0 / math.sqrt(k))
+    bias = torch.randn(n, generator=g, device="cuda")
+    res = _rand((m, n), g)
+    obuf = torch.zeros((m, n + 320), device="cuda", dtype=torch.float16)
+    out = obuf[:, 320:]
+    ops.linear(a, w, out, bias=bias, residual=res)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert_close("linear_bias_residual_pitched", out, ref, atol=2e-2, rtol=2e-3)
+    assert float(obuf[:, :320].abs().max()) == 0.0
+
+
+def test_linear_group_bias_silu(ops):
+    g = _gen(2)
+    m, n, k = 512, 256, 128
+    a = _rand((m, k), g)
+    w = _rand((n, k), g, 1.0 / math.sqrt(k))
+    bias = torch.randn(4, n, generator=g, device="cuda")  # one bias row per 128 output rows
+    out = torch.empty((m, n), device="cuda", dtype=torch.float16)
+    ops.linear(a, w, out, bias=bias, bias_group_rows=128, flags=ops.EPI_SILU)
+    torch.cuda.synchronize()
+    ref = F.silu(a.float() @ w.float().t() + bias.repeat_interleave(128, dim=0))
+    assert_close("linear_group_bias_silu", out, ref, atol=2e-2, rtol=2e-3)
+
+
+@pytest.mark.parametrize("m,c,bn", [(512, 320, 256), (1024, 640, 128)])
+def test_linear_geglu(ops, m, c, bn):
+    """FeedForward GEGLU: proj(x).chunk(2) -> a * gelu(g); weight rows interleaved per tile (value half, gate half)."""
+    g = _gen(3)
+    inner = 4 * c
+    a = _rand((m, c), g)
+    w = _rand((2 * inner, c), g, 1.0 / math.sqrt(c))   # upstream layout: rows [0,inner) value, [inner,2inner) gate
+    b = torch.randn(2 * inner, generator=g, device="cuda")
+    from b200sd.weights import pack_geglu
+    wp, bp = pack_geglu(w, b, bn)
+    out = torch.empty((m, inner), device="cuda", dtype=torch.float16)
+    ops.linear(a, wp, out, bias=bp, flags=ops.EPI_GEGLU, block_n=bn)
+    torch.cuda.synchronize()
+    y = a.float() @ w.float().t() + b
+    ref = y[:, :inner] * F.gelu(y[:, inner:])
+    assert_close(f"linear_geglu m{m} c{c}", out, ref, atol=3e-2, rtol=3e-3)
+
+
+def test_linear_bf16(ops):
+    g = _gen(4)
+    m, n, k = 384, 256, 256
+    a = _rand((m, k), g, dtype=torch.bfloat16)
+    w = _rand((n, k), g, 1.0 / math.sqrt(k), dtype=torch.bfloat16)
+    out = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+    ops.linear(a, w, out)
+    torch.cuda.synchronize()
+    assert_close("linear_bf16", out, a.float() @ w.float().t(), atol=5e-2, rtol=1e-2)
+
+
+# ----------------------------------------------------------------------------------------------- conv
+def _conv_ref(x_nhwc, w_packed, ksize, stride, pad, pad_end, bias=None):
+    nb, h, w_, c = x_nhwc.shape
+    cout = w_packed.shape[0]
+    wt = w_packed.float().reshape(cout, ksize, ksize, c).permute(0, 3, 1, 2)
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    x = F.pad(x, (pad, pad_end, pad, pad_end))
+    y = F.conv2d(x, wt, bias=bias, stride=stride)
+    return y.permute(0, 2, 3, 1).reshape(-1, cout)
+
+
+@pytest.mark.parametrize("nb,h,w,c,cout,k,s,bn", [
+    (2, 16, 16, 64, 64, 3, 1, 64), (2, 64, 64, 320, 320, 3, 1, 160), (3, 8, 8, 1280, 1280, 3, 1, 256),
+    (2, 32, 32, 640, 640, 3, 1, 128), (1, 128, 128, 128, 128, 3, 1, 128), (1, 4, 256, 64, 128, 3, 1, 128),
+    (1, 2, 512, 128, 128, 3, 1, 128), (2, 32, 32, 128, 128, 3, 2, 128), (2, 64, 64, 320, 320, 3, 2, 160),
+    (2, 16, 16, 640, 320, 1, 1, 160), (1, 24, 40, 64, 64, 3, 1, 64), (5, 8, 8, 64, 32, 3, 1, 32),
+])
+def test_conv2d(ops, nb, h, w, c, cout, k, s, bn):
+    g = _gen(nb * 100 + h + c)
+    x = _rand((nb, h, w, c), g)
+    wt = _rand((cout, k * k * c), g, 1.0 / math.sqrt(k * k * c))
+    bias = torch.randn(cout, generator=g, device="cuda")
+    pad = 1 if k == 3 else 0
+    ho = (h + 2 * pad - k) // s + 1
+    wo = (w + 2 * pad - k) // s + 1
+    out = torch.full((nb * ho * wo, cout), float("nan"), device="cuda", dtype=torch.float16)
+    ops.conv2d(x, wt, out, ksize=k, stride=s, pad=pad, bias=bias, block_n=bn)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, wt, k, s, pad, pad, bias)
+    assert_close(f"conv nb{nb} {h}x{w} c{c}->{cout} k{k} s{s}", out, ref, atol=2e-2, rtol=2e-3)
+
+
+def test_conv2d_asym_pad_stride2(ops):
+    """VAE encoder Downsample: pad (0,1,0,1) then 3x3 stride 2, no padding."""
+    g = _gen(11)
+    x = _rand((1, 64, 64, 128), g)
+    wt = _rand((128, 9 * 128), g, 1.0 / math.sqrt(9 * 128))
+    out = torch.empty((32 * 32, 128), device="cuda", dtype=torch.float16)
+    ops.conv2d(x, wt, out, ksize=3, stride=2, pad=0, pad_end=1)
+    torch.cuda.synchronize()
+    assert_close("conv_asym_pad_s2", out, _conv_ref(x, wt, 3, 2, 0, 1), atol=2e-2, rtol=2e-3)
+
+
+def test_conv2d_per_image_bias_residual_channel_slice(ops):
+    """ResBlock conv1 (+ per-image time-embedding bias) reading a channel slice of a wider skip-concat buffer."""
+    g = _gen(12)
+    nb, h, w, c, cout = 4, 16, 16, 128, 192
+    buf = _rand((nb, h, w, c + 64), g)
+    x = buf[..., 64:]
+    wt = _rand((cout, 9 * c), g, 1.0 / math.sqrt(9 * c))
+    bias = torch.randn(nb, cout, generator=g, device="cuda")
+    res = _rand((nb * h * w, cout), g)
+    out = torch.empty((nb * h * w, cout), device="cuda", dtype=torch.float16)
+    ops.conv2d(x, wt, out, ksize=3, bias=bias, bias_group_rows=h * w, residual=res, block_n=64)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, wt, 3, 1, 1, 1) + bias.repeat_interleave(h * w, dim=0) + res.float()
+    assert_close("conv_per_image_bias_residual_slice", out, ref, atol=2e-2, rtol=2e-3)
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, heads, d, d_pad, scale):
+    b, sq, _ = q.shape
+    skv = k.shape[1]
+    qh = q.float().reshape(b, sq, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
+    kh = k.float().reshape(b, skv, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
+    vh = v.float().reshape(b, skv, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    return (p @ vh).permute(0, 2, 1, 3).reshape(b, sq, heads * d)
+
+
+def _padded_heads(b, s, heads, d, d_pad, g):
+    t = torch.zeros((b, s, heads, d_pad), device="cuda", dtype=torch.float16)
+    t[..., :d] = _rand((b, s, heads, d), g)
+    return t.reshape(b, s, heads * d_pad)
+
+
+@pytest.mark.parametrize("b,heads,sq,skv,d", [
+    (1, 2, 128, 128, 64), (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
+    (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 256, 77, 160), (1, 10, 1024, 1024, 64), (1, 4, 200, 300, 40),
+])
+def test_attention(ops, b, heads, sq, skv, d):
+    g = _gen(sq + skv + d)
+    d_pad = (d + 63) // 64 * 64
+    q = _padded_heads(b, sq, heads, d, d_pad, g)
+    k = _padded_heads(b, skv, heads, d, d_pad, g)
+    v = _padded_heads(b, skv, heads, d, d_pad, g)
+    out = torch.full((b, sq, heads * d), float("nan"), device="cuda", dtype=torch.float16)
+    scale = d ** -0.5
+    ops.attention(q, k, v, out, heads, d, d_pad, scale)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, heads, d, d_pad, scale)
+    assert_close(f"attention b{b} h{heads} sq{sq} skv{skv} d{d}", out, ref, atol=4e-3, rtol=1e-2)
+
+
+def test_attention_fused_qkv_buffer(ops):
+    """Q, K, V as column slices of one projection output (pitch 3*heads*d_pad), large logits."""
+    g = _gen(21)
+    b, heads, s, d, d_pad = 2, 8, 512, 40, 64
+    qkv = torch.zeros((b, s, 3, heads, d_pad), device="cuda", dtype=torch.float16)
+    qkv[..., :d] = _rand((b, s, 3, heads, d), g, 3.0)
+    flat = qkv.reshape(b, s, 3 * heads * d_pad)
+    q, k, v = (flat[..., i * heads * d_pad:(i + 1) * heads * d_pad] for i in range(3))
+    out = torch.empty((b, s, heads * d), device="cuda", dtype=torch.float16)
+    ops.attention(q, k, v, out, heads, d, d_pad, d ** -0.5)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, heads, d, d_pad, d ** -0.5)
+    assert_close("attention_fused_qkv", out, ref, atol=1e-2, rtol=1e-2)
+
+
+# ----------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("nb,hw,c,silu,eps", [(2, 4096, 320, True, 1e-5), (3, 64, 1280, True, 1e-5),
+                                              (2, 1024, 1920, True, 1e-5), (1, 16384, 128, True, 1e-6),
+                                              (2, 256, 2560, False, 1e-6), (2, 1024, 960, True, 1e-5)])
+def test_groupnorm(ops, nb, hw, c, silu, eps):
+    g = _gen(hw + c)
+    x = _rand((nb, hw, c), g, 2.0) + 0.5
+    gamma = torch.randn(c, generator=g, device="cuda")
+    beta = torch.randn(c, generator=g, device="cuda")
+    out = torch.empty_like(x)
+    stats = torch.zeros((nb, 32, 2), device="cuda")
+    ops.groupnorm(x, out, stats, gamma, beta, 32, eps, silu)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert_close(f"groupnorm nb{nb} hw{hw} c{c}", out, ref, atol=1e-2, rtol=4e-3)
+
+
+@pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (77, 1280), (64, 2048)])
+def test_layernorm(ops, rows, c):
+    g = _gen(rows + c)
+    x = _rand((rows, c), g, 2.0) + 1.0
+    gamma = torch.randn(c, generator=g, device="cuda")
+    beta = torch.randn(c, generator=g, device="cuda")
+    out = torch.empty_like(x)
+    ops.layernorm(x, out, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    assert_close(f"layernorm {rows}x{c}", out, F.layer_norm(x.float(), (c,), gamma, beta, 1e-5), atol=1e-2, rtol=4e-3)
+
+
+# ----------------------------------------------------------------------------------------------- small ops
+def test_upsample2x(ops):
+    g = _gen(31)
+    x = _rand((2, 8, 16, 64), g)
+    out = torch.empty((2, 16, 32, 64), device="cuda", dtype=torch.float16)
+    ops.upsample2x(x, out)
+    torch.cuda.synchronize()
+    ref = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(out, ref)
+
+
+def test_softmax_rows(ops):
+    g = _gen(32)
+    s = _rand((300, 4096), g, 4.0)
+    ref = torch.softmax(s.float() * 0.125, dim=-1)
+    ops.softmax_rows_(s, 0.125)
+    torch.cuda.synchronize()
+    assert_close("softmax_rows", s, ref, atol=1e-4, rtol=4e-3)
+
+
+def test_silu_and_timestep_embedding(ops):
+    g = _gen(33)
+    x = _rand((20, 1280), g, 3.0)
+    out = torch.empty_like(x)
+    ops.silu(x, out)
+    t = torch.tensor([1.0, 51.0, 501.0, 951.0], device="cuda")
+    emb = torch.empty((4, 320), device="cuda", dtype=torch.float16)
+    ops.timestep_embedding(t, emb)
+    torch.cuda.synchronize()
+    assert_close("silu", out, F.silu(x.float()), atol=1e-3, rtol=2e-3)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(160, device="cuda", dtype=torch.float32) / 160)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    assert_close("timestep_embedding", emb, ref, atol=2e-3, rtol=0)
+
+
+def test_fold_and_select_bias(ops):
+    g = _gen(34)
+    emb = _rand((20, 640), g)
+    bias = torch.randn(640, generator=g, device="cuda")
+    table = torch.empty((20, 640), device="cuda")
+    ops.fold_bias(emb, bias, table)
+    step = torch.tensor([7], device="cuda", dtype=torch.int32)
+    cur = torch.empty(640, device="cuda")
+    ops.select_step(table, step, cur)
+    torch.cuda.synchronize()
+    assert torch.allclose(table, emb.float() + bias)
+    assert torch.equal(cur, table[7])
+
+
+def test_cfg_ddim_step_and_pack(ops):
+    g = _gen(35)
+    b, hw = 3, 4096
+    x = torch.randn((b, hw, 4), generator=g, device="cuda")
+    x0 = x.clone()
+    xin = torch.zeros((2 * b, hw, 64), device="cuda", dtype=torch.float16)
+    ops.pack_unet_input(x, xin, 1.0)
+    eps = torch.zeros((2 * b, hw, 32), device="cuda", dtype=torch.float16)
+    eps[..., :4] = _rand((2 * b, hw, 4), g)
+    coef = torch.tensor([[0.3, 0.95, 0.4, 0.92], [0.5, 0.87, 0.6, 0.8]], device="cuda")
+    step = torch.tensor([1], device="cuda", dtype=torch.int32)
+    torch.cuda.synchronize()
+    assert torch.equal(xin[:b, :, :4], x0.half()) and torch.equal(xin[b:, :, :4], x0.half())
+    assert float(xin[..., 4:].abs().max()) == 0.0
+    ops.cfg_ddim_step(eps, x, xin, 7.0, coef, step)
+    torch.cuda.synchronize()
+    ec, eu = eps[:b, :, :4].float(), eps[b:, :, :4].float()
+    e = eu + 7.0 * (ec - eu)
+    pred_x0 = (x0 - 0.87 * e) / 0.5
+    ref = 0.6 * pred_x0 + 0.8 * e
+    assert torch.allclose(x, ref, atol=1e-4, rtol=1e-5)
+    assert int(step.item()) == 2
+    assert torch.equal(xin[b:, :, :4], x.half())
+
+
+def test_cfg_euler_a_step(ops):
+    g = _gen(36)
+    b, hw = 2, 1024
+    x = torch.randn((b, hw, 4), generator=g, device="cuda") * 10
+    x0 = x.clone()
+    noise = torch.randn((3, b, hw, 4), generator=g, device="cuda")
+    xin = torch.zeros((2 * b, hw, 64), device="cuda", dtype=torch.float16)
+    eps = torch.zeros((2 * b, hw, 32), device="cuda", dtype=torch.float16)
+    eps[..., :4] = _rand((2 * b, hw, 4), g)
+    coef = torch.tensor([[14.6, 9.0, 5.0, 0.1], [10.3, 7.0, 3.0, 0.12], [7.0, 5.0, 2.0, 0.2]], device="cuda")
+    step = torch.tensor([1], device="cuda", dtype=torch.int32)
+    ops.cfg_euler_a_step(eps, x, noise, xin, 5.0, coef, step)
+    torch.cuda.synchronize()
+    ec, eu = eps[:b, :, :4].float(), eps[b:, :, :4].float()
+    e = eu + 5.0 * (ec - eu)
+    ref = x0 + e * (7.0 - 10.3) + noise[1] * 3.0
+    assert torch.allclose(x, ref, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(xin[:b, :, :4].float(), ref * 0.12, atol=2e-2, rtol=2e-3)
+
+
+def test_quantize_u8(ops):
+    g = _gen(37)
+    img = torch.zeros((2, 1000, 32), device="cuda", dtype=torch.float16)
+    img[..., :3] = _rand((2, 1000, 3), g, 0.8)
+    out = torch.empty((2, 1000, 3), device="cuda", dtype=torch.uint8)
+    ops.quantize_u8(img, out)
+    torch.cuda.synchronize()
+    ref = (255.0 * ((img[..., :3].float() + 1.0) * 0.5).clamp(0, 1)).to(torch.uint8)
+    assert torch.equal(out, ref)
