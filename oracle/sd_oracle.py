@@ -1,0 +1,463 @@
+"""oracle/sd_oracle.py — plain PyTorch fp32 restatement of the numeric path the reference dispatches to.
+
+TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` leg — never by the product path (stable-diffusion-webui-distributed_b200/).
+
+PARITY UNPINNED: the reference (papuSpartan/stable-diffusion-webui-distributed @ 8fd65ebd) contains none of this
+arithmetic and ships no tests or golden vectors.  Its call sites into the numeric path are
+  scripts/spartan/world.py:196   process_images(p)                     (master's share / sample_master)
+  scripts/spartan/worker.py:432  session.post(.../sdapi/v1/txt2img|img2img)  (remote sdwui: UNet x steps, VAE)
+The arithmetic lives in un-vendored third parties (AUTOMATIC1111 sdwui -> CompVis `ldm` openaimodel / model.py /
+attention.py, k-diffusion sampling.py); none is installable offline and the extension pins no version.  This file
+restates their published algorithms with ldm state_dict key names so a real checkpoint loads.
+
+Everything here is NCHW fp32 (or whatever dtype/device the caller's tensors have), functional over a dict of
+parameters.  Function docstrings name the upstream symbol they follow.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+# ------------------------------------------------------------------------------------------------ configs
+@dataclass
+class UNetConfig:
+    """ldm/modules/diffusionmodules/openaimodel.py::UNetModel ctor args (v1-inference.yaml)."""
+    in_channels: int = 4
+    out_channels: int = 4
+    model_channels: int = 320
+    channel_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    attention_levels: Tuple[int, ...] = (0, 1, 2)   # levels (index into channel_mult) that carry transformers
+    num_heads: int = 8
+    context_dim: int = 768
+    transformer_depth: int = 1
+
+    @property
+    def time_embed_dim(self):
+        return 4 * self.model_channels
+
+
+@dataclass
+class VAEConfig:
+    """ldm/modules/diffusionmodules/model.py Encoder/Decoder args (kl-f8)."""
+    ch: int = 128
+    ch_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    z_channels: int = 4
+    out_ch: int = 3
+    scale_factor: float = 0.18215
+
+
+@dataclass
+class CLIPConfig:
+    vocab: int = 49408
+    width: int = 768
+    layers: int = 12
+    heads: int = 12
+    ctx: int = 77
+
+
+SD15_UNET = UNetConfig()
+SD15_VAE = VAEConfig()
+SD15_CLIP = CLIPConfig()
+# reduced-width models with the same topology, for fast CPU tests
+TINY_UNET = UNetConfig(model_channels=64, num_heads=2, context_dim=64)
+TINY_VAE = VAEConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1)
+TINY_CLIP = CLIPConfig(vocab=1000, width=64, layers=2, heads=2)
+
+
+# ------------------------------------------------------------------------------------------------ UNet topology
+def unet_layout(cfg: UNetConfig):
+    """Block list of UNetModel.__init__: returns (input_blocks, middle, output_blocks); each block is a list of
+    ('conv_in', cin, cout) | ('res', cin, cout) | ('attn', c) | ('down', c) | ('up', c)."""
+    mc = cfg.model_channels
+    inputs = [[("conv_in", cfg.in_channels, mc)]]
+    chans = [mc]
+    ch = mc
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            blk = [("res", ch, mult * mc)]
+            ch = mult * mc
+            if level in cfg.attention_levels:
+                blk.append(("attn", ch))
+            inputs.append(blk)
+            chans.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            inputs.append([("down", ch)])
+            chans.append(ch)
+    middle = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    outputs = []
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            blk = [("res", ch + ich, mult * mc)]
+            ch = mult * mc
+            if level in cfg.attention_levels:
+                blk.append(("attn", ch))
+            if level and i == cfg.num_res_blocks:
+                blk.append(("up", ch))
+            outputs.append(blk)
+    return inputs, middle, outputs
+
+
+# ------------------------------------------------------------------------------------------------ UNet forward
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """ldm/modules/diffusionmodules/util.py::timestep_embedding (cos first, then sin)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def _gn(x, sd, key, eps):
+    return F.group_norm(x.float(), 32, sd[key + ".weight"].float(), sd[key + ".bias"].float(), eps).to(x.dtype)
+
+
+def res_block(sd: SD, p: str, x, emb):
+    """openaimodel.ResBlock._forward: GN32-SiLU-conv3x3, + Linear(SiLU(emb)), GN32-SiLU-conv3x3, + skip."""
+    h = F.silu(_gn(x, sd, p + ".in_layers.0", 1e-5))
+    h = F.conv2d(h, sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.2.bias"], padding=1)
+    e = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
+    h = h + e[:, :, None, None]
+    h = F.silu(_gn(h, sd, p + ".out_layers.0", 1e-5))
+    h = F.conv2d(h, sd[p + ".out_layers.3.weight"], sd[p + ".out_layers.3.bias"], padding=1)
+    if p + ".skip_connection.weight" in sd:
+        x = F.conv2d(x, sd[p + ".skip_connection.weight"], sd[p + ".skip_connection.bias"])
+    return x + h
+
+
+def cross_attention(sd: SD, p: str, x, context, heads: int):
+    """ldm/modules/attention.py::CrossAttention.forward: softmax(q k^T * d^-0.5) v, to_out with bias."""
+    ctx = x if context is None else context
+    q = F.linear(x, sd[p + ".to_q.weight"])
+    k = F.linear(ctx, sd[p + ".to_k.weight"])
+    v = F.linear(ctx, sd[p + ".to_v.weight"])
+    b, n, c = q.shape
+    d = c // heads
+    q, k, v = (t.reshape(b, -1, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+    out = torch.matmul(torch.softmax(sim.float(), dim=-1).to(v.dtype), v)
+    out = out.permute(0, 2, 1, 3).reshape(b, n, c)
+    return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+
+
+def _ln(x, sd, key):
+    return F.layer_norm(x.float(), (x.shape[-1],), sd[key + ".weight"].float(), sd[key + ".bias"].float(), 1e-5).to(x.dtype)
+
+
+def transformer_block(sd: SD, p: str, x, context, heads: int):
+    """attention.py::BasicTransformerBlock._forward (attn1 self, attn2 cross, GEGLU feed-forward)."""
+    x = cross_attention(sd, p + ".attn1", _ln(x, sd, p + ".norm1"), None, heads) + x
+    x = cross_attention(sd, p + ".attn2", _ln(x, sd, p + ".norm2"), context, heads) + x
+    h = F.linear(_ln(x, sd, p + ".norm3"), sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"])
+    a, g = h.chunk(2, dim=-1)
+    h = a * F.gelu(g)
+    return F.linear(h, sd[p + ".ff.net.2.weight"], sd[p + ".ff.net.2.bias"]) + x
+
+
+def spatial_transformer(sd: SD, p: str, x, context, heads: int, depth: int = 1):
+    """attention.py::SpatialTransformer.forward (conv proj_in/out, SD1.x)."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = _gn(x, sd, p + ".norm", 1e-6)
+    x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+    for i in range(depth):
+        x = transformer_block(sd, f"{p}.transformer_blocks.{i}", x, context, heads)
+    x = x.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+    return x + x_in
+
+
+def _run_block(sd, cfg, prefix, blk, h, emb, context):
+    for j, layer in enumerate(blk):
+        p = f"{prefix}.{j}"
+        kind = layer[0]
+        if kind == "conv_in":
+            h = F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1)
+        elif kind == "res":
+            h = res_block(sd, p, h, emb)
+        elif kind == "attn":
+            h = spatial_transformer(sd, p, h, context, cfg.num_heads, cfg.transformer_depth)
+        elif kind == "down":
+            h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
+        elif kind == "up":
+            h = F.interpolate(h, scale_factor=2, mode="nearest")
+            h = F.conv2d(h, sd[p + ".conv.weight"], sd[p + ".conv.bias"], padding=1)
+    return h
+
+
+def unet_forward(sd: SD, cfg: UNetConfig, x, t, context, prefix: str = "model.diffusion_model."):
+    """openaimodel.UNetModel.forward(x, timesteps, context) -> eps."""
+    sdp = _Prefixed(sd, prefix)
+    inputs, middle, outputs = unet_layout(cfg)
+    emb = timestep_embedding(t, cfg.model_channels).to(x.dtype)
+    emb = F.linear(emb, sdp["time_embed.0.weight"], sdp["time_embed.0.bias"])
+    emb = F.linear(F.silu(emb), sdp["time_embed.2.weight"], sdp["time_embed.2.bias"])
+    hs = []
+    h = x
+    for i, blk in enumerate(inputs):
+        h = _run_block(sdp, cfg, f"input_blocks.{i}", blk, h, emb, context)
+        hs.append(h)
+    h = _run_block(sdp, cfg, "middle_block", middle, h, emb, context)
+    for i, blk in enumerate(outputs):
+        h = torch.cat([h, hs.pop()], dim=1)
+        h = _run_block(sdp, cfg, f"output_blocks.{i}", blk, h, emb, context)
+    h = F.silu(_gn(h, sdp, "out.0", 1e-5))
+    return F.conv2d(h, sdp["out.2.weight"], sdp["out.2.bias"], padding=1)
+
+
+class _Prefixed:
+    """dict view adding a key prefix (ldm checkpoints prefix the UNet with 'model.diffusion_model.')."""
+
+    def __init__(self, sd, prefix):
+        self.sd, self.prefix = sd, prefix
+
+    def __getitem__(self, k):
+        return self.sd[self.prefix + k]
+
+    def __contains__(self, k):
+        return (self.prefix + k) in self.sd
+
+
+# ------------------------------------------------------------------------------------------------ VAE
+def _vae_res(sd, p, x):
+    """model.py::ResnetBlock.forward (swish, GN eps 1e-6, temb unused)."""
+    h = F.conv2d(F.silu(_gn(x, sd, p + ".norm1", 1e-6)), sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn(h, sd, p + ".norm2", 1e-6)), sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], padding=1)
+    if p + ".nin_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[p + ".nin_shortcut.weight"], sd[p + ".nin_shortcut.bias"])
+    return x + h
+
+
+def _vae_attn(sd, p, x):
+    """model.py::AttnBlock.forward: single head, d = C, softmax(q^T k * C^-0.5)."""
+    h = _gn(x, sd, p + ".norm", 1e-6)
+    q = F.conv2d(h, sd[p + ".q.weight"], sd[p + ".q.bias"])
+    k = F.conv2d(h, sd[p + ".k.weight"], sd[p + ".k.bias"])
+    v = F.conv2d(h, sd[p + ".v.weight"], sd[p + ".v.bias"])
+    b, c, hh, ww = q.shape
+    q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+    k = k.reshape(b, c, hh * ww)
+    w_ = torch.softmax((torch.bmm(q, k) * (c ** -0.5)).float(), dim=2).to(q.dtype)
+    v = v.reshape(b, c, hh * ww)
+    h = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+
+
+def vae_decode(sd: SD, cfg: VAEConfig, z, prefix: str = "first_stage_model."):
+    """AutoencoderKL.decode: post_quant_conv then model.py::Decoder.forward. z is the UNscaled latent."""
+    s = _Prefixed(sd, prefix)
+    z = F.conv2d(z, s["post_quant_conv.weight"], s["post_quant_conv.bias"])
+    h = F.conv2d(z, s["decoder.conv_in.weight"], s["decoder.conv_in.bias"], padding=1)
+    h = _vae_res(s, "decoder.mid.block_1", h)
+    h = _vae_attn(s, "decoder.mid.attn_1", h)
+    h = _vae_res(s, "decoder.mid.block_2", h)
+    nlev = len(cfg.ch_mult)
+    for lvl in reversed(range(nlev)):
+        for i in range(cfg.num_res_blocks + 1):
+            h = _vae_res(s, f"decoder.up.{lvl}.block.{i}", h)
+        if lvl != 0:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, s[f"decoder.up.{lvl}.upsample.conv.weight"], s[f"decoder.up.{lvl}.upsample.conv.bias"], padding=1)
+    h = F.silu(_gn(h, s, "decoder.norm_out", 1e-6))
+    return F.conv2d(h, s["decoder.conv_out.weight"], s["decoder.conv_out.bias"], padding=1)
+
+
+def vae_encode_mean(sd: SD, cfg: VAEConfig, x, prefix: str = "first_stage_model."):
+    """AutoencoderKL.encode -> DiagonalGaussianDistribution.mean (the oracle uses the mean, not a sample:
+    upstream samples with the global RNG)."""
+    s = _Prefixed(sd, prefix)
+    h = F.conv2d(x, s["encoder.conv_in.weight"], s["encoder.conv_in.bias"], padding=1)
+    nlev = len(cfg.ch_mult)
+    for lvl in range(nlev):
+        for i in range(cfg.num_res_blocks):
+            h = _vae_res(s, f"encoder.down.{lvl}.block.{i}", h)
+        if lvl != nlev - 1:
+            h = F.pad(h, (0, 1, 0, 1))
+            h = F.conv2d(h, s[f"encoder.down.{lvl}.downsample.conv.weight"], s[f"encoder.down.{lvl}.downsample.conv.bias"], stride=2)
+    h = _vae_res(s, "encoder.mid.block_1", h)
+    h = _vae_attn(s, "encoder.mid.attn_1", h)
+    h = _vae_res(s, "encoder.mid.block_2", h)
+    h = F.silu(_gn(h, s, "encoder.norm_out", 1e-6))
+    h = F.conv2d(h, s["encoder.conv_out.weight"], s["encoder.conv_out.bias"], padding=1)
+    moments = F.conv2d(h, s["quant_conv.weight"], s["quant_conv.bias"])
+    return moments.chunk(2, dim=1)[0]
+
+
+# ------------------------------------------------------------------------------------------------ CLIP text
+def clip_text_encode(sd: SD, cfg: CLIPConfig, tokens, prefix: str = "cond_stage_model.transformer.text_model."):
+    """CLIP ViT-L/14 text tower (transformers CLIPTextModel): causal mask, quick-gelu MLP, final LN; last hidden state."""
+    s = _Prefixed(sd, prefix)
+    x = s["embeddings.token_embedding.weight"][tokens] + s["embeddings.position_embedding.weight"][None, :tokens.shape[1]]
+    n = tokens.shape[1]
+    mask = torch.full((n, n), float("-inf"), device=x.device, dtype=x.dtype).triu(1)
+    d = cfg.width // cfg.heads
+    for i in range(cfg.layers):
+        p = f"encoder.layers.{i}"
+        h = F.layer_norm(x, (cfg.width,), s[p + ".layer_norm1.weight"], s[p + ".layer_norm1.bias"], 1e-5)
+        q = F.linear(h, s[p + ".self_attn.q_proj.weight"], s[p + ".self_attn.q_proj.bias"])
+        k = F.linear(h, s[p + ".self_attn.k_proj.weight"], s[p + ".self_attn.k_proj.bias"])
+        v = F.linear(h, s[p + ".self_attn.v_proj.weight"], s[p + ".self_attn.v_proj.bias"])
+        b = x.shape[0]
+        q, k, v = (t.reshape(b, n, cfg.heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+        att = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5 + mask, dim=-1) @ v
+        att = att.permute(0, 2, 1, 3).reshape(b, n, cfg.width)
+        x = x + F.linear(att, s[p + ".self_attn.out_proj.weight"], s[p + ".self_attn.out_proj.bias"])
+        h = F.layer_norm(x, (cfg.width,), s[p + ".layer_norm2.weight"], s[p + ".layer_norm2.bias"], 1e-5)
+        h = F.linear(h, s[p + ".mlp.fc1.weight"], s[p + ".mlp.fc1.bias"])
+        h = h * torch.sigmoid(1.702 * h)
+        x = x + F.linear(h, s[p + ".mlp.fc2.weight"], s[p + ".mlp.fc2.bias"])
+    return F.layer_norm(x, (cfg.width,), s["final_layer_norm.weight"], s["final_layer_norm.bias"], 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ schedule / samplers
+def alphas_cumprod() -> torch.Tensor:
+    """ldm DDPM.register_schedule('linear', 1000, 0.00085, 0.012): fp64 math, stored fp32."""
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).to(torch.float32)
+
+
+def ddim_timesteps(steps: int) -> torch.Tensor:
+    """sdwui sd_samplers_timesteps: uniform discretisation, clip(arange(0,1000,1000//steps)+1, 0, 999)."""
+    return torch.clamp(torch.arange(0, 1000, 1000 // steps) + 1, 0, 999)
+
+
+def ddim_coefficients(steps: int) -> List[Tuple[int, float, float, float, float]]:
+    """Per executed step, in execution order: (t, sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)) with eta=0.
+    sdwui sd_samplers_timesteps_impl.ddim: alphas_prev = alphas_cumprod[pad(ts[:-1], (1, 0))] (index 0 pads to
+    alphas_cumprod[0]); `for i in trange(len(ts) - 1): index = len(ts) - 1 - i` — i.e. index runs from len(ts)-1
+    down to 1, so `steps - 1` UNet evaluations are executed for `steps` timesteps (19 for the 20-step configs)."""
+    ac = alphas_cumprod().double()
+    ts = ddim_timesteps(steps)
+    alphas = ac[ts]
+    alphas_prev = ac[torch.cat([ts[:1] * 0, ts[:-1]])]
+    out = []
+    for i in range(len(ts) - 1, 0, -1):
+        a_t, a_p = float(alphas[i]), float(alphas_prev[i])
+        out.append((int(ts[i]), math.sqrt(a_t), math.sqrt(1.0 - a_t), math.sqrt(a_p), math.sqrt(1.0 - a_p)))
+    return out
+
+
+def cfg_eps(unet, x, t: int, cond, uncond, cfg_scale: float):
+    """sdwui CFGDenoiser: one UNet call on cat([x, x]) with cat([cond, uncond]); uncond + s * (cond - uncond)."""
+    b = x.shape[0]
+    tt = torch.full((2 * b,), float(t), device=x.device)
+    e = unet(torch.cat([x, x]), tt, torch.cat([cond, uncond]))
+    ec, eu = e[:b], e[b:]
+    return eu + cfg_scale * (ec - eu)
+
+
+def sample_ddim(unet, x_T, cond, uncond, steps: int, cfg_scale: float, start_index: int = 0):
+    x = x_T
+    for (t, sa, s1a, sap, s1ap) in ddim_coefficients(steps)[start_index:]:
+        e = cfg_eps(unet, x, t, cond, uncond, cfg_scale)
+        x0 = (x - s1a * e) / sa
+        x = sap * x0 + s1ap * e
+    return x
+
+
+def karras_sigmas_compvis(steps: int):
+    """k-diffusion DiscreteSchedule.get_sigmas(n): t = linspace(999, 0, n), log-sigma interpolation, append 0."""
+    ac = alphas_cumprod().double()
+    sig = ((1 - ac) / ac) ** 0.5
+    log_sig = sig.log()
+    t = torch.linspace(len(sig) - 1, 0, steps, dtype=torch.float64)
+    lo = t.floor().long()
+    hi = t.ceil().long()
+    w = t - lo
+    s = ((1 - w) * log_sig[lo] + w * log_sig[hi]).exp()
+    return torch.cat([s, s.new_zeros(1)]), log_sig
+
+
+def sigma_to_t(sigma: float, log_sig: torch.Tensor) -> float:
+    """k-diffusion DiscreteSchedule.sigma_to_t (quantize=False): fractional timestep by log-sigma interpolation."""
+    ls = math.log(sigma)
+    dists = ls - log_sig
+    low = int((dists >= 0).cumsum(0).argmax().clamp(max=len(log_sig) - 2))
+    high = low + 1
+    lo, hi = float(log_sig[low]), float(log_sig[high])
+    w = min(max((lo - ls) / (lo - hi), 0.0), 1.0)
+    return (1 - w) * low + w * high
+
+
+def euler_a_coefficients(steps: int):
+    """Per step: (t, sigma, sigma_down, sigma_up, c_in, c_in_next) — k-diffusion sample_euler_ancestral + CompVisDenoiser."""
+    sig, log_sig = karras_sigmas_compvis(steps)
+    out = []
+    for i in range(steps):
+        s, sn = float(sig[i]), float(sig[i + 1])
+        up = min(sn, (sn ** 2 * (s ** 2 - sn ** 2) / s ** 2) ** 0.5)
+        down = (sn ** 2 - up ** 2) ** 0.5
+        out.append((sigma_to_t(s, log_sig), s, down, up, 1.0 / math.sqrt(s * s + 1.0), 1.0 / math.sqrt(sn * sn + 1.0)))
+    return out
+
+
+def sample_euler_a(unet, x_T, cond, uncond, steps: int, cfg_scale: float, noises):
+    """noises[i] is the N(0,1) draw used after step i (per-image generators upstream; injected here)."""
+    coefs = euler_a_coefficients(steps)
+    x = x_T * coefs[0][1]
+    for i, (t, s, down, up, c_in, _) in enumerate(coefs):
+        e = cfg_eps(unet, x * c_in, t, cond, uncond, cfg_scale)
+        x = x + e * (down - s)       # d = (x - denoised) / sigma = eps ; x += d * (sigma_down - sigma)
+        if up > 0:
+            x = x + noises[i] * up
+    return x
+
+
+# ------------------------------------------------------------------------------------------------ images / rng
+def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0) -> torch.Tensor:
+    """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k."""
+    out = []
+    for k in range(n):
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
+        out.append(torch.randn(shape, generator=g, dtype=torch.float32))
+    return torch.stack(out)
+
+
+def random_prompt_tokens(n: int, seed: int = 1234, vocab_hi: int = 49405) -> torch.Tensor:
+    """SURVEY.md §8d synthetic prompts: [BOS] + 75 random ids + [EOS]."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    body = torch.randint(0, vocab_hi, (n, 75), generator=g)
+    bos = torch.full((n, 1), vocab_hi + 1)
+    eos = torch.full((n, 1), vocab_hi + 2)
+    return torch.cat([bos, body, eos], dim=1)
+
+
+def empty_prompt_tokens(n: int, vocab_hi: int = 49405) -> torch.Tensor:
+    t = torch.full((n, 77), vocab_hi + 2)
+    t[:, 0] = vocab_hi + 1
+    return t
+
+
+def to_uint8(decoded: torch.Tensor) -> torch.Tensor:
+    """sdwui process_images_inner: clamp((x+1)/2, 0, 1) -> (255 * x).astype(uint8) (truncation), HWC."""
+    x = torch.clamp((decoded.float() + 1.0) / 2.0, 0.0, 1.0)
+    return (255.0 * x).permute(0, 2, 3, 1).to(torch.uint8)
+
+
+def txt2img(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, steps: int = 20, cfg_scale: float = 7.0,
+            height: int = 512, width: int = 512, sampler: str = "DDIM", device="cpu"):
+    """End-to-end oracle for one batch: returns (uint8 images [B,H,W,3], final latents, decoded float)."""
+    b = tokens.shape[0]
+    dsd = {k: v.to(device) for k, v in sd.items()}
+    cond = clip_text_encode(dsd, clip_cfg, tokens.to(device))
+    uncond = clip_text_encode(dsd, clip_cfg, neg_tokens.to(device))
+    x_T = per_image_noise(seed, b, (unet_cfg.in_channels, height // 8, width // 8)).to(device)
+
+    def unet(x, t, c):
+        return unet_forward(dsd, unet_cfg, x, t, c)
+
+    if sampler == "DDIM":
+        z = sample_ddim(unet, x_T, cond, uncond, steps, cfg_scale)
+    else:
+        raise ValueError(sampler)
+    dec = vae_decode(dsd, vae_cfg, z / vae_cfg.scale_factor)
+    return to_uint8(dec), z, dec

@@ -283,6 +283,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 static int g_attn_max_smem = 0;
+static bool g_attn_dev_ready[64] = {};
 
 int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
                  long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int is_bf16,
@@ -296,14 +297,19 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   if (ldq < static_cast<long long>(heads) * d_pad || ldk < static_cast<long long>(heads) * d_pad ||
       ldv < static_cast<long long>(heads) * d_pad || ldo < static_cast<long long>(heads) * d)
     return B200SD_ERR_INVALID;
-  if (g_attn_max_smem == 0) {
+  {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return B200SD_ERR_CUDA;
-    if (cudaDeviceGetAttribute(&g_attn_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
-      return B200SD_ERR_CUDA;
-    if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_attn_max_smem) !=
-        cudaSuccess)
-      return B200SD_ERR_CUDA;
+    if (dev < 0 || dev >= 64) return B200SD_ERR_UNSUPPORTED;
+    if (!g_attn_dev_ready[dev]) {  // per-device opt-in to large dynamic smem; first call must be outside capture
+      int smem = 0;
+      if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return B200SD_ERR_CUDA;
+      if (cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return B200SD_ERR_CUDA;
+      g_attn_max_smem = smem;
+      g_attn_dev_ready[dev] = true;
+    }
   }
   AttnParams p{};
   p.B = B; p.heads = heads; p.Sq = Sq; p.Skv = Skv; p.d = d; p.d_pad = d_pad;

@@ -305,16 +305,23 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 static int g_max_smem = 0;
+static bool g_dev_ready[64] = {};
+// per-device one-time setup (the dynamic-smem opt-in is per context): safe to call from several host threads
+// that each drive their own device, and must first happen OUTSIDE any stream capture (warm-up run).
 static int device_props() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return B200SD_ERR_CUDA;
-    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200SD_ERR_CUDA;
-    if (cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200SD_ERR_CUDA;
+  if (dev < 0 || dev >= 64) return B200SD_ERR_UNSUPPORTED;
+  if (!g_dev_ready[dev]) {
+    int sms = 0, smem = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200SD_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
       return B200SD_ERR_CUDA;
-    if (cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200SD_ERR_CUDA;
+    g_num_sms = sms;
+    g_max_smem = smem;
+    g_dev_ready[dev] = true;
   }
   return B200SD_OK;
 }

@@ -1,0 +1,252 @@
+"""SDEngine — the local executor a Worker binds instead of POST /sdapi/v1/txt2img (reference worker.py:432-435).
+
+One engine per GPU: packed weights, per-shape execution plans (UNet step graph, VAE decode graph), samplers.
+Images of one request are independent given (prompt, seed + k) — the property the reference's seed offsetting
+relies on (scripts/distributed.py:297-305) — so a request's batch is sharded across engines with no per-step
+exchange; results meet once, at the end (bench: one NCCL all-gather; plugin path: the collector thread join).
+"""
+import contextlib
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .clip_text import ClipText
+from .config import CLIPConfig, UNetConfig, VAEConfig
+from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
+from .vae_exec import VAEDecoderProgram, VAEDecoderWeights
+
+MAX_STEPS = 256
+
+
+# ------------------------------------------------------------------------------------------------ schedules
+def alphas_cumprod() -> torch.Tensor:
+    """ldm linear schedule (linear_start 0.00085, linear_end 0.012, 1000 steps), fp64 math, fp32 storage."""
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).to(torch.float32)
+
+
+def ddim_plan(steps: int) -> Tuple[List[float], List[List[float]]]:
+    """sdwui sd_samplers_timesteps(_impl).ddim, eta = 0.  Returns (timesteps, coef rows) in execution order;
+    `steps` timesteps give steps-1 UNet evaluations (index len-1 .. 1)."""
+    ac = alphas_cumprod().double()
+    ts = torch.clamp(torch.arange(0, 1000, 1000 // steps) + 1, 0, 999)
+    a = ac[ts]
+    a_prev = ac[torch.cat([ts.new_zeros(1), ts[:-1]])]
+    t_out, rows = [], []
+    for i in range(len(ts) - 1, 0, -1):
+        at, ap = float(a[i]), float(a_prev[i])
+        t_out.append(float(ts[i]))
+        rows.append([math.sqrt(at), math.sqrt(1 - at), math.sqrt(ap), math.sqrt(1 - ap)])
+    return t_out, rows
+
+
+def euler_a_plan(steps: int):
+    """k-diffusion sample_euler_ancestral over CompVisDenoiser sigmas.  Returns (timesteps, coef rows, sigma0):
+    row = [sigma, sigma_down, sigma_up, c_in of the NEXT step]."""
+    ac = alphas_cumprod().double()
+    sig_all = ((1 - ac) / ac) ** 0.5
+    log_sig = sig_all.log()
+    tt = torch.linspace(999, 0, steps, dtype=torch.float64)
+    lo, hi = tt.floor().long(), tt.ceil().long()
+    wgt = tt - lo
+    sig = torch.cat([((1 - wgt) * log_sig[lo] + wgt * log_sig[hi]).exp(), tt.new_zeros(1)])
+
+    def sigma_to_t(s: float) -> float:
+        ls = math.log(s)
+        dists = ls - log_sig
+        low = int((dists >= 0).cumsum(0).argmax().clamp(max=len(log_sig) - 2))
+        l0, h0 = float(log_sig[low]), float(log_sig[low + 1])
+        w = min(max((l0 - ls) / (l0 - h0), 0.0), 1.0)
+        return (1 - w) * low + w * (low + 1)
+
+    t_out, rows = [], []
+    for i in range(steps):
+        s, sn = float(sig[i]), float(sig[i + 1])
+        up = min(sn, (sn ** 2 * (s ** 2 - sn ** 2) / s ** 2) ** 0.5)
+        down = (sn ** 2 - up ** 2) ** 0.5
+        t_out.append(sigma_to_t(s))
+        rows.append([s, down, up, 1.0 / math.sqrt(sn * sn + 1.0)])
+    return t_out, rows, float(sig[0])
+
+
+def per_image_noise(seed: int, n: int, shape, draws: int = 1) -> torch.Tensor:
+    """sdwui ImageRNG with randn_source = 'CPU': image k owns torch.Generator('cpu').manual_seed(seed + k);
+    `draws` successive tensors per image (x_T, then ancestral noises).  Returns [draws, n, *shape] fp32 (host)."""
+    out = torch.empty((draws, n, *shape), dtype=torch.float32)
+    for k in range(n):
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
+        for d in range(draws):
+            out[d, k] = torch.randn(shape, generator=g, dtype=torch.float32)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ plans
+class Plan:
+    """Everything shape-dependent for (images per call b, latent h x w) on one device."""
+
+    def __init__(self, eng: "SDEngine", b: int, h: int, w: int, vae_chunk: int):
+        dev = eng.device
+        self.b, self.h, self.w = b, h, w
+        self.unet = UNetProgram(eng.unet_w, 2 * b, h, w)
+        self.vae_chunk = min(vae_chunk, b)
+        self.vae = VAEDecoderProgram(eng.vae_w, self.vae_chunk, h, w)
+        self.x = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)
+        self.step = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.coef = torch.zeros((MAX_STEPS, 4), device=dev, dtype=torch.float32)
+        self.table = torch.zeros((MAX_STEPS, eng.unet_w.emb_total), device=dev, dtype=torch.float32)
+        self.noise = None
+        self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.u8 = torch.empty((b, 8 * h * 8 * w, 3), device=dev, dtype=torch.uint8) if False else None
+
+    # one sampler step = select this step's biases, UNet on [cond | uncond], CFG + update + repack
+    def step_ddim(self, cfg_scale: float):
+        ops.select_step(self.table, self.step, self.unet.cur_bias)
+        self.unet.run()
+        ops.cfg_ddim_step(self.unet.eps, self.x, self.unet.xin, cfg_scale, self.coef, self.step)
+
+    def step_euler_a(self, cfg_scale: float):
+        ops.select_step(self.table, self.step, self.unet.cur_bias)
+        self.unet.run()
+        ops.cfg_euler_a_step(self.unet.eps, self.x, self.noise, self.unet.xin, cfg_scale, self.coef, self.step)
+
+
+class SDEngine:
+    _require_cuda = True  # tests/test_programs_cpu.py flips this together with an emulated ops module
+
+    def _ctx(self):
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
+    def __init__(self, sd: Dict[str, torch.Tensor], unet_cfg: UNetConfig, vae_cfg: VAEConfig, clip_cfg: CLIPConfig,
+                 device="cuda:0", dtype=torch.float16, use_graphs: bool = True, vae_chunk: int = 8):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" and self._require_cuda:
+            raise RuntimeError("SDEngine needs a CUDA device: the hot path is sm_100a kernels only (no CPU fallback)")
+        self.dtype = dtype
+        self.unet_cfg, self.vae_cfg, self.clip_cfg = unet_cfg, vae_cfg, clip_cfg
+        self.use_graphs = use_graphs
+        self.vae_chunk = vae_chunk
+        with self._ctx():
+            self.unet_w = UNetWeights(sd, unet_cfg, self.device, dtype)
+            self.vae_w = VAEDecoderWeights(sd, vae_cfg, self.device, dtype)
+            self.clip = ClipText(sd, clip_cfg, self.device, dtype)
+            self.temb = TimeEmbedding(self.unet_w)
+        self.plans: Dict[Tuple[int, int, int], Plan] = {}
+        self.interrupted = False
+        self.last_unet_evals = 0
+
+    def plan(self, b: int, h: int, w: int) -> Plan:
+        key = (b, h, w)
+        if key not in self.plans:
+            with self._ctx():
+                self.plans[key] = Plan(self, b, h, w, self.vae_chunk)
+        return self.plans[key]
+
+    @torch.no_grad()
+    def encode_prompts(self, tokens: torch.Tensor) -> torch.Tensor:
+        with self._ctx():
+            return self.clip(tokens)
+
+    def _graph(self, plan: Plan, name: str, fn):
+        """Run fn eagerly once (per-device kernel attribute setup must not happen under capture), then capture."""
+        if not self.use_graphs or self.device.type != "cuda":
+            return None
+        if name not in plan.graphs:
+            # eager warm-up on scratch state: save what the step mutates
+            saved = (plan.x.clone(), plan.step.clone(), plan.unet.xin.clone())
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn()
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            plan.graphs[name] = g
+            plan.x.copy_(saved[0]); plan.step.copy_(saved[1]); plan.unet.xin.copy_(saved[2])
+        return plan.graphs[name]
+
+    @torch.no_grad()
+    def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
+               sampler: str = "DDIM", noises: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device).
+        Returns the final latents fp32 [b, h*w, 4] (NHWC, a view of plan state)."""
+        b, _, h, w = x_T.shape
+        with self._ctx():
+            plan = self.plan(b, h, w)
+            plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
+            if sampler == "DDIM":
+                ts, rows = ddim_plan(steps)
+                scale0, in0 = 1.0, 1.0
+                step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
+            elif sampler == "Euler a":
+                ts, rows, sigma0 = euler_a_plan(steps)
+                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                step_fn = lambda: plan.step_euler_a(cfg_scale)  # noqa: E731
+                if noises is None:
+                    raise ValueError("Euler a needs the per-image ancestral noises")
+                plan.noise = noises.to(self.device, torch.float32).permute(0, 1, 3, 4, 2).reshape(len(rows), b, h * w, 4).contiguous()
+            else:
+                raise ValueError(f"sampler {sampler!r} is not implemented on the local executor")
+            n_evals = len(ts)
+            if n_evals > MAX_STEPS:
+                raise ValueError("too many steps")
+            plan.table[:n_evals].copy_(self.temb.table(torch.tensor(ts, dtype=torch.float32)))
+            plan.coef[:n_evals].copy_(torch.tensor(rows, dtype=torch.float32))
+            plan.x.copy_((x_T.to(self.device, torch.float32) * scale0).permute(0, 2, 3, 1).reshape(b, h * w, 4))
+            plan.step.zero_()
+            ops.pack_unet_input(plan.x, plan.unet.xin, in0)
+            g = self._graph(plan, f"{sampler}:{cfg_scale}", step_fn)
+            self.last_unet_evals = 0
+            for _ in range(n_evals):
+                if self.interrupted:
+                    break
+                if g is not None:
+                    g.replay()
+                else:
+                    step_fn()
+                self.last_unet_evals += 1
+            return plan.x
+
+    @torch.no_grad()
+    def decode(self, latents: torch.Tensor, h: int, w: int) -> torch.Tensor:
+        """latents fp32 [b, h*w, 4] (scaled) -> uint8 [b, 8h, 8w, 3] on device."""
+        b = latents.shape[0]
+        with self._ctx():
+            plan = self.plan(b, h, w)
+            vae = plan.vae
+            out = torch.empty((b, vae.out_h * vae.out_w, 3), device=self.device, dtype=torch.uint8)
+            c = plan.vae_chunk
+            for i in range(0, b, c):
+                chunk = latents[i:i + c]
+                if chunk.shape[0] < c:  # ragged tail: pad with the last latent, drop the surplus images
+                    chunk = torch.cat([chunk, chunk[-1:].expand(c - chunk.shape[0], -1, -1)]).contiguous()
+                vae.set_latents(chunk.contiguous(), self.vae_cfg.scale_factor)
+                if self.use_graphs and self.device.type == "cuda":
+                    if "vae" not in plan.graphs:
+                        vae.run()
+                        torch.cuda.current_stream().synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            vae.run()
+                        plan.graphs["vae"] = g
+                    plan.graphs["vae"].replay()
+                else:
+                    vae.run()
+                n = min(c, b - i)
+                out[i:i + n].copy_(vae.u8[:n])
+            return out.reshape(b, vae.out_h, vae.out_w, 3)
+
+    @torch.no_grad()
+    def txt2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20, cfg_scale: float = 7.0,
+                height: int = 512, width: int = 512, sampler: str = "DDIM") -> torch.Tensor:
+        """Whole request for this engine's share: returns uint8 [b, H, W, 3] on device."""
+        b = tokens.shape[0]
+        h, w = height // 8, width // 8
+        cond = self.encode_prompts(tokens)
+        uncond = self.encode_prompts(neg_tokens)
+        draws = 1 + (steps if sampler == "Euler a" else 0)
+        nz = per_image_noise(seed, b, (4, h, w), draws)
+        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None)
+        return self.decode(lat, h, w)

@@ -1,0 +1,101 @@
+"""Host-side logic of the executor on CPU: the UNet / VAE programs, weight packing, per-step bias table and sampler
+bookkeeping are run with b200sd.ops replaced by a torch emulation (tests/ops_emulator.py) and compared with the
+fp32 oracle.  fp32 buffers, so agreement is to rounding (1e-4): any mismatch is a plumbing bug, not precision."""
+import pytest
+import torch
+
+import ops_emulator
+
+
+@pytest.fixture()
+def env(monkeypatch):
+    from b200sd import config as C, engine as E, ops, synth
+    from oracle import sd_oracle as O
+    ops_emulator.install(monkeypatch, ops)
+    monkeypatch.setattr(E.SDEngine, "_require_cuda", False)
+    cfgs = (C.TINY_UNET, C.TINY_VAE, C.TINY_CLIP)
+    sd = synth.make_state_dict(*cfgs, seed=0)
+    eng = E.SDEngine(sd, *cfgs, device="cpu", dtype=torch.float32, use_graphs=False, vae_chunk=2)
+    return C, E, O, cfgs, sd, eng
+
+
+def test_layouts_match_oracle(env):
+    C, E, O, cfgs, sd, eng = env
+    assert C.unet_layout(C.SD15_UNET) == O.unet_layout(O.SD15_UNET)
+    assert C.unet_layout(C.TINY_UNET) == O.unet_layout(O.TINY_UNET)
+    assert sum(v.numel() for k, v in sd.items() if k.startswith(C.UNET_PREFIX)) > 0
+
+
+def test_schedules_match_oracle(env):
+    C, E, O, cfgs, sd, eng = env
+    for steps in (5, 20, 50):
+        ts, rows = E.ddim_plan(steps)
+        ref = O.ddim_coefficients(steps)
+        assert len(ts) == steps - 1 == len(ref)
+        for t, r, o in zip(ts, rows, ref):
+            assert t == o[0] and all(abs(a - b) < 1e-12 for a, b in zip(r, o[1:]))
+        ts, rows, s0 = E.euler_a_plan(steps)
+        ref = O.euler_a_coefficients(steps)
+        for t, r, o in zip(ts, rows, ref):
+            assert abs(t - o[0]) < 1e-9 and abs(r[0] - o[1]) < 1e-12 and abs(r[1] - o[2]) < 1e-12
+            assert abs(r[2] - o[3]) < 1e-12 and abs(r[3] - o[5]) < 1e-12
+    assert torch.equal(E.per_image_noise(5, 3, (4, 8, 8))[0], O.per_image_noise(5, 3, (4, 8, 8)))
+
+
+@pytest.mark.parametrize("b,hw", [(1, 8), (2, 16)])
+def test_unet_program_matches_oracle(env, b, hw):
+    C, E, O, cfgs, sd, eng = env
+    from b200sd import ops
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    x = O.per_image_noise(1000, b, (4, hw, hw))
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfgs[0], torch.cat([x, x]), torch.full((2 * b,), 651.0), torch.cat([cond, unc]))
+    plan = eng.plan(b, hw, hw)
+    plan.unet.set_context(torch.cat([cond, unc]))
+    plan.table[:1].copy_(eng.temb.table(torch.tensor([651.0])))
+    plan.x.copy_(x.permute(0, 2, 3, 1).reshape(b, hw * hw, 4))
+    ops.pack_unet_input(plan.x, plan.unet.xin, 1.0)
+    ops.select_step(plan.table, plan.step, plan.unet.cur_bias)
+    plan.unet.run()
+    got = plan.unet.eps[..., :4].reshape(2 * b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float(plan.unet.eps[..., 4:].abs().max()) == 0.0
+    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+
+
+def test_clip_text_matches_oracle(env):
+    C, E, O, cfgs, sd, eng = env
+    tok = O.random_prompt_tokens(3, vocab_hi=997)
+    assert torch.allclose(eng.encode_prompts(tok), O.clip_text_encode(sd, cfgs[2], tok), atol=1e-4, rtol=1e-4)
+
+
+def test_txt2img_matches_oracle_ddim(env):
+    C, E, O, cfgs, sd, eng = env
+    b, hw, steps = 3, 8, 5  # b=3 with vae_chunk=2 exercises the ragged decode tail
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    with torch.no_grad():
+        ref_u8, ref_z, ref_dec = O.txt2img(sd, *cfgs, tok, neg, seed=1000, steps=steps, height=hw * 8, width=hw * 8)
+    got = eng.txt2img(tok, neg, seed=1000, steps=steps, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler="DDIM")
+    assert eng.last_unet_evals == steps - 1
+    z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float((z - ref_z).abs().max()) <= 1e-3 * float(ref_z.abs().max())
+    assert got.shape == ref_u8.shape
+    d = (got.int() - ref_u8.int()).abs()
+    assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
+
+
+def test_sample_matches_oracle_euler_a(env):
+    C, E, O, cfgs, sd, eng = env
+    b, hw, steps = 2, 8, 4
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    nz = E.per_image_noise(2000, b, (4, hw, hw), 1 + steps)
+    with torch.no_grad():
+        ref = O.sample_euler_a(lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c), nz[0], cond, unc, steps, 7.0,
+                               list(nz[1:]))
+    lat = eng.sample(cond, unc, nz[0], steps, 7.0, "Euler a", noises=nz[1:])
+    z = lat.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
