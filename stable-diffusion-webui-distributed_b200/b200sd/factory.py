@@ -1,0 +1,70 @@
+"""Engine construction for the local-GPU workers: one SDEngine per CUDA device, built lazily and cached.
+
+Weights: `SD_CKPT=/path/model.safetensors` (ldm key names) when present, otherwise the seeded synthetic SD1.5
+weights of synth.py (no checkpoint exists offline — every benchmark / parity number in this repo uses those).
+"""
+import os
+import threading
+import zlib
+from typing import Dict, List
+
+import torch
+
+from . import config as C
+from .engine import SDEngine
+from .synth import make_state_dict
+
+_LOCK = threading.Lock()
+_ENGINES: Dict[str, SDEngine] = {}
+_STATE: Dict[str, Dict[str, torch.Tensor]] = {}
+
+
+def _load_safetensors(path: str) -> Dict[str, torch.Tensor]:
+    from safetensors.torch import load_file  # optional dependency; only needed for a real checkpoint
+    return load_file(path)
+
+
+def state_dict(size: str = "sd15", seed: int = 0) -> Dict[str, torch.Tensor]:
+    key = f"{size}:{seed}:{os.environ.get('SD_CKPT', '')}"
+    with _LOCK:
+        if key not in _STATE:
+            ckpt = os.environ.get("SD_CKPT")
+            if ckpt and size == "sd15":
+                _STATE[key] = _load_safetensors(ckpt)
+            else:
+                cfgs = configs(size)
+                _STATE[key] = make_state_dict(*cfgs, seed=seed)
+        return _STATE[key]
+
+
+def configs(size: str = "sd15"):
+    if size == "sd15":
+        return C.SD15_UNET, C.SD15_VAE, C.SD15_CLIP
+    if size == "tiny":
+        return C.TINY_UNET, C.TINY_VAE, C.TINY_CLIP
+    raise ValueError(size)
+
+
+def default_engine_factory(device: str, size: str = None) -> SDEngine:
+    size = size or os.environ.get("B200SD_MODEL", "sd15")
+    key = f"{device}:{size}"
+    with _LOCK:
+        eng = _ENGINES.get(key)
+    if eng is None:
+        eng = SDEngine(state_dict(size), *configs(size), device=device)
+        with _LOCK:
+            _ENGINES[key] = eng
+    return eng
+
+
+def synthetic_tokens(prompts: List[str], vocab: int, ctx: int = 77) -> torch.Tensor:
+    """Deterministic stand-in for the CLIP BPE tokenizer (its vocabulary files are not available offline):
+    [BOS] + one id per whitespace-separated word (crc32 mod vocab-3) + [EOS] padding, length 77."""
+    bos, eos = vocab - 2, vocab - 1
+    out = torch.full((len(prompts), ctx), eos, dtype=torch.long)
+    out[:, 0] = bos
+    for i, text in enumerate(prompts):
+        ids = [zlib.crc32(w.encode("utf-8")) % (vocab - 3) for w in (text or "").split()][: ctx - 2]
+        if ids:
+            out[i, 1:1 + len(ids)] = torch.tensor(ids)
+    return out

@@ -1,0 +1,198 @@
+"""LocalGPUWorker — a Worker whose request() runs on a GPU of this box instead of POSTing to a remote sdwui.
+
+This is THE boundary of the build: the reference's `Worker.request(payload, option_payload,
+sync_options)` (scripts/spartan/worker.py:288-504) does `session.post(full_url("txt2img"|"img2img"))` (:432-435) and
+stores the JSON reply in `self.response`; here the same call, with the same payload dict and the same side effects
+(`self.response`, `self.response_time`, `self.state`, `self.jobs_requested`), drives a b200sd.SDEngine on
+`cuda:<device_index>`.  The reply keeps the API schema read by scripts/distributed.py:78-93,:152,:347
+(`images`, `parameters`, `info` JSON string) and adds `tensors` — the decoded uint8 images on the host — so the
+collector can skip PNG + base64 (the reference's per-image wire format) when both sides are local.
+
+Error mapping (reference worker.py:494-500): a CUDA / kernel-library failure marks the device UNAVAILABLE and leaves
+`response = None` (the collector skips the job, distributed.py:148); anything else re-raises InvalidWorkerResponse.
+"""
+import base64
+import io
+import json
+import time
+from threading import Thread
+
+import torch
+from modules.shared import state as master_state
+
+from .shared import logger
+from .worker import InvalidWorkerResponse, State, Worker
+
+SUPPORTED_SAMPLERS = ("DDIM", "Euler a")
+
+
+class LocalGPUWorker(Worker):
+    is_local_gpu = True
+
+    def __init__(self, device_index: int, engine_factory, label: str = None, avg_ipm: float = 0.0, png_images=False,
+                 **kw):
+        kw.pop("address", None)
+        kw.pop("port", None)
+        kw.pop("verify_remotes", None)
+        kw.pop("master", None)
+        super().__init__(address=f"cuda:{device_index}", port=device_index, label=label or f"gpu{device_index}",
+                         verify_remotes=False, avg_ipm=avg_ipm, **kw)
+        self.device_index = device_index
+        self.device = f"cuda:{device_index}"
+        self._factory = engine_factory
+        self._engine = None
+        self.png_images = png_images  # also fill response["images"] with base64 PNGs (API-exact, slower)
+        self.queried = True
+
+    # ------------------------------------------------------------------ engine access
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = self._factory(self.device)
+        return self._engine
+
+    # ------------------------------------------------------------------ transport overrides (no HTTP)
+    def reachable(self) -> bool:
+        try:
+            ok = torch.cuda.is_available() and self.device_index < torch.cuda.device_count()
+        except Exception:  # pragma: no cover
+            ok = False
+        self.response = None
+        return ok
+
+    def query_scripts(self) -> dict:
+        return {"txt2img": [], "img2img": []}
+
+    def load_options(self, model, vae=None):
+        """weights are replicated on every device at engine construction; just record what is loaded"""
+        self.loaded_model, self.loaded_vae = model, vae
+        return self
+
+    def interrupt(self):
+        if self._engine is not None:
+            self._engine.interrupted = True
+        self.set_state(State.INTERRUPTED)
+
+    def refresh_checkpoints(self):
+        return None
+
+    def available_models(self):
+        return []
+
+    def restart(self) -> bool:
+        self._engine = None
+        return True
+
+    # ------------------------------------------------------------------ the request boundary
+    def request(self, payload: dict, option_payload: dict, sync_options: bool):
+        eta = None
+        try:
+            self._wait_for_idle()
+            self.set_state(State.WORKING)
+            if sync_options is True and option_payload is not None:
+                self.load_options(model=option_payload["sd_model_checkpoint"], vae=option_payload["sd_vae"])
+            if self.benchmarked:
+                eta = self.eta(payload=payload) * payload.get("n_iter", 1)
+            begin = time.time()
+            result = {}
+
+            def work():
+                try:
+                    result["response"] = self._generate(payload)
+                except Exception as e:  # forwarded to the request thread
+                    result["error"] = e
+
+            t = Thread(target=work, name=f"{self.label}_generate")
+            t.start()
+            interrupting = False
+            while t.is_alive():  # same shape as the reference's poll loop, 20 ms instead of 0.5 s
+                if not interrupting and master_state.interrupted is True:
+                    self.interrupt()
+                    interrupting = True
+                t.join(0.02)
+            if "error" in result:
+                raise result["error"]
+            self.response = result["response"]
+            if self.benchmarked and self.state != State.INTERRUPTED:
+                self.response_time = time.time() - begin
+                self.record_eta_error(eta, self.response_time)
+        except Exception as e:
+            self.response = None
+            if self._is_device_failure(e):
+                logger.error(f"'{self.label}' ({self.device}) failed: {e}")
+                self.set_state(State.UNAVAILABLE)
+                return
+            self.set_state(State.IDLE)
+            raise InvalidWorkerResponse(e)
+        self.set_state(State.IDLE)
+        self.jobs_requested += 1
+
+    @staticmethod
+    def _is_device_failure(e: Exception) -> bool:
+        name = type(e).__name__
+        return name in ("B200SDError", "OutOfMemoryError", "AcceleratorError") or \
+            (isinstance(e, RuntimeError) and "CUDA" in str(e))
+
+    def _generate(self, payload: dict) -> dict:
+        from b200sd.factory import synthetic_tokens
+        eng = self.engine
+        eng.interrupted = False
+        batch = int(payload["batch_size"])
+        n_iter = int(payload.get("n_iter", 1))
+        steps = int(payload["steps"])
+        width, height = int(payload["width"]), int(payload["height"])
+        sampler = payload.get("sampler_name") or payload.get("sampler_index") or "Euler a"
+        if sampler not in SUPPORTED_SAMPLERS:
+            logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")
+            sampler = "Euler a"
+        if payload.get("init_images"):
+            raise NotImplementedError("img2img is not implemented on the local executor yet")
+        prompt = payload.get("prompt", "") or ""
+        negative = payload.get("negative_prompt", "") or ""
+        seed = int(payload["seed"])
+        subseed = int(payload.get("subseed", -1))
+        cfg_scale = float(payload.get("cfg_scale", 7.0))
+        vocab = eng.clip_cfg.vocab
+        if "prompt_tokens" in payload:  # benchmark / tests hand pre-tokenised prompts through
+            tok_all = torch.as_tensor(payload["prompt_tokens"]).long().reshape(-1, 77)
+        else:
+            tok_all = synthetic_tokens([prompt] * batch, vocab)
+        neg_all = synthetic_tokens([negative] * batch, vocab)
+        chunks = []
+        for it in range(n_iter):
+            tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
+            u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
+                             width=width, sampler=sampler)
+            chunks.append(u8)
+            if eng.interrupted:
+                break
+        images = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
+        host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(images, non_blocking=True)
+        torch.cuda.current_stream(images.device).synchronize()
+        n = host.shape[0]
+        seeds = [seed + i for i in range(n)]
+        subseeds = [subseed + i for i in range(n)]
+        infotexts = [f"{prompt}\nNegative prompt: {negative}\nSteps: {steps}, Sampler: {sampler}, CFG scale: {cfg_scale}, "
+                     f"Seed: {s}, Size: {width}x{height}" for s in seeds]
+        info = {"all_seeds": seeds, "all_subseeds": subseeds, "all_prompts": [prompt] * n,
+                "all_negative_prompts": [negative] * n, "infotexts": infotexts, "seed": seeds[0], "subseed": subseeds[0],
+                "prompt": prompt, "negative_prompt": negative}
+        return {"images": [self._png_b64(host[i]) for i in range(n)] if self.png_images else [None] * n,
+                "tensors": host,
+                "parameters": {"batch_size": batch, "n_iter": n_iter, "steps": steps, "width": width, "height": height,
+                               "sampler_name": sampler, "cfg_scale": cfg_scale, "seed": seed},
+                "info": json.dumps(info)}
+
+    @staticmethod
+    def _png_b64(hwc_u8: torch.Tensor) -> str:
+        from PIL import Image
+        buf = io.BytesIO()
+        Image.fromarray(hwc_u8.numpy()).save(buf, format="PNG")
+        return base64.b64encode(buf.getvalue()).decode("utf-8")
+
+    # ------------------------------------------------------------------ benchmark: measured it/s of the executor
+    def benchmark(self, sample_function: callable = None) -> float:
+        """Same protocol as the reference (2 warm-up + 3 timed generations of the benchmark payload, mean ipm,
+        worker.py:506-575) but timed around the local executor; the first warm-up also builds plans and graphs."""
+        return super().benchmark(sample_function=sample_function)

@@ -5,7 +5,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXT_DIR = os.path.join(ROOT, "stable-diffusion-webui-distributed_b200")
-for p in (ROOT, EXT_DIR):
+HOSTSTUB = os.path.join(ROOT, "tests", "hoststub")   # stand-in for sdwui's `modules` / `gradio` (test infrastructure)
+for p in (ROOT, EXT_DIR, HOSTSTUB):
     if p not in sys.path:
         sys.path.insert(0, p)
 
