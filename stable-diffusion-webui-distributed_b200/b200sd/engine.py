@@ -98,7 +98,7 @@ class Plan:
         self.table = torch.zeros((MAX_STEPS, eng.unet_w.emb_total), device=dev, dtype=torch.float32)
         self.noise = None
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
-        self.u8 = torch.empty((b, 8 * h * 8 * w, 3), device=dev, dtype=torch.uint8) if False else None
+        self.graph_launches: Dict[str, int] = {}
 
     # one sampler step = select this step's biases, UNet on [cond | uncond], CFG + update + repack
     def step_ddim(self, cfg_scale: float):
@@ -135,6 +135,7 @@ class SDEngine:
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
         self.interrupted = False
         self.last_unet_evals = 0
+        self.graph_replayed_launches = 0   # b200sd kernels launched through graph replays (bench.py gpu_launches)
 
     def plan(self, b: int, h: int, w: int) -> Plan:
         key = (b, h, w)
@@ -161,8 +162,10 @@ class SDEngine:
                 fn()
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
+            l0 = ops.LAUNCHES
             with torch.cuda.graph(g):
                 fn()
+            plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
             plan.graphs[name] = g
             plan.x.copy_(saved[0]); plan.step.copy_(saved[1]); plan.unet.xin.copy_(saved[2])
         return plan.graphs[name]
@@ -204,6 +207,7 @@ class SDEngine:
                     break
                 if g is not None:
                     g.replay()
+                    self.graph_replayed_launches += plan.graph_launches[f"{sampler}:{cfg_scale}"]
                 else:
                     step_fn()
                 self.last_unet_evals += 1
@@ -228,10 +232,13 @@ class SDEngine:
                         vae.run()
                         torch.cuda.current_stream().synchronize()
                         g = torch.cuda.CUDAGraph()
+                        l0 = ops.LAUNCHES
                         with torch.cuda.graph(g):
                             vae.run()
+                        plan.graph_launches["vae"] = ops.LAUNCHES - l0
                         plan.graphs["vae"] = g
                     plan.graphs["vae"].replay()
+                    self.graph_replayed_launches += plan.graph_launches["vae"]
                 else:
                     vae.run()
                 n = min(c, b - i)

@@ -1,0 +1,104 @@
+"""The drop-in boundary on a GPU: DistributedScript hooks -> LocalGPUWorker.request() -> SDEngine, thin-client world.
+Uses the reduced-width model (same topology) so the whole file runs in seconds."""
+import logging
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import modules.processing as processing
+    import modules.scripts as mscripts
+    from b200sd import config as C, engine as E, synth
+    from scripts.distributed import DistributedScript
+    from scripts.spartan import pmodels, shared as sh
+    from scripts.spartan.worker import State
+    logging.getLogger("distributed").setLevel(logging.ERROR)
+    cfgs = (C.TINY_UNET, C.TINY_VAE, C.TINY_CLIP)
+    sd = synth.make_state_dict(*cfgs, seed=0)
+    eng = E.SDEngine(sd, *cfgs, device="cuda:0")
+    sh.benchmark_payload = pmodels.Benchmark_Payload()
+    return processing, mscripts, DistributedScript, eng, State, sh
+
+
+def _fresh_world(DistributedScript, factory, ipm=600.0):
+    from scripts.spartan.world import World
+    w = World(verify_remotes=False)
+    DistributedScript.world = w
+    wk = w.add_local_gpus(factory, devices=[0], avg_ipm=ipm)[0]
+    wk.benchmarked = True
+    w.thin_client_mode = True
+    w.benchmark = lambda *a, **k: None
+    return w, wk
+
+
+def _request(processing, mscripts, script, batch, tokens, steps=6, size=128, sampler="DDIM"):
+    p = processing.StableDiffusionProcessingTxt2Img(
+        prompt="a synthetic prompt", negative_prompt="", seed=1000, subseed=5, subseed_strength=0, batch_size=batch,
+        n_iter=1, steps=steps, width=size, height=size, sampler_name=sampler, cfg_scale=7.0,
+        scripts=mscripts.ScriptRunner([script]), script_args=[])
+    p.prompt_tokens = tokens.tolist()
+    return p, processing.process_images(p)
+
+
+def test_plugin_path_matches_direct_engine_call(env):
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng)
+    script = DistributedScript()
+    script.args_from = script.args_to = 0
+    g = torch.Generator().manual_seed(3)
+    tokens = torch.randint(0, 990, (4, 77), generator=g)
+    p, out = _request(processing, mscripts, script, 4, tokens)
+    assert len(out.images) == 4 and p.seeds == [1000, 1001, 1002, 1003] and p.subseeds == [5, 6, 7, 8]
+    assert all("Worker Label: gpu0" in t for t in out.infotexts[:4])
+    assert wk.state == State.IDLE and wk.jobs_requested == 1 and wk.response is None  # cleared by postprocess
+    from b200sd.factory import synthetic_tokens
+    direct = eng.txt2img(tokens, synthetic_tokens([""] * 4, eng.clip_cfg.vocab), 1000, steps=6, cfg_scale=7.0, height=128,
+                         width=128, sampler="DDIM").cpu()
+    import numpy as np
+    got = torch.stack([torch.from_numpy(np.asarray(im)) for im in out.images])
+    assert torch.equal(got, direct)  # same kernels, same seeds: bit-identical through the hook chain
+
+
+def test_worker_reply_schema_and_png_lane(env):
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng)
+    wk.png_images = True
+    payload = {"prompt": "x y", "negative_prompt": "", "seed": 7, "subseed": 9, "subseed_strength": 0, "batch_size": 2,
+               "n_iter": 1, "steps": 4, "width": 64, "height": 64, "sampler_name": "Euler a", "cfg_scale": 5.0}
+    wk.request(dict(payload), {"sd_model_checkpoint": "m", "sd_vae": None}, True)
+    r = wk.response
+    import base64, io, json
+    from PIL import Image
+    import numpy as np
+    assert set(r) >= {"images", "parameters", "info", "tensors"} and len(r["images"]) == 2
+    info = json.loads(r["info"])
+    assert info["all_seeds"] == [7, 8] and info["all_subseeds"] == [9, 10] and len(info["infotexts"]) == 2
+    png = np.asarray(Image.open(io.BytesIO(base64.b64decode(r["images"][1]))))
+    assert np.array_equal(png, r["tensors"][1].numpy())
+    assert wk.loaded_model == "m" and wk.response_time is not None and len(wk.eta_percent_error) <= 1
+
+
+def test_device_failure_marks_worker_unavailable(env):
+    processing, mscripts, DistributedScript, eng, State, sh = env
+
+    def broken(dev):
+        raise RuntimeError("CUDA error: an illegal memory access was encountered (injected)")
+
+    w, wk = _fresh_world(DistributedScript, broken)
+    script = DistributedScript()
+    script.args_from = script.args_to = 0
+    tokens = torch.zeros((2, 77), dtype=torch.long)
+    p, out = _request(processing, mscripts, script, 2, tokens)
+    assert wk.state == State.UNAVAILABLE and len(out.images) == 0
+
+
+def test_local_benchmark_sets_ipm(env):
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng, ipm=0.0)
+    wk.benchmarked = False
+    ipm = wk.benchmark()
+    assert ipm > 0 and wk.avg_ipm == ipm and wk.benchmarked and wk.state == State.IDLE
