@@ -100,6 +100,29 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cpus() -> int:
+    """host cores this process may really use: affinity mask, capped by the cgroup CPU quota (containers often
+    advertise every core of the host in os.cpu_count() while being limited to a few)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,7 +189,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
+        threads = usable_cpus()
         t0 = time.perf_counter()
         best = None
         for _ in range(max(1, min(args.steps, 2))):
@@ -306,7 +329,7 @@ def main():
                           "tflop_per_image": tflop_per_image, "peak_source": pk["source"] + " (sustained)"},
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(n_evals, os.cpu_count() or 1).items()
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(n_evals, usable_cpus()).items()
                                 if k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
     if world > 1:

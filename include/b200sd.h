@@ -65,10 +65,12 @@ int b200sd_conv2d(const void* X, long long pitch_c, int NB, int Hin, int Win, in
                   const b200sd_epilogue* epi, int dtype, int max_ctas, void* stream);
 
 /* O[b,s,h*d] = softmax(Q K^T * scale) V per (batch, head); Q/K/V rows are tokens, head h occupies columns
- * [h*d_pad, h*d_pad+d) (zero padded to d_pad, a multiple of 64).  (upstream CrossAttention.forward) */
+ * [h*d_pad, h*d_pad+d) (zero padded to d_pad, a multiple of 64).  (upstream CrossAttention.forward)
+ * v_ones_col != 0 (needs d < d_pad): V[:, h*d_pad + d] == 1 for every head — the P.V tensor-core product then also
+ * yields the softmax denominators (column d of the accumulator), so no CUDA-core row sums are computed. */
 int b200sd_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                      void* O, long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale,
-                     int dtype, void* stream);
+                     int v_ones_col, int dtype, void* stream);
 
 /* ---- HBM-bound ops ------------------------------------------------------------------------------- */
 

@@ -16,7 +16,7 @@ extern "C" int b200sd_conv2d(const void* X, long long pitch_c, int NB, int Hin, 
 
 extern "C" int b200sd_attention(const void* Q, long long ldq, const void* K, long long ldk, const void* V,
                                 long long ldv, void* O, long long ldo, int B, int heads, int Sq, int Skv, int d,
-                                int d_pad, float scale, int dtype, void* stream) {
-  return b200sd::attention_tc(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Sq, Skv, d, d_pad, scale,
+                                int d_pad, float scale, int v_ones_col, int dtype, void* stream) {
+  return b200sd::attention_tc(Q, ldq, K, ldk, V, ldv, O, ldo, B, heads, Sq, Skv, d, d_pad, scale, v_ones_col,
                               dtype == B200SD_BF16 ? 1 : 0, static_cast<cudaStream_t>(stream));
 }

@@ -35,6 +35,8 @@ struct AttnParams {
   int chunks;        // d_pad / 64
   int k_stages, v_stages;
   int tmem_cols;
+  int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
+  int resc_cols;     // O columns touched by a rescale (multiple of 16, covers l_col)
   float scale_log2;  // softmax scale * log2(e)
   void* O;
   long long ldo;
@@ -58,6 +60,84 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, bool bf16) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// exact row maximum of the S tile (raw logits), kv columns >= nvalid ignored
+template <bool kFull>
+__device__ __forceinline__ float row_max(uint32_t tmem_row, int nvalid) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    if (!kFull && c * 32 >= nvalid) break;
+    uint32_t v[32];
+    tmem_ld_x32(tmem_row + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
+      if (!kFull) {
+        if (c * 32 + i >= nvalid) a = -INFINITY;
+        if (c * 32 + i + 1 >= nvalid) b2 = -INFINITY;
+      }
+      mx = fmax3(mx, a, b2);
+    }
+  }
+  return mx;
+}
+
+// One pass over the S tile: P = exp2(S * scale - m_used) as fp16 into the K-major SWIZZLE_128B P tile, tracking the
+// tile's row maximum (raw logits) and, when the denominator is not produced by the MMA, the row sum.
+template <bool kFull>
+__device__ __forceinline__ void softmax_tile(uint32_t tmem_row, uint8_t* sP, int r, int nvalid, float scale_log2,
+                                             float m_used, bool bf, bool sum_here, float& tile_max, float& lsum) {
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16];
+    if (kFull || c * 32 < nvalid) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_row + c * 32, v);
+      tmem_ld_wait();
+      float e[32];
+      float mx = tile_max;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
+        float ea = fast_exp2(fmaf(a, scale_log2, -m_used));
+        float eb = fast_exp2(fmaf(b2, scale_log2, -m_used));
+        if (!kFull) {
+          if (c * 32 + i >= nvalid) { a = -INFINITY; ea = 0.f; }
+          if (c * 32 + i + 1 >= nvalid) { b2 = -INFINITY; eb = 0.f; }
+        }
+        mx = fmax3(mx, a, b2);
+        e[i] = ea;
+        e[i + 1] = eb;
+      }
+      tile_max = mx;
+      if (sum_here) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lsum += e[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1], bf);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    }
+    uint8_t* atom = sP + (c >> 1) * 16384;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t chunk16 = static_cast<uint32_t>((c & 1) * 4 + q);
+      *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk16)) =
+          make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    }
+  }
+}
+
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -175,36 +255,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     // ------------------------------------ softmax warps ------------------------------------
+    // Lazy-max online softmax: each S element is read from TMEM ONCE.  P is computed against the running max
+    // m_used of earlier tiles; the tile's own max is tracked on the fly and only if it exceeds m_used by more than
+    // 2^8 (P would leave fp16's comfortable range) the tile is redone after rescaling O — rare after tile 0.
+    // With a ones column in V (l_col >= 0) the softmax denominator is column l_col of O: the tensor core sums P.
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const bool bf = p.is_bf16 != 0;
-    float m_scaled = -INFINITY;  // running max, already multiplied by scale_log2
+    const bool sum_here = p.l_col < 0;
+    float m_used = -INFINITY;  // in the scaled log2 domain
     float l = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
+      const bool full = nvalid == kKvTile;
       mbar_wait(&bars->s_full, j & 1, 17);
       tc_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        if (c * 32 >= nvalid) break;
-        uint32_t v[32];
-        tmem_ld_x32(tmem_S + lane_base + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      if (j > 0) mbar_wait(&bars->o_full, (j - 1) & 1, 18);  // already complete (in-order MMA pipe); keeps phases aligned
+      if (j == 0) {
+        const float mx = full ? row_max<true>(tmem_S + lane_base, nvalid) : row_max<false>(tmem_S + lane_base, nvalid);
+        m_used = mx * p.scale_log2;
       }
-      const float m_new = fmaxf(m_scaled, mx * p.scale_log2);
-      const float alpha = fast_exp2(m_scaled - m_new);
-      if (j > 0) {
-        // P and O are still owned by P.V of the previous block until it retires
-        mbar_wait(&bars->o_full, (j - 1) & 1, 18);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          for (int c = 0; c < p.d16 / 16; ++c) {
+      float tile_max = -INFINITY, lsum = 0.f;
+      if (full) softmax_tile<true>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
+      else      softmax_tile<false>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
+      const float tm = tile_max * p.scale_log2;
+      if (__any_sync(0xffffffffu, tm > m_used + 8.0f)) {
+        const float m_new = fmaxf(m_used, tm);
+        const float alpha = fast_exp2(m_used - m_new);
+        if (j > 0) {
+          tc_fence_after();
+          for (int c = 0; c < p.resc_cols / 16; ++c) {
             uint32_t o[16];
             tmem_ld_x16(tmem_O + lane_base + c * 16, o);
             tmem_ld_wait();
@@ -214,38 +295,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           tmem_st_wait();
         }
+        l *= alpha;
+        m_used = m_new;
+        tile_max = -INFINITY;
+        lsum = 0.f;
+        if (full) softmax_tile<true>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
+        else      softmax_tile<false>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
       }
-      l *= alpha;
-      m_scaled = m_new;
-      // pass 2: P = exp2(S * scale - m), row sum, fp16 -> swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (c * 32 < nvalid) {
-          uint32_t v[32];
-          tmem_ld_x32(tmem_S + lane_base + c * 32, v);
-          tmem_ld_wait();
-          float e[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float t = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-            e[i] = (c * 32 + i < nvalid) ? t : 0.f;
-            l += e[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1], bf);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        }
-        uint8_t* atom = sP + (c >> 1) * 16384;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk16 = static_cast<uint32_t>((c & 1) * 4 + q);
-          *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk16)) =
-              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-      }
+      l += lsum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bars->p_full);
@@ -253,6 +310,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---- epilogue: O / l -> global ----
     mbar_wait(&bars->o_full, (nkv - 1) & 1, 19);
     tc_fence_after();
+    if (!sum_here) {
+      uint32_t o[16];
+      tmem_ld_x16(tmem_O + lane_base + (p.l_col / 16) * 16, o);
+      tmem_ld_wait();
+      l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
+    }
     const float inv_l = 1.0f / l;
     const int srow = q0 + r;
     const bool valid = srow < p.Sq;
@@ -286,8 +352,8 @@ static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
 
 int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
-                 long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int is_bf16,
-                 cudaStream_t stream) {
+                 long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int v_ones_col,
+                 int is_bf16, cudaStream_t stream) {
   if (B <= 0 || heads <= 0 || Sq <= 0) return B200SD_OK;
   if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 64 != 0 || d_pad < d || d > 240) return B200SD_ERR_INVALID;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return B200SD_ERR_INVALID;
@@ -318,6 +384,9 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
   p.dpv = d_pad;
+  if (v_ones_col && d >= d_pad) return B200SD_ERR_INVALID;  // needs a free pad column
+  p.l_col = v_ones_col ? d : -1;
+  p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
   if (p.dpv > 256) return B200SD_ERR_UNSUPPORTED;
   p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
   const size_t tile = static_cast<size_t>(p.chunks) * 16384;

@@ -25,7 +25,8 @@ namespace b200sd {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 halfs = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;
@@ -59,7 +60,18 @@ struct __align__(8) GemmBarriers {
   uint32_t pad;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the fp16
+// output rounding): two MUFU ops (rcp, ex2) + a degree-5 Horner chain instead of erff()'s branchy ~30 instructions.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -80,9 +92,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   }
 }
 
+// One epilogue warp's share of a tile: row = TMEM lane (quarter*32 + lane), 32-column chunks c = half, half+2, ...
+// The residual chunks are fetched into registers BEFORE waiting for the accumulator, so their HBM latency hides
+// behind the tile's remaining MMAs instead of serialising inside the (short) epilogue.
 template <bool kBf16>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t tmem_acc, int m_tile, int n_tile,
-                                              int quarter, int lane) {
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint64_t* tmem_full_bar, uint32_t full_parity,
+                                              uint32_t tmem_acc, int m_tile, int n_tile, int quarter, int half,
+                                              int lane) {
   const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
   long long row;
   bool valid;
@@ -112,7 +128,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
   const uint8_t* rrow =
       p.residual ? reinterpret_cast<const uint8_t*>(p.residual) + (valid ? row : 0) * p.ldr * 2 : nullptr;
 
-  for (int c = 0; c < nchunks; ++c) {
+  constexpr int kMaxMine = 4;  // block_n <= 256 -> at most 8 chunks, every second one is mine
+  uint4 rv[2][4];              // residual of my next two chunks (register double buffer)
+  const bool use_res = rrow != nullptr && valid;
+  auto load_res = [&](int slot, int c) {
+    const uint4* rp = reinterpret_cast<const uint4*>(rrow + static_cast<long long>(n_tile * out_bn + c * 32) * 2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rv[slot][q] = __ldg(rp + q);
+  };
+  if (use_res) {
+    if (half < nchunks) load_res(0, half);
+    if (half + 2 < nchunks) load_res(1, half + 2);
+  }
+  mbar_wait(tmem_full_bar, full_parity, 4);
+  tc_fence_after();
+
+#pragma unroll
+  for (int ci = 0; ci < kMaxMine; ++ci) {
+    const int c = half + 2 * ci;
+    if (c >= nchunks) break;
     uint32_t v[32];
     tmem_ld_x32(taddr_row + c * 32, v);
     tmem_ld_wait();
@@ -145,11 +179,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
     const int col_out = n_tile * out_bn + c * 32;
     if (valid) {
       if (rrow) {
-        const uint4* rp = reinterpret_cast<const uint4*>(rrow + static_cast<long long>(col_out) * 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 rv = __ldg(rp + q);
-          const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+          const uint32_t w[4] = {rv[ci & 1][q].x, rv[ci & 1][q].y, rv[ci & 1][q].z, rv[ci & 1][q].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 t = unpack2<kBf16>(w[e]);
@@ -157,6 +189,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
             f[q * 8 + e * 2 + 1] += t.y;
           }
         }
+        if (c + 4 < nchunks) load_res(ci & 1, c + 4);  // refill this slot for my chunk after next
       }
       if (p.flags & B200SD_EPI_SILU) {
 #pragma unroll
@@ -198,7 +231,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 128);
+      mbar_init(&bars->tmem_empty[a], 32 * kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -275,18 +308,17 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // which of the quarter's two warps: takes chunks half, half+2, ...
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
-      mbar_wait(&bars->tmem_full[acc], acc_phase, 4);
-      tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
-      if (p.is_bf16) epilogue_tile<true>(p, tmem_acc, m_tile, n_tile, quarter, lane);
-      else           epilogue_tile<false>(p, tmem_acc, m_tile, n_tile, quarter, lane);
+      if (p.is_bf16) epilogue_tile<true>(p, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile, n_tile, quarter, half, lane);
+      else           epilogue_tile<false>(p, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile, n_tile, quarter, half, lane);
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[acc]);
     }

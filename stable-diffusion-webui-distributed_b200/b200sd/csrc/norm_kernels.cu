@@ -4,6 +4,9 @@
 //   groupnorm_apply  : y = (x - mean) * rstd * gamma + beta [, SiLU]       1 read + 1 write
 //   layernorm        : one warp per token row, two passes in registers     1 read + 1 write
 //
+// All three keep several independent 16-byte loads in flight per thread (unrolled pixel / row loops) and run at
+// high occupancy: they are latency-bound otherwise (ncu round 1: 17-20 % of HBM peak with one load in flight).
+//
 // Upstream: ldm GroupNorm32 (ResBlock.in_layers/out_layers, out), Normalize (SpatialTransformer.norm, VAE),
 // BasicTransformerBlock.norm1/2/3 (SURVEY.md §8 a-ext x3, x9; not in /root/reference).
 #include <cuda_bf16.h>
@@ -42,40 +45,66 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// block = (C/8, PY): thread (v, py) owns channels [8v, 8v+8) for pixels py, py+PY, ... of its pixel range.
+constexpr int kGnUnroll = 4;
+
+// block = (C/8, PY): thread (v, py) owns channels [8v, 8v+8) for pixels p0+py, p0+py+PY, ... of its pixel range.
+// Per-thread partials go to smem [PY][2C] (no atomics), are summed over PY, folded into groups, and one global
+// atomicAdd per (group, stat) and block lands in stats[n][g][2].
 template <bool kBf16>
 __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long pitch, int HW, int C, int G,
                                        int pix_per_cta, float* __restrict__ stats) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ float sh[];  // [PY][2C] partials, then [2C] channel totals reuse row 0
   const int n = blockIdx.y;
   const int v = threadIdx.x;
+  const int py = threadIdx.y;
+  const int PY = blockDim.y;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) sh[i] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   const uint8_t* base = X + (static_cast<long long>(n) * HW) * pitch * 2 + static_cast<long long>(v) * 16;
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * pitch * 2));
+  const long long rowb = pitch * 2;
+  int p = p0 + py;
+  for (; p + (kGnUnroll - 1) * PY < p1; p += kGnUnroll * PY) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + k * PY) * rowb));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      float f[8];
+      unpack8<kBf16>(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+  }
+  for (; p < p1; p += PY) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * rowb));
     float f[8];
     unpack8<kBf16>(u, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(&sh[v * 8 + i], s[i]);
-    atomicAdd(&sh[C + v * 8 + i], q[i]);
+  float* mine = sh + static_cast<size_t>(py) * 2 * C;
+  *reinterpret_cast<float4*>(mine + v * 8) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(mine + v * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(mine + C + v * 8) = make_float4(q[0], q[1], q[2], q[3]);
+  *reinterpret_cast<float4*>(mine + C + v * 8 + 4) = make_float4(q[4], q[5], q[6], q[7]);
+  __syncthreads();
+  const int tid = py * blockDim.x + v;
+  const int nthreads = blockDim.x * PY;
+  for (int i = tid; i < 2 * C; i += nthreads) {
+    float a = 0.f;
+    for (int k = 0; k < PY; ++k) a += sh[static_cast<size_t>(k) * 2 * C + i];
+    sh[i] = a;  // row 0 is only read at index i by this same thread: no hazard
   }
   __syncthreads();
   const int cpg = C / G;
-  for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < G; g += blockDim.x * blockDim.y) {
-    float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sh[c]; b += sh[C + c]; }
-    atomicAdd(&stats[(static_cast<long long>(n) * G + g) * 2], a);
-    atomicAdd(&stats[(static_cast<long long>(n) * G + g) * 2 + 1], b);
+  for (int g = tid; g < 2 * G; g += nthreads) {
+    const int grp = g >> 1, st = g & 1;
+    float a = 0.f;
+    for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) a += sh[st * C + c];
+    atomicAdd(&stats[(static_cast<long long>(n) * G + grp) * 2 + st], a);
   }
 }
 
@@ -86,6 +115,7 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
                                        const float* __restrict__ beta, float eps, int silu) {
   const int n = blockIdx.y;
   const int v = threadIdx.x;
+  const int PY = blockDim.y;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
   const int cpg = C / G;
@@ -105,73 +135,89 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
   }
   const uint8_t* xb = X + (static_cast<long long>(n) * HW) * pitch_x * 2 + static_cast<long long>(v) * 16;
   uint8_t* yb = Y + (static_cast<long long>(n) * HW) * pitch_y * 2 + static_cast<long long>(v) * 16;
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(p) * pitch_x * 2));
+  const long long rx = pitch_x * 2, ry = pitch_y * 2;
+  auto emit = [&](const uint4& u, int p) {
     float f[8];
     unpack8<kBf16>(u, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float t = fmaf(f[i], a[i], b[i]);
-      if (silu) t = t / (1.0f + __expf(-t));
+      if (silu) t = __fdividef(t, 1.0f + __expf(-t));
       f[i] = t;
     }
-    *reinterpret_cast<uint4*>(yb + static_cast<long long>(p) * pitch_y * 2) = pack8<kBf16>(f);
+    *reinterpret_cast<uint4*>(yb + p * ry) = pack8<kBf16>(f);
+  };
+  int p = p0 + threadIdx.y;
+  for (; p + (kGnUnroll - 1) * PY < p1; p += kGnUnroll * PY) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (p + k * PY) * rx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) emit(u[k], p + k * PY);
   }
+  for (; p < p1; p += PY) emit(__ldg(reinterpret_cast<const uint4*>(xb + p * rx)), p);
 }
 
-// one warp per row; C <= 2048, C % 8 == 0
-template <bool kBf16>
-__global__ void layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy,
-                                 int rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per row, VPT 16-byte vectors per lane (C <= 256 * VPT); gamma/beta staged in smem once per CTA;
+// persistent CTAs stride over rows so the staging is amortised and many rows are in flight per SM.
+template <bool kBf16, int VPT>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy, int rows, int C,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  extern __shared__ float gb[];  // gamma[C], beta[C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    gb[i] = gamma[i];
+    gb[C + i] = beta[i];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int warps_per_cta = blockDim.x >> 5;
   const int nvec = C / 8;
-  const uint8_t* xr = X + static_cast<long long>(warp) * ldx * 2;
-  uint8_t* yr = Y + static_cast<long long>(warp) * ldy * 2;
-  constexpr int kMaxIter = 8;  // 8 * 32 * 8 = 2048 channels
-  float f[kMaxIter][8];
-  float sum = 0.f;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (int row = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_cta) {
+    const uint8_t* xr = X + static_cast<long long>(row) * ldx * 2;
+    uint8_t* yr = Y + static_cast<long long>(row) * ldy * 2;
+    float f[VPT][8];
+    float sum = 0.f;
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int vec = it * 32 + lane;
-    if (vec < nvec) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long long>(vec) * 16));
-      unpack8<kBf16>(u, f[it]);
+    for (int it = 0; it < VPT; ++it) {
+      const int vec = it * 32 + lane;
+      if (vec < nvec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long long>(vec) * 16));
+        unpack8<kBf16>(u, f[it]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sum += f[it][i];
+        for (int i = 0; i < 8; ++i) sum += f[it][i];
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / static_cast<float>(C);
-  float var = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float var = 0.f;
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int vec = it * 32 + lane;
-    if (vec < nvec) {
+    for (int it = 0; it < VPT; ++it) {
+      if (it * 32 + lane < nvec) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = f[it][i] - mean; var += d * d; }
+        for (int i = 0; i < 8; ++i) { const float d = f[it][i] - mean; var = fmaf(d, d, var); }
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * inv_c + eps);
 #pragma unroll
-  for (int it = 0; it < kMaxIter; ++it) {
-    const int vec = it * 32 + lane;
-    if (vec < nvec) {
-      float o8[8];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vec * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vec * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int it = 0; it < VPT; ++it) {
+      const int vec = it * 32 + lane;
+      if (vec < nvec) {
+        float o8[8];
+        const float4 g0 = *reinterpret_cast<const float4*>(gb + vec * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gb + vec * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(gb + C + vec * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(gb + C + vec * 8 + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o8[i] = (f[it][i] - mean) * rstd * gg[i] + bb[i];
-      *reinterpret_cast<uint4*>(yr + static_cast<long long>(vec) * 16) = pack8<kBf16>(o8);
+        for (int i = 0; i < 8; ++i) o8[i] = fmaf((f[it][i] - mean) * rstd, gg[i], bb[i]);
+        *reinterpret_cast<uint4*>(yr + static_cast<long long>(vec) * 16) = pack8<kBf16>(o8);
+      }
     }
   }
 }
@@ -183,14 +229,28 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
   if (py < 1) py = 1;
   if (py > HW) py = HW;
   block = dim3(vx, py, 1);
-  // aim for ~4 CTAs per SM over the whole grid; every CTA gets a whole multiple of py pixels
-  int want = (148 * 4 + NB - 1) / NB;
+  // ~2 waves of (up to) 4 resident CTAs per SM over the whole grid; a CTA owns a multiple of py*unroll pixels
+  int want = (148 * 8 + NB - 1) / NB;
   int ppc = (HW + want - 1) / want;
-  ppc = ((ppc + py - 1) / py) * py;
-  if (ppc < py) ppc = py;
+  const int quantum = py * kGnUnroll;
+  ppc = ((ppc + quantum - 1) / quantum) * quantum;
+  if (ppc < quantum) ppc = quantum;
   pix_per_cta = ppc;
   grid = dim3((HW + ppc - 1) / ppc, NB, 1);
   return B200SD_OK;
+}
+
+template <bool kBf16>
+static void launch_ln(int vpt, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx, uint8_t* Y,
+                      long long ldy, int rows, int C, const float* gamma, const float* beta, float eps) {
+  switch (vpt) {
+    case 1: layernorm_kernel<kBf16, 1><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 2: layernorm_kernel<kBf16, 2><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 3: layernorm_kernel<kBf16, 3><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 4: layernorm_kernel<kBf16, 4><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 5: layernorm_kernel<kBf16, 5><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    default: layernorm_kernel<kBf16, 8><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+  }
 }
 
 }  // namespace b200sd
@@ -205,7 +265,8 @@ extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, in
   int ppc;
   int rc = gn_geometry(NB, HW, C, block, grid, ppc);
   if (rc != B200SD_OK) return rc;
-  const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
+  const size_t sh = static_cast<size_t>(block.y) * 2 * C * sizeof(float);
+  if (sh > 48 * 1024) return B200SD_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
     groupnorm_stats_kernel<true><<<grid, block, sh, st>>>(static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
@@ -241,19 +302,19 @@ extern "C" int b200sd_layernorm(const void* X, long long ldx, void* Y, long long
                                 const float* gamma, const float* beta, float eps, int dtype, void* stream) {
   if (rows <= 0) return B200SD_OK;
   if (C % 8 != 0 || C > 2048 || ldx % 8 != 0 || ldy % 8 != 0 ||
-      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(gamma) |
-        reinterpret_cast<uintptr_t>(beta)) & 15))
+      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15))
     return B200SD_ERR_INVALID;
+  const int vpt = (C / 8 + 31) / 32;
   const int warps_per_block = 8;
-  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
-    layernorm_kernel<true><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const uint8_t*>(X), ldx,
-                                                                    static_cast<uint8_t*>(Y), ldy, rows, C, gamma, beta,
-                                                                    eps);
+    launch_ln<true>(vpt, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
+                    gamma, beta, eps);
   else
-    layernorm_kernel<false><<<blocks, warps_per_block * 32, 0, st>>>(static_cast<const uint8_t*>(X), ldx,
-                                                                     static_cast<uint8_t*>(Y), ldy, rows, C, gamma,
-                                                                     beta, eps);
+    launch_ln<false>(vpt, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
+                     gamma, beta, eps);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }

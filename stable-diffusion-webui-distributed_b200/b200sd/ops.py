@@ -63,11 +63,29 @@ def _epi(bias, bias_group_rows, residual, flags):
     return e
 
 
-def pick_block_n(n: int, geglu: bool = False) -> int:
-    for bn in (256, 192, 160, 128, 96, 64, 32):
-        if n % bn == 0 and (not geglu or bn % 64 == 0):
-            return bn
-    raise ValueError(f"N={n} has no supported tile width")
+NUM_SMS = 148
+
+
+def pick_block_n(n: int, geglu: bool = False, m: Optional[int] = None) -> int:
+    """Tile width of the persistent GEMM.  Without `m` (and always for GEGLU, whose weights are interleaved per tile at
+    pack time) the widest divisor of N; with `m`, the divisor that wastes the fewest SM-slots in the last wave of
+    ceil(M/128) * N/bn tiles over 148 SMs, with a mild preference for wide MMAs."""
+    cands = [bn for bn in (256, 192, 160, 128, 96, 64, 32) if n % bn == 0 and (not geglu or bn % 64 == 0)]
+    if not cands:
+        raise ValueError(f"N={n} has no supported tile width")
+    if geglu or m is None:
+        return cands[0]
+    mt = (m + 127) // 128
+    best = None
+    for bn in cands:
+        if bn < 128 <= cands[0]:
+            continue
+        tiles = mt * (n // bn)
+        waves = -(-tiles // NUM_SMS)
+        score = tiles / (waves * NUM_SMS) * (1.0 if bn >= 192 else 0.97 if bn >= 160 else 0.93)
+        if best is None or score > best[0] + 1e-9:
+            best = (score, bn)
+    return best[1]
 
 
 def linear(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -80,7 +98,7 @@ def linear(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, bias: Optional[
     mo, no, ldd = _rows2d(out)
     geglu = bool(flags & EPI_GEGLU)
     assert mo == m and no == (n // 2 if geglu else n), (mo, m, no, n)
-    bn = block_n or pick_block_n(n, geglu)
+    bn = block_n or pick_block_n(n, geglu, m)
     e = _epi(bias, bias_group_rows, residual, flags)
     rc = _lib.lib().b200sd_linear(_p(a), ctypes.c_longlong(lda), _p(wt), _p(out), ctypes.c_longlong(ldd), m, n, k, bn,
                                   ctypes.byref(e), _dt(a), max_ctas, _stream())
@@ -99,7 +117,7 @@ def conv2d(x: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, ksize: int, str
     assert kk == ksize * ksize * c and wt.is_contiguous()
     pe = pad if pad_end is None else pad_end
     mo, no, ldd = _rows2d(out)
-    bn = block_n or pick_block_n(cout)
+    bn = block_n or pick_block_n(cout, False, mo)
     e = _epi(bias, bias_group_rows, residual, flags)
     rc = _lib.lib().b200sd_conv2d(_p(x), ctypes.c_longlong(x.stride(2)), nb, h, w, c, _p(wt), ksize, stride, pad, pe,
                                   _p(out), ctypes.c_longlong(ldd), cout, bn, ctypes.byref(e), _dt(x), max_ctas,
@@ -110,15 +128,17 @@ def conv2d(x: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, ksize: int, str
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, heads: int, d: int, d_pad: int,
-              scale: float):
-    """q [B, Sq, >=heads*d_pad], k/v [B, Skv, >=heads*d_pad] (pitch = stride(1)), out [B, Sq, heads*d]."""
+              scale: float, v_ones_col: bool = False):
+    """q [B, Sq, >=heads*d_pad], k/v [B, Skv, >=heads*d_pad] (pitch = stride(1)), out [B, Sq, heads*d].
+    v_ones_col: v[..., h*d_pad + d] == 1 for every head (softmax denominators come out of the P.V MMA)."""
     b, sq, _ = q.shape
     skv = k.shape[1]
     for t in (q, k, v, out):
         assert t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1)
     rc = _lib.lib().b200sd_attention(_p(q), ctypes.c_longlong(q.stride(1)), _p(k), ctypes.c_longlong(k.stride(1)),
                                      _p(v), ctypes.c_longlong(v.stride(1)), _p(out), ctypes.c_longlong(out.stride(1)),
-                                     b, heads, sq, skv, d, d_pad, ctypes.c_float(scale), _dt(q), _stream())
+                                     b, heads, sq, skv, d, d_pad, ctypes.c_float(scale), int(bool(v_ones_col)), _dt(q),
+                                     _stream())
     check(rc, f"b200sd_attention B={b} h={heads} Sq={sq} Skv={skv} d={d}")
     _count()
     return out

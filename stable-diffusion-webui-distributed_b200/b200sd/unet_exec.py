@@ -127,6 +127,15 @@ class UNetWeights:
                     self._norm(f"{t}.{n}", f"{t}.{n}")
                 qkv = torch.cat([pad_heads(self._w(f"{t}.attn1.to_{n}.weight"), heads, d, dp) for n in "qkv"])
                 self.t[f"{t}.attn1.qkv.w"] = self._dev(qkv)
+                # V's first pad column of every head is driven to exactly 1 through the bias: the P.V MMA then
+                # returns the softmax denominators in accumulator column d (b200sd_attention v_ones_col)
+                ones = torch.zeros((heads, dp))
+                if dp > d:
+                    ones[:, d] = 1.0
+                self.t[f"{t}.attn1.qkv.b"] = self._dev(torch.cat([torch.zeros(2 * heads * dp), ones.reshape(-1)]),
+                                                       torch.float32)
+                self.t[f"{t}.attn2.kv.b"] = self._dev(torch.cat([torch.zeros(heads * dp), ones.reshape(-1)]),
+                                                      torch.float32)
                 self._lin(f"{t}.attn1.out", f"{t}.attn1.to_out.0")
                 self.t[f"{t}.attn2.q.w"] = self._dev(pad_heads(self._w(f"{t}.attn2.to_q.weight"), heads, d, dp))
                 kv = torch.cat([pad_heads(self._w(f"{t}.attn2.to_{n}.weight"), heads, d, dp) for n in "kv"])
@@ -197,7 +206,7 @@ class UNetProgram:
         assert n == self.n and l == self.ctx_len
         ctx2 = ctx.reshape(n * l, c)
         for key, buf in self.ctx_kv.items():
-            ops.linear(ctx2, self.w.t[key + ".attn2.kv.w"], buf.reshape(n * l, -1))
+            ops.linear(ctx2, self.w.t[key + ".attn2.kv.w"], buf.reshape(n * l, -1), bias=self.w.t[key + ".attn2.kv.b"])
 
     # ---------------------------------------------------------------- program construction
     def _emit(self, fn, *a, **k):
@@ -246,10 +255,10 @@ class UNetProgram:
             # --- self attention
             self._emit(ops.layernorm, hcur, a, t[tb + ".norm1.g"], t[tb + ".norm1.beta"], 1e-5)
             qkv = self.pool.get(n, hw, 3 * heads * dp)
-            self._emit(ops.linear, a, t[tb + ".attn1.qkv.w"], qkv)
+            self._emit(ops.linear, a, t[tb + ".attn1.qkv.w"], qkv, bias=t[tb + ".attn1.qkv.b"])
             q, k, v = (qkv[..., j * heads * dp:(j + 1) * heads * dp] for j in range(3))
             o = self.pool.get(n, hw, c)
-            self._emit(ops.attention, q, k, v, o, heads, d, dp, scale)
+            self._emit(ops.attention, q, k, v, o, heads, d, dp, scale, dp > d)
             self.pool.put(qkv)
             h1 = self.pool.get(n, hw, c)
             self._emit(ops.linear, o, t[tb + ".attn1.out.w"], h1, bias=t[tb + ".attn1.out.b"], residual=hcur)
@@ -260,7 +269,7 @@ class UNetProgram:
             self._emit(ops.linear, a, t[tb + ".attn2.q.w"], q2)
             kv = torch.zeros((n, self.ctx_len, 2 * heads * dp), device=self.dev, dtype=self.dt)
             self.ctx_kv[tb] = kv
-            self._emit(ops.attention, q2, kv[..., :heads * dp], kv[..., heads * dp:], o, heads, d, dp, scale)
+            self._emit(ops.attention, q2, kv[..., :heads * dp], kv[..., heads * dp:], o, heads, d, dp, scale, dp > d)
             self.pool.put(q2)
             h2 = self.pool.get(n, hw, c)
             self._emit(ops.linear, o, t[tb + ".attn2.out.w"], h2, bias=t[tb + ".attn2.out.b"], residual=h1)

@@ -149,8 +149,14 @@ class LocalGPUWorker(Worker):
             raise NotImplementedError("img2img is not implemented on the local executor yet")
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
-        seed = int(payload["seed"])
+        seed = int(payload.get("seed", -1))
         subseed = int(payload.get("subseed", -1))
+        if seed == -1:   # API default (the benchmark payload carries no seed): draw one like sdwui's fix_seed
+            import random
+            seed = random.randrange(4294967294)
+        if subseed == -1:
+            import random
+            subseed = random.randrange(4294967294)
         cfg_scale = float(payload.get("cfg_scale", 7.0))
         vocab = eng.clip_cfg.vocab
         if "prompt_tokens" in payload:  # benchmark / tests hand pre-tokenised prompts through

@@ -70,11 +70,13 @@ def conv2d(x, wt, out, ksize, stride=1, pad=1, pad_end=None, bias=None, bias_gro
     return out
 
 
-def attention(q, k, v, out, heads, d, d_pad, scale):
+def attention(q, k, v, out, heads, d, d_pad, scale, v_ones_col=False):
     b, sq, _ = q.shape
     skv = k.shape[1]
     qh = q.float().reshape(b, sq, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
     kh = k.float().reshape(b, skv, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
+    if v_ones_col:
+        assert bool((v.float().reshape(b, skv, heads, d_pad)[..., d] == 1).all()), "V lacks its ones column"
     vh = v.float().reshape(b, skv, heads, d_pad)[..., :d].permute(0, 2, 1, 3)
     p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
     _store(out, (p @ vh).permute(0, 2, 1, 3).reshape(b, sq, heads * d))

@@ -175,28 +175,54 @@ def _attn_ref(q, k, v, heads, d, d_pad, scale):
     return (p @ vh).permute(0, 2, 1, 3).reshape(b, sq, heads * d)
 
 
-def _padded_heads(b, s, heads, d, d_pad, g):
+def _padded_heads(b, s, heads, d, d_pad, g, ones_col=False):
     t = torch.zeros((b, s, heads, d_pad), device="cuda", dtype=torch.float16)
     t[..., :d] = _rand((b, s, heads, d), g)
+    if ones_col:
+        t[..., d] = 1.0
     return t.reshape(b, s, heads * d_pad)
 
 
+@pytest.mark.parametrize("ones_col", [False, True])
 @pytest.mark.parametrize("b,heads,sq,skv,d", [
     (1, 2, 128, 128, 64), (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
     (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 256, 77, 160), (1, 10, 1024, 1024, 64), (1, 4, 200, 300, 40),
 ])
-def test_attention(ops, b, heads, sq, skv, d):
+def test_attention(ops, b, heads, sq, skv, d, ones_col):
     g = _gen(sq + skv + d)
     d_pad = (d + 63) // 64 * 64
+    if ones_col and d == d_pad:
+        pytest.skip("no pad column to carry the ones")
     q = _padded_heads(b, sq, heads, d, d_pad, g)
     k = _padded_heads(b, skv, heads, d, d_pad, g)
-    v = _padded_heads(b, skv, heads, d, d_pad, g)
+    v = _padded_heads(b, skv, heads, d, d_pad, g, ones_col)
     out = torch.full((b, sq, heads * d), float("nan"), device="cuda", dtype=torch.float16)
     scale = d ** -0.5
-    ops.attention(q, k, v, out, heads, d, d_pad, scale)
+    ops.attention(q, k, v, out, heads, d, d_pad, scale, ones_col)
     torch.cuda.synchronize()
     ref = _attn_ref(q, k, v, heads, d, d_pad, scale)
-    assert_close(f"attention b{b} h{heads} sq{sq} skv{skv} d{d}", out, ref, atol=4e-3, rtol=1e-2)
+    assert_close(f"attention b{b} h{heads} sq{sq} skv{skv} d{d} ones{int(ones_col)}", out, ref, atol=4e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("ones_col", [False, True])
+def test_attention_growing_logits_forces_rescale(ops, ones_col):
+    """Keys ordered so that the row maximum keeps rising tile after tile by far more than 2^8: exercises the lazy-max
+    redo path (O rescale in TMEM) on every tile."""
+    g = _gen(99)
+    b, heads, s, d, d_pad = 1, 2, 1024, 40, 64
+    q = _padded_heads(b, s, heads, d, d_pad, g)
+    k = _padded_heads(b, s, heads, d, d_pad, g)
+    v = _padded_heads(b, s, heads, d, d_pad, g, ones_col)
+    ramp = torch.linspace(0.2, 6.0, s, device="cuda").reshape(1, s, 1, 1)
+    kk = k.reshape(b, s, heads, d_pad).float()
+    qq = q.reshape(b, s, heads, d_pad).float()
+    kk[..., :d] = ramp * qq[:, :1, :, :d].abs().clamp(min=0.3) * torch.sign(qq[:, :1, :, :d] + 1e-3)
+    k = kk.half().reshape(b, s, heads * d_pad)
+    out = torch.empty((b, s, heads * d), device="cuda", dtype=torch.float16)
+    ops.attention(q, k, v, out, heads, d, d_pad, 1.0, ones_col)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, heads, d, d_pad, 1.0)
+    assert_close(f"attention_growing_logits ones{int(ones_col)}", out, ref, atol=6e-3, rtol=2e-2)
 
 
 def test_attention_fused_qkv_buffer(ops):
