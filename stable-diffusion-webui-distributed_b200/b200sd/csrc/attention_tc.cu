@@ -10,20 +10,26 @@
 // rows), so each 64-half chunk of a tile is exactly one TMA SWIZZLE_128B box.  O is written unpadded
 // ([b, s, h*d]) because it feeds the out-projection GEMM as a plain K-major A operand.
 //
-// One CTA = one 128-row Q tile of one (batch, head).  192 threads:
-//   warp 0   TMA producer (Q once; K ring, V ring)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer:  S = Q K^T  (M128 x N<=128 x K=d),
-//            O (+)= P V  (M128 x N=d16 x K<=128, V consumed MN-major straight from its TMA tile)
-//   warps 2-5 softmax: thread == query row (TMEM lane); online max/sum in fp32, P written as fp16 into a
-//            K-major SWIZZLE_128B smem tile, O rescaled in TMEM when the running max moves.
-// For d <= 64 the CTA needs 96 KB smem and 256 TMEM columns, so two CTAs share an SM and one's softmax
-// overlaps the other's MMAs.
+// One CTA = one 128-row Q tile of one (batch, head).  320 threads:
+//   warp 0    TMA producer (Q once; K ring, V ring)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S = Q K^T  (M128 x N<=128 x K=d),
+//             O (+)= P V  (M128 x N=d_pad x K<=128, V consumed MN-major straight from its TMA tile)
+//   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane, and the two warps of a lane
+//             quarter split the 128 kv columns of the tile in halves (one 64-column P swizzle atom each).
+// Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) is computed against the running maximum of earlier
+// tiles while the tile's own maximum is tracked; only if that exceeds m_used by more than 2^8 is the tile redone after
+// rescaling O in TMEM (a block-wide bar.red vote; rare after the first tile).  Each S element is read from TMEM
+// once, TMEM loads of the next 16 columns are in flight while the current 16 are exponentiated, and with a ones
+// column in V (v_ones_col) the row sums come out of the P.V MMA instead of CUDA-core adds.
+// d <= 64: 96 KB smem + 256 TMEM columns per CTA -> two CTAs per SM, one's softmax overlaps the other's MMAs.
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
 
 namespace b200sd {
 
-constexpr int kAttnThreads = 192;
+constexpr int kSoftmaxWarps = 8;
+constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
+constexpr int kAttnThreads = 64 + kSoftmaxThreads;
 constexpr int kQTile = 128;
 constexpr int kKvTile = 128;
 constexpr int kMaxRing = 2;
@@ -43,22 +49,25 @@ struct AttnParams {
   int is_bf16;
 };
 
-struct __align__(8) AttnBarriers {
+struct __align__(16) AttnShared {
   uint64_t q_full;
   uint64_t k_full[kMaxRing], k_empty[kMaxRing];
   uint64_t v_full[kMaxRing], v_empty[kMaxRing];
   uint64_t s_full, p_full, o_full;
   uint32_t tmem_base;
   uint32_t pad;
+  float xch[2][kQTile];  // row maxima exchanged between the two column halves
 };
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b, bool bf16) {
-  if (bf16) {
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  if constexpr (kBf16) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -67,22 +76,40 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// exact row maximum of the S tile (raw logits), kv columns >= nvalid ignored
+// named barrier 1: the 256 softmax threads only
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory"); }
+__device__ __forceinline__ bool softmax_bar_or(bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "bar.red.or.pred p, 1, %2, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "n"(kSoftmaxThreads)
+      : "memory");
+  return out != 0;
+}
+
+// maximum of my 64 columns [col0, col0+64) of the S tile (raw logits); kv columns >= nvalid ignored
 template <bool kFull>
-__device__ __forceinline__ float row_max(uint32_t tmem_row, int nvalid) {
+__device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int nvalid) {
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    if (!kFull && c * 32 >= nvalid) break;
-    uint32_t v[32];
-    tmem_ld_x32(tmem_row + c * 32, v);
+  for (int s = 0; s < 4; ++s) {
+    const int cbase = col0 + s * 16;
+    if (!kFull && cbase >= nvalid) break;
+    uint32_t v[16];
+    tmem_ld_x16(tmem_row + cbase, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < 16; i += 2) {
       float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
       if (!kFull) {
-        if (c * 32 + i >= nvalid) a = -INFINITY;
-        if (c * 32 + i + 1 >= nvalid) b2 = -INFINITY;
+        if (cbase + i >= nvalid) a = -INFINITY;
+        if (cbase + i + 1 >= nvalid) b2 = -INFINITY;
       }
       mx = fmax3(mx, a, b2);
     }
@@ -90,54 +117,145 @@ __device__ __forceinline__ float row_max(uint32_t tmem_row, int nvalid) {
   return mx;
 }
 
-// One pass over the S tile: P = exp2(S * scale - m_used) as fp16 into the K-major SWIZZLE_128B P tile, tracking the
-// tile's row maximum (raw logits) and, when the denominator is not produced by the MMA, the row sum.
-template <bool kFull>
-__device__ __forceinline__ void softmax_tile(uint32_t tmem_row, uint8_t* sP, int r, int nvalid, float scale_log2,
-                                             float m_used, bool bf, bool sum_here, float& tile_max, float& lsum) {
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t pk[16];
-    if (kFull || c * 32 < nvalid) {
-      uint32_t v[32];
-      tmem_ld_x32(tmem_row + c * 32, v);
-      tmem_ld_wait();
-      float e[32];
-      float mx = tile_max;
+// exponentiate 16 columns, track their maximum / sum, write them as two 16-byte chunks of the swizzled P atom
+template <bool kFull, bool kBf16, bool kSum>
+__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* atom, int r, int cbase, int sub, int nvalid,
+                                          float scale_log2, float m_used, float& tile_max, float& lsum) {
+  uint32_t pk[8];
+  float mx = tile_max, acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
-        float ea = fast_exp2(fmaf(a, scale_log2, -m_used));
-        float eb = fast_exp2(fmaf(b2, scale_log2, -m_used));
-        if (!kFull) {
-          if (c * 32 + i >= nvalid) { a = -INFINITY; ea = 0.f; }
-          if (c * 32 + i + 1 >= nvalid) { b2 = -INFINITY; eb = 0.f; }
-        }
-        mx = fmax3(mx, a, b2);
-        e[i] = ea;
-        e[i + 1] = eb;
-      }
-      tile_max = mx;
-      if (sum_here) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) lsum += e[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1], bf);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+  for (int i = 0; i < 16; i += 2) {
+    float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
+    float ea = fast_exp2(fmaf(a, scale_log2, -m_used));
+    float eb = fast_exp2(fmaf(b2, scale_log2, -m_used));
+    if (!kFull) {
+      if (cbase + i >= nvalid) { a = -INFINITY; ea = 0.f; }
+      if (cbase + i + 1 >= nvalid) { b2 = -INFINITY; eb = 0.f; }
     }
-    uint8_t* atom = sP + (c >> 1) * 16384;
+    mx = fmax3(mx, a, b2);
+    if constexpr (kSum) acc += ea + eb;
+    pk[i >> 1] = pack_h2<kBf16>(ea, eb);
+  }
+  tile_max = mx;
+  if constexpr (kSum) lsum += acc;
+  *reinterpret_cast<uint4*>(atom + sw128_offset(r, static_cast<uint32_t>(sub * 2))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(atom + sw128_offset(r, static_cast<uint32_t>(sub * 2 + 1))) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// One pass over my 64 columns: the TMEM load of sub-chunk s+1 is in flight while sub-chunk s is processed.
+template <bool kFull, bool kBf16, bool kSum>
+__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint8_t* atom, int r, int col0, int nvalid,
+                                             float scale_log2, float m_used, float& tile_max, float& lsum) {
+  uint32_t va[16], vb[16];
+  tmem_ld_x16(tmem_row + col0, va);
+  tmem_ld_wait();
+  tmem_ld_x16(tmem_row + col0 + 16, vb);
+  softmax16<kFull, kBf16, kSum>(va, atom, r, col0, 0, nvalid, scale_log2, m_used, tile_max, lsum);
+  tmem_ld_wait();
+  tmem_ld_x16(tmem_row + col0 + 32, va);
+  softmax16<kFull, kBf16, kSum>(vb, atom, r, col0 + 16, 1, nvalid, scale_log2, m_used, tile_max, lsum);
+  tmem_ld_wait();
+  tmem_ld_x16(tmem_row + col0 + 48, vb);
+  softmax16<kFull, kBf16, kSum>(va, atom, r, col0 + 32, 2, nvalid, scale_log2, m_used, tile_max, lsum);
+  tmem_ld_wait();
+  softmax16<kFull, kBf16, kSum>(vb, atom, r, col0 + 48, 3, nvalid, scale_log2, m_used, tile_max, lsum);
+}
+
+template <bool kBf16, bool kSum>
+__device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_S,
+                                              uint32_t tmem_O, int warp, int lane, int q0, int head, int b, int nkv) {
+  const int quarter = warp & 3;
+  const int half = (warp - 2) >> 2;   // which 64-column half of the kv tile (== which P swizzle atom) is mine
+  const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
+  const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+  const uint32_t s_row = tmem_S + lane_base;
+  const uint32_t o_row = tmem_O + lane_base;
+  uint8_t* atom = sP + half * 16384;
+  const int col0 = half * 64;
+  constexpr bool sum_here = kSum;
+  float m_used = -INFINITY;  // scaled log2 domain
+  float l = 0.f;
+  for (int j = 0; j < nkv; ++j) {
+    const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
+    const bool full = nvalid == kKvTile;
+    mbar_wait(&sh->s_full, j & 1, 17);
+    tc_fence_after();
+    if (j > 0) mbar_wait(&sh->o_full, (j - 1) & 1, 18);  // already complete (in-order MMA pipe); keeps phases aligned
+    if (j == 0) {
+      const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
+      sh->xch[half][r] = mx;
+      softmax_bar_sync();
+      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * p.scale_log2;
+    }
+    float tile_max = -INFINITY, lsum = 0.f;
+    if (full) softmax_half<true, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    else      softmax_half<false, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    const float tm = tile_max * p.scale_log2;
+    if (softmax_bar_or(tm > m_used + 8.0f)) {
+      // rare path: the running maximum moved by more than 2^8 for some row of this Q tile
+      sh->xch[half][r] = tm;
+      softmax_bar_sync();
+      const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
+      const float alpha = fast_exp2(m_used - m_new);
+      if (j > 0) {
+        for (int c = half; c < p.resc_cols / 16; c += 2) {
+          uint32_t o[16];
+          tmem_ld_x16(o_row + c * 16, o);
+          tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t chunk16 = static_cast<uint32_t>((c & 1) * 4 + q);
-      *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk16)) =
-          make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x16(o_row + c * 16, o);
+        }
+        tmem_st_wait();
+      }
+      l *= alpha;
+      m_used = m_new;
+      tile_max = -INFINITY;
+      lsum = 0.f;
+      if (full) softmax_half<true, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      else      softmax_half<false, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    }
+    l += lsum;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(&sh->p_full);
+  }
+  // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
+  mbar_wait(&sh->o_full, (nkv - 1) & 1, 19);
+  tc_fence_after();
+  if (sum_here) {
+    softmax_bar_sync();  // every thread is past its last xch read
+    sh->xch[half][r] = l;
+    softmax_bar_sync();
+    l = sh->xch[0][r] + sh->xch[1][r];
+  } else {
+    uint32_t o[16];
+    tmem_ld_x16(o_row + (p.l_col / 16) * 16, o);
+    tmem_ld_wait();
+    l = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
+  }
+  const float inv_l = 1.0f / l;
+  const int srow = q0 + r;
+  const bool valid = srow < p.Sq;
+  uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
+                  ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
+  for (int c = half; c < p.d16 / 16; c += 2) {
+    uint32_t o[16];
+    tmem_ld_x16(o_row + c * 16, o);
+    tmem_ld_wait();
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      h[i] = pack_h2<kBf16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+    if (valid) {
+      if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
     }
   }
 }
-
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -149,7 +267,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sP = sQ + tile_bytes;  // 2 x 16 KB (kv columns 0-63, 64-127)
   uint8_t* sK = sP + 32768;
   uint8_t* sV = sK + static_cast<size_t>(p.k_stages) * tile_bytes;
-  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(sV + static_cast<size_t>(p.v_stages) * tile_bytes);
+  AttnShared* sh = reinterpret_cast<AttnShared*>(sV + static_cast<size_t>(p.v_stages) * tile_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,45 +281,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(&bars->q_full, 1);
+    mbar_init(&sh->q_full, 1);
     for (int s = 0; s < kMaxRing; ++s) {
-      mbar_init(&bars->k_full[s], 1);
-      mbar_init(&bars->k_empty[s], 1);
-      mbar_init(&bars->v_full[s], 1);
-      mbar_init(&bars->v_empty[s], 1);
+      mbar_init(&sh->k_full[s], 1);
+      mbar_init(&sh->k_empty[s], 1);
+      mbar_init(&sh->v_full[s], 1);
+      mbar_init(&sh->v_empty[s], 1);
     }
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->p_full, 128);
-    mbar_init(&bars->o_full, 1);
+    mbar_init(&sh->s_full, 1);
+    mbar_init(&sh->p_full, kSoftmaxThreads);
+    mbar_init(&sh->o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == 1) tmem_alloc(&sh->tmem_base, static_cast<uint32_t>(p.tmem_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = sh->tmem_base;
   const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
-  const uint32_t tmem_O = tmem_base + 128;  // dpv fp32 columns (first d16 carry data)
+  const uint32_t tmem_O = tmem_base + 128;  // dpv fp32 columns (first d16 carry data, column l_col the row sums)
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full, tile_bytes);
-      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &bars->q_full, col0 + c * 64, q0, b);
+      mbar_arrive_expect_tx(&sh->q_full, tile_bytes);
+      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
         const int ks = j % p.k_stages;
         const uint32_t kph = (j / p.k_stages) & 1;
-        mbar_wait(&bars->k_empty[ks], kph ^ 1u, 11);
-        mbar_arrive_expect_tx(&bars->k_full[ks], tile_bytes);
+        mbar_wait(&sh->k_empty[ks], kph ^ 1u, 11);
+        mbar_arrive_expect_tx(&sh->k_full[ks], tile_bytes);
         for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sK + static_cast<size_t>(ks) * tile_bytes + c * 16384, &tmK, &bars->k_full[ks], col0 + c * 64,
+          tma_load_3d(sK + static_cast<size_t>(ks) * tile_bytes + c * 16384, &tmK, &sh->k_full[ks], col0 + c * 64,
                       j * kKvTile, b);
         const int vs = j % p.v_stages;
         const uint32_t vph = (j / p.v_stages) & 1;
-        mbar_wait(&bars->v_empty[vs], vph ^ 1u, 12);
-        mbar_arrive_expect_tx(&bars->v_full[vs], tile_bytes);
+        mbar_wait(&sh->v_empty[vs], vph ^ 1u, 12);
+        mbar_arrive_expect_tx(&sh->v_full[vs], tile_bytes);
         for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sV + static_cast<size_t>(vs) * tile_bytes + c * 16384, &tmV, &bars->v_full[vs], col0 + c * 64,
+          tma_load_3d(sV + static_cast<size_t>(vs) * tile_bytes + c * 16384, &tmV, &sh->v_full[vs], col0 + c * 64,
                       j * kKvTile, b);
       }
     }
@@ -210,7 +328,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       const bool bf = p.is_bf16 != 0;
       const int ksteps_qk = p.d16 / 16;
-      mbar_wait(&bars->q_full, 0, 13);
+      mbar_wait(&sh->q_full, 0, 13);
       for (int j = 0; j < nkv; ++j) {
         const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
         const int n16 = (nvalid + 15) & ~15;
@@ -219,7 +337,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int vs = j % p.v_stages;
         const uint32_t vph = (j / p.v_stages) & 1;
         // ---- S = Q K^T ----  (S is free: softmax(j-1) finished reading it before arriving on p_full(j-1))
-        mbar_wait(&bars->k_full[ks], kph, 14);
+        mbar_wait(&sh->k_full[ks], kph, 14);
         tc_fence_after();
         {
           const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
@@ -230,12 +348,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss(tmem_S, make_sdesc_sw128(aQ + off, 16, 1024), make_sdesc_sw128(aK + off, 16, 1024), idesc,
                         k != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->k_empty[ks]);
-          umma_commit(&bars->s_full);
+          umma_commit(&sh->k_empty[ks]);
+          umma_commit(&sh->s_full);
         }
         // ---- O (+)= P V ----
-        mbar_wait(&bars->p_full, j & 1, 15);
-        mbar_wait(&bars->v_full[vs], vph, 16);
+        mbar_wait(&sh->p_full, j & 1, 15);
+        mbar_wait(&sh->v_full[vs], vph, 16);
         tc_fence_after();
         {
           const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
@@ -248,94 +366,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, 16384, 1024),
                         idesc, (j | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->v_empty[vs]);
-          umma_commit(&bars->o_full);
+          umma_commit(&sh->v_empty[vs]);
+          umma_commit(&sh->o_full);
         }
       }
     }
   } else {
-    // ------------------------------------ softmax warps ------------------------------------
-    // Lazy-max online softmax: each S element is read from TMEM ONCE.  P is computed against the running max
-    // m_used of earlier tiles; the tile's own max is tracked on the fly and only if it exceeds m_used by more than
-    // 2^8 (P would leave fp16's comfortable range) the tile is redone after rescaling O — rare after tile 0.
-    // With a ones column in V (l_col >= 0) the softmax denominator is column l_col of O: the tensor core sums P.
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const bool bf = p.is_bf16 != 0;
     const bool sum_here = p.l_col < 0;
-    float m_used = -INFINITY;  // in the scaled log2 domain
-    float l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
-      const bool full = nvalid == kKvTile;
-      mbar_wait(&bars->s_full, j & 1, 17);
-      tc_fence_after();
-      if (j > 0) mbar_wait(&bars->o_full, (j - 1) & 1, 18);  // already complete (in-order MMA pipe); keeps phases aligned
-      if (j == 0) {
-        const float mx = full ? row_max<true>(tmem_S + lane_base, nvalid) : row_max<false>(tmem_S + lane_base, nvalid);
-        m_used = mx * p.scale_log2;
-      }
-      float tile_max = -INFINITY, lsum = 0.f;
-      if (full) softmax_tile<true>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
-      else      softmax_tile<false>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
-      const float tm = tile_max * p.scale_log2;
-      if (__any_sync(0xffffffffu, tm > m_used + 8.0f)) {
-        const float m_new = fmaxf(m_used, tm);
-        const float alpha = fast_exp2(m_used - m_new);
-        if (j > 0) {
-          tc_fence_after();
-          for (int c = 0; c < p.resc_cols / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_x16(tmem_O + lane_base + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(tmem_O + lane_base + c * 16, o);
-          }
-          tmem_st_wait();
-        }
-        l *= alpha;
-        m_used = m_new;
-        tile_max = -INFINITY;
-        lsum = 0.f;
-        if (full) softmax_tile<true>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
-        else      softmax_tile<false>(tmem_S + lane_base, sP, r, nvalid, p.scale_log2, m_used, bf, sum_here, tile_max, lsum);
-      }
-      l += lsum;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bars->p_full);
-    }
-    // ---- epilogue: O / l -> global ----
-    mbar_wait(&bars->o_full, (nkv - 1) & 1, 19);
-    tc_fence_after();
-    if (!sum_here) {
-      uint32_t o[16];
-      tmem_ld_x16(tmem_O + lane_base + (p.l_col / 16) * 16, o);
-      tmem_ld_wait();
-      l = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
-    }
-    const float inv_l = 1.0f / l;
-    const int srow = q0 + r;
-    const bool valid = srow < p.Sq;
-    uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
-                    ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
-    for (int c = 0; c < p.d16 / 16; ++c) {
-      uint32_t o[16];
-      tmem_ld_x16(tmem_O + lane_base + c * 16, o);
-      tmem_ld_wait();
-      uint32_t h[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        h[i] = pack_h2(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l, bf);
-      if (valid) {
-        if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
-        if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-      }
+    if (p.is_bf16) {
+      if (sum_here) softmax_warps<true, true>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
+      else          softmax_warps<true, false>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
+    } else {
+      if (sum_here) softmax_warps<false, true>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
+      else          softmax_warps<false, false>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
     }
   }
 
@@ -384,13 +427,13 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
   p.dpv = d_pad;
+  if (p.dpv > 256) return B200SD_ERR_UNSUPPORTED;
   if (v_ones_col && d >= d_pad) return B200SD_ERR_INVALID;  // needs a free pad column
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
-  if (p.dpv > 256) return B200SD_ERR_UNSUPPORTED;
   p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
   const size_t tile = static_cast<size_t>(p.chunks) * 16384;
-  const size_t fixed = 1024 + tile /*Q*/ + 32768 /*P*/ + sizeof(AttnBarriers) + 64;
+  const size_t fixed = 1024 + tile /*Q*/ + 32768 /*P*/ + sizeof(AttnShared) + 64;
   const size_t budget = static_cast<size_t>(g_attn_max_smem);
   // K ring first (its prefetch hides the next block's load), then V
   if (fixed + 4 * tile <= budget && p.chunks > 1) { p.k_stages = 2; p.v_stages = 2; }

@@ -10,8 +10,12 @@
 //             (dx - pad, dy - pad) — TMA's out-of-bounds zero fill is the convolution padding, and
 //             elementStrides = 2 gives the stride-2 Downsample.  Weights are packed [Cout][tap][Cin].
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / per-image bias / residual / GEGLU -> global).
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..9 = epilogue, two groups of four warps (one warp per TMEM lane quarter) that take alternate 32-column
+// chunks of the accumulator:  TMEM -> registers -> (+bias, +residual, SiLU / GEGLU) -> fp16 -> a SWIZZLE_64B
+// staging tile in shared memory -> TMA store.  The residual tile arrives the same way (TMA load into a staging
+// tile, two chunks ahead), so ALL global traffic of the kernel is bulk, coalesced and asynchronous; out-of-range
+// rows (M tail, partial pixel boxes) are clipped / zero-filled by the tensor maps instead of predicated.
 // Two TMEM accumulators (columns 0 and 256) let tile i's epilogue overlap tile i+1's MMAs.
 //
 // Upstream ops this kernel stands in for (not in /root/reference; reached from world.py:196 / worker.py:432):
@@ -25,17 +29,20 @@ namespace b200sd {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 halfs = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int kEpiWarps = 8;  // two groups of 4 warps
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;
+constexpr int kChunkCols = 32;
+constexpr uint32_t kStageTileBytes = kBlockM * kChunkCols * 2;  // 8 KB: 128 rows x 32 halfs, SWIZZLE_64B
+constexpr uint32_t kStagingBytes = 4 * kStageTileBytes;         // [group][buffer]
 
 struct GemmKernelParams {
   int M, N, K;
   int block_n;
   int num_m_tiles, num_n_tiles, num_k_blocks, num_stages;
-  uint32_t a_bytes, b_bytes;
+  uint32_t a_bytes, b_bytes, d_bytes;  // d_bytes: bytes one staging box moves (rows of the tile actually stored)
   int mode;                        // 0 = GEMM, 1 = CONV
   int H, W, NB;                    // CONV: output height / width / images
   int bw, bh, bn;                  // CONV: output-pixel box
@@ -43,10 +50,7 @@ struct GemmKernelParams {
   int taps, cblocks, stride, pad;  // CONV
   const float* bias;               // [groups][N] fp32 or nullptr
   int bias_group_rows;             // rows (output pixels) sharing one bias row; <= 0 -> single row
-  const void* residual;            // [M][N-ish] same dtype as D, row pitch ldr, or nullptr
-  long long ldr;
-  void* D;
-  long long ldd;
+  int has_residual;
   int flags;                       // B200SD_EPI_*
   int is_bf16;
 };
@@ -56,6 +60,7 @@ struct __align__(8) GemmBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[2][2];  // [group][buffer]: residual staging tile landed
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -92,68 +97,82 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   }
 }
 
-// One epilogue warp's share of a tile: row = TMEM lane (quarter*32 + lane), 32-column chunks c = half, half+2, ...
-// The residual chunks are fetched into registers BEFORE waiting for the accumulator, so their HBM latency hides
-// behind the tile's remaining MMAs instead of serialising inside the (short) epilogue.
-template <bool kBf16>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint64_t* tmem_full_bar, uint32_t full_parity,
-                                              uint32_t tmem_acc, int m_tile, int n_tile, int quarter, int half,
-                                              int lane) {
-  const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
-  long long row;
-  bool valid;
+__device__ __forceinline__ void group_bar_sync(int group) {  // named barriers 1, 2: the 128 threads of one group
+  asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+}
+
+struct TileCoord {
+  int c1, c2, c3;  // coordinates of the tile's first output row in the D / residual tensor maps (after the column)
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int m_tile) {
+  TileCoord t;
   if (p.mode == 0) {
-    row = static_cast<long long>(m_tile) * kBlockM + r;
-    valid = row < p.M;
+    t.c1 = m_tile * kBlockM; t.c2 = 0; t.c3 = 0;
   } else {
-    const int tx = m_tile % p.tiles_x;
-    const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-    const int tn = m_tile / (p.tiles_x * p.tiles_y);
-    const int x = tx * p.bw + r % p.bw;
-    const int y = ty * p.bh + (r / p.bw) % p.bh;
-    const int n = tn * p.bn + r / (p.bw * p.bh);
-    valid = (r < p.bw * p.bh * p.bn) && x < p.W && y < p.H && n < p.NB;
-    row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+    t.c1 = (m_tile % p.tiles_x) * p.bw;
+    t.c2 = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+    t.c3 = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn;
   }
-  const float* bias_row = nullptr;
-  if (p.bias != nullptr) {
-    const long long g = (p.bias_group_rows > 0 && valid) ? row / p.bias_group_rows : 0;
-    bias_row = p.bias + g * p.N;
-  }
-  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  return t;
+}
+
+// One epilogue group's share of a tile.  `uses` counts how often each residual buffer of this group has been
+// filled so far (mbarrier phase bookkeeping, identical in all 128 threads).
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const CUtensorMap* tmD, const CUtensorMap* tmR,
+                                              GemmBarriers* bars, uint8_t* stage_d, uint8_t* stage_r,
+                                              uint64_t* tmem_full_bar, uint32_t full_parity, uint32_t tmem_acc,
+                                              int m_tile, int n_tile, int quarter, int group, int lane,
+                                              uint32_t (&uses)[2]) {
+  const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
+  const bool leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
+  const TileCoord tc = tile_coord(p, m_tile);
   const bool geglu = (p.flags & B200SD_EPI_GEGLU) != 0;
   const int out_bn = geglu ? p.block_n / 2 : p.block_n;
-  const int nchunks = out_bn / 32;
-  uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) + (valid ? row : 0) * p.ldd * 2;
-  const uint8_t* rrow =
-      p.residual ? reinterpret_cast<const uint8_t*>(p.residual) + (valid ? row : 0) * p.ldr * 2 : nullptr;
+  const int nchunks = out_bn / kChunkCols;
+  const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  uint8_t* my_d = stage_d + group * 2 * kStageTileBytes;
+  uint8_t* my_r = stage_r + group * 2 * kStageTileBytes;
 
-  constexpr int kMaxMine = 4;  // block_n <= 256 -> at most 8 chunks, every second one is mine
-  uint4 rv[2][4];              // residual of my next two chunks (register double buffer)
-  const bool use_res = rrow != nullptr && valid;
-  auto load_res = [&](int slot, int c) {
-    const uint4* rp = reinterpret_cast<const uint4*>(rrow + static_cast<long long>(n_tile * out_bn + c * 32) * 2);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) rv[slot][q] = __ldg(rp + q);
+  auto load_residual = [&](int buf, int c) {  // leader only
+    mbar_arrive_expect_tx(&bars->res_full[group][buf], p.d_bytes);
+    const int col = n_tile * out_bn + c * kChunkCols;
+    if (p.mode == 0) tma_load_2d(my_r + buf * kStageTileBytes, tmR, &bars->res_full[group][buf], col, tc.c1);
+    else tma_load_4d(my_r + buf * kStageTileBytes, tmR, &bars->res_full[group][buf], col, tc.c1, tc.c2, tc.c3);
   };
-  if (use_res) {
-    if (half < nchunks) load_res(0, half);
-    if (half + 2 < nchunks) load_res(1, half + 2);
+
+  // per-row bias group (per-image bias): needs the global output row of this thread
+  const float* bias_row = p.bias;
+  if (p.bias != nullptr && p.bias_group_rows > 0) {
+    long long row;
+    if (p.mode == 0) {
+      row = static_cast<long long>(m_tile) * kBlockM + r;
+      if (row >= p.M) row = 0;
+    } else {
+      const int x = tc.c1 + r % p.bw, y = tc.c2 + (r / p.bw) % p.bh, n = tc.c3 + r / (p.bw * p.bh);
+      row = (x < p.W && y < p.H && n < p.NB && r < p.bw * p.bh * p.bn) ? (static_cast<long long>(n) * p.H + y) * p.W + x : 0;
+    }
+    bias_row = p.bias + (row / p.bias_group_rows) * p.N;
+  }
+
+  if (p.has_residual && leader) {  // two chunks ahead; the buffers are free (last tile's barriers passed)
+    if (group < nchunks) load_residual(0, group);
+    if (group + 2 < nchunks) load_residual(1, group + 2);
   }
   mbar_wait(tmem_full_bar, full_parity, 4);
   tc_fence_after();
 
-#pragma unroll
-  for (int ci = 0; ci < kMaxMine; ++ci) {
-    const int c = half + 2 * ci;
-    if (c >= nchunks) break;
+  int ci = 0;
+  for (int c = group; c < nchunks; c += 2, ++ci) {
+    const int buf = ci & 1;
     uint32_t v[32];
-    tmem_ld_x32(taddr_row + c * 32, v);
+    tmem_ld_x32(taddr_row + c * kChunkCols, v);
     tmem_ld_wait();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    const int col_in = n_tile * p.block_n + c * 32;  // column in the [N] space of the GEMM (bias index)
+    const int col_in = n_tile * p.block_n + c * kChunkCols;  // column in the [N] space of the GEMM (bias index)
     if (bias_row) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -163,7 +182,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint64_
     }
     if (geglu) {
       uint32_t g[32];
-      tmem_ld_x32(taddr_row + out_bn + c * 32, g);
+      tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);
       tmem_ld_wait();
       const int gcol = col_in + out_bn;
 #pragma unroll
@@ -176,47 +195,60 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint64_
         f[j + 3] *= gelu_erf(__uint_as_float(g[j + 3]) + b.w);
       }
     }
-    const int col_out = n_tile * out_bn + c * 32;
-    if (valid) {
-      if (rrow) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t w[4] = {rv[ci & 1][q].x, rv[ci & 1][q].y, rv[ci & 1][q].z, rv[ci & 1][q].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 t = unpack2<kBf16>(w[e]);
-            f[q * 8 + e * 2] += t.x;
-            f[q * 8 + e * 2 + 1] += t.y;
-          }
-        }
-        if (c + 4 < nchunks) load_res(ci & 1, c + 4);  // refill this slot for my chunk after next
-      }
-      if (p.flags & B200SD_EPI_SILU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
-      }
-      uint4* dp = reinterpret_cast<uint4*>(drow + static_cast<long long>(col_out) * 2);
+    if (p.has_residual) {
+      mbar_wait(&bars->res_full[group][buf], uses[buf] & 1u, 5);
+      uses[buf]++;
+      const uint8_t* rt = my_r + buf * kStageTileBytes;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint4 o;
-        o.x = pack2<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
-        o.y = pack2<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
-        o.z = pack2<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
-        o.w = pack2<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
-        dp[q] = o;
+        const uint4 rv = *reinterpret_cast<const uint4*>(rt + sw64_offset(r, q));
+        const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = unpack2<kBf16>(w[e]);
+          f[q * 8 + e * 2] += t.x;
+          f[q * 8 + e * 2 + 1] += t.y;
+        }
       }
+    }
+    if (p.flags & B200SD_EPI_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+    }
+    uint8_t* dt = my_d + buf * kStageTileBytes;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = pack2<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
+      o.y = pack2<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
+      o.z = pack2<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
+      o.w = pack2<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
+      *reinterpret_cast<uint4*>(dt + sw64_offset(r, q)) = o;
+    }
+    fence_proxy_async_smem();          // my staging writes (and residual reads) -> visible / ordered for the async proxy
+    if (leader) bulk_wait_read<0>();   // the previous chunk's store has finished reading the OTHER staging buffer
+    group_bar_sync(group);
+    if (leader) {
+      const int col = n_tile * out_bn + c * kChunkCols;
+      if (p.mode == 0) tma_store_2d(tmD, dt, col, tc.c1);
+      else tma_store_4d(tmD, dt, col, tc.c1, tc.c2, tc.c3);
+      bulk_commit();
+      if (p.has_residual && c + 4 < nchunks) load_residual(buf, c + 4);  // everyone is past reading this buffer
     }
   }
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                     const GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
-  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(smem + static_cast<size_t>(p.num_stages) * stage_bytes);
+  uint8_t* stage_d = smem + static_cast<size_t>(p.num_stages) * stage_bytes;
+  uint8_t* stage_r = stage_d + kStagingBytes;
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_r + (p.has_residual ? kStagingBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -225,6 +257,8 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (p.has_residual) tma_prefetch_desc(&tmR);
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -232,6 +266,8 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 32 * kEpiWarps);
+      mbar_init(&bars->res_full[a][0], 1);
+      mbar_init(&bars->res_full[a][1], 1);
     }
     fence_mbar_init();
   }
@@ -308,8 +344,9 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------
-    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which of the quarter's two warps: takes chunks half, half+2, ...
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may access
+    const int group = (warp - 2) >> 2;  // warps 2-5 / 6-9: chunks group, group+2, ...
+    uint32_t uses[2] = {0u, 0u};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -317,11 +354,16 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = tile / p.num_n_tiles;
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
-      if (p.is_bf16) epilogue_tile<true>(p, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile, n_tile, quarter, half, lane);
-      else           epilogue_tile<false>(p, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile, n_tile, quarter, half, lane);
+      if (p.is_bf16)
+        epilogue_tile<true>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
+                            n_tile, quarter, group, lane, uses);
+      else
+        epilogue_tile<false>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
+                             n_tile, quarter, group, lane, uses);
       tc_fence_before();
       mbar_arrive(&bars->tmem_empty[acc]);
     }
+    bulk_wait<0>();  // the issuing threads' TMA stores must have completed before the CTA (and its smem) goes away
   }
 
   tc_fence_before();
@@ -358,28 +400,37 @@ static int device_props() {
   return B200SD_OK;
 }
 
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmKernelParams& p, int max_ctas,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmR,
+                  GemmKernelParams& p, int max_ctas, cudaStream_t stream) {
   int rc = device_props();
   if (rc != B200SD_OK) return rc;
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
-  const int budget = g_max_smem - 1024 /*align*/ - static_cast<int>(sizeof(GemmBarriers)) - 64;
+  const int staging = static_cast<int>(kStagingBytes) * (p.has_residual ? 2 : 1);
+  const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return B200SD_ERR_UNSUPPORTED;
   p.num_stages = stages;
-  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + sizeof(GemmBarriers) + 64;
+  size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + staging + sizeof(GemmBarriers) + 64;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the kernel owns all 512 TMEM columns
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid <= 0) return B200SD_OK;
-  gemm_conv_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  gemm_conv_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmD, tmR, p);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 
-static int fill_common(GemmKernelParams& p, int M, int N, int K, int block_n, const b200sd_epilogue* epi, void* D,
-                       long long ldd, int is_bf16) {
+struct OutSpec {
+  void* D;
+  long long ldd;
+  const void* residual;
+  long long ldr;
+  int n_out;
+};
+
+static int fill_common(GemmKernelParams& p, OutSpec& o, int M, int N, int K, int block_n, const b200sd_epilogue* epi,
+                       void* D, long long ldd, int is_bf16) {
   if (block_n < 32 || block_n > 256 || block_n % 32 != 0 || N % block_n != 0 || K % kBlockK != 0) return B200SD_ERR_INVALID;
   p.M = M; p.N = N; p.K = K; p.block_n = block_n;
   p.num_n_tiles = N / block_n;
@@ -387,14 +438,50 @@ static int fill_common(GemmKernelParams& p, int M, int N, int K, int block_n, co
   p.b_bytes = static_cast<uint32_t>(block_n) * 128u;
   p.bias = epi ? epi->bias : nullptr;
   p.bias_group_rows = epi ? epi->bias_group_rows : 0;
-  p.residual = epi ? epi->residual : nullptr;
-  p.ldr = epi ? epi->ldr : 0;
   p.flags = epi ? epi->flags : 0;
-  p.D = D; p.ldd = ldd; p.is_bf16 = is_bf16;
-  if ((p.flags & B200SD_EPI_GEGLU) && block_n % 64 != 0) return B200SD_ERR_INVALID;
+  p.is_bf16 = is_bf16;
+  o.D = D; o.ldd = ldd;
+  o.residual = epi ? epi->residual : nullptr;
+  o.ldr = epi ? epi->ldr : 0;
+  p.has_residual = o.residual != nullptr ? 1 : 0;
+  const bool geglu = (p.flags & B200SD_EPI_GEGLU) != 0;
+  if (geglu && block_n % 64 != 0) return B200SD_ERR_INVALID;
+  o.n_out = geglu ? N / 2 : N;
   if (ldd % 8 != 0 || (reinterpret_cast<uintptr_t>(D) & 15) != 0) return B200SD_ERR_INVALID;
-  if (p.residual && (p.ldr % 8 != 0 || (reinterpret_cast<uintptr_t>(p.residual) & 15) != 0)) return B200SD_ERR_INVALID;
+  if (o.residual && (o.ldr % 8 != 0 || (reinterpret_cast<uintptr_t>(o.residual) & 15) != 0)) return B200SD_ERR_INVALID;
   if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0) return B200SD_ERR_INVALID;
+  return B200SD_OK;
+}
+
+// tensor maps of the output (store) and residual (load): same geometry as the tile's rows, 32-column SWIZZLE_64B boxes
+static int make_out_maps(const GemmKernelParams& p, const OutSpec& o, CUtensorMap* tmD, CUtensorMap* tmR) {
+  int rc;
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? o.D : o.residual;
+    const long long ld = which == 0 ? o.ldd : o.ldr;
+    CUtensorMap* out = which == 0 ? tmD : tmR;
+    if (base == nullptr) {  // no residual: a valid (unused) map keeps the kernel signature fixed
+      *tmR = *tmD;
+      continue;
+    }
+    if (p.mode == 0) {
+      const uint64_t dims[2] = {static_cast<uint64_t>(o.n_out), static_cast<uint64_t>(p.M)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+      const uint32_t box[2] = {kChunkCols, kBlockM};
+      const uint32_t es[2] = {1, 1};
+      rc = make_tmap_sw64(out, base, 2, dims, strides, box, es);
+    } else {
+      const uint64_t dims[4] = {static_cast<uint64_t>(o.n_out), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                                static_cast<uint64_t>(p.NB)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * p.W,
+                                   static_cast<uint64_t>(ld) * 2 * p.W * p.H};
+      const uint32_t box[4] = {kChunkCols, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh),
+                               static_cast<uint32_t>(p.bn)};
+      const uint32_t es[4] = {1, 1, 1, 1};
+      rc = make_tmap_sw64(out, base, 4, dims, strides, box, es);
+    }
+    if (rc != B200SD_OK) return rc;
+  }
   return B200SD_OK;
 }
 
@@ -402,14 +489,16 @@ int gemm_tc(const void* A, long long lda, const void* Wt, void* D, long long ldd
             const b200sd_epilogue* epi, int is_bf16, int max_ctas, cudaStream_t stream) {
   if (M <= 0) return B200SD_OK;
   GemmKernelParams p{};
-  int rc = fill_common(p, M, N, K, block_n, epi, D, ldd, is_bf16);
+  OutSpec o{};
+  int rc = fill_common(p, o, M, N, K, block_n, epi, D, ldd, is_bf16);
   if (rc != B200SD_OK) return rc;
   if (lda % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 || (reinterpret_cast<uintptr_t>(Wt) & 15) != 0)
     return B200SD_ERR_INVALID;
   p.mode = 0;
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
   p.a_bytes = 16384u;
-  CUtensorMap tmA, tmB;
+  p.d_bytes = kStageTileBytes;
+  CUtensorMap tmA, tmB, tmD, tmR;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
@@ -426,7 +515,9 @@ int gemm_tc(const void* A, long long lda, const void* Wt, void* D, long long ldd
     rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
     if (rc != B200SD_OK) return rc;
   }
-  return launch(tmA, tmB, p, max_ctas, stream);
+  rc = make_out_maps(p, o, &tmD, &tmR);
+  if (rc != B200SD_OK) return rc;
+  return launch(tmA, tmB, tmD, tmR, p, max_ctas, stream);
 }
 
 int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, const void* Wt, int ksize, int stride,
@@ -442,7 +533,8 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
   const int Wo = (Win + pad + pad_end - ksize) / stride + 1;
   if (Ho <= 0 || Wo <= 0) return B200SD_ERR_INVALID;
   GemmKernelParams p{};
-  int rc = fill_common(p, NB * Ho * Wo, Cout, taps * C, block_n, epi, D, ldd, is_bf16);
+  OutSpec o{};
+  int rc = fill_common(p, o, NB * Ho * Wo, Cout, taps * C, block_n, epi, D, ldd, is_bf16);
   if (rc != B200SD_OK) return rc;
   p.mode = 1;
   p.H = Ho; p.W = Wo; p.NB = NB;
@@ -456,7 +548,8 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
   const int tiles_n = (NB + p.bn - 1) / p.bn;
   p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
   p.a_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bn) * 128u;
-  CUtensorMap tmA, tmB;
+  p.d_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bn) * kChunkCols * 2u;
+  CUtensorMap tmA, tmB, tmD, tmR;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                               static_cast<uint64_t>(NB)};
@@ -479,7 +572,9 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
     rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
     if (rc != B200SD_OK) return rc;
   }
-  return launch(tmA, tmB, p, max_ctas, stream);
+  rc = make_out_maps(p, o, &tmD, &tmR);
+  if (rc != B200SD_OK) return rc;
+  return launch(tmA, tmB, tmD, tmR, p, max_ctas, stream);
 }
 
 }  // namespace b200sd

@@ -211,6 +211,38 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
   return row * 128u + (((chunk16 ^ (row & 7u)) & 7u) << 4);
 }
 
+// Same for a SWIZZLE_64B tile with 64-byte rows (32 halfs), chunk16 in 0..3.  Swizzle<2,4,3>: chunk ^= (row/2) % 4.
+__host__ __device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t chunk16) {
+  return row * 64u + (((chunk16 ^ ((row >> 1) & 3u)) & 3u) << 4);
+}
+
+// ----------------------------------------------------------------------------------------------
+// TMA stores (shared -> global, bulk-group completion).  OOB parts of the box are clipped.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... have completed entirely (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // Host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 // ----------------------------------------------------------------------------------------------
@@ -224,5 +256,8 @@ PFN_encodeTiled get_encode_tiled();
 // dims/strides innermost first; strides[i] = byte stride of dim i+1. Returns B200SD_* code.
 int make_tmap_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, const uint32_t* elem_strides);
+// same, SWIZZLE_64B with a 32-element (64 B) inner box: the epilogue staging tiles of the GEMM kernel
+int make_tmap_sw64(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides);
 
 }  // namespace b200sd
