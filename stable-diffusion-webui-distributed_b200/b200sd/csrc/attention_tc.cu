@@ -10,18 +10,22 @@
 // rows), so each 64-half chunk of a tile is exactly one TMA SWIZZLE_128B box.  O is written unpadded
 // ([b, s, h*d]) because it feeds the out-projection GEMM as a plain K-major A operand.
 //
-// One CTA = one 128-row Q tile of one (batch, head).  320 threads:
+// One CTA = one 128-row Q tile of one (batch, head), kv consumed in tiles of 64.  320 threads:
 //   warp 0    TMA producer (Q once; K ring, V ring)
-//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S = Q K^T  (M128 x N<=128 x K=d),
-//             O (+)= P V  (M128 x N=d_pad x K<=128, V consumed MN-major straight from its TMA tile)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%2] = Q K_j^T (M128 x N<=64 x K=d),
+//             O (+)= P[j%2] V_j (M128 x N=d_pad x K<=64, V consumed MN-major straight from its TMA tile)
 //   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane, and the two warps of a lane
-//             quarter split the 128 kv columns of the tile in halves (one 64-column P swizzle atom each).
-// Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) is computed against the running maximum of earlier
-// tiles while the tile's own maximum is tracked; only if that exceeds m_used by more than 2^8 is the tile redone after
-// rescaling O in TMEM (a block-wide bar.red vote; rare after the first tile).  Each S element is read from TMEM
-// once, TMEM loads of the next 16 columns are in flight while the current 16 are exponentiated, and with a ones
-// column in V (v_ones_col) the row sums come out of the P.V MMA instead of CUDA-core adds.
-// d <= 64: 96 KB smem + 256 TMEM columns per CTA -> two CTAs per SM, one's softmax overlaps the other's MMAs.
+//             quarter split the 64 kv columns of the tile in halves.
+// S and P are DOUBLE BUFFERED (S in TMEM, P in shared memory): Q K_{j+2}^T is issued as soon as softmax j has
+// consumed its S buffer, and P_j V_j runs while softmax j+1 is already exponentiating — in steady state the softmax
+// warps never wait for the tensor pipe, which matters because for d = 40 this kernel is bound by the exp (MUFU)
+// rate, not by the MMAs (16 exps per 96 MMA-FLOPs).
+// Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) uses the running maximum of earlier tiles while the
+// tile's own maximum is tracked; only if that exceeds m_used by more than 2^8 (P would leave fp16's comfortable
+// range) is the tile redone after rescaling O in TMEM — a vote between the two warps of a row quarter, rare after
+// the first tile.  Each S element is read from TMEM once, the TMEM load of the next 16 columns is in flight while
+// the current 16 are exponentiated, and with a ones column in V (v_ones_col) the row sums come out of the P.V MMA
+// instead of CUDA-core adds.  d <= 64: 80 KB smem + 256 TMEM columns per CTA -> two CTAs per SM.
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
 
@@ -31,15 +35,17 @@ constexpr int kSoftmaxWarps = 8;
 constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
 constexpr int kAttnThreads = 64 + kSoftmaxThreads;
 constexpr int kQTile = 128;
-constexpr int kKvTile = 128;
-constexpr int kMaxRing = 2;
+constexpr int kKv = 64;                              // kv rows per tile
+constexpr uint32_t kQChunkBytes = kQTile * 128;      // 128 rows x 64 halfs
+constexpr uint32_t kKvChunkBytes = kKv * 128;        // 64 rows x 64 halfs
+constexpr uint32_t kPBytes = kQTile * kKv * 2;       // one K-major SWIZZLE_128B atom: 128 rows x 64 halfs
+constexpr int kRing = 2;
 
 struct AttnParams {
   int B, heads, Sq, Skv, d, d_pad;
   int d16;           // d rounded up to 16 (MMA K of Q.K^T; O columns that carry data)
   int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
   int chunks;        // d_pad / 64
-  int k_stages, v_stages;
   int tmem_cols;
   int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
   int resc_cols;     // O columns touched by a rescale (multiple of 16, covers l_col)
@@ -51,12 +57,12 @@ struct AttnParams {
 
 struct __align__(16) AttnShared {
   uint64_t q_full;
-  uint64_t k_full[kMaxRing], k_empty[kMaxRing];
-  uint64_t v_full[kMaxRing], v_empty[kMaxRing];
-  uint64_t s_full, p_full, o_full;
+  uint64_t k_full[kRing], k_empty[kRing];
+  uint64_t v_full[kRing], v_empty[kRing];
+  uint64_t s_full[2], p_full[2], o_full;
   uint32_t tmem_base;
   uint32_t pad;
-  float xch[2][kQTile];  // row maxima exchanged between the two column halves
+  float xch[2][kQTile];  // row maxima / sums exchanged between the two column halves
 };
 
 template <bool kBf16>
@@ -76,29 +82,31 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
-// named barrier 1: the 256 softmax threads only
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxThreads) : "memory"); }
-__device__ __forceinline__ bool softmax_bar_or(bool pred) {
+// named barriers 1..4: the two warps (64 threads) that share one TMEM lane quarter, i.e. the thread pairs of 32 rows
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+__device__ __forceinline__ bool pair_bar_or(int quarter, bool pred) {
   uint32_t out;
   asm volatile(
       "{\n\t"
       ".reg .pred p, q;\n\t"
       "setp.ne.u32 q, %1, 0;\n\t"
-      "bar.red.or.pred p, 1, %2, q;\n\t"
+      "bar.red.or.pred p, %2, 64, q;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(out)
-      : "r"(static_cast<uint32_t>(pred)), "n"(kSoftmaxThreads)
+      : "r"(static_cast<uint32_t>(pred)), "r"(quarter + 1)
       : "memory");
   return out != 0;
 }
 
-// maximum of my 64 columns [col0, col0+64) of the S tile (raw logits); kv columns >= nvalid ignored
+// maximum of my 32 columns [col0, col0+32) of the S tile (raw logits); kv columns >= nvalid ignored
 template <bool kFull>
 __device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int nvalid) {
   float mx = -INFINITY;
-#pragma unroll 1
-  for (int s = 0; s < 4; ++s) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
     const int cbase = col0 + s * 16;
     if (!kFull && cbase >= nvalid) break;
     uint32_t v[16];
@@ -119,7 +127,7 @@ __device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int n
 
 // exponentiate 16 columns, track their maximum / sum, write them as two 16-byte chunks of the swizzled P atom
 template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* atom, int r, int cbase, int sub, int nvalid,
+__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* sPj, int r, int cbase, int nvalid,
                                           float scale_log2, float m_used, float& tile_max, float& lsum) {
   uint32_t pk[8];
   float mx = tile_max, acc = 0.f;
@@ -138,66 +146,62 @@ __device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* atom
   }
   tile_max = mx;
   if constexpr (kSum) lsum += acc;
-  *reinterpret_cast<uint4*>(atom + sw128_offset(r, static_cast<uint32_t>(sub * 2))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(atom + sw128_offset(r, static_cast<uint32_t>(sub * 2 + 1))) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  const uint32_t chunk16 = static_cast<uint32_t>(cbase >> 3);  // 8 halfs per 16-byte chunk
+  *reinterpret_cast<uint4*>(sPj + sw128_offset(r, chunk16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(sPj + sw128_offset(r, chunk16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
-// One pass over my 64 columns: the TMEM load of sub-chunk s+1 is in flight while sub-chunk s is processed.
+// One pass over my 32 columns: the TMEM load of the second 16 is in flight while the first 16 are processed.
 template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint8_t* atom, int r, int col0, int nvalid,
+__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint8_t* sPj, int r, int col0, int nvalid,
                                              float scale_log2, float m_used, float& tile_max, float& lsum) {
   uint32_t va[16], vb[16];
   tmem_ld_x16(tmem_row + col0, va);
   tmem_ld_wait();
   tmem_ld_x16(tmem_row + col0 + 16, vb);
-  softmax16<kFull, kBf16, kSum>(va, atom, r, col0, 0, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(va, sPj, r, col0, nvalid, scale_log2, m_used, tile_max, lsum);
   tmem_ld_wait();
-  tmem_ld_x16(tmem_row + col0 + 32, va);
-  softmax16<kFull, kBf16, kSum>(vb, atom, r, col0 + 16, 1, nvalid, scale_log2, m_used, tile_max, lsum);
-  tmem_ld_wait();
-  tmem_ld_x16(tmem_row + col0 + 48, vb);
-  softmax16<kFull, kBf16, kSum>(va, atom, r, col0 + 32, 2, nvalid, scale_log2, m_used, tile_max, lsum);
-  tmem_ld_wait();
-  softmax16<kFull, kBf16, kSum>(vb, atom, r, col0 + 48, 3, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(vb, sPj, r, col0 + 16, nvalid, scale_log2, m_used, tile_max, lsum);
 }
 
 template <bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_S,
-                                              uint32_t tmem_O, int warp, int lane, int q0, int head, int b, int nkv) {
+__device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_base,
+                                              int warp, int lane, int q0, int head, int b, int nkv) {
   const int quarter = warp & 3;
-  const int half = (warp - 2) >> 2;   // which 64-column half of the kv tile (== which P swizzle atom) is mine
+  const int half = (warp - 2) >> 2;   // which 32-column half of the kv tile is mine
   const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
   const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-  const uint32_t s_row = tmem_S + lane_base;
-  const uint32_t o_row = tmem_O + lane_base;
-  uint8_t* atom = sP + half * 16384;
-  const int col0 = half * 64;
-  constexpr bool sum_here = kSum;
+  const uint32_t o_row = tmem_base + 128 + lane_base;
+  const int col0 = half * 32;
   float m_used = -INFINITY;  // scaled log2 domain
   float l = 0.f;
   for (int j = 0; j < nkv; ++j) {
-    const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
-    const bool full = nvalid == kKvTile;
-    mbar_wait(&sh->s_full, j & 1, 17);
+    const int buf = j & 1;
+    const int nvalid = min(kKv, p.Skv - j * kKv);
+    const bool full = nvalid == kKv;
+    const uint32_t s_row = tmem_base + buf * kKv + lane_base;
+    uint8_t* sPj = sP + buf * kPBytes;
+    mbar_wait(&sh->s_full[buf], (j >> 1) & 1, 17);
     tc_fence_after();
-    if (j > 0) mbar_wait(&sh->o_full, (j - 1) & 1, 18);  // already complete (in-order MMA pipe); keeps phases aligned
     if (j == 0) {
       const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
       sh->xch[half][r] = mx;
-      softmax_bar_sync();
+      pair_bar_sync(quarter);
       m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * p.scale_log2;
     }
     float tile_max = -INFINITY, lsum = 0.f;
-    if (full) softmax_half<true, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-    else      softmax_half<false, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    if (full) softmax_half<true, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    else      softmax_half<false, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
     const float tm = tile_max * p.scale_log2;
-    if (softmax_bar_or(tm > m_used + 8.0f)) {
-      // rare path: the running maximum moved by more than 2^8 for some row of this Q tile
+    if (pair_bar_or(quarter, tm > m_used + 8.0f)) {
+      // rare path: the running maximum moved by more than 2^8 for some row of this quarter
       sh->xch[half][r] = tm;
-      softmax_bar_sync();
+      pair_bar_sync(quarter);
       const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
       const float alpha = fast_exp2(m_used - m_new);
       if (j > 0) {
+        mbar_wait(&sh->o_full, (j - 1) & 1, 18);  // P.V of the previous tile must have landed in O
+        tc_fence_after();
         for (int c = half; c < p.resc_cols / 16; c += 2) {
           uint32_t o[16];
           tmem_ld_x16(o_row + c * 16, o);
@@ -212,21 +216,25 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       m_used = m_new;
       tile_max = -INFINITY;
       lsum = 0.f;
-      if (full) softmax_half<true, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-      else      softmax_half<false, kBf16, kSum>(s_row, atom, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      if (full) softmax_half<true, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      else      softmax_half<false, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
     }
     l += lsum;
+    // Observe every phase of o_full (P.V of the previous tile: issued a whole softmax ago, normally complete) so that
+    // parity waits on it can never alias an older phase.  It must happen BEFORE this tile's arrive: P.V of this tile
+    // cannot complete (and flip the phase again) until all 256 arrivals are in.
+    if (j > 0) mbar_wait(&sh->o_full, (j - 1) & 1, 20);
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(&sh->p_full);
+    mbar_arrive(&sh->p_full[buf]);
   }
   // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
   mbar_wait(&sh->o_full, (nkv - 1) & 1, 19);
   tc_fence_after();
-  if (sum_here) {
-    softmax_bar_sync();  // every thread is past its last xch read
+  if constexpr (kSum) {
+    pair_bar_sync(quarter);  // both threads of every pair are past their last xch read
     sh->xch[half][r] = l;
-    softmax_bar_sync();
+    pair_bar_sync(quarter);
     l = sh->xch[0][r] + sh->xch[1][r];
   } else {
     uint32_t o[16];
@@ -262,19 +270,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t tile_bytes = static_cast<uint32_t>(p.chunks) * 16384u;  // one 128-row x d_pad operand tile
+  const uint32_t q_bytes = static_cast<uint32_t>(p.chunks) * kQChunkBytes;
+  const uint32_t kv_bytes = static_cast<uint32_t>(p.chunks) * kKvChunkBytes;
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + tile_bytes;  // 2 x 16 KB (kv columns 0-63, 64-127)
-  uint8_t* sK = sP + 32768;
-  uint8_t* sV = sK + static_cast<size_t>(p.k_stages) * tile_bytes;
-  AttnShared* sh = reinterpret_cast<AttnShared*>(sV + static_cast<size_t>(p.v_stages) * tile_bytes);
+  uint8_t* sP = sQ + q_bytes;  // 2 x 16 KB
+  uint8_t* sK = sP + 2 * kPBytes;
+  uint8_t* sV = sK + kRing * kv_bytes;
+  AttnShared* sh = reinterpret_cast<AttnShared*>(sV + kRing * kv_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQTile;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
-  const int nkv = (p.Skv + kKvTile - 1) / kKvTile;
+  const int nkv = (p.Skv + kKv - 1) / kKv;
   const int col0 = head * p.d_pad;
 
   if (warp == 0 && lane == 0) {
@@ -282,14 +291,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(&sh->q_full, 1);
-    for (int s = 0; s < kMaxRing; ++s) {
+    for (int s = 0; s < kRing; ++s) {
       mbar_init(&sh->k_full[s], 1);
       mbar_init(&sh->k_empty[s], 1);
       mbar_init(&sh->v_full[s], 1);
       mbar_init(&sh->v_empty[s], 1);
+      mbar_init(&sh->s_full[s], 1);
+      mbar_init(&sh->p_full[s], kSoftmaxThreads);
     }
-    mbar_init(&sh->s_full, 1);
-    mbar_init(&sh->p_full, kSoftmaxThreads);
     mbar_init(&sh->o_full, 1);
     fence_mbar_init();
   }
@@ -297,30 +306,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;
-  const uint32_t tmem_S = tmem_base;        // 128 fp32 columns
-  const uint32_t tmem_O = tmem_base + 128;  // dpv fp32 columns (first d16 carry data, column l_col the row sums)
+  const uint32_t tmem_base = sh->tmem_base;  // S0 @ +0, S1 @ +64 (64 fp32 columns each), O @ +128 (dpv columns)
+  const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&sh->q_full, tile_bytes);
-      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * 16384, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
+      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
+      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int ks = j % p.k_stages;
-        const uint32_t kph = (j / p.k_stages) & 1;
-        mbar_wait(&sh->k_empty[ks], kph ^ 1u, 11);
-        mbar_arrive_expect_tx(&sh->k_full[ks], tile_bytes);
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&sh->k_empty[st], ph ^ 1u, 11);
+        mbar_arrive_expect_tx(&sh->k_full[st], kv_bytes);
         for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sK + static_cast<size_t>(ks) * tile_bytes + c * 16384, &tmK, &sh->k_full[ks], col0 + c * 64,
-                      j * kKvTile, b);
-        const int vs = j % p.v_stages;
-        const uint32_t vph = (j / p.v_stages) & 1;
-        mbar_wait(&sh->v_empty[vs], vph ^ 1u, 12);
-        mbar_arrive_expect_tx(&sh->v_full[vs], tile_bytes);
+          tma_load_3d(sK + st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[st], col0 + c * 64, j * kKv, b);
+        mbar_wait(&sh->v_empty[st], ph ^ 1u, 12);
+        mbar_arrive_expect_tx(&sh->v_full[st], kv_bytes);
         for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sV + static_cast<size_t>(vs) * tile_bytes + c * 16384, &tmV, &sh->v_full[vs], col0 + c * 64,
-                      j * kKvTile, b);
+          tma_load_3d(sV + st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[st], col0 + c * 64, j * kKv, b);
       }
     }
   } else if (warp == 1) {
@@ -328,57 +332,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       const bool bf = p.is_bf16 != 0;
       const int ksteps_qk = p.d16 / 16;
-      mbar_wait(&sh->q_full, 0, 13);
-      for (int j = 0; j < nkv; ++j) {
-        const int nvalid = min(kKvTile, p.Skv - j * kKvTile);
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
+        const int st = j & 1;
+        const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
-        const int ks = j % p.k_stages;
-        const uint32_t kph = (j / p.k_stages) & 1;
-        const int vs = j % p.v_stages;
-        const uint32_t vph = (j / p.v_stages) & 1;
-        // ---- S = Q K^T ----  (S is free: softmax(j-1) finished reading it before arriving on p_full(j-1))
-        mbar_wait(&sh->k_full[ks], kph, 14);
+        mbar_wait(&sh->k_full[st], (j >> 1) & 1, 14);
         tc_fence_after();
-        {
-          const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
-          const uint32_t aQ = smem_u32(sQ);
-          const uint32_t aK = smem_u32(sK + static_cast<size_t>(ks) * tile_bytes);
-          for (int k = 0; k < ksteps_qk; ++k) {
-            const uint32_t off = static_cast<uint32_t>(k >> 2) * 16384u + static_cast<uint32_t>(k & 3) * 32u;
-            umma_f16_ss(tmem_S, make_sdesc_sw128(aQ + off, 16, 1024), make_sdesc_sw128(aK + off, 16, 1024), idesc,
-                        k != 0 ? 1u : 0u);
-          }
-          umma_commit(&sh->k_empty[ks]);
-          umma_commit(&sh->s_full);
+        const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
+        const uint32_t aK = smem_u32(sK + st * kv_bytes);
+        for (int k = 0; k < ksteps_qk; ++k) {
+          const uint32_t offq = static_cast<uint32_t>(k >> 2) * kQChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
+          const uint32_t offk = static_cast<uint32_t>(k >> 2) * kKvChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
+          umma_f16_ss(tmem_base + st * kKv, make_sdesc_sw128(aQ + offq, 16, 1024), make_sdesc_sw128(aK + offk, 16, 1024),
+                      idesc, k != 0 ? 1u : 0u);
         }
-        // ---- O (+)= P V ----
-        mbar_wait(&sh->p_full, j & 1, 15);
-        mbar_wait(&sh->v_full[vs], vph, 16);
+        umma_commit(&sh->k_empty[st]);
+        umma_commit(&sh->s_full[st]);
+      };
+      mbar_wait(&sh->q_full, 0, 13);
+      issue_qk(0);
+      if (nkv > 1) issue_qk(1);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int nvalid = min(kKv, p.Skv - j * kKv);
+        const int n16 = (nvalid + 15) & ~15;
+        // ---- O (+)= P_j V_j ----
+        mbar_wait(&sh->p_full[st], ph, 15);
+        mbar_wait(&sh->v_full[st], ph, 16);
         tc_fence_after();
         {
           const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
-          const uint32_t aP = smem_u32(sP);
-          const uint32_t aV = smem_u32(sV + static_cast<size_t>(vs) * tile_bytes);
+          const uint32_t aP = smem_u32(sP + st * kPBytes);
+          const uint32_t aV = smem_u32(sV + st * kv_bytes);
           const int ksteps_pv = n16 / 16;
           for (int k = 0; k < ksteps_pv; ++k) {
-            const uint32_t offP = static_cast<uint32_t>(k >> 2) * 16384u + static_cast<uint32_t>(k & 3) * 32u;
+            const uint32_t offP = static_cast<uint32_t>(k) * 32u;    // 16 halfs inside the 128-byte swizzle row
             const uint32_t offV = static_cast<uint32_t>(k) * 2048u;  // 16 kv rows x 128 B
-            umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, 16384, 1024),
+            umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, kKvChunkBytes, 1024),
                         idesc, (j | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&sh->v_empty[vs]);
+          umma_commit(&sh->v_empty[st]);
           umma_commit(&sh->o_full);
         }
+        // ---- softmax j has released S[st]: refill it two tiles ahead ----
+        if (j + 2 < nkv) issue_qk(j + 2);
       }
     }
   } else {
     const bool sum_here = p.l_col < 0;
     if (p.is_bf16) {
-      if (sum_here) softmax_warps<true, true>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
-      else          softmax_warps<true, false>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
+      if (sum_here) softmax_warps<true, true>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
+      else          softmax_warps<true, false>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
     } else {
-      if (sum_here) softmax_warps<false, true>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
-      else          softmax_warps<false, false>(p, sh, sP, tmem_S, tmem_O, warp, lane, q0, head, b, nkv);
+      if (sum_here) softmax_warps<false, true>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
+      else          softmax_warps<false, false>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
     }
   }
 
@@ -432,34 +441,29 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
   p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
-  const size_t tile = static_cast<size_t>(p.chunks) * 16384;
-  const size_t fixed = 1024 + tile /*Q*/ + 32768 /*P*/ + sizeof(AttnShared) + 64;
-  const size_t budget = static_cast<size_t>(g_attn_max_smem);
-  // K ring first (its prefetch hides the next block's load), then V
-  if (fixed + 4 * tile <= budget && p.chunks > 1) { p.k_stages = 2; p.v_stages = 2; }
-  else if (fixed + 3 * tile <= budget) { p.k_stages = 2; p.v_stages = 1; }
-  else if (fixed + 2 * tile <= budget) { p.k_stages = 1; p.v_stages = 1; }
-  else return B200SD_ERR_UNSUPPORTED;
-  const size_t smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * tile;
+  const size_t smem = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + 2 * kPBytes +
+                      2 * kRing * static_cast<size_t>(p.chunks) * kKvChunkBytes + sizeof(AttnShared) + 64;
+  if (smem > static_cast<size_t>(g_attn_max_smem)) return B200SD_ERR_UNSUPPORTED;
 
   CUtensorMap tmQ, tmK, tmV;
-  const uint32_t box[3] = {64, 128, 1};
   const uint32_t es[3] = {1, 1, 1};
   int rc;
   {
+    const uint32_t box[3] = {64, kQTile, 1};
     const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Sq), static_cast<uint64_t>(B)};
     const uint64_t st[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * Sq};
     if ((rc = make_tmap_sw128(&tmQ, Q, 3, dims, st, box, es)) != B200SD_OK) return rc;
   }
+  const uint32_t kvbox[3] = {64, kKv, 1};
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Skv), static_cast<uint64_t>(B)};
     const uint64_t st[2] = {static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(ldk) * 2 * Skv};
-    if ((rc = make_tmap_sw128(&tmK, K, 3, dims, st, box, es)) != B200SD_OK) return rc;
+    if ((rc = make_tmap_sw128(&tmK, K, 3, dims, st, kvbox, es)) != B200SD_OK) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(heads) * d_pad, static_cast<uint64_t>(Skv), static_cast<uint64_t>(B)};
     const uint64_t st[2] = {static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
-    if ((rc = make_tmap_sw128(&tmV, V, 3, dims, st, box, es)) != B200SD_OK) return rc;
+    if ((rc = make_tmap_sw128(&tmV, V, 3, dims, st, kvbox, es)) != B200SD_OK) return rc;
   }
   dim3 grid((Sq + kQTile - 1) / kQTile, heads, B);
   attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
