@@ -21,6 +21,8 @@
 // Upstream ops this kernel stands in for (not in /root/reference; reached from world.py:196 / worker.py:432):
 // ldm ResBlock conv3x3 / skip 1x1, Up/Downsample conv, SpatialTransformer proj_in/out, CrossAttention
 // to_q/k/v/out, FeedForward GEGLU + out, AutoencoderKL decoder convs (SURVEY.md §8 a-ext x1,x2,x5,x7,x8,x9,x11).
+#include <math.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
 
@@ -53,6 +55,7 @@ struct GemmKernelParams {
   int has_residual;
   int flags;                       // B200SD_EPI_*
   int is_bf16;
+  int pair;                        // 1: launched as CTA pairs (tcgen05 cta_group::2, 256-row tiles)
 };
 
 struct __align__(8) GemmBarriers {
@@ -238,6 +241,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
   }
 }
 
+// kPair = false: one CTA per tile (M = 128).
+// kPair = true : launched as clusters of two CTAs; the pair computes a 256 x block_n tile with tcgen05 cta_group::2.
+//   CTA `rank` owns output rows [128*rank, 128*rank+128) of the pair tile (its own A rows, accumulator and epilogue)
+//   and stages B rows [rank*bn/2, (rank+1)*bn/2).  Only the leader (rank 0) issues MMAs; the `full` barriers that
+//   gate them live in the leader and collect the TMA bytes of both CTAs; commits are multicast to both CTAs.
+template <bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -245,14 +254,21 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
+  const int bn_local = kPair ? p.block_n / 2 : p.block_n;  // B rows staged by this CTA
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(bn_local) * 128u;
   uint8_t* stage_d = smem + static_cast<size_t>(p.num_stages) * stage_bytes;
   uint8_t* stage_r = stage_d + kStagingBytes;
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_r + (p.has_residual ? kStagingBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+  // work items: (m_tile or m_pair, n_tile); a pair covers m_tiles 2*m_pair and 2*m_pair + 1 (the second may be a
+  // phantom beyond the problem: its loads are zero-filled and its stores clipped by the tensor maps)
+  const int m_items = kPair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int num_items = m_items * p.num_n_tiles;
+  const int first_item = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -265,15 +281,19 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 32 * kEpiWarps);
+      mbar_init(&bars->tmem_empty[a], (kPair ? 2 : 1) * 32 * kEpiWarps);  // pair: both CTAs' epilogues release it
       mbar_init(&bars->res_full[a][0], 1);
       mbar_init(&bars->res_full[a][1], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair(&bars->tmem_base, kTmemCols);
+    else tmem_alloc(&bars->tmem_base, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -282,9 +302,9 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
+      for (int item = first_item; item < num_items; item += item_step) {
+        const int n_tile = item % p.num_n_tiles;
+        const int m_tile = kPair ? 2 * (item / p.num_n_tiles) + rank : item / p.num_n_tiles;
         int cx = 0, cy = 0, cn = 0;
         if (p.mode == 1) {
           const int tx = m_tile % p.tiles_x;
@@ -297,29 +317,38 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
           uint8_t* sA = smem + static_cast<size_t>(stage) * stage_bytes;
           uint8_t* sB = sA + 16384;
-          mbar_arrive_expect_tx(&bars->full[stage], p.a_bytes + p.b_bytes);
-          if (p.mode == 0) {
-            tma_load_2d(sA, &tmA, &bars->full[stage], kb * kBlockK, m_tile * kBlockM);
-          } else {
-            const int tap = kb / p.cblocks;
-            const int cb = kb - tap * p.cblocks;
-            const int dy = (p.taps == 9) ? tap / 3 : 0;
-            const int dx = (p.taps == 9) ? tap - dy * 3 : 0;
-            tma_load_4d(sA, &tmA, &bars->full[stage], cb * kBlockK, cx + dx, cy + dy, cn);
+          int tap = 0, cb = kb, dy = 0, dx = 0;
+          if (p.mode == 1) {
+            tap = kb / p.cblocks;
+            cb = kb - tap * p.cblocks;
+            dy = (p.taps == 9) ? tap / 3 : 0;
+            dx = (p.taps == 9) ? tap - dy * 3 : 0;
           }
-          tma_load_2d(sB, &tmB, &bars->full[stage], kb * kBlockK, n_tile * p.block_n);
+          if constexpr (kPair) {
+            // both CTAs' bytes land on the LEADER's barrier; only the leader arms it (for the bytes of both)
+            const uint32_t lead_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (p.a_bytes + p.b_bytes));
+            if (p.mode == 0) tma_load_2d_pair(sA, &tmA, lead_bar, kb * kBlockK, m_tile * kBlockM);
+            else tma_load_4d_pair(sA, &tmA, lead_bar, cb * kBlockK, cx + dx, cy + dy, cn);
+            tma_load_2d_pair(sB, &tmB, lead_bar, kb * kBlockK, n_tile * p.block_n + rank * bn_local);
+          } else {
+            mbar_arrive_expect_tx(&bars->full[stage], p.a_bytes + p.b_bytes);
+            if (p.mode == 0) tma_load_2d(sA, &tmA, &bars->full[stage], kb * kBlockK, m_tile * kBlockM);
+            else tma_load_4d(sA, &tmA, &bars->full[stage], cb * kBlockK, cx + dx, cy + dy, cn);
+            tma_load_2d(sB, &tmB, &bars->full[stage], kb * kBlockK, n_tile * p.block_n);
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, p.is_bf16 != 0, false, false);
+    // ------------------------------- MMA issuer (leader CTA only in pair mode) --
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_f16(kPair ? 2 * kBlockM : kBlockM, p.block_n, p.is_bf16 != 0, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = first_item; item < num_items; item += item_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u, 2);
@@ -334,12 +363,17 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = make_sdesc_sw128(sA + k * (kUmmaK * 2), 16, 1024);
             const uint64_t db = make_sdesc_sw128(sB + k * (kUmmaK * 2), 16, 1024);
-            umma_f16_ss(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kPair) umma_f16_ss_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&bars->empty[stage]);  // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if constexpr (kPair) umma_commit_pair(&bars->empty[stage]);
+          else umma_commit(&bars->empty[stage]);
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (kPair) umma_commit_pair(&bars->tmem_full[acc]);
+        else umma_commit(&bars->tmem_full[acc]);
       }
     }
   } else {
@@ -348,11 +382,11 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int group = (warp - 2) >> 2;  // warps 2-5 / 6-9: chunks group, group+2, ...
     uint32_t uses[2] = {0u, 0u};
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int item = first_item; item < num_items; item += item_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = item % p.num_n_tiles;
+      const int m_tile = kPair ? 2 * (item / p.num_n_tiles) + rank : item / p.num_n_tiles;
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
       if (p.is_bf16)
         epilogue_tile<true>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
@@ -361,16 +395,20 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_tile<false>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
                              n_tile, quarter, group, lane, uses);
       tc_fence_before();
-      mbar_arrive(&bars->tmem_empty[acc]);
+      // the MMA issuer (leader CTA) may overwrite this accumulator once BOTH CTAs have drained theirs
+      if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+      else mbar_arrive(&bars->tmem_empty[acc]);
     }
     bulk_wait<0>();  // the issuing threads' TMA stores must have completed before the CTA (and its smem) goes away
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // no CTA of the pair may exit while the other can still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -391,7 +429,9 @@ static int device_props() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200SD_ERR_CUDA;
     if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
       return B200SD_ERR_CUDA;
-    if (cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(gemm_conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return B200SD_ERR_CUDA;
     g_num_sms = sms;
     g_max_smem = smem;
@@ -400,11 +440,36 @@ static int device_props() {
   return B200SD_OK;
 }
 
+// Pair mode pays when it shortens the (waves x per-tile time) product: a pair tile does two M tiles in the time of
+// one, and its per-SM smem fill per FLOP is lower (B is split between the two CTAs), so the L2->SM port (~64 B/clk/SM,
+// the limiter of 128-row tiles: ncu round 1) caps the tensor pipe later.  eff = min(1, arithmetic intensity / 128).
+static int pair_env() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("B200SD_PAIR");
+    v = e ? atoi(e) : -1;  // -1 = heuristic, 0 = never, 1 = whenever legal
+  }
+  return v;
+}
+static bool decide_pair(const GemmKernelParams& p, int num_sms) {
+  if (p.num_m_tiles < 2 || p.block_n % 32 != 0 || p.block_n < 64) return false;
+  const int env = pair_env();
+  if (env == 0) return false;
+  if (env == 1) return true;
+  const double bn = p.block_n;
+  const double eff1 = fmin(1.0, bn / (128.0 + bn));
+  const double eff2 = fmin(1.0, bn / (128.0 + 0.5 * bn));
+  const long long items1 = static_cast<long long>(p.num_m_tiles) * p.num_n_tiles;
+  const long long items2 = static_cast<long long>((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const double t1 = static_cast<double>((items1 + num_sms - 1) / num_sms) / eff1;
+  const double t2 = static_cast<double>((items2 + num_sms / 2 - 1) / (num_sms / 2)) / eff2;
+  return t2 < 0.97 * t1;
+}
+
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmR,
                   GemmKernelParams& p, int max_ctas, cudaStream_t stream) {
-  int rc = device_props();
-  if (rc != B200SD_OK) return rc;
-  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(p.block_n) * 128u;
+  const int bn_local = p.pair ? p.block_n / 2 : p.block_n;
+  const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(bn_local) * 128u;
   const int staging = static_cast<int>(kStagingBytes) * (p.has_residual ? 2 : 1);
   const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);
@@ -413,12 +478,32 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   p.num_stages = stages;
   size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + staging + sizeof(GemmBarriers) + 64;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the kernel owns all 512 TMEM columns
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (grid <= 0) return B200SD_OK;
-  gemm_conv_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmD, tmR, p);
-  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+  if (!p.pair) {
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid <= 0) return B200SD_OK;
+    gemm_conv_tc_kernel<false><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmD, tmR, p);
+    return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+  }
+  const int num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  int clusters = num_items < g_num_sms / 2 ? num_items : g_num_sms / 2;
+  if (max_ctas > 1 && clusters > max_ctas / 2) clusters = max_ctas / 2;
+  if (clusters <= 0) return B200SD_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_conv_tc_kernel<true>, tmA, tmB, tmD, tmR, p) == cudaSuccess ? B200SD_OK
+                                                                                                    : B200SD_ERR_CUDA;
 }
 
 struct OutSpec {
@@ -498,6 +583,10 @@ int gemm_tc(const void* A, long long lda, const void* Wt, void* D, long long ldd
   p.num_m_tiles = (M + kBlockM - 1) / kBlockM;
   p.a_bytes = 16384u;
   p.d_bytes = kStageTileBytes;
+  rc = device_props();
+  if (rc != B200SD_OK) return rc;
+  p.pair = decide_pair(p, g_num_sms) ? 1 : 0;
+  if (p.pair) p.b_bytes /= 2;
   CUtensorMap tmA, tmB, tmD, tmR;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -510,7 +599,7 @@ int gemm_tc(const void* A, long long lda, const void* Wt, void* D, long long ldd
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(p.pair ? block_n / 2 : block_n)};
     const uint32_t es[2] = {1, 1};
     rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
     if (rc != B200SD_OK) return rc;
@@ -549,6 +638,10 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
   p.num_m_tiles = p.tiles_x * p.tiles_y * tiles_n;
   p.a_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bn) * 128u;
   p.d_bytes = static_cast<uint32_t>(p.bw * p.bh * p.bn) * kChunkCols * 2u;
+  rc = device_props();
+  if (rc != B200SD_OK) return rc;
+  p.pair = decide_pair(p, g_num_sms) ? 1 : 0;
+  if (p.pair) p.b_bytes /= 2;
   CUtensorMap tmA, tmB, tmD, tmR;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
@@ -567,7 +660,7 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
     const uint64_t K = static_cast<uint64_t>(taps) * C;
     const uint64_t dims[2] = {K, static_cast<uint64_t>(Cout)};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(block_n)};
+    const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(p.pair ? block_n / 2 : block_n)};
     const uint32_t es[2] = {1, 1};
     rc = make_tmap_sw128(&tmB, Wt, 2, dims, strides, box, es);
     if (rc != B200SD_OK) return rc;
