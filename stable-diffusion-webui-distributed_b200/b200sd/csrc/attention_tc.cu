@@ -39,13 +39,14 @@ constexpr int kKv = 64;                              // kv rows per tile
 constexpr uint32_t kQChunkBytes = kQTile * 128;      // 128 rows x 64 halfs
 constexpr uint32_t kKvChunkBytes = kKv * 128;        // 64 rows x 64 halfs
 constexpr uint32_t kPBytes = kQTile * kKv * 2;       // one K-major SWIZZLE_128B atom: 128 rows x 64 halfs
-constexpr int kRing = 2;
+constexpr int kMaxRing = 4;
 
 struct AttnParams {
   int B, heads, Sq, Skv, d, d_pad;
   int d16;           // d rounded up to 16 (MMA K of Q.K^T; O columns that carry data)
   int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
   int chunks;        // d_pad / 64
+  int k_stages, v_stages;  // K / V ring depths (<= kMaxRing), as deep as shared memory allows
   int tmem_cols;
   int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
   int resc_cols;     // O columns touched by a rescale (multiple of 16, covers l_col)
@@ -57,8 +58,8 @@ struct AttnParams {
 
 struct __align__(16) AttnShared {
   uint64_t q_full;
-  uint64_t k_full[kRing], k_empty[kRing];
-  uint64_t v_full[kRing], v_empty[kRing];
+  uint64_t k_full[kMaxRing], k_empty[kMaxRing];
+  uint64_t v_full[kMaxRing], v_empty[kMaxRing];
   uint64_t s_full[2], p_full[2], o_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -275,8 +276,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + q_bytes;  // 2 x 16 KB
   uint8_t* sK = sP + 2 * kPBytes;
-  uint8_t* sV = sK + kRing * kv_bytes;
-  AttnShared* sh = reinterpret_cast<AttnShared*>(sV + kRing * kv_bytes);
+  uint8_t* sV = sK + p.k_stages * kv_bytes;
+  AttnShared* sh = reinterpret_cast<AttnShared*>(sV + p.v_stages * kv_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,21 +287,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nkv = (p.Skv + kKv - 1) / kKv;
   const int col0 = head * p.d_pad;
 
+  // K / V loads are issued by one thread that polls both rings, so a full V ring never delays a K load (or vice
+  // versa); the first loads go out before the block-wide sync, overlapping the TMEM allocation.
+  int next_k = 0, next_v = 0;
+  auto issue_k = [&](int j) {
+    const int st = j % p.k_stages;
+    mbar_arrive_expect_tx(&sh->k_full[st], kv_bytes);
+    for (int c = 0; c < p.chunks; ++c)
+      tma_load_3d(sK + st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[st], col0 + c * 64, j * kKv, b);
+  };
+  auto issue_v = [&](int j) {
+    const int st = j % p.v_stages;
+    mbar_arrive_expect_tx(&sh->v_full[st], kv_bytes);
+    for (int c = 0; c < p.chunks; ++c)
+      tma_load_3d(sV + st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[st], col0 + c * 64, j * kKv, b);
+  };
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(&sh->q_full, 1);
-    for (int s = 0; s < kRing; ++s) {
+    for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&sh->k_full[s], 1);
       mbar_init(&sh->k_empty[s], 1);
       mbar_init(&sh->v_full[s], 1);
       mbar_init(&sh->v_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&sh->s_full[s], 1);
       mbar_init(&sh->p_full[s], kSoftmaxThreads);
     }
     mbar_init(&sh->o_full, 1);
     fence_mbar_init();
+    mbar_arrive_expect_tx(&sh->q_full, q_bytes);
+    for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
+    for (; next_k < nkv && next_k < p.k_stages; ++next_k) issue_k(next_k);
+    for (; next_v < nkv && next_v < p.v_stages; ++next_v) issue_v(next_v);
   }
   if (warp == 1) tmem_alloc(&sh->tmem_base, static_cast<uint32_t>(p.tmem_cols));
   tc_fence_before();
@@ -312,19 +334,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
-      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&sh->k_empty[st], ph ^ 1u, 11);
-        mbar_arrive_expect_tx(&sh->k_full[st], kv_bytes);
-        for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sK + st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[st], col0 + c * 64, j * kKv, b);
-        mbar_wait(&sh->v_empty[st], ph ^ 1u, 12);
-        mbar_arrive_expect_tx(&sh->v_full[st], kv_bytes);
-        for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sV + st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[st], col0 + c * 64, j * kKv, b);
+      uint32_t spins = 0;
+      while (next_k < nkv || next_v < nkv) {
+        bool progress = false;
+        if (next_k < nkv && mbar_try_wait(&sh->k_empty[next_k % p.k_stages], ((next_k / p.k_stages) & 1) ^ 1u)) {
+          issue_k(next_k++);
+          progress = true;
+        }
+        if (next_v < nkv && mbar_try_wait(&sh->v_empty[next_v % p.v_stages], ((next_v / p.v_stages) & 1) ^ 1u)) {
+          issue_v(next_v++);
+          progress = true;
+        }
+        if (progress) spins = 0;
+        else if (++spins > B200SD_SPIN_LIMIT) {
+          printf("b200sd: attention producer timeout block=(%d,%d,%d) k=%d v=%d\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                 next_k, next_v);
+          __trap();
+        }
       }
     }
   } else if (warp == 1) {
@@ -334,20 +360,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int ksteps_qk = p.d16 / 16;
       const uint32_t aQ = smem_u32(sQ);
       auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
-        const int st = j & 1;
+        const int st = j & 1;                // S buffer
+        const int ks = j % p.k_stages;       // K ring slot
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
-        mbar_wait(&sh->k_full[st], (j >> 1) & 1, 14);
+        mbar_wait(&sh->k_full[ks], (j / p.k_stages) & 1, 14);
         tc_fence_after();
         const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
-        const uint32_t aK = smem_u32(sK + st * kv_bytes);
+        const uint32_t aK = smem_u32(sK + ks * kv_bytes);
         for (int k = 0; k < ksteps_qk; ++k) {
           const uint32_t offq = static_cast<uint32_t>(k >> 2) * kQChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
           const uint32_t offk = static_cast<uint32_t>(k >> 2) * kKvChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
           umma_f16_ss(tmem_base + st * kKv, make_sdesc_sw128(aQ + offq, 16, 1024), make_sdesc_sw128(aK + offk, 16, 1024),
                       idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&sh->k_empty[st]);
+        umma_commit(&sh->k_empty[ks]);
         umma_commit(&sh->s_full[st]);
       };
       mbar_wait(&sh->q_full, 0, 13);
@@ -359,13 +386,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
         // ---- O (+)= P_j V_j ----
+        const int vs = j % p.v_stages;
         mbar_wait(&sh->p_full[st], ph, 15);
-        mbar_wait(&sh->v_full[st], ph, 16);
+        mbar_wait(&sh->v_full[vs], (j / p.v_stages) & 1, 16);
         tc_fence_after();
         {
           const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
           const uint32_t aP = smem_u32(sP + st * kPBytes);
-          const uint32_t aV = smem_u32(sV + st * kv_bytes);
+          const uint32_t aV = smem_u32(sV + vs * kv_bytes);
           const int ksteps_pv = n16 / 16;
           for (int k = 0; k < ksteps_pv; ++k) {
             const uint32_t offP = static_cast<uint32_t>(k) * 32u;    // 16 halfs inside the 128-byte swizzle row
@@ -373,7 +401,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, kKvChunkBytes, 1024),
                         idesc, (j | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&sh->v_empty[st]);
+          umma_commit(&sh->v_empty[vs]);
           umma_commit(&sh->o_full);
         }
         // ---- softmax j has released S[st]: refill it two tiles ahead ----
@@ -441,10 +469,19 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
   p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
-  const size_t smem = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + 2 * kPBytes +
-                      2 * kRing * static_cast<size_t>(p.chunks) * kKvChunkBytes + sizeof(AttnShared) + 64;
-  if (smem > static_cast<size_t>(g_attn_max_smem)) return B200SD_ERR_UNSUPPORTED;
-
+  // ring depths: two CTAs per SM when a Q tile + both P buffers + 4 K + 3 V tiles fit in half an SM (d <= 64),
+  // otherwise whatever one CTA can hold
+  const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
+  const size_t fixed = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + 2 * kPBytes + sizeof(AttnShared) + 64;
+  const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
+  size_t budget = (p.tmem_cols <= 256 && fixed + 4 * kvt <= half_sm) ? half_sm : static_cast<size_t>(g_attn_max_smem);
+  if (fixed + 2 * kvt > budget) return B200SD_ERR_UNSUPPORTED;
+  int total = static_cast<int>((budget - fixed) / kvt);
+  if (total > 2 * kMaxRing - 1) total = 2 * kMaxRing - 1;
+  p.k_stages = (total + 1) / 2;
+  p.v_stages = total / 2;
+  if (p.v_stages < 1) return B200SD_ERR_UNSUPPORTED;
+  const size_t smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t es[3] = {1, 1, 1};
   int rc;
