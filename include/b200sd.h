@@ -120,6 +120,14 @@ int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float* x, const 
  * trunc(255 * clamp((v+1)/2, 0, 1))  (sdwui process_images_inner) */
 int b200sd_quantize_u8(const void* img, long long pitch, unsigned char* out, int B, int HW, int dtype, void* stream);
 
+/* img2img input: uint8 [B,HW,3] RGB -> [B,HW,pitch] with channel c < 3 = 2*x/255 - 1 (channels >= 3 untouched: zero
+ * from allocation).  (sdwui StableDiffusionProcessingImg2Img.init) */
+int b200sd_image_to_nhwc(const unsigned char* img, void* out, long long pitch, int B, int HW, int dtype, void* stream);
+/* VAE encoder moments [B,HW,pitch] (first 4 channels = posterior mean) -> scaled latents fp32 [B,HW,4] = mean * scale
+ * (AutoencoderKL.encode(...).mean * scale_factor) */
+int b200sd_unpack_latent(const void* moments, long long pitch, float* x, int B, int HW, float scale, int dtype,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

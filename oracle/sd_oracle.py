@@ -461,3 +461,49 @@ def txt2img(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, 
         raise ValueError(sampler)
     dec = vae_decode(dsd, vae_cfg, z / vae_cfg.scale_factor)
     return to_uint8(dec), z, dec
+
+
+# ------------------------------------------------------------------------------------------------ img2img
+def image_to_model_input(img_u8: torch.Tensor) -> torch.Tensor:
+    """sdwui StableDiffusionProcessingImg2Img.init: uint8 HWC -> float NCHW in [-1, 1] (2 * x/255 - 1)."""
+    return img_u8.permute(0, 3, 1, 2).float().div(255.0).mul(2.0).sub(1.0)
+
+
+def ddim_img2img_coefficients(steps: int, denoising_strength: float):
+    """sdwui sd_samplers_timesteps.sample_img2img: t_enc = int(min(d, 0.999) * steps); the sampler runs on
+    timesteps[:t_enc] (so t_enc - 1 UNet evaluations), starting from
+    x = init * sqrt(a[ts[t_enc]]) + noise * sqrt(1 - a[ts[t_enc]]).
+    Returns (sqrt_a_start, sqrt_1m_a_start, rows) with rows as in ddim_coefficients."""
+    ac = alphas_cumprod().double()
+    ts = ddim_timesteps(steps)
+    t_enc = int(min(denoising_strength, 0.999) * steps)
+    t_enc = max(1, min(t_enc, len(ts) - 1))
+    a_start = float(ac[ts[t_enc]])
+    sub = ts[:t_enc]
+    alphas = ac[sub]
+    alphas_prev = ac[torch.cat([sub[:1] * 0, sub[:-1]])]
+    rows = []
+    for i in range(len(sub) - 1, 0, -1):
+        a_t, a_p = float(alphas[i]), float(alphas_prev[i])
+        rows.append((int(sub[i]), math.sqrt(a_t), math.sqrt(1.0 - a_t), math.sqrt(a_p), math.sqrt(1.0 - a_p)))
+    return math.sqrt(a_start), math.sqrt(1.0 - a_start), rows
+
+
+def img2img(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, init_u8: torch.Tensor,
+            denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, device="cpu"):
+    """End-to-end img2img oracle: encode (posterior MEAN, see vae_encode_mean) -> noise to t_enc -> DDIM -> decode."""
+    b = tokens.shape[0]
+    dsd = {k: v.to(device) for k, v in sd.items()}
+    cond = clip_text_encode(dsd, clip_cfg, tokens.to(device))
+    uncond = clip_text_encode(dsd, clip_cfg, neg_tokens.to(device))
+    x_in = image_to_model_input(init_u8.to(device))
+    init = vae_encode_mean(dsd, vae_cfg, x_in) * vae_cfg.scale_factor
+    noise = per_image_noise(seed, b, tuple(init.shape[1:])).to(device)
+    sa, s1a, rows = ddim_img2img_coefficients(steps, denoising_strength)
+    x = init * sa + noise * s1a
+    for (t, c_sa, c_s1a, c_sap, c_s1ap) in rows:
+        e = cfg_eps(lambda a, tt, c: unet_forward(dsd, unet_cfg, a, tt, c), x, t, cond, uncond, cfg_scale)
+        x0 = (x - c_s1a * e) / c_sa
+        x = c_sap * x0 + c_s1ap * e
+    dec = vae_decode(dsd, vae_cfg, x / vae_cfg.scale_factor)
+    return to_uint8(dec), x, init

@@ -11,21 +11,31 @@
 // ([b, s, h*d]) because it feeds the out-projection GEMM as a plain K-major A operand.
 //
 // One CTA = one 128-row Q tile of one (batch, head), kv consumed in tiles of 64.  320 threads:
-//   warp 0    TMA producer (Q once; K ring, V ring)
-//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%2] = Q K_j^T (M128 x N<=64 x K=d),
+//   warp 0    TMA producer (Q once; K ring, V ring — loads issued in the order the MMAs consume them)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%sb] = Q K_j^T (M128 x N<=64 x K=d),
 //             O (+)= P[j%2] V_j (M128 x N=d_pad x K<=64, V consumed MN-major straight from its TMA tile)
 //   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane, and the two warps of a lane
 //             quarter split the 64 kv columns of the tile in halves.
-// S and P are DOUBLE BUFFERED (S in TMEM, P in shared memory): Q K_{j+2}^T is issued as soon as softmax j has
-// consumed its S buffer, and P_j V_j runs while softmax j+1 is already exponentiating — in steady state the softmax
-// warps never wait for the tensor pipe, which matters because for d = 40 this kernel is bound by the exp (MUFU)
-// rate, not by the MMAs (16 exps per 96 MMA-FLOPs).
+// S is buffered sb = 3 deep in TMEM when d_pad == 64 (3 x 64 + 64 columns for O = 256, two CTAs per SM), else
+// 2 deep; P is double buffered in shared memory.  Q K_{j+sb}^T is issued as soon as softmax j has consumed its S
+// buffer and P_j V_j runs while softmax j+1 is already exponentiating, so in steady state the softmax warps wait
+// neither for the tensor pipe nor for its completion latency — which matters because for d = 40 this kernel is
+// bound by the exp (MUFU) rate and by instruction issue, not by the MMAs (16 exps per 96 MMA-FLOPs).
 // Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) uses the running maximum of earlier tiles while the
 // tile's own maximum is tracked; only if that exceeds m_used by more than 2^8 (P would leave fp16's comfortable
 // range) is the tile redone after rescaling O in TMEM — a vote between the two warps of a row quarter, rare after
 // the first tile.  Each S element is read from TMEM once, the TMEM load of the next 16 columns is in flight while
 // the current 16 are exponentiated, and with a ones column in V (v_ones_col) the row sums come out of the P.V MMA
-// instead of CUDA-core adds.  d <= 64: 80 KB smem + 256 TMEM columns per CTA -> two CTAs per SM.
+// instead of CUDA-core adds.
+//
+// mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
+//   o_full[2]  P.V of tile j commits to o_full[j&1].  Every softmax thread waits for tile j-2 on o_full[j&1] before
+//              it overwrites P[j&1] (tcgen05 MMAs complete in issue order, but S[j] being ready only proves P.V of
+//              tile j-sb+... older tiles), so it observes every phase of both barriers; the rare-path wait for tile
+//              j-1 and the final wait are therefore at most one phase behind.
+//   s_full[sb] / p_full[2] / ring barriers: one waiter each side, strictly alternating.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
 
@@ -40,13 +50,15 @@ constexpr uint32_t kQChunkBytes = kQTile * 128;      // 128 rows x 64 halfs
 constexpr uint32_t kKvChunkBytes = kKv * 128;        // 64 rows x 64 halfs
 constexpr uint32_t kPBytes = kQTile * kKv * 2;       // one K-major SWIZZLE_128B atom: 128 rows x 64 halfs
 constexpr int kMaxRing = 4;
+constexpr int kMaxSBufs = 3;
 
 struct AttnParams {
   int B, heads, Sq, Skv, d, d_pad;
   int d16;           // d rounded up to 16 (MMA K of Q.K^T; O columns that carry data)
   int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
   int chunks;        // d_pad / 64
-  int k_stages, v_stages;  // K / V ring depths (<= kMaxRing), as deep as shared memory allows
+  int s_bufs;        // S buffers in TMEM (2 or 3); O lives behind them at column s_bufs * 64
+  int k_stages, v_stages;  // K / V ring depths (<= kMaxRing)
   int tmem_cols;
   int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
   int resc_cols;     // O columns touched by a rescale (multiple of 16, covers l_col)
@@ -60,7 +72,7 @@ struct __align__(16) AttnShared {
   uint64_t q_full;
   uint64_t k_full[kMaxRing], k_empty[kMaxRing];
   uint64_t v_full[kMaxRing], v_empty[kMaxRing];
-  uint64_t s_full[2], p_full[2], o_full;
+  uint64_t s_full[kMaxSBufs], p_full[2], o_full[2];
   uint32_t tmem_base;
   uint32_t pad;
   float xch[2][kQTile];  // row maxima / sums exchanged between the two column halves
@@ -81,6 +93,10 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // named barriers 1..4: the two warps (64 threads) that share one TMEM lane quarter, i.e. the thread pairs of 32 rows
@@ -126,9 +142,10 @@ __device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int n
   return mx;
 }
 
-// exponentiate 16 columns, track their maximum / sum, write them as two 16-byte chunks of the swizzled P atom
+// exponentiate 16 columns, track their maximum / sum, write them as two 16-byte chunks of the swizzled P atom.
+// p_row = shared-space address of my row of the P buffer, rx = row & 7 (the 128-byte swizzle phase).
 template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* sPj, int r, int cbase, int nvalid,
+__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint32_t p_row, uint32_t rx, int cbase, int nvalid,
                                           float scale_log2, float m_used, float& tile_max, float& lsum) {
   uint32_t pk[8];
   float mx = tile_max, acc = 0.f;
@@ -148,21 +165,21 @@ __device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint8_t* sPj,
   tile_max = mx;
   if constexpr (kSum) lsum += acc;
   const uint32_t chunk16 = static_cast<uint32_t>(cbase >> 3);  // 8 halfs per 16-byte chunk
-  *reinterpret_cast<uint4*>(sPj + sw128_offset(r, chunk16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(sPj + sw128_offset(r, chunk16 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  sts128(p_row + ((chunk16 ^ rx) << 4), pk[0], pk[1], pk[2], pk[3]);
+  sts128(p_row + (((chunk16 + 1) ^ rx) << 4), pk[4], pk[5], pk[6], pk[7]);
 }
 
 // One pass over my 32 columns: the TMEM load of the second 16 is in flight while the first 16 are processed.
 template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint8_t* sPj, int r, int col0, int nvalid,
+__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint32_t p_row, uint32_t rx, int col0, int nvalid,
                                              float scale_log2, float m_used, float& tile_max, float& lsum) {
   uint32_t va[16], vb[16];
   tmem_ld_x16(tmem_row + col0, va);
   tmem_ld_wait();
   tmem_ld_x16(tmem_row + col0 + 16, vb);
-  softmax16<kFull, kBf16, kSum>(va, sPj, r, col0, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(va, p_row, rx, col0, nvalid, scale_log2, m_used, tile_max, lsum);
   tmem_ld_wait();
-  softmax16<kFull, kBf16, kSum>(vb, sPj, r, col0 + 16, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(vb, p_row, rx, col0 + 16, nvalid, scale_log2, m_used, tile_max, lsum);
 }
 
 template <bool kBf16, bool kSum>
@@ -172,17 +189,23 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
   const int half = (warp - 2) >> 2;   // which 32-column half of the kv tile is mine
   const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
   const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-  const uint32_t o_row = tmem_base + 128 + lane_base;
+  const uint32_t o_row = tmem_base + static_cast<uint32_t>(p.s_bufs * kKv) + lane_base;
+  const uint32_t p_row0 = smem_u32(sP) + static_cast<uint32_t>(r) * 128u;
+  const uint32_t rx = static_cast<uint32_t>(r) & 7u;
   const int col0 = half * 32;
   float m_used = -INFINITY;  // scaled log2 domain
   float l = 0.f;
+  int sb = 0;                // S buffer of tile j and the parity of its s_full phase
+  uint32_t s_par = 0;
   for (int j = 0; j < nkv; ++j) {
-    const int buf = j & 1;
+    const int pb = j & 1;
     const int nvalid = min(kKv, p.Skv - j * kKv);
     const bool full = nvalid == kKv;
-    const uint32_t s_row = tmem_base + buf * kKv + lane_base;
-    uint8_t* sPj = sP + buf * kPBytes;
-    mbar_wait(&sh->s_full[buf], (j >> 1) & 1, 17);
+    const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
+    const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
+    mbar_wait(&sh->s_full[sb], s_par, 17);
+    // P[pb] was last read by P.V of tile j-2 (issued two softmax tiles ago, normally long complete)
+    if (j >= 2) mbar_wait(&sh->o_full[pb], ((j >> 1) - 1) & 1, 20);
     tc_fence_after();
     if (j == 0) {
       const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
@@ -191,8 +214,8 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * p.scale_log2;
     }
     float tile_max = -INFINITY, lsum = 0.f;
-    if (full) softmax_half<true, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-    else      softmax_half<false, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+    else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
     const float tm = tile_max * p.scale_log2;
     if (pair_bar_or(quarter, tm > m_used + 8.0f)) {
       // rare path: the running maximum moved by more than 2^8 for some row of this quarter
@@ -201,7 +224,7 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
       const float alpha = fast_exp2(m_used - m_new);
       if (j > 0) {
-        mbar_wait(&sh->o_full, (j - 1) & 1, 18);  // P.V of the previous tile must have landed in O
+        mbar_wait(&sh->o_full[pb ^ 1], ((j - 1) >> 1) & 1, 18);  // P.V of the previous tile must have landed in O
         tc_fence_after();
         for (int c = half; c < p.resc_cols / 16; c += 2) {
           uint32_t o[16];
@@ -217,20 +240,20 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       m_used = m_new;
       tile_max = -INFINITY;
       lsum = 0.f;
-      if (full) softmax_half<true, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-      else      softmax_half<false, kBf16, kSum>(s_row, sPj, r, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
     }
     l += lsum;
-    // Observe every phase of o_full (P.V of the previous tile: issued a whole softmax ago, normally complete) so that
-    // parity waits on it can never alias an older phase.  It must happen BEFORE this tile's arrive: P.V of this tile
-    // cannot complete (and flip the phase again) until all 256 arrivals are in.
-    if (j > 0) mbar_wait(&sh->o_full, (j - 1) & 1, 20);
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(&sh->p_full[buf]);
+    mbar_arrive(&sh->p_full[pb]);
+    if (++sb == p.s_bufs) {
+      sb = 0;
+      s_par ^= 1u;
+    }
   }
   // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
-  mbar_wait(&sh->o_full, (nkv - 1) & 1, 19);
+  mbar_wait(&sh->o_full[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1, 19);
   tc_fence_after();
   if constexpr (kSum) {
     pair_bar_sync(quarter);  // both threads of every pair are past their last xch read
@@ -287,21 +310,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nkv = (p.Skv + kKv - 1) / kKv;
   const int col0 = head * p.d_pad;
 
-  // K / V loads are issued by one thread that polls both rings, so a full V ring never delays a K load (or vice
-  // versa); the first loads go out before the block-wide sync, overlapping the TMEM allocation.
-  int next_k = 0, next_v = 0;
-  auto issue_k = [&](int j) {
-    const int st = j % p.k_stages;
-    mbar_arrive_expect_tx(&sh->k_full[st], kv_bytes);
-    for (int c = 0; c < p.chunks; ++c)
-      tma_load_3d(sK + st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[st], col0 + c * 64, j * kKv, b);
-  };
-  auto issue_v = [&](int j) {
-    const int st = j % p.v_stages;
-    mbar_arrive_expect_tx(&sh->v_full[st], kv_bytes);
-    for (int c = 0; c < p.chunks; ++c)
-      tma_load_3d(sV + st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[st], col0 + c * 64, j * kKv, b);
-  };
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -313,44 +321,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&sh->v_full[s], 1);
       mbar_init(&sh->v_empty[s], 1);
     }
+    for (int s = 0; s < kMaxSBufs; ++s) mbar_init(&sh->s_full[s], 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sh->s_full[s], 1);
       mbar_init(&sh->p_full[s], kSoftmaxThreads);
+      mbar_init(&sh->o_full[s], 1);
     }
-    mbar_init(&sh->o_full, 1);
     fence_mbar_init();
-    mbar_arrive_expect_tx(&sh->q_full, q_bytes);
-    for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
-    for (; next_k < nkv && next_k < p.k_stages; ++next_k) issue_k(next_k);
-    for (; next_v < nkv && next_v < p.v_stages; ++next_v) issue_v(next_v);
   }
   if (warp == 1) tmem_alloc(&sh->tmem_base, static_cast<uint32_t>(p.tmem_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;  // S0 @ +0, S1 @ +64 (64 fp32 columns each), O @ +128 (dpv columns)
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_base = sh->tmem_base;  // S buffers (64 fp32 columns each) at +0, +64[, +128]; O behind them
+  const uint32_t tmem_O = tmem_base + static_cast<uint32_t>(p.s_bufs * kKv);
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
+    // Loads go out in exactly the order the MMA thread consumes (and therefore frees) tiles:
+    //   K_0 .. K_{sb-1},  then  V_j, K_{j+sb}  for j = 0, 1, ...   so a blocking wait never holds back a tile that is
+    // needed earlier than the one being waited for.
     if (lane == 0) {
-      uint32_t spins = 0;
-      while (next_k < nkv || next_v < nkv) {
-        bool progress = false;
-        if (next_k < nkv && mbar_try_wait(&sh->k_empty[next_k % p.k_stages], ((next_k / p.k_stages) & 1) ^ 1u)) {
-          issue_k(next_k++);
-          progress = true;
+      int kj = 0, k_st = 0, v_st = 0;
+      uint32_t k_par = 0, v_par = 0;
+      auto load_k = [&]() {
+        mbar_wait(&sh->k_empty[k_st], k_par ^ 1u, 11);
+        mbar_arrive_expect_tx(&sh->k_full[k_st], kv_bytes);
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[k_st], col0 + c * 64, kj * kKv, b);
+        ++kj;
+        if (++k_st == p.k_stages) {
+          k_st = 0;
+          k_par ^= 1u;
         }
-        if (next_v < nkv && mbar_try_wait(&sh->v_empty[next_v % p.v_stages], ((next_v / p.v_stages) & 1) ^ 1u)) {
-          issue_v(next_v++);
-          progress = true;
+      };
+      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
+      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
+      for (int i = 0; i < p.s_bufs && i < nkv; ++i) load_k();
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&sh->v_empty[v_st], v_par ^ 1u, 12);
+        mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
+        for (int c = 0; c < p.chunks; ++c)
+          tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
+        if (++v_st == p.v_stages) {
+          v_st = 0;
+          v_par ^= 1u;
         }
-        if (progress) spins = 0;
-        else if (++spins > B200SD_SPIN_LIMIT) {
-          printf("b200sd: attention producer timeout block=(%d,%d,%d) k=%d v=%d\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                 next_k, next_v);
-          __trap();
-        }
+        if (kj < nkv) load_k();
       }
     }
   } else if (warp == 1) {
@@ -359,40 +375,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool bf = p.is_bf16 != 0;
       const int ksteps_qk = p.d16 / 16;
       const uint32_t aQ = smem_u32(sQ);
-      auto issue_qk = [&](int j) {  // S[j&1] = Q K_j^T
-        const int st = j & 1;                // S buffer
-        const int ks = j % p.k_stages;       // K ring slot
-        const int nvalid = min(kKv, p.Skv - j * kKv);
+      int qj = 0, q_sb = 0, q_ks = 0;  // next Q.K^T: tile, S buffer, K ring slot (+ parity of its k_full phase)
+      uint32_t q_kpar = 0;
+      auto issue_qk = [&]() {  // S[q_sb] = Q K_qj^T
+        const int nvalid = min(kKv, p.Skv - qj * kKv);
         const int n16 = (nvalid + 15) & ~15;
-        mbar_wait(&sh->k_full[ks], (j / p.k_stages) & 1, 14);
+        mbar_wait(&sh->k_full[q_ks], q_kpar, 14);
         tc_fence_after();
         const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
-        const uint32_t aK = smem_u32(sK + ks * kv_bytes);
+        const uint32_t aK = smem_u32(sK + q_ks * kv_bytes);
         for (int k = 0; k < ksteps_qk; ++k) {
           const uint32_t offq = static_cast<uint32_t>(k >> 2) * kQChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
           const uint32_t offk = static_cast<uint32_t>(k >> 2) * kKvChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
-          umma_f16_ss(tmem_base + st * kKv, make_sdesc_sw128(aQ + offq, 16, 1024), make_sdesc_sw128(aK + offk, 16, 1024),
-                      idesc, k != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + static_cast<uint32_t>(q_sb * kKv), make_sdesc_sw128(aQ + offq, 16, 1024),
+                      make_sdesc_sw128(aK + offk, 16, 1024), idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&sh->k_empty[ks]);
-        umma_commit(&sh->s_full[st]);
+        umma_commit(&sh->k_empty[q_ks]);
+        umma_commit(&sh->s_full[q_sb]);
+        ++qj;
+        if (++q_sb == p.s_bufs) q_sb = 0;
+        if (++q_ks == p.k_stages) {
+          q_ks = 0;
+          q_kpar ^= 1u;
+        }
       };
       mbar_wait(&sh->q_full, 0, 13);
-      issue_qk(0);
-      if (nkv > 1) issue_qk(1);
+      for (int i = 0; i < p.s_bufs && i < nkv; ++i) issue_qk();
+      int vs = 0;
+      uint32_t v_par = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int pb = j & 1;
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
         // ---- O (+)= P_j V_j ----
-        const int vs = j % p.v_stages;
-        mbar_wait(&sh->p_full[st], ph, 15);
-        mbar_wait(&sh->v_full[vs], (j / p.v_stages) & 1, 16);
+        mbar_wait(&sh->p_full[pb], (j >> 1) & 1, 15);
+        mbar_wait(&sh->v_full[vs], v_par, 16);
         tc_fence_after();
         {
           const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
-          const uint32_t aP = smem_u32(sP + st * kPBytes);
+          const uint32_t aP = smem_u32(sP + pb * kPBytes);
           const uint32_t aV = smem_u32(sV + vs * kv_bytes);
           const int ksteps_pv = n16 / 16;
           for (int k = 0; k < ksteps_pv; ++k) {
@@ -402,10 +423,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         idesc, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(&sh->v_empty[vs]);
-          umma_commit(&sh->o_full);
+          umma_commit(&sh->o_full[pb]);
         }
-        // ---- softmax j has released S[st]: refill it two tiles ahead ----
-        if (j + 2 < nkv) issue_qk(j + 2);
+        if (++vs == p.v_stages) {
+          vs = 0;
+          v_par ^= 1u;
+        }
+        // ---- softmax j has released its S buffer: refill it s_bufs tiles ahead ----
+        if (qj < nkv) issue_qk();
       }
     }
   } else {
@@ -430,6 +455,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
+
+// tuning overrides for experiments: B200SD_ATTN_SBUFS=2|3, B200SD_ATTN_RING="k,v" (ring depths, 1..4 each)
+static void attn_env(int* s_bufs, int* k_st, int* v_st) {
+  static int cached = 0, e_sb = 0, e_k = 0, e_v = 0;
+  if (!cached) {
+    if (const char* s = std::getenv("B200SD_ATTN_SBUFS")) e_sb = std::atoi(s);
+    if (const char* s = std::getenv("B200SD_ATTN_RING")) {
+      e_k = std::atoi(s);
+      const char* c = s;
+      while (*c && *c != ',') ++c;
+      e_v = *c ? std::atoi(c + 1) : e_k;
+    }
+    cached = 1;
+  }
+  *s_bufs = e_sb;
+  *k_st = e_k;
+  *v_st = e_v;
+}
 
 int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
                  long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int v_ones_col,
@@ -468,20 +511,22 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   if (v_ones_col && d >= d_pad) return B200SD_ERR_INVALID;  // needs a free pad column
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
-  p.tmem_cols = (128 + p.dpv <= 256) ? 256 : 512;
-  // ring depths: two CTAs per SM when a Q tile + both P buffers + 4 K + 3 V tiles fit in half an SM (d <= 64),
-  // otherwise whatever one CTA can hold
+  int e_sb, e_k, e_v;
+  attn_env(&e_sb, &e_k, &e_v);
+  // three S buffers when they fit next to O in 256 TMEM columns (d_pad == 64: two CTAs per SM stay possible)
+  p.s_bufs = (3 * kKv + p.dpv <= 256) ? 3 : 2;
+  if (e_sb == 2 || (e_sb == 3 && 3 * kKv + p.dpv <= 512)) p.s_bufs = e_sb;
+  p.tmem_cols = (p.s_bufs * kKv + p.dpv <= 256) ? 256 : 512;
+  // ring depths: K 3 / V 2 when that keeps two CTAs per SM, otherwise 2 / 2
   const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
   const size_t fixed = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + 2 * kPBytes + sizeof(AttnShared) + 64;
   const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
-  size_t budget = (p.tmem_cols <= 256 && fixed + 4 * kvt <= half_sm) ? half_sm : static_cast<size_t>(g_attn_max_smem);
-  if (fixed + 2 * kvt > budget) return B200SD_ERR_UNSUPPORTED;
-  int total = static_cast<int>((budget - fixed) / kvt);
-  if (total > 2 * kMaxRing - 1) total = 2 * kMaxRing - 1;
-  p.k_stages = (total + 1) / 2;
-  p.v_stages = total / 2;
-  if (p.v_stages < 1) return B200SD_ERR_UNSUPPORTED;
+  p.k_stages = (p.tmem_cols <= 256 && fixed + 5 * kvt <= half_sm) ? 3 : 2;
+  p.v_stages = 2;
+  if (e_k >= 1 && e_k <= kMaxRing) p.k_stages = e_k;
+  if (e_v >= 1 && e_v <= kMaxRing) p.v_stages = e_v;
   const size_t smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;
+  if (smem > static_cast<size_t>(g_attn_max_smem)) return B200SD_ERR_UNSUPPORTED;
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t es[3] = {1, 1, 1};
   int rc;

@@ -224,6 +224,22 @@ __global__ void quantize_u8_kernel(const void* img, long long pitch, unsigned ch
   }
 }
 
+template <bool kBf16>
+__global__ void image_to_nhwc_kernel(const unsigned char* __restrict__ img, void* out, long long pitch, long long npix) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store1<kBf16>(out, i * pitch + c, static_cast<float>(img[i * 3 + c]) * (2.0f / 255.0f) - 1.0f);
+}
+
+template <bool kBf16>
+__global__ void unpack_latent_kernel(const void* m, long long pitch, float4* x, long long npix, float scale) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= npix) return;
+  x[i] = make_float4(load1<kBf16>(m, i * pitch) * scale, load1<kBf16>(m, i * pitch + 1) * scale,
+                     load1<kBf16>(m, i * pitch + 2) * scale, load1<kBf16>(m, i * pitch + 3) * scale);
+}
+
 }  // namespace b200sd
 
 using namespace b200sd;
@@ -330,6 +346,30 @@ extern "C" int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float
     cfg_euler_a_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
   bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_image_to_nhwc(const unsigned char* img, void* out, long long pitch, int B, int HW, int dtype,
+                                    void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (pitch < 3) return B200SD_ERR_INVALID;
+  const long long n = static_cast<long long>(B) * HW;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (dtype == B200SD_BF16) image_to_nhwc_kernel<true><<<blocks, 256, 0, ST(stream)>>>(img, out, pitch, n);
+  else image_to_nhwc_kernel<false><<<blocks, 256, 0, ST(stream)>>>(img, out, pitch, n);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_unpack_latent(const void* moments, long long pitch, float* x, int B, int HW, float scale,
+                                    int dtype, void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (pitch < 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return B200SD_ERR_INVALID;
+  const long long n = static_cast<long long>(B) * HW;
+  const int blocks = static_cast<int>((n + 255) / 256);
+  if (dtype == B200SD_BF16)
+    unpack_latent_kernel<true><<<blocks, 256, 0, ST(stream)>>>(moments, pitch, reinterpret_cast<float4*>(x), n, scale);
+  else
+    unpack_latent_kernel<false><<<blocks, 256, 0, ST(stream)>>>(moments, pitch, reinterpret_cast<float4*>(x), n, scale);
   RET_LAUNCH();
 }
 

@@ -15,7 +15,7 @@ from . import ops
 from .clip_text import ClipText
 from .config import CLIPConfig, UNetConfig, VAEConfig
 from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
-from .vae_exec import VAEDecoderProgram, VAEDecoderWeights
+from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
 
 MAX_STEPS = 256
 
@@ -40,6 +40,25 @@ def ddim_plan(steps: int) -> Tuple[List[float], List[List[float]]]:
         t_out.append(float(ts[i]))
         rows.append([math.sqrt(at), math.sqrt(1 - at), math.sqrt(ap), math.sqrt(1 - ap)])
     return t_out, rows
+
+
+def ddim_img2img_plan(steps: int, denoising_strength: float):
+    """sdwui sd_samplers_timesteps.sample_img2img: t_enc = int(min(d, 0.999) * steps); DDIM runs on timesteps[:t_enc]
+    (t_enc - 1 UNet evaluations) from x = init * sqrt(a[ts[t_enc]]) + noise * sqrt(1 - a[ts[t_enc]]).
+    Returns (sqrt_a_start, sqrt_1m_a_start, timesteps, coef rows)."""
+    ac = alphas_cumprod().double()
+    ts = torch.clamp(torch.arange(0, 1000, 1000 // steps) + 1, 0, 999)
+    t_enc = max(1, min(int(min(denoising_strength, 0.999) * steps), len(ts) - 1))
+    a_start = float(ac[ts[t_enc]])
+    sub = ts[:t_enc]
+    a = ac[sub]
+    a_prev = ac[torch.cat([sub.new_zeros(1), sub[:-1]])]
+    t_out, rows = [], []
+    for i in range(len(sub) - 1, 0, -1):
+        at, ap = float(a[i]), float(a_prev[i])
+        t_out.append(float(sub[i]))
+        rows.append([math.sqrt(at), math.sqrt(1 - at), math.sqrt(ap), math.sqrt(1 - ap)])
+    return math.sqrt(a_start), math.sqrt(1 - a_start), t_out, rows
 
 
 def euler_a_plan(steps: int):
@@ -130,9 +149,11 @@ class SDEngine:
         with self._ctx():
             self.unet_w = UNetWeights(sd, unet_cfg, self.device, dtype)
             self.vae_w = VAEDecoderWeights(sd, vae_cfg, self.device, dtype)
+            self.vae_enc_w = VAEEncoderWeights(sd, vae_cfg, self.device, dtype)
             self.clip = ClipText(sd, clip_cfg, self.device, dtype)
             self.temb = TimeEmbedding(self.unet_w)
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
+        self.encoders: Dict[Tuple[int, int, int], VAEEncoderProgram] = {}
         self.interrupted = False
         self.last_unet_evals = 0
         self.graph_replayed_launches = 0   # b200sd kernels launched through graph replays (bench.py gpu_launches)
@@ -172,15 +193,16 @@ class SDEngine:
 
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
-               sampler: str = "DDIM", noises: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device).
+               sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None) -> torch.Tensor:
+        """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device): the start latents.
+        `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way).
         Returns the final latents fp32 [b, h*w, 4] (NHWC, a view of plan state)."""
         b, _, h, w = x_T.shape
         with self._ctx():
             plan = self.plan(b, h, w)
             plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
             if sampler == "DDIM":
-                ts, rows = ddim_plan(steps)
+                ts, rows = schedule if schedule is not None else ddim_plan(steps)
                 scale0, in0 = 1.0, 1.0
                 step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
             elif sampler == "Euler a":
@@ -244,6 +266,44 @@ class SDEngine:
                 n = min(c, b - i)
                 out[i:i + n].copy_(vae.u8[:n])
             return out.reshape(b, vae.out_h, vae.out_w, 3)
+
+    @torch.no_grad()
+    def encode(self, images_u8: torch.Tensor) -> torch.Tensor:
+        """images uint8 [b, H, W, 3] (host or device) -> scaled latents fp32 [b, 4, H/f, W/f] (posterior mean), in
+        chunks of `vae_chunk` images."""
+        b, hh, ww, _ = images_u8.shape
+        with self._ctx():
+            c = min(self.vae_chunk, b)
+            key = (c, hh, ww)
+            if key not in self.encoders:
+                self.encoders[key] = VAEEncoderProgram(self.vae_enc_w, c, hh, ww)
+            enc = self.encoders[key]
+            imgs = images_u8.to(self.device).reshape(b, hh * ww, 3)
+            out = torch.empty((b, enc.lat_h * enc.lat_w, 4), device=self.device, dtype=torch.float32)
+            for i in range(0, b, c):
+                chunk = imgs[i:i + c]
+                n = chunk.shape[0]
+                enc.img_u8[:n].copy_(chunk)
+                if n < c:
+                    enc.img_u8[n:].copy_(chunk[-1:].expand(c - n, -1, -1))
+                enc.run()
+                out[i:i + n].copy_(enc.latents[:n])
+            return out.reshape(b, enc.lat_h, enc.lat_w, 4).permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def img2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, init_u8: torch.Tensor,
+                denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0) -> torch.Tensor:
+        """img2img with DDIM: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining
+        timesteps, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device."""
+        b = tokens.shape[0]
+        cond = self.encode_prompts(tokens)
+        uncond = self.encode_prompts(neg_tokens)
+        init = self.encode(init_u8)
+        _, _, h, w = init.shape
+        noise = per_image_noise(seed, b, (4, h, w))[0].to(self.device)
+        sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
+        lat = self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows))
+        return self.decode(lat, h, w)
 
     @torch.no_grad()
     def txt2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20, cfg_scale: float = 7.0,

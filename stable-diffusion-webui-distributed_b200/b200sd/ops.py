@@ -254,6 +254,27 @@ def cfg_euler_a_step(eps: torch.Tensor, x: torch.Tensor, noise: Optional[torch.T
     _count(2)
 
 
+def image_to_nhwc(img_u8: torch.Tensor, out: torch.Tensor):
+    """img_u8 uint8 [B, HW, 3] -> out [B, HW, pitch] channels 0..2 = 2*x/255 - 1"""
+    b, hw, _ = img_u8.shape
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    rc = _lib.lib().b200sd_image_to_nhwc(_p(img_u8), _p(out), ctypes.c_longlong(out.stride(1)), b, hw, _dt(out), _stream())
+    check(rc, "b200sd_image_to_nhwc")
+    _count()
+    return out
+
+
+def unpack_latent(moments: torch.Tensor, x: torch.Tensor, scale: float):
+    """moments [B, HW, pitch] (first 4 channels = posterior mean) -> x fp32 [B, HW, 4] = mean * scale"""
+    b, hw, _ = moments.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rc = _lib.lib().b200sd_unpack_latent(_p(moments), ctypes.c_longlong(moments.stride(1)), _p(x), b, hw,
+                                         ctypes.c_float(scale), _dt(moments), _stream())
+    check(rc, "b200sd_unpack_latent")
+    _count()
+    return x
+
+
 def quantize_u8(img: torch.Tensor, out: torch.Tensor):
     """img [B, HW, pitch>=3] -> out uint8 [B, HW, 3]"""
     b, hw, _ = img.shape

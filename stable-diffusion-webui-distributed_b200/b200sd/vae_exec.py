@@ -1,7 +1,9 @@
-"""kl-f8 VAE decoder as a static program of libb200sd kernels (NHWC fp16).
+"""kl-f8 VAE decoder / encoder as static programs of libb200sd kernels (NHWC fp16).
 
-Stands in for upstream `AutoencoderKL.decode` (ldm/modules/diffusionmodules/model.py::Decoder) + sdwui's
+Decoder: stands in for upstream `AutoencoderKL.decode` (ldm/modules/diffusionmodules/model.py::Decoder) + sdwui's
 clamp/255/uint8 conversion — the "final VAE decode" of the north star (SURVEY.md §8 a-ext x11).
+Encoder: `AutoencoderKL.encode(...).mean` (model.py::Encoder + quant_conv) for img2img (§8 a-ext x12); its Downsample
+(pad (0,1,0,1), 3x3 stride 2, no padding) is the conv kernel with pad=0 / pad_end=1 and TMA elementStrides=2.
 
 The single-head d=C mid-block attention is expressed with the GEMM kernel: per image S = q k^T, row softmax,
 V^T = Wv h^T (so P.V needs no transpose), O = P V^T^T; the v bias is folded into proj_out's bias (softmax rows sum
@@ -17,77 +19,115 @@ from .unet_exec import Pool
 from .weights import pack_conv
 
 
+class _Packer:
+    """ldm VAE state_dict -> kernel layouts on `device` (shared by decoder and encoder)."""
+
+    def __init__(self, sd, device, dtype):
+        self.sd, self.device, self.dtype = sd, device, dtype
+        self.t: Dict[str, torch.Tensor] = {}
+        self.p = VAE_PREFIX
+
+    def dev(self, t, dt=None):
+        return t.to(device=self.device, dtype=dt or self.dtype).contiguous()
+
+    def conv(self, name, key, cin_pad=0, cout_pad=0):
+        self.t[name + ".w"] = self.dev(pack_conv(self.sd[self.p + key + ".weight"], cin_pad, cout_pad))
+        b = self.sd[self.p + key + ".bias"]
+        if cout_pad > b.numel():
+            b = torch.cat([b, b.new_zeros(cout_pad - b.numel())])
+        self.t[name + ".b"] = self.dev(b, torch.float32)
+
+    def norm(self, name, key):
+        self.t[name + ".g"] = self.dev(self.sd[self.p + key + ".weight"], torch.float32)
+        self.t[name + ".beta"] = self.dev(self.sd[self.p + key + ".bias"], torch.float32)
+
+    def res(self, name, key, cin, cout):
+        self.norm(name + ".gn1", key + ".norm1")
+        self.conv(name + ".conv1", key + ".conv1")
+        self.norm(name + ".gn2", key + ".norm2")
+        self.conv(name + ".conv2", key + ".conv2")
+        if cin != cout:
+            self.conv(name + ".skip", key + ".nin_shortcut")
+
+    def attn(self, key, c):
+        self.norm("attn.norm", key + ".norm")
+        for n in ("q", "k", "v", "proj_out"):
+            self.conv("attn." + n, f"{key}.{n}")
+        wp = self.sd[self.p + key + ".proj_out.weight"].reshape(c, c).double()
+        bv = self.sd[self.p + key + ".v.bias"].double()
+        self.t["attn.proj_out.b"] = self.dev((self.sd[self.p + key + ".proj_out.bias"].double() + wp @ bv).float(),
+                                             torch.float32)
+
+
 class VAEDecoderWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: VAEConfig, device, dtype=torch.float16):
         self.cfg, self.device, self.dtype = cfg, device, dtype
-        self.t: Dict[str, torch.Tensor] = {}
-        p = VAE_PREFIX
-
-        def dev(t, dt=None):
-            return t.to(device=device, dtype=dt or dtype).contiguous()
-
-        def conv(name, key, cin_pad=0, cout_pad=0):
-            self.t[name + ".w"] = dev(pack_conv(sd[p + key + ".weight"], cin_pad, cout_pad))
-            b = sd[p + key + ".bias"]
-            if cout_pad > b.numel():
-                b = torch.cat([b, b.new_zeros(cout_pad - b.numel())])
-            self.t[name + ".b"] = dev(b, torch.float32)
-
-        def norm(name, key):
-            self.t[name + ".g"] = dev(sd[p + key + ".weight"], torch.float32)
-            self.t[name + ".beta"] = dev(sd[p + key + ".bias"], torch.float32)
-
-        def res(name, key, cin, cout):
-            norm(name + ".gn1", key + ".norm1")
-            conv(name + ".conv1", key + ".conv1")
-            norm(name + ".gn2", key + ".norm2")
-            conv(name + ".conv2", key + ".conv2")
-            if cin != cout:
-                conv(name + ".skip", key + ".nin_shortcut")
-
-        # post_quant_conv: 1x1 z->z, both sides padded to 64 channels
-        conv("post_quant", "post_quant_conv", cin_pad=64, cout_pad=64)
+        pk = _Packer(sd, device, dtype)
+        self.t = pk.t
+        pk.conv("post_quant", "post_quant_conv", cin_pad=64, cout_pad=64)  # 1x1 z->z, both sides padded to 64
         nlev = len(cfg.ch_mult)
         cin = cfg.ch * cfg.ch_mult[-1]
-        conv("conv_in", "decoder.conv_in", cin_pad=64)
-        res("mid1", "decoder.mid.block_1", cin, cin)
-        norm("attn.norm", "decoder.mid.attn_1.norm")
-        for n in ("q", "k", "v", "proj_out"):
-            conv("attn." + n, "decoder.mid.attn_1." + n)
-        wp = sd[p + "decoder.mid.attn_1.proj_out.weight"].reshape(cin, cin).double()
-        bv = sd[p + "decoder.mid.attn_1.v.bias"].double()
-        self.t["attn.proj_out.b"] = dev((sd[p + "decoder.mid.attn_1.proj_out.bias"].double() + wp @ bv).float(),
-                                        torch.float32)
-        res("mid2", "decoder.mid.block_2", cin, cin)
+        pk.conv("conv_in", "decoder.conv_in", cin_pad=64)
+        pk.res("mid1", "decoder.mid.block_1", cin, cin)
+        pk.attn("decoder.mid.attn_1", cin)
+        pk.res("mid2", "decoder.mid.block_2", cin, cin)
         self.levels = []
         for lvl in reversed(range(nlev)):
             cout = cfg.ch * cfg.ch_mult[lvl]
             blocks = []
             for b in range(cfg.num_res_blocks + 1):
-                res(f"up{lvl}.{b}", f"decoder.up.{lvl}.block.{b}", cin, cout)
+                pk.res(f"up{lvl}.{b}", f"decoder.up.{lvl}.block.{b}", cin, cout)
                 blocks.append((cin, cout))
                 cin = cout
             if lvl != 0:
-                conv(f"up{lvl}.upsample", f"decoder.up.{lvl}.upsample.conv")
+                pk.conv(f"up{lvl}.upsample", f"decoder.up.{lvl}.upsample.conv")
             self.levels.append((lvl, blocks))
-        norm("norm_out", "decoder.norm_out")
-        conv("conv_out", "decoder.conv_out", cout_pad=32)
+        pk.norm("norm_out", "decoder.norm_out")
+        pk.conv("conv_out", "decoder.conv_out", cout_pad=32)
         self.mid_ch = cfg.ch * cfg.ch_mult[-1]
         self.out_ch = cin
 
 
-class VAEDecoderProgram:
-    """Decode `b` latents of size h x w -> uint8 [b, 8h*.., 3].  run() is allocation- and sync-free."""
+class VAEEncoderWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: VAEConfig, device, dtype=torch.float16):
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        pk = _Packer(sd, device, dtype)
+        self.t = pk.t
+        pk.conv("conv_in", "encoder.conv_in", cin_pad=64)   # RGB padded to 64 input channels
+        nlev = len(cfg.ch_mult)
+        cin = cfg.ch
+        self.levels = []
+        for lvl in range(nlev):
+            cout = cfg.ch * cfg.ch_mult[lvl]
+            blocks = []
+            for b in range(cfg.num_res_blocks):
+                pk.res(f"down{lvl}.{b}", f"encoder.down.{lvl}.block.{b}", cin, cout)
+                blocks.append((cin, cout))
+                cin = cout
+            if lvl != nlev - 1:
+                pk.conv(f"down{lvl}.downsample", f"encoder.down.{lvl}.downsample.conv")
+            self.levels.append((lvl, blocks))
+        pk.res("mid1", "encoder.mid.block_1", cin, cin)
+        pk.attn("encoder.mid.attn_1", cin)
+        pk.res("mid2", "encoder.mid.block_2", cin, cin)
+        pk.norm("norm_out", "encoder.norm_out")
+        pk.conv("conv_out", "encoder.conv_out", cout_pad=64)      # 2z = 8 moment channels, padded to 64
+        pk.conv("quant", "quant_conv", cin_pad=64, cout_pad=64)   # 1x1 on the moments
+        self.mid_ch = cin
 
-    def __init__(self, w: VAEDecoderWeights, b: int, h: int, wd: int):
-        self.w, self.b, self.h, self.wd = w, b, h, wd
-        self.dev, self.dt = w.device, w.dtype
+
+class _VAEProgram:
+    """Shared layer emitters: every op is recorded once, run() replays them (allocation- and sync-free)."""
+
+    def __init__(self, weights, b: int):
+        self.w, self.b = weights, b
+        self.dev, self.dt = weights.device, weights.dtype
         self.pool = Pool(self.dev, self.dt)
-        self.zin = torch.zeros((2 * b, h * wd, 64), device=self.dev, dtype=self.dt)  # pack_unet_input writes both halves
         self.ops: List = []
         self.gn_stats: List = []
-        self._build()
-        self.stats_all = torch.zeros((len(self.gn_stats), b, 32, 2), device=self.dev, dtype=torch.float32)
+
+    def _finish(self):
+        self.stats_all = torch.zeros((max(1, len(self.gn_stats)), self.b, 32, 2), device=self.dev, dtype=torch.float32)
         for i, holder in enumerate(self.gn_stats):
             holder[0] = self.stats_all[i]
 
@@ -145,6 +185,29 @@ class VAEDecoderProgram:
             self.pool.put(tmp)
         return out
 
+    def _mid(self, x, c, h, wd):
+        for stage in ("mid1", "attn", "mid2"):
+            y = self._attn(x, c, h, wd) if stage == "attn" else self._res(stage, x, c, c, h, wd)
+            self.pool.put(x)
+            x = y
+        return x
+
+    def run(self):
+        self.stats_all.zero_()
+        for fn, a, k in self.ops:
+            fn(*a, **k)
+
+
+class VAEDecoderProgram(_VAEProgram):
+    """Decode `b` latents of size h x w -> uint8 [b, 8h*.., 3]."""
+
+    def __init__(self, w: VAEDecoderWeights, b: int, h: int, wd: int):
+        super().__init__(w, b)
+        self.h, self.wd = h, wd
+        self.zin = torch.zeros((2 * b, h * wd, 64), device=self.dev, dtype=self.dt)  # pack_unet_input writes both halves
+        self._build()
+        self._finish()
+
     def _build(self):
         b, h, wd, t = self.b, self.h, self.wd, self.w.t
         c = self.w.mid_ch
@@ -153,10 +216,7 @@ class VAEDecoderProgram:
         x = self.pool.get(b, h * wd, c)
         self._emit(ops.conv2d, z.unflatten(1, (h, wd)), t["conv_in.w"], x, ksize=3, bias=t["conv_in.b"])
         self.pool.put(z)
-        for stage in ("mid1", "attn", "mid2"):
-            y = self._attn(x, c, h, wd) if stage == "attn" else self._res(stage, x, c, c, h, wd)
-            self.pool.put(x)
-            x = y
+        x = self._mid(x, c, h, wd)
         for lvl, blocks in self.w.levels:
             for i, (cin, cout) in enumerate(blocks):
                 y = self._res(f"up{lvl}.{i}", x, cin, cout, h, wd)
@@ -187,7 +247,54 @@ class VAEDecoderProgram:
         ops.pack_unet_input(x, self.zin, 1.0 / scale_factor)
 
     def run(self):
-        self.stats_all.zero_()
-        for fn, a, k in self.ops:
-            fn(*a, **k)
+        super().run()
         return self.u8
+
+
+class VAEEncoderProgram(_VAEProgram):
+    """Encode `b` RGB images of size H x W (uint8) -> scaled latents fp32 [b, (H/f)*(W/f), 4] (posterior mean)."""
+
+    def __init__(self, w: VAEEncoderWeights, b: int, height: int, width: int):
+        super().__init__(w, b)
+        self.height, self.width = height, width
+        self.img_u8 = torch.zeros((b, height * width, 3), device=self.dev, dtype=torch.uint8)
+        self.xin = torch.zeros((b, height * width, 64), device=self.dev, dtype=self.dt)  # RGB in channels 0..2
+        self._build()
+        self._finish()
+
+    def _build(self):
+        b, h, wd, t = self.b, self.height, self.width, self.w.t
+        self._emit(ops.image_to_nhwc, self.img_u8, self.xin)
+        c = self.w.cfg.ch
+        x = self.pool.get(b, h * wd, c)
+        self._emit(ops.conv2d, self.xin.unflatten(1, (h, wd)), t["conv_in.w"], x, ksize=3, bias=t["conv_in.b"])
+        nlev = len(self.w.levels)
+        for lvl, blocks in self.w.levels:
+            for i, (cin, cout) in enumerate(blocks):
+                y = self._res(f"down{lvl}.{i}", x, cin, cout, h, wd)
+                self.pool.put(x)
+                x = y
+                c = cout
+            if lvl != nlev - 1:
+                ho, wo = h // 2, wd // 2
+                y = self.pool.get(b, ho * wo, c)
+                self._emit(ops.conv2d, x.unflatten(1, (h, wd)), t[f"down{lvl}.downsample.w"], y, ksize=3, stride=2, pad=0,
+                           pad_end=1, bias=t[f"down{lvl}.downsample.b"])
+                self.pool.put(x)
+                x, h, wd = y, ho, wo
+        x = self._mid(x, c, h, wd)
+        a = self.pool.get(b, h * wd, c)
+        self._gn(x, a, "norm_out", True)
+        self.pool.put(x)
+        m = self.pool.get(b, h * wd, 64)
+        self._emit(ops.conv2d, a.unflatten(1, (h, wd)), t["conv_out.w"], m, ksize=3, bias=t["conv_out.b"])
+        self.pool.put(a)
+        moments = self.pool.get(b, h * wd, 64)
+        self._emit(ops.linear, m, t["quant.w"], moments, bias=t["quant.b"])
+        self.lat_h, self.lat_w = h, wd
+        self.latents = torch.empty((b, h * wd, 4), device=self.dev, dtype=torch.float32)
+        self._emit(ops.unpack_latent, moments, self.latents, self.w.cfg.scale_factor)
+
+    def run(self):
+        super().run()
+        return self.latents

@@ -145,8 +145,15 @@ class LocalGPUWorker(Worker):
         if sampler not in SUPPORTED_SAMPLERS:
             logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")
             sampler = "Euler a"
+        init_u8 = None
         if payload.get("init_images"):
-            raise NotImplementedError("img2img is not implemented on the local executor yet")
+            if payload.get("image_mask") is not None or payload.get("mask") is not None:
+                raise NotImplementedError("inpainting masks are not implemented on the local executor")
+            init_u8 = self._init_images_u8(payload["init_images"], batch, width, height)
+            if sampler != "DDIM":
+                logger.warning(f"img2img on worker {self.label} runs DDIM ('{sampler}' start-from-noise-level is not implemented)")
+                sampler = "DDIM"
+        denoise = float(payload.get("denoising_strength", 0.75) or 0.75)
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
         seed = int(payload.get("seed", -1))
@@ -167,8 +174,12 @@ class LocalGPUWorker(Worker):
         chunks = []
         for it in range(n_iter):
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
-            u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
-                             width=width, sampler=sampler)
+            if init_u8 is not None:
+                u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
+                                 cfg_scale=cfg_scale)
+            else:
+                u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
+                                 width=width, sampler=sampler)
             chunks.append(u8)
             if eng.interrupted:
                 break
@@ -189,6 +200,27 @@ class LocalGPUWorker(Worker):
                 "parameters": {"batch_size": batch, "n_iter": n_iter, "steps": steps, "width": width, "height": height,
                                "sampler_name": sampler, "cfg_scale": cfg_scale, "seed": seed},
                 "info": json.dumps(info)}
+
+    @staticmethod
+    def _init_images_u8(init_images, batch: int, width: int, height: int) -> torch.Tensor:
+        """payload['init_images'] (PIL images, as sdwui holds them, or the API's base64 PNG strings) -> uint8
+        [batch, H, W, 3]; image i of the job uses init_images[i % len] (sdwui repeats a single init image per batch)."""
+        import numpy as np
+        from PIL import Image
+        out = []
+        for item in init_images:
+            if isinstance(item, str):
+                data = item.split(",", 1)[1] if item.startswith("data:") else item
+                item = Image.open(io.BytesIO(base64.b64decode(data)))
+            if isinstance(item, torch.Tensor):
+                arr = item.to(torch.uint8).cpu().numpy()
+            else:
+                img = item.convert("RGB")
+                if img.size != (width, height):
+                    img = img.resize((width, height), Image.LANCZOS)
+                arr = np.asarray(img)
+            out.append(torch.from_numpy(np.ascontiguousarray(arr)))
+        return torch.stack([out[i % len(out)] for i in range(batch)])
 
     @staticmethod
     def _png_b64(hwc_u8: torch.Tensor) -> str:

@@ -169,9 +169,19 @@ def quantize_u8(img, out):
     return out
 
 
+def image_to_nhwc(img_u8, out):
+    out[..., :3] = (img_u8.float() * (2.0 / 255.0) - 1.0).to(out.dtype)
+    return out
+
+
+def unpack_latent(moments, x, scale):
+    x.copy_(moments[..., :4].float() * scale)
+    return x
+
+
 ALL = ["linear", "pick_block_n", "conv2d", "attention", "groupnorm", "layernorm", "upsample2x", "softmax_rows_", "silu",
        "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step",
-       "quantize_u8"]
+       "quantize_u8", "image_to_nhwc", "unpack_latent"]
 
 
 def install(monkeypatch, ops_module):

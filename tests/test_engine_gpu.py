@@ -140,6 +140,31 @@ def test_txt2img_parity(mods, size, b, hw, steps, graphs):
     assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
 
 
+@pytest.mark.parametrize("size,b,px,steps", [("tiny", 3, 64, 8), ("sd15", 2, 512, 20)])
+def test_img2img_parity(mods, size, b, px, steps):
+    """config C3: VAE encode (posterior mean) + noise to t_enc + DDIM remainder + decode, vs the fp32 oracle."""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, size)
+    g = torch.Generator().manual_seed(4321)
+    init = torch.randint(0, 256, (b, px, px, 3), generator=g, dtype=torch.uint8)
+    tok = O.random_prompt_tokens(b, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    with torch.no_grad():
+        ref_u8, ref_x, ref_init = O.img2img(dsd, *cfgs, tok, neg, 1000, init, 0.75, steps=steps, device="cuda")
+    lat0 = eng.encode(init)
+    enc_rel = float((lat0 - ref_init).abs().max() / ref_init.abs().max())
+    eng.use_graphs = True
+    got = eng.img2img(tok, neg, 1000, init, 0.75, steps=steps, cfg_scale=7.0)
+    torch.cuda.synchronize()
+    eng.use_graphs = False
+    assert eng.last_unet_evals == int(0.75 * steps) - 1
+    du8 = (got.int() - ref_u8.int()).abs().float()
+    _record(f"img2img {size} b{b} {px}px steps{steps}", enc_rel_max=enc_rel, u8_mean=float(du8.mean()),
+            u8_max=float(du8.max()), u8_within2=float((du8 <= 2).float().mean()), u8_exact=float((du8 == 0).float().mean()))
+    assert enc_rel <= 2e-2
+    assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
+
+
 def test_euler_a_parity_tiny(mods):
     C, E, S, O = mods
     cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")

@@ -85,6 +85,28 @@ def test_worker_reply_schema_and_png_lane(env):
     assert wk.loaded_model == "m" and wk.response_time is not None and len(wk.eta_percent_error) <= 1
 
 
+def test_worker_img2img_request(env):
+    """img2img payload as the reference sends it: init_images are PIL images in p.__dict__ (worker.py:365-373)."""
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng)
+    import numpy as np
+    from PIL import Image
+    g = torch.Generator().manual_seed(5)
+    arr = torch.randint(0, 256, (64, 64, 3), generator=g, dtype=torch.uint8)
+    payload = {"prompt": "a b", "negative_prompt": "", "seed": 11, "subseed": 1, "subseed_strength": 0, "batch_size": 2,
+               "n_iter": 1, "steps": 8, "width": 64, "height": 64, "sampler_name": "DDIM", "cfg_scale": 7.0,
+               "denoising_strength": 0.75, "init_images": [Image.fromarray(arr.numpy())]}
+    wk.request(dict(payload), None, False)
+    r = wk.response
+    assert r is not None and tuple(r["tensors"].shape) == (2, 64, 64, 3) and wk.state == State.IDLE
+    from b200sd.factory import synthetic_tokens
+    vocab = eng.clip_cfg.vocab
+    direct = eng.img2img(synthetic_tokens(["a b"] * 2, vocab), synthetic_tokens([""] * 2, vocab), 11,
+                         arr[None].expand(2, -1, -1, -1).contiguous(), 0.75, steps=8, cfg_scale=7.0).cpu()
+    diff = (r["tensors"].int() - direct.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff == 0).float().mean()) >= 0.90
+
+
 def test_device_failure_marks_worker_unavailable(env):
     processing, mscripts, DistributedScript, eng, State, sh = env
 

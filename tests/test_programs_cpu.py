@@ -99,3 +99,25 @@ def test_sample_matches_oracle_euler_a(env):
     lat = eng.sample(cond, unc, nz[0], steps, 7.0, "Euler a", noises=nz[1:])
     z = lat.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def test_img2img_matches_oracle(env):
+    """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
+    C, E, O, cfgs, sd, eng = env
+    b, size, steps = 3, 32, 8   # the reduced VAE is f2: 32 px -> 16 x 16 latents; b=3 exercises the ragged chunk
+    g = torch.Generator().manual_seed(4321)
+    init = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    with torch.no_grad():
+        ref_u8, ref_x, ref_init = O.img2img(sd, *cfgs, tok, neg, 1000, init, 0.75, steps=steps)
+    lat0 = eng.encode(init)
+    assert float((lat0 - ref_init).abs().max()) <= 1e-3 * float(ref_init.abs().max())
+    sa, s1a, ts, rows = E.ddim_img2img_plan(steps, 0.75)
+    rsa, rs1a, rrows = O.ddim_img2img_coefficients(steps, 0.75)
+    assert abs(sa - rsa) < 1e-12 and abs(s1a - rs1a) < 1e-12 and len(rows) == len(rrows) == int(0.75 * steps) - 1
+    got = eng.img2img(tok, neg, 1000, init, 0.75, steps=steps, cfg_scale=7.0)
+    assert eng.last_unet_evals == len(rrows)
+    assert got.shape == ref_u8.shape
+    d = (got.int() - ref_u8.int()).abs()
+    assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99

@@ -44,10 +44,11 @@ def main():
     elif case == "attn":
         qkv = torch.zeros((nb, 4096, 3, 8, 64), device="cuda", dtype=torch.half)
         qkv[..., :40] = rnd(nb, 4096, 3, 8, 40)
+        qkv[:, :, 2, :, 40] = 1.0  # ones column of V, as the UNet's qkv bias produces it
         flat = qkv.reshape(nb, 4096, 1536)
         q, k, v = flat[..., :512], flat[..., 512:1024], flat[..., 1024:]
         o = torch.empty((nb, 4096, 320), device="cuda", dtype=torch.half)
-        fn = lambda: ops.attention(q, k, v, o, 8, 40, 64, 40 ** -0.5)  # noqa: E731
+        fn = lambda: ops.attention(q, k, v, o, 8, 40, 64, 40 ** -0.5, v_ones_col=True)  # noqa: E731
     elif case == "gn":
         x, o = rnd(nb, 4096, 320), torch.empty((nb, 4096, 320), device="cuda", dtype=torch.half)
         st = torch.zeros((nb, 32, 2), device="cuda")
