@@ -17,23 +17,26 @@
 //   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane, and the two warps of a lane
 //             quarter split the 64 kv columns of the tile in halves.
 // S is buffered sb = 3 deep in TMEM when d_pad == 64 (3 x 64 + 64 columns for O = 256, two CTAs per SM), else
-// 2 deep; P is double buffered in shared memory.  Q K_{j+sb}^T is issued as soon as softmax j has consumed its S
-// buffer and P_j V_j runs while softmax j+1 is already exponentiating, so in steady state the softmax warps wait
-// neither for the tensor pipe nor for its completion latency — which matters because for d = 40 this kernel is
-// bound by the exp (MUFU) rate and by instruction issue, not by the MMAs (16 exps per 96 MMA-FLOPs).
-// Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) uses the running maximum of earlier tiles while the
-// tile's own maximum is tracked; only if that exceeds m_used by more than 2^8 (P would leave fp16's comfortable
-// range) is the tile redone after rescaling O in TMEM — a vote between the two warps of a row quarter, rare after
-// the first tile.  Each S element is read from TMEM once, the TMEM load of the next 16 columns is in flight while
-// the current 16 are exponentiated, and with a ones column in V (v_ones_col) the row sums come out of the P.V MMA
-// instead of CUDA-core adds.
+// 2 deep; P is buffered pb = 3 (or 2) deep in shared memory.  Q K_{j+sb}^T is issued as soon as softmax j has consumed
+// its S buffer and P_j V_j runs while softmax j+1 .. j+pb-1 are already exponentiating, so a fast softmax warp can run
+// pb tiles ahead of the slowest one before it has to wait — which matters because for d = 40 this kernel is bound by
+// the exp (MUFU) rate and by instruction issue, not by the MMAs (16 exps per 96 MMA-FLOPs).
+// Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) uses the running maximum of earlier tiles; the
+// maximum of the produced P values is tracked on the packed 16-bit pairs (3-input VHMNMX), and only if it exceeds 2^8
+// (P would leave fp16's comfortable range) is the tile redone with an exact new maximum after rescaling O in TMEM — a
+// vote between the two warps of a row quarter, rare after the first tile.  S*scale - m is a packed FFMA2, each S
+// element is read from TMEM once, the TMEM load of the next 16 columns is in flight while the current 16 are
+// exponentiated, and with a ones column in V (v_ones_col) the row sums come out of the P.V MMA instead of CUDA-core
+// adds.
 //
 // mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
-//   o_full[2]  P.V of tile j commits to o_full[j&1].  Every softmax thread waits for tile j-2 on o_full[j&1] before
-//              it overwrites P[j&1] (tcgen05 MMAs complete in issue order, but S[j] being ready only proves P.V of
-//              tile j-sb+... older tiles), so it observes every phase of both barriers; the rare-path wait for tile
-//              j-1 and the final wait are therefore at most one phase behind.
-//   s_full[sb] / p_full[2] / ring barriers: one waiter each side, strictly alternating.
+//   o_full[pb] P.V of tile j commits to o_full[j%pb].  Every softmax thread waits for tile j-pb on o_full[j%pb] before
+//              it overwrites P[j%pb] (S[j] being ready proves nothing about P.V of that tile), so it observes every
+//              phase of every o_full barrier; the rare-path wait for tile j-1 and the final wait are therefore at most
+//              one phase behind, and P.V of tile j cannot complete before the waiter itself has arrived on p_full.
+//   s_full[sb] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
+// Waits in the softmax loop use try_wait with a suspend hint: a polling loop without it steals issue slots from the
+// warps doing the exponentials (measured: a polling TMA producer cost 25 % of this kernel's time).
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -51,6 +54,7 @@ constexpr uint32_t kKvChunkBytes = kKv * 128;        // 64 rows x 64 halfs
 constexpr uint32_t kPBytes = kQTile * kKv * 2;       // one K-major SWIZZLE_128B atom: 128 rows x 64 halfs
 constexpr int kMaxRing = 4;
 constexpr int kMaxSBufs = 3;
+constexpr int kMaxPBufs = 3;
 
 struct AttnParams {
   int B, heads, Sq, Skv, d, d_pad;
@@ -58,6 +62,7 @@ struct AttnParams {
   int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
   int chunks;        // d_pad / 64
   int s_bufs;        // S buffers in TMEM (2 or 3); O lives behind them at column s_bufs * 64
+  int p_bufs;        // P buffers in shared memory (2 or 3)
   int k_stages, v_stages;  // K / V ring depths (<= kMaxRing)
   int tmem_cols;
   int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
@@ -72,7 +77,7 @@ struct __align__(16) AttnShared {
   uint64_t q_full;
   uint64_t k_full[kMaxRing], k_empty[kMaxRing];
   uint64_t v_full[kMaxRing], v_empty[kMaxRing];
-  uint64_t s_full[kMaxSBufs], p_full[2], o_full[2];
+  uint64_t s_full[kMaxSBufs], p_full[kMaxPBufs], o_full[kMaxPBufs];
   uint32_t tmem_base;
   uint32_t pad;
   float xch[2][kQTile];  // row maxima / sums exchanged between the two column halves
@@ -142,27 +147,70 @@ __device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int n
   return mx;
 }
 
-// exponentiate 16 columns, track their maximum / sum, write them as two 16-byte chunks of the swizzled P atom.
-// p_row = shared-space address of my row of the P buffer, rx = row & 7 (the 128-byte swizzle phase).
+// Blackwell packed fp32 FMA (FFMA2): (a.x, a.y) * (b.x, b.y) + (c.x, c.y)
+__device__ __forceinline__ uint64_t pack_f2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void ffma2(float& x, float& y, uint32_t a_lo, uint32_t a_hi, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f2(a_lo, a_hi)), "l"(b), "l"(c));
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(d));
+  x = __uint_as_float(lo);
+  y = __uint_as_float(hi);
+}
+// running maximum over packed 16-bit pairs (two of these fuse into one 3-input VHMNMX)
+template <bool kBf16>
+__device__ __forceinline__ uint32_t max3_h2(uint32_t m, uint32_t a, uint32_t b) {
+  uint32_t r;
+  if constexpr (kBf16) {
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(a));
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(b));
+  } else {
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(m), "r"(a));
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(b));
+  }
+  return r;
+}
+template <bool kBf16>
+__device__ __forceinline__ float h2_hmax(uint32_t v) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+    return fmaxf(__low2float(h), __high2float(h));
+  } else {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return fmaxf(__low2float(h), __high2float(h));
+  }
+}
+
+// P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
+constexpr float kPRedo = 256.0f;
+
+// exponentiate 16 columns, track the maximum of the produced P values (packed, 16-bit) / their sum, and write them as
+// two 16-byte chunks of the swizzled P atom.  p_row = shared-space address of my row of the P buffer, rx = row & 7
+// (the 128-byte swizzle phase); scale2 / negm2 = (scale_log2, scale_log2) / (-m_used, -m_used) packed for FFMA2.
 template <bool kFull, bool kBf16, bool kSum>
 __device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint32_t p_row, uint32_t rx, int cbase, int nvalid,
-                                          float scale_log2, float m_used, float& tile_max, float& lsum) {
+                                          uint64_t scale2, uint64_t negm2, uint32_t& pmax, float& lsum) {
   uint32_t pk[8];
-  float mx = tile_max, acc = 0.f;
+  float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
-    float a = __uint_as_float(v[i]), b2 = __uint_as_float(v[i + 1]);
-    float ea = fast_exp2(fmaf(a, scale_log2, -m_used));
-    float eb = fast_exp2(fmaf(b2, scale_log2, -m_used));
+    float xa, xb;
+    ffma2(xa, xb, v[i], v[i + 1], scale2, negm2);
+    float ea = fast_exp2(xa);
+    float eb = fast_exp2(xb);
     if (!kFull) {
-      if (cbase + i >= nvalid) { a = -INFINITY; ea = 0.f; }
-      if (cbase + i + 1 >= nvalid) { b2 = -INFINITY; eb = 0.f; }
+      if (cbase + i >= nvalid) ea = 0.f;
+      if (cbase + i + 1 >= nvalid) eb = 0.f;
     }
-    mx = fmax3(mx, a, b2);
     if constexpr (kSum) acc += ea + eb;
     pk[i >> 1] = pack_h2<kBf16>(ea, eb);
   }
-  tile_max = mx;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) pmax = max3_h2<kBf16>(pmax, pk[i], pk[i + 1]);
   if constexpr (kSum) lsum += acc;
   const uint32_t chunk16 = static_cast<uint32_t>(cbase >> 3);  // 8 halfs per 16-byte chunk
   sts128(p_row + ((chunk16 ^ rx) << 4), pk[0], pk[1], pk[2], pk[3]);
@@ -170,16 +218,21 @@ __device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint32_t p_ro
 }
 
 // One pass over my 32 columns: the TMEM load of the second 16 is in flight while the first 16 are processed.
+// Returns true when some P value left the comfortable range (the caller votes on a redo).
 template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax_half(uint32_t tmem_row, uint32_t p_row, uint32_t rx, int col0, int nvalid,
-                                             float scale_log2, float m_used, float& tile_max, float& lsum) {
+__device__ __forceinline__ bool softmax_half(uint32_t tmem_row, uint32_t p_row, uint32_t rx, int col0, int nvalid,
+                                             float scale_log2, float m_used, float& lsum) {
   uint32_t va[16], vb[16];
   tmem_ld_x16(tmem_row + col0, va);
+  const uint64_t scale2 = pack_f2(__float_as_uint(scale_log2), __float_as_uint(scale_log2));
+  const uint64_t negm2 = pack_f2(__float_as_uint(-m_used), __float_as_uint(-m_used));
+  uint32_t pmax = 0u;
   tmem_ld_wait();
   tmem_ld_x16(tmem_row + col0 + 16, vb);
-  softmax16<kFull, kBf16, kSum>(va, p_row, rx, col0, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(va, p_row, rx, col0, nvalid, scale2, negm2, pmax, lsum);
   tmem_ld_wait();
-  softmax16<kFull, kBf16, kSum>(vb, p_row, rx, col0 + 16, nvalid, scale_log2, m_used, tile_max, lsum);
+  softmax16<kFull, kBf16, kSum>(vb, p_row, rx, col0 + 16, nvalid, scale2, negm2, pmax, lsum);
+  return h2_hmax<kBf16>(pmax) > kPRedo;
 }
 
 template <bool kBf16, bool kSum>
@@ -192,39 +245,44 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
   const uint32_t o_row = tmem_base + static_cast<uint32_t>(p.s_bufs * kKv) + lane_base;
   const uint32_t p_row0 = smem_u32(sP) + static_cast<uint32_t>(r) * 128u;
   const uint32_t rx = static_cast<uint32_t>(r) & 7u;
+  const uint32_t a_s_full = smem_u32(&sh->s_full[0]);
+  const uint32_t a_p_full = smem_u32(&sh->p_full[0]);
+  const uint32_t a_o_full = smem_u32(&sh->o_full[0]);
   const int col0 = half * 32;
+  const int s_bufs = p.s_bufs, p_bufs = p.p_bufs, skv = p.Skv;
+  const float scale_log2 = p.scale_log2;
   float m_used = -INFINITY;  // scaled log2 domain
   float l = 0.f;
-  int sb = 0;                // S buffer of tile j and the parity of its s_full phase
-  uint32_t s_par = 0;
+  int sb = 0, pb = 0;        // S / P buffer of tile j and the parities of their current barrier phases
+  uint32_t s_par = 0, p_par = 0;
   for (int j = 0; j < nkv; ++j) {
-    const int pb = j & 1;
-    const int nvalid = min(kKv, p.Skv - j * kKv);
+    const int nvalid = min(kKv, skv - j * kKv);
     const bool full = nvalid == kKv;
     const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
     const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
-    mbar_wait(&sh->s_full[sb], s_par, 17);
-    // P[pb] was last read by P.V of tile j-2 (issued two softmax tiles ago, normally long complete)
-    if (j >= 2) mbar_wait(&sh->o_full[pb], ((j >> 1) - 1) & 1, 20);
+    mbar_wait_a(a_s_full + sb * 8, s_par, 17);
+    // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
+    if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
     tc_fence_after();
     if (j == 0) {
       const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
       sh->xch[half][r] = mx;
       pair_bar_sync(quarter);
-      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * p.scale_log2;
+      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * scale_log2;
     }
-    float tile_max = -INFINITY, lsum = 0.f;
-    if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-    else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-    const float tm = tile_max * p.scale_log2;
-    if (pair_bar_or(quarter, tm > m_used + 8.0f)) {
+    float lsum = 0.f;
+    const bool over = full ? softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum)
+                           : softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
+    if (pair_bar_or(quarter, over)) {
       // rare path: the running maximum moved by more than 2^8 for some row of this quarter
-      sh->xch[half][r] = tm;
+      const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
+      sh->xch[half][r] = mx * scale_log2;
       pair_bar_sync(quarter);
       const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
       const float alpha = fast_exp2(m_used - m_new);
       if (j > 0) {
-        mbar_wait(&sh->o_full[pb ^ 1], ((j - 1) >> 1) & 1, 18);  // P.V of the previous tile must have landed in O
+        // P.V of the previous tile must have landed in O
+        mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
         tc_fence_after();
         for (int c = half; c < p.resc_cols / 16; c += 2) {
           uint32_t o[16];
@@ -238,22 +296,25 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       }
       l *= alpha;
       m_used = m_new;
-      tile_max = -INFINITY;
       lsum = 0.f;
-      if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
-      else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, p.scale_log2, m_used, tile_max, lsum);
+      if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
+      else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
     }
     l += lsum;
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive(&sh->p_full[pb]);
-    if (++sb == p.s_bufs) {
+    mbar_arrive_a(a_p_full + pb * 8);
+    if (++sb == s_bufs) {
       sb = 0;
       s_par ^= 1u;
     }
+    if (++pb == p_bufs) {
+      pb = 0;
+      p_par ^= 1u;
+    }
   }
   // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
-  mbar_wait(&sh->o_full[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1, 19);
+  mbar_wait_a(a_o_full + ((nkv - 1) % p_bufs) * 8, ((nkv - 1) / p_bufs) & 1, 19);
   tc_fence_after();
   if constexpr (kSum) {
     pair_bar_sync(quarter);  // both threads of every pair are past their last xch read
@@ -297,8 +358,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t q_bytes = static_cast<uint32_t>(p.chunks) * kQChunkBytes;
   const uint32_t kv_bytes = static_cast<uint32_t>(p.chunks) * kKvChunkBytes;
   uint8_t* sQ = smem;
-  uint8_t* sP = sQ + q_bytes;  // 2 x 16 KB
-  uint8_t* sK = sP + 2 * kPBytes;
+  uint8_t* sP = sQ + q_bytes;  // p_bufs x 16 KB
+  uint8_t* sK = sP + p.p_bufs * kPBytes;
   uint8_t* sV = sK + p.k_stages * kv_bytes;
   AttnShared* sh = reinterpret_cast<AttnShared*>(sV + p.v_stages * kv_bytes);
 
@@ -322,7 +383,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&sh->v_empty[s], 1);
     }
     for (int s = 0; s < kMaxSBufs; ++s) mbar_init(&sh->s_full[s], 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxPBufs; ++s) {
       mbar_init(&sh->p_full[s], kSoftmaxThreads);
       mbar_init(&sh->o_full[s], 1);
     }
@@ -401,14 +462,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       mbar_wait(&sh->q_full, 0, 13);
       for (int i = 0; i < p.s_bufs && i < nkv; ++i) issue_qk();
-      int vs = 0;
-      uint32_t v_par = 0;
+      int vs = 0, pb = 0;
+      uint32_t v_par = 0, p_par = 0;
       for (int j = 0; j < nkv; ++j) {
-        const int pb = j & 1;
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
         // ---- O (+)= P_j V_j ----
-        mbar_wait(&sh->p_full[pb], (j >> 1) & 1, 15);
+        mbar_wait(&sh->p_full[pb], p_par, 15);
         mbar_wait(&sh->v_full[vs], v_par, 16);
         tc_fence_after();
         {
@@ -428,6 +488,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (++vs == p.v_stages) {
           vs = 0;
           v_par ^= 1u;
+        }
+        if (++pb == p.p_bufs) {
+          pb = 0;
+          p_par ^= 1u;
         }
         // ---- softmax j has released its S buffer: refill it s_bufs tiles ahead ----
         if (qj < nkv) issue_qk();
@@ -457,10 +521,11 @@ static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
 
 // tuning overrides for experiments: B200SD_ATTN_SBUFS=2|3, B200SD_ATTN_RING="k,v" (ring depths, 1..4 each)
-static void attn_env(int* s_bufs, int* k_st, int* v_st) {
-  static int cached = 0, e_sb = 0, e_k = 0, e_v = 0;
+static void attn_env(int* s_bufs, int* p_bufs, int* k_st, int* v_st) {
+  static int cached = 0, e_sb = 0, e_pb = 0, e_k = 0, e_v = 0;
   if (!cached) {
     if (const char* s = std::getenv("B200SD_ATTN_SBUFS")) e_sb = std::atoi(s);
+    if (const char* s = std::getenv("B200SD_ATTN_PBUFS")) e_pb = std::atoi(s);
     if (const char* s = std::getenv("B200SD_ATTN_RING")) {
       e_k = std::atoi(s);
       const char* c = s;
@@ -470,6 +535,7 @@ static void attn_env(int* s_bufs, int* k_st, int* v_st) {
     cached = 1;
   }
   *s_bufs = e_sb;
+  *p_bufs = e_pb;
   *k_st = e_k;
   *v_st = e_v;
 }
@@ -511,17 +577,23 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   if (v_ones_col && d >= d_pad) return B200SD_ERR_INVALID;  // needs a free pad column
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
-  int e_sb, e_k, e_v;
-  attn_env(&e_sb, &e_k, &e_v);
+  int e_sb, e_pb, e_k, e_v;
+  attn_env(&e_sb, &e_pb, &e_k, &e_v);
   // three S buffers when they fit next to O in 256 TMEM columns (d_pad == 64: two CTAs per SM stay possible)
   p.s_bufs = (3 * kKv + p.dpv <= 256) ? 3 : 2;
   if (e_sb == 2 || (e_sb == 3 && 3 * kKv + p.dpv <= 512)) p.s_bufs = e_sb;
   p.tmem_cols = (p.s_bufs * kKv + p.dpv <= 256) ? 256 : 512;
-  // ring depths: K 3 / V 2 when that keeps two CTAs per SM, otherwise 2 / 2
+  // shared memory: Q + p_bufs P atoms + K/V rings.  Three P buffers and a K 3 / V 2 ring when that keeps two CTAs per
+  // SM (d_pad == 64) or simply fits (one CTA per SM), otherwise two and 2 / 2.
   const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
-  const size_t fixed = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + 2 * kPBytes + sizeof(AttnShared) + 64;
+  const size_t base = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + sizeof(AttnShared) + 64;
   const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
-  p.k_stages = (p.tmem_cols <= 256 && fixed + 5 * kvt <= half_sm) ? 3 : 2;
+  const size_t budget = (p.tmem_cols <= 256 && base + 2 * kPBytes + 4 * kvt <= half_sm)
+                            ? half_sm : static_cast<size_t>(g_attn_max_smem);
+  p.p_bufs = (base + 3 * kPBytes + 4 * kvt <= budget) ? 3 : 2;
+  if (e_pb == 2 || e_pb == 3) p.p_bufs = e_pb;
+  const size_t fixed = base + static_cast<size_t>(p.p_bufs) * kPBytes;
+  p.k_stages = (fixed + 5 * kvt <= budget) ? 3 : 2;
   p.v_stages = 2;
   if (e_k >= 1 && e_k <= kMaxRing) p.k_stages = e_k;
   if (e_v >= 1 && e_v <= kMaxRing) p.v_stages = e_v;

@@ -477,6 +477,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  {
+    static int cap = -1;  // experiment knob: B200SD_GEMM_STAGES caps the operand ring depth
+    if (cap < 0) {
+      const char* e = getenv("B200SD_GEMM_STAGES");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap >= 2 && stages > cap) stages = cap;
+  }
   if (stages < 2) return B200SD_ERR_UNSUPPORTED;
   p.num_stages = stages;
   size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + staging + sizeof(GemmBarriers) + 64;

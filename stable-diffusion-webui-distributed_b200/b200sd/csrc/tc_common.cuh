@@ -78,6 +78,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Shared-space-address variants for hot loops: no generic->shared conversion per call, and the try_wait carries a
+// suspend-time hint so a waiting warp sleeps in hardware instead of re-issuing the poll (which would compete for issue
+// slots with the warps that do the math).
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0, ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    if (++spins > (B200SD_SPIN_LIMIT >> 4)) {
+      printf("b200sd: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA loads (tile mode). Coordinates innermost first. OOB elements are zero-filled.
 // ----------------------------------------------------------------------------------------------

@@ -11,8 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-webui-distributed_b200"))
 
-CONFIGS = [  # (S buffers, "k,v" ring depths)
-    ("3", "3,2"), ("3", "2,2"), ("3", "3,3"), ("3", "4,3"), ("2", "2,2"), ("2", "3,2"), ("2", "4,3"),
+CONFIGS = [  # (S buffers, P buffers, "k,v" ring depths)
+    ("3", "3", "3,2"), ("3", "3", "2,2"), ("3", "2", "3,2"), ("3", "2", "2,2"), ("2", "2", "2,2"), ("2", "3", "2,2"),
+    ("3", "2", "4,3"),
 ]
 
 
@@ -42,15 +43,15 @@ def one():
     ref = torch.softmax(qq @ kk.T * 40 ** -0.5, dim=-1) @ vv
     err = float((o[0].reshape(4096, 8, 40)[:, 3].float() - ref).abs().max())
     exps = nb * 8 * 4096 * 4096
-    print(f"sbufs={os.environ.get('B200SD_ATTN_SBUFS', '-')} ring={os.environ.get('B200SD_ATTN_RING', '-')} "
+    print(f"sbufs={os.environ.get('B200SD_ATTN_SBUFS', '-')} pbufs={os.environ.get('B200SD_ATTN_PBUFS', '-')} ring={os.environ.get('B200SD_ATTN_RING', '-')} "
           f"nb={nb}: {ms:.4f} ms  ({exps / ms / 1e9:.2f} Texp/s)  max_err={err:.2e}", flush=True)
 
 
 def main():
     if "--one" in sys.argv:
         return one()
-    for sb, ring in CONFIGS:
-        env = dict(os.environ, B200SD_ATTN_SBUFS=sb, B200SD_ATTN_RING=ring)
+    for sb, pb, ring in CONFIGS:
+        env = dict(os.environ, B200SD_ATTN_SBUFS=sb, B200SD_ATTN_PBUFS=pb, B200SD_ATTN_RING=ring)
         subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env=env, check=False, timeout=300)
     subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], env={k: v for k, v in os.environ.items()
                                                                               if not k.startswith("B200SD_ATTN")},
