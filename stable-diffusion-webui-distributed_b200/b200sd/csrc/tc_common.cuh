@@ -50,8 +50,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// B200SD_WAIT_HINT_NS > 0: every mbar_wait carries a suspend-time hint (the waiting thread sleeps in hardware and is
+// woken by barrier traffic) instead of re-issuing the poll back to back.
+#ifndef B200SD_WAIT_HINT_NS
+#define B200SD_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if B200SD_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(B200SD_WAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
@@ -61,6 +77,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (CUDA error on the host) instead of hanging the GPU box.
