@@ -121,13 +121,16 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int m
 }
 
 // One epilogue group's share of a tile.  `uses` counts how often each residual buffer of this group has been
-// filled so far (mbarrier phase bookkeeping, identical in all 128 threads).
+// filled so far (mbarrier phase bookkeeping, identical in all 128 threads).  `chunk_count` is the number of chunks this
+// group has staged since the kernel started: the two staging buffers alternate ACROSS tiles, never per tile — the TMA
+// store of a tile's last chunk may still be reading its buffer when the next tile's first chunk is written, and only
+// the buffer of the store before that is known to be drained (bulk_wait_read precedes every store).
 template <bool kBf16>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const CUtensorMap* tmD, const CUtensorMap* tmR,
                                               GemmBarriers* bars, uint8_t* stage_d, uint8_t* stage_r,
                                               uint64_t* tmem_full_bar, uint32_t full_parity, uint32_t tmem_acc,
                                               int m_tile, int n_tile, int quarter, int group, int lane,
-                                              uint32_t (&uses)[2]) {
+                                              uint32_t (&uses)[2], uint32_t& chunk_count) {
   const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
   const bool leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
   const TileCoord tc = tile_coord(p, m_tile);
@@ -159,16 +162,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
     bias_row = p.bias + (row / p.bias_group_rows) * p.N;
   }
 
+  const uint32_t base = chunk_count;
   if (p.has_residual && leader) {  // two chunks ahead; the buffers are free (last tile's barriers passed)
-    if (group < nchunks) load_residual(0, group);
-    if (group + 2 < nchunks) load_residual(1, group + 2);
+    if (group < nchunks) load_residual(base & 1u, group);
+    if (group + 2 < nchunks) load_residual((base + 1u) & 1u, group + 2);
   }
   mbar_wait(tmem_full_bar, full_parity, 4);
   tc_fence_after();
 
-  int ci = 0;
+  uint32_t ci = 0;
   for (int c = group; c < nchunks; c += 2, ++ci) {
-    const int buf = ci & 1;
+    const int buf = static_cast<int>((base + ci) & 1u);
     uint32_t v[32];
     tmem_ld_x32(taddr_row + c * kChunkCols, v);
     tmem_ld_wait();
@@ -239,6 +243,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       if (p.has_residual && c + 4 < nchunks) load_residual(buf, c + 4);  // everyone is past reading this buffer
     }
   }
+  chunk_count = base + ci;
 }
 
 // kPair = false: one CTA per tile (M = 128).
@@ -381,6 +386,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;      // TMEM lane quarter this warp may access
     const int group = (warp - 2) >> 2;  // warps 2-5 / 6-9: chunks group, group+2, ...
     uint32_t uses[2] = {0u, 0u};
+    uint32_t chunk_count = 0u;
     int it = 0;
     for (int item = first_item; item < num_items; item += item_step, ++it) {
       const int acc = it & 1;
@@ -390,10 +396,10 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
       if (p.is_bf16)
         epilogue_tile<true>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                            n_tile, quarter, group, lane, uses);
+                            n_tile, quarter, group, lane, uses, chunk_count);
       else
         epilogue_tile<false>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                             n_tile, quarter, group, lane, uses);
+                             n_tile, quarter, group, lane, uses, chunk_count);
       tc_fence_before();
       // the MMA issuer (leader CTA) may overwrite this accumulator once BOTH CTAs have drained theirs
       if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));

@@ -46,6 +46,32 @@ def test_linear_plain(ops, m, n, k, bn):
     assert_close(f"linear_plain m{m} n{n} k{k} bn{bn}", out, ref, atol=2e-2, rtol=2e-3)
 
 
+@pytest.mark.parametrize("residual", [False, True])
+def test_linear_many_short_tiles_per_cta(ops, residual):
+    """Persistent CTAs walking many tiles whose MMA phase is one k-block long, with an odd number of 32-column chunks
+    per epilogue group (bn = 160 -> 3 + 2): the TMA store of a tile's last chunk is still in flight when the next
+    tile's first chunk is staged.  Regression test for the staging-buffer reuse across tiles (exact compare, repeated)."""
+    g = _gen(11)
+    m, n, k = 148 * 128 * 8, 320, 64
+    a = _rand((m, k), g)
+    w = _rand((n, k), g, 1.0 / math.sqrt(k))
+    res = _rand((m, n), g) if residual else None
+    ref = a.float() @ w.float().t()
+    if residual:
+        ref = ref + res.float()
+    ref16 = ref.half()
+    out = torch.empty((m, n), device="cuda", dtype=torch.float16)
+    worst = 0
+    for _ in range(5):
+        out.fill_(float("nan"))
+        ops.linear(a, w, out, residual=res, block_n=160)
+        torch.cuda.synchronize()
+        # fp32 accumulation of a 64-term dot product rounds to the same half as the reference up to 1 ulp
+        bad = int(((out.float() - ref16.float()).abs() > 2e-3 * ref16.float().abs() + 2e-3).sum())
+        worst = max(worst, bad)
+    assert worst == 0, f"{worst} corrupted outputs"
+
+
 def test_linear_bias_residual_pitched(ops):
     g = _gen(1)
     m, n, k = 1024, 640, 640
