@@ -345,7 +345,6 @@ def kernel_rooflines(eng, b, pk):
     ops.select_step(plan.table, plan.step * 0, plan.unet.cur_bias)
     torch.cuda.synchronize()
     recs = []
-    plan.unet.stats_all.zero_()
     for fn, a, k in plan.unet.ops:
         name = getattr(fn, "__name__", "op")
         name = "groupnorm" if name == "<lambda>" else name

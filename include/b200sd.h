@@ -74,8 +74,12 @@ int b200sd_attention(const void* Q, long long ldq, const void* K, long long ldk,
 
 /* ---- HBM-bound ops ------------------------------------------------------------------------------- */
 
-/* GroupNorm statistics: stats[n][g] += (sum, sumsq) over the group's channels and all HW pixels.
- * `stats` ([NB][G][2] fp32) must be zero on entry. (upstream GroupNorm32 / Normalize) */
+/* GroupNorm statistics: stats[n][g] = (sum, sumsq) over the group's channels and all HW pixels, bit-reproducible
+ * run to run (per-CTA partial sums combined in a fixed order; no floating-point atomics).
+ * `stats` holds b200sd_groupnorm_stats_floats() floats: the [NB][G][2] results first, then the kernel's scratch.
+ * The buffer must be zero-filled once when it is allocated (the scratch contains arrival counters that the kernel
+ * leaves at zero); it may be shared by successive calls on one stream. (upstream GroupNorm32 / Normalize) */
+long long b200sd_groupnorm_stats_floats(int NB, int HW, int C, int G);
 int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, int HW, int C, int G, float* stats, int dtype,
                            void* stream);
 /* Y = (X - mean) * rstd * gamma + beta, optional SiLU; mean/rstd from `stats`. */

@@ -51,6 +51,7 @@ def load(path: str = LIB_PATH) -> ctypes.CDLL:
         if not hasattr(lib, name):
             raise B200SDError(f"{path} does not export {name}")
     lib.b200sd_version.restype = ctypes.c_char_p
+    lib.b200sd_groupnorm_stats_floats.restype = ctypes.c_longlong
     return lib
 
 

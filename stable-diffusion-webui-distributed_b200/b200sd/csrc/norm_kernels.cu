@@ -99,13 +99,49 @@ __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long 
     sh[i] = a;  // row 0 is only read at index i by this same thread: no hazard
   }
   __syncthreads();
+  // Deterministic cross-CTA reduction (no float atomics): every CTA publishes its 2G group partials; the CTA that
+  // arrives last for image n (integer ticket) adds all of them in CTA-index order and writes stats[n].  The ticket
+  // counter is left at zero again, so the scratch area needs zeroing only once, at allocation.
   const int cpg = C / G;
+  const int parts = gridDim.x;
+  float* out_stats = stats + static_cast<long long>(n) * G * 2;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats + static_cast<long long>(gridDim.y) * G * 2);
+  float* partials = stats + static_cast<long long>(gridDim.y) * G * 2 + gridDim.y +
+                    static_cast<long long>(n) * parts * 2 * G;
   for (int g = tid; g < 2 * G; g += nthreads) {
     const int grp = g >> 1, st = g & 1;
     float a = 0.f;
     for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) a += sh[st * C + c];
-    atomicAdd(&stats[(static_cast<long long>(n) * G + grp) * 2 + st], a);
+    if (parts == 1) out_stats[g] = a;
+    else __stcg(&partials[static_cast<long long>(blockIdx.x) * 2 * G + g], a);
   }
+  if (parts == 1) return;
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&tickets[n], 1u) == static_cast<unsigned int>(parts - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  // slices of the CTA-index range are summed by different threads, then combined in slice order: still a fixed order
+  const int items = 2 * G;
+  const int slices = max(1, min(nthreads / items, 8));
+  float* red = sh;  // [slices][items], the channel totals are dead by now
+  for (int idx = tid; idx < slices * items; idx += nthreads) {
+    const int item = idx % items, sl = idx / items;
+    const int per = (parts + slices - 1) / slices;
+    const int lo = sl * per, hi = min(parts, lo + per);
+    float a = 0.f;
+    for (int k = lo; k < hi; ++k) a += __ldcg(&partials[static_cast<long long>(k) * items + item]);
+    red[sl * items + item] = a;
+  }
+  __syncthreads();
+  for (int g = tid; g < items; g += nthreads) {
+    float a = 0.f;
+    for (int sl = 0; sl < slices; ++sl) a += red[sl * items + g];
+    out_stats[g] = a;
+  }
+  if (tid == 0) tickets[n] = 0u;
 }
 
 template <bool kBf16>
@@ -256,6 +292,15 @@ static void launch_ln(int vpt, int blocks, size_t sh, cudaStream_t st, const uin
 }  // namespace b200sd
 
 using namespace b200sd;
+
+extern "C" long long b200sd_groupnorm_stats_floats(int NB, int HW, int C, int G) {
+  if (NB <= 0 || HW <= 0 || G <= 0) return 0;
+  dim3 block, grid;
+  int ppc;
+  if (gn_geometry(NB, HW, C, block, grid, ppc) != B200SD_OK) return -1;
+  // [NB][G][2] results | NB arrival tickets | [NB][CTAs per image][2G] partial sums
+  return static_cast<long long>(NB) * G * 2 + NB + static_cast<long long>(NB) * grid.x * 2 * G;
+}
 
 extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, int HW, int C, int G, float* stats,
                                       int dtype, void* stream) {

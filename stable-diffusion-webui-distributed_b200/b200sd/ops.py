@@ -144,12 +144,23 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     return out
 
 
+def groupnorm_stats_floats(nb: int, hw: int, c: int, groups: int) -> int:
+    """fp32 elements a `stats` buffer for groupnorm() must hold (results + the reduction's scratch)"""
+    n = int(_lib.lib().b200sd_groupnorm_stats_floats(nb, hw, c, groups))
+    if n < 0:
+        raise _lib.B200SDError(f"groupnorm: unsupported shape C={c}")
+    return n
+
+
 def groupnorm(x: torch.Tensor, out: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
               groups: int, eps: float, silu: bool):
-    """x, out [NB, HW, C] (pitch = stride(1)); stats [NB, groups, 2] fp32, zero on entry."""
+    """x, out [NB, HW, C] (pitch = stride(1)); stats: flat fp32 buffer of groupnorm_stats_floats(...) elements,
+    zero-filled once at allocation (may be shared by successive calls on one stream); its first NB*groups*2 elements
+    receive (sum, sumsq) per (image, group) — deterministically, run to run."""
     nb, hw, c = x.shape
     assert x.stride(2) == 1 and out.stride(2) == 1 and x.stride(0) == hw * x.stride(1)
-    assert stats.dtype == torch.float32 and stats.numel() >= nb * groups * 2
+    assert stats.dtype == torch.float32 and stats.is_contiguous()
+    assert stats.numel() >= groupnorm_stats_floats(nb, hw, c, groups), "stats buffer too small"
     L = _lib.lib()
     rc = L.b200sd_groupnorm_stats(_p(x), ctypes.c_longlong(x.stride(1)), nb, hw, c, groups, _p(stats), _dt(x), _stream())
     check(rc, "b200sd_groupnorm_stats")

@@ -192,12 +192,14 @@ class UNetProgram:
         self.eps = torch.zeros((n, h * wd, 32), device=self.dev, dtype=self.dt)    # eps channels 0..3
         self.cur_bias = torch.zeros((w.emb_total,), device=self.dev, dtype=torch.float32)
         self.gn_stats: List[torch.Tensor] = []
+        self.gn_need = 0
         self.ctx_kv: Dict[str, torch.Tensor] = {}
         self.ops: List = []
         self._build()
-        self.stats_all = torch.zeros((len(self.gn_stats), n, 32, 2), device=self.dev, dtype=torch.float32)
-        for i, holder in enumerate(self.gn_stats):
-            holder[0] = self.stats_all[i]
+        # one statistics buffer serves every GroupNorm (they run back to back on one stream); zeroed once, here
+        self.stats_all = torch.zeros((max(1, self.gn_need),), device=self.dev, dtype=torch.float32)
+        for holder in self.gn_stats:
+            holder[0] = self.stats_all
 
     # ---------------------------------------------------------------- per-request precompute
     def set_context(self, ctx: torch.Tensor):
@@ -215,6 +217,7 @@ class UNetProgram:
     def _gn(self, x, out, name, eps, silu):
         holder = [None]
         self.gn_stats.append(holder)
+        self.gn_need = max(self.gn_need, ops.groupnorm_stats_floats(x.shape[0], x.shape[1], x.shape[2], 32))
         g, b = self.w.t[name + ".g"], self.w.t[name + ".beta"]
         self._emit(lambda: ops.groupnorm(x, out, holder[0], g, b, 32, eps, silu))
 
@@ -380,7 +383,6 @@ class UNetProgram:
 
     # ---------------------------------------------------------------- execution
     def run(self):
-        self.stats_all.zero_()
         for fn, a, k in self.ops:
             fn(*a, **k)
 

@@ -125,11 +125,13 @@ class _VAEProgram:
         self.pool = Pool(self.dev, self.dt)
         self.ops: List = []
         self.gn_stats: List = []
+        self.gn_need = 0
 
     def _finish(self):
-        self.stats_all = torch.zeros((max(1, len(self.gn_stats)), self.b, 32, 2), device=self.dev, dtype=torch.float32)
-        for i, holder in enumerate(self.gn_stats):
-            holder[0] = self.stats_all[i]
+        # one statistics buffer serves every GroupNorm (they run back to back on one stream); zeroed once, here
+        self.stats_all = torch.zeros((max(1, self.gn_need),), device=self.dev, dtype=torch.float32)
+        for holder in self.gn_stats:
+            holder[0] = self.stats_all
 
     def _emit(self, fn, *a, **k):
         self.ops.append((fn, a, k))
@@ -137,6 +139,7 @@ class _VAEProgram:
     def _gn(self, x, out, name, silu):
         holder = [None]
         self.gn_stats.append(holder)
+        self.gn_need = max(self.gn_need, ops.groupnorm_stats_floats(x.shape[0], x.shape[1], x.shape[2], 32))
         g, beta = self.w.t[name + ".g"], self.w.t[name + ".beta"]
         self._emit(lambda: ops.groupnorm(x, out, holder[0], g, beta, 32, 1e-6, silu))
 
@@ -193,7 +196,6 @@ class _VAEProgram:
         return x
 
     def run(self):
-        self.stats_all.zero_()
         for fn, a, k in self.ops:
             fn(*a, **k)
 

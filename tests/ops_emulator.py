@@ -83,6 +83,10 @@ def attention(q, k, v, out, heads, d, d_pad, scale, v_ones_col=False):
     return out
 
 
+def groupnorm_stats_floats(nb, hw, c, groups):
+    return nb * groups * 2
+
+
 def groupnorm(x, out, stats, gamma, beta, groups, eps, silu):
     y = F.group_norm(x.float().permute(0, 2, 1), groups, gamma, beta, eps).permute(0, 2, 1)
     if silu:
@@ -179,7 +183,7 @@ def unpack_latent(moments, x, scale):
     return x
 
 
-ALL = ["linear", "pick_block_n", "conv2d", "attention", "groupnorm", "layernorm", "upsample2x", "softmax_rows_", "silu",
+ALL = ["linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
        "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step",
        "quantize_u8", "image_to_nhwc", "unpack_latent"]
 

@@ -140,6 +140,21 @@ def test_txt2img_parity(mods, size, b, hw, steps, graphs):
     assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
 
 
+def test_sd15_sampler_is_bit_reproducible(mods):
+    """No kernel on the path uses floating-point atomics or an unordered reduction: the same request twice gives the
+    same bytes (also a sharp race detector: 148 persistent CTAs x thousands of tiles per run)."""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    tok = O.random_prompt_tokens(3, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(3, vocab_hi=vocab_hi)
+    eng.use_graphs = True
+    runs = [eng.txt2img(tok, neg, seed=77, steps=8, cfg_scale=7.0, height=512, width=512, sampler="DDIM").clone()
+            for _ in range(3)]
+    eng.use_graphs = False
+    torch.cuda.synchronize()
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+
+
 @pytest.mark.parametrize("size,b,px,steps", [("tiny", 3, 64, 8), ("sd15", 2, 512, 20)])
 def test_img2img_parity(mods, size, b, px, steps):
     """config C3: VAE encode (posterior mean) + noise to t_enc + DDIM remainder + decode, vs the fp32 oracle."""

@@ -276,9 +276,19 @@ def test_groupnorm(ops, nb, hw, c, silu, eps):
     gamma = torch.randn(c, generator=g, device="cuda")
     beta = torch.randn(c, generator=g, device="cuda")
     out = torch.empty_like(x)
-    stats = torch.zeros((nb, 32, 2), device="cuda")
+    stats = torch.zeros((ops.groupnorm_stats_floats(nb, hw, c, 32),), device="cuda")
     ops.groupnorm(x, out, stats, gamma, beta, 32, eps, silu)
     torch.cuda.synchronize()
+    # statistics: exact sums in fp32 order-of-magnitude, and bit-identical on a second run over the same (reused,
+    # never re-zeroed) buffer — the cross-CTA reduction is ordered, not atomic
+    first = stats[:nb * 64].clone()
+    xs = x.float().reshape(nb, hw, 32, c // 32)
+    ref_stats = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1).reshape(-1)
+    assert torch.allclose(first, ref_stats, rtol=2e-4, atol=1e-2)
+    out2 = torch.empty_like(x)
+    ops.groupnorm(x, out2, stats, gamma, beta, 32, eps, silu)
+    torch.cuda.synchronize()
+    assert torch.equal(stats[:nb * 64], first) and torch.equal(out, out2)
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps).permute(0, 2, 1)
     if silu:
         ref = F.silu(ref)
