@@ -24,6 +24,13 @@ if [ "$SKIP_NCU" != "1" ]; then
         -o gpurun_out/prof_$c -f python tools/ncu_cases.py $c > gpurun_out/ncu_$c.log 2>&1
   done
 fi
+if [ "$TRAFFIC" = "1" ]; then
+  # DRAM bytes of every GEMM/conv launch of one UNet evaluation at bench.py's batch -> roofline.traffic
+  NCU_NB=64 timeout 900 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum \
+      --clock-control none -k regex:gemm_conv --csv --log-file gpurun_out/traffic_gemm.csv \
+      python tools/ncu_cases.py unet > gpurun_out/ncu_traffic.log 2>&1
+fi
 tail -3 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_pair.log
 tail -1 gpurun_out/smoke.log; head -c 300 gpurun_out/bench.json; echo; tail -2 gpurun_out/bench.err
-[ "$SWEEPS" = "1" ] && cat gpurun_out/attn_sweep.log gpurun_out/gemm_sweep.log
+if [ "$SWEEPS" = "1" ]; then cat gpurun_out/attn_sweep.log gpurun_out/gemm_sweep.log; fi
+exit 0

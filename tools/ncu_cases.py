@@ -19,7 +19,7 @@ def rnd(*shape, scale=1.0):
 
 def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "unet"
-    nb = 16
+    nb = int(os.environ.get("NCU_NB", "16"))  # UNet batch (2 x images); bench.py's per-GPU batch 32 is NCU_NB=64
     if case == "unet":
         from b200sd import config as C, engine as E, synth
         cfgs = (C.SD15_UNET, C.SD15_VAE, C.SD15_CLIP)
