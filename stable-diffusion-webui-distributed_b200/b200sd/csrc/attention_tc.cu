@@ -235,6 +235,47 @@ __device__ __forceinline__ bool softmax_half(uint32_t tmem_row, uint32_t p_row, 
   return h2_hmax<kBf16>(pmax) > kPRedo;
 }
 
+#ifndef B200SD_ATTN_PREFETCH
+#define B200SD_ATTN_PREFETCH 0
+#endif
+
+// 32 columns at once from registers (loaded earlier, so the TMEM latency is hidden): P values packed into pk[16].
+// Returns true when some P value left the comfortable range.
+template <bool kFull, bool kBf16, bool kSum>
+__device__ __forceinline__ bool softmax32(const uint32_t (&v)[32], uint32_t (&pk)[16], int col0, int nvalid,
+                                          float scale_log2, float m_used, float& lsum) {
+  const uint64_t scale2 = pack_f2(__float_as_uint(scale_log2), __float_as_uint(scale_log2));
+  const uint64_t negm2 = pack_f2(__float_as_uint(-m_used), __float_as_uint(-m_used));
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float xa, xb;
+    ffma2(xa, xb, v[i], v[i + 1], scale2, negm2);
+    float ea = fast_exp2(xa);
+    float eb = fast_exp2(xb);
+    if (!kFull) {
+      if (col0 + i >= nvalid) ea = 0.f;
+      if (col0 + i + 1 >= nvalid) eb = 0.f;
+    }
+    if constexpr (kSum) acc += ea + eb;
+    pk[i >> 1] = pack_h2<kBf16>(ea, eb);
+  }
+  uint32_t pm0 = 0u, pm1 = 0u;  // two chains
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    pm0 = max3_h2<kBf16>(pm0, pk[i], pk[i + 1]);
+    pm1 = max3_h2<kBf16>(pm1, pk[i + 2], pk[i + 3]);
+  }
+  if constexpr (kSum) lsum += acc;
+  return fmaxf(h2_hmax<kBf16>(pm0), h2_hmax<kBf16>(pm1)) > kPRedo;
+}
+__device__ __forceinline__ void p_store32(const uint32_t (&pk)[16], uint32_t p_row, uint32_t rx, int col0) {
+  const uint32_t chunk0 = static_cast<uint32_t>(col0 >> 3);  // 8 halfs per 16-byte chunk
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    sts128(p_row + (((chunk0 + c) ^ rx) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
 template <bool kBf16, bool kSum>
 __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_base,
                                               int warp, int lane, int q0, int head, int b, int nkv) {
@@ -255,6 +296,92 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
   float l = 0.f;
   int sb = 0, pb = 0;        // S / P buffer of tile j and the parities of their current barrier phases
   uint32_t s_par = 0, p_par = 0;
+#if B200SD_ATTN_PREFETCH
+  // Software-pipelined variant: the 32 S values of tile j+1 are requested from TMEM as soon as tile j's have been
+  // exponentiated, so the s_full wait and the TMEM round trip overlap the vote / proxy fence / arrive of tile j.
+  {
+    uint32_t v[32];
+    mbar_wait_a(a_s_full, 0u, 17);
+    tc_fence_after();
+    {
+      const int nvalid0 = min(kKv, skv);
+      const uint32_t s_row0 = tmem_base + lane_base;
+      const float mx = nvalid0 == kKv ? half_row_max<true>(s_row0, col0, nvalid0) : half_row_max<false>(s_row0, col0, nvalid0);
+      sh->xch[half][r] = mx;
+      pair_bar_sync(quarter);
+      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * scale_log2;
+      tmem_ld_x32(s_row0 + col0, v);
+    }
+    for (int j = 0; j < nkv; ++j) {
+      const int nvalid = min(kKv, skv - j * kKv);
+      const bool full = nvalid == kKv;
+      const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
+      const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
+      int sb_n = sb + 1;
+      uint32_t s_par_n = s_par;
+      if (sb_n == s_bufs) {
+        sb_n = 0;
+        s_par_n ^= 1u;
+      }
+      const uint32_t s_row_n = tmem_base + static_cast<uint32_t>(sb_n * kKv) + lane_base;
+      uint32_t pk[16];
+      float lsum = 0.f;
+      tmem_ld_wait();
+      const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
+                             : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+      if (j + 1 < nkv) {  // v is dead: fetch the next tile's S into it
+        mbar_wait_a(a_s_full + sb_n * 8, s_par_n, 17);
+        tc_fence_after();
+        tmem_ld_x32(s_row_n + col0, v);
+      }
+      // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
+      if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
+      p_store32(pk, p_row, rx, col0);
+      if (pair_bar_or(quarter, over)) {
+        // rare path: the running maximum moved by more than 2^8 for some row of this quarter
+        tmem_ld_wait();  // drain the prefetch; v is refilled below
+        const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
+        sh->xch[half][r] = mx * scale_log2;
+        pair_bar_sync(quarter);
+        const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
+        const float alpha = fast_exp2(m_used - m_new);
+        if (j > 0) {
+          mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
+          tc_fence_after();
+          for (int c = half; c < p.resc_cols / 16; c += 2) {
+            uint32_t o[16];
+            tmem_ld_x16(o_row + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(o_row + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m_used = m_new;
+        lsum = 0.f;
+        tmem_ld_x32(s_row + col0, v);
+        tmem_ld_wait();
+        if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+        else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+        p_store32(pk, p_row, rx, col0);
+        if (j + 1 < nkv) tmem_ld_x32(s_row_n + col0, v);
+      }
+      l += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
+      sb = sb_n;
+      s_par = s_par_n;
+      if (++pb == p_bufs) {
+        pb = 0;
+        p_par ^= 1u;
+      }
+    }
+  }
+#else
   for (int j = 0; j < nkv; ++j) {
     const int nvalid = min(kKv, skv - j * kKv);
     const bool full = nvalid == kKv;
@@ -303,7 +430,8 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
     l += lsum;
     fence_proxy_async_smem();
     tc_fence_before();
-    mbar_arrive_a(a_p_full + pb * 8);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
     if (++sb == s_bufs) {
       sb = 0;
       s_par ^= 1u;
@@ -313,6 +441,7 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       p_par ^= 1u;
     }
   }
+#endif
   // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
   mbar_wait_a(a_o_full + ((nkv - 1) % p_bufs) * 8, ((nkv - 1) / p_bufs) & 1, 19);
   tc_fence_after();
@@ -384,7 +513,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int s = 0; s < kMaxSBufs; ++s) mbar_init(&sh->s_full[s], 1);
     for (int s = 0; s < kMaxPBufs; ++s) {
-      mbar_init(&sh->p_full[s], kSoftmaxThreads);
+      mbar_init(&sh->p_full[s], kSoftmaxWarps);
       mbar_init(&sh->o_full[s], 1);
     }
     fence_mbar_init();

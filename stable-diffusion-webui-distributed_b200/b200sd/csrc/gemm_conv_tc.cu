@@ -286,7 +286,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], (kPair ? 2 : 1) * 32 * kEpiWarps);  // pair: both CTAs' epilogues release it
+      mbar_init(&bars->tmem_empty[a], (kPair ? 2 : 1) * kEpiWarps);  // one arrival per epilogue warp (both CTAs')
       mbar_init(&bars->res_full[a][0], 1);
       mbar_init(&bars->res_full[a][1], 1);
     }
@@ -402,8 +402,12 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                              n_tile, quarter, group, lane, uses, chunk_count);
       tc_fence_before();
       // the MMA issuer (leader CTA) may overwrite this accumulator once BOTH CTAs have drained theirs
-      if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
-      else mbar_arrive(&bars->tmem_empty[acc]);
+      // one (possibly remote) arrival per warp: 256 remote arrivals per tile cost more than a short tile's MMAs
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+        else mbar_arrive(&bars->tmem_empty[acc]);
+      }
     }
     bulk_wait<0>();  // the issuing threads' TMA stores must have completed before the CTA (and its smem) goes away
   }
