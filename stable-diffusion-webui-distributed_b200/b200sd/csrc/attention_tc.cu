@@ -12,31 +12,34 @@
 //
 // One CTA = one 128-row Q tile of one (batch, head), kv consumed in tiles of 64.  320 threads:
 //   warp 0    TMA producer (Q once; K ring, V ring — loads issued in the order the MMAs consume them)
-//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%sb] = Q K_j^T (M128 x N<=64 x K=d),
-//             O (+)= P[j%2] V_j (M128 x N=d_pad x K<=64, V consumed MN-major straight from its TMA tile)
-//   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane, and the two warps of a lane
-//             quarter split the 64 kv columns of the tile in halves.
-// S is buffered sb = 3 deep in TMEM when d_pad == 64 (3 x 64 + 64 columns for O = 256, two CTAs per SM), else
-// 2 deep; P is buffered pb = 3 (or 2) deep in shared memory.  Q K_{j+sb}^T is issued as soon as softmax j has consumed
-// its S buffer and P_j V_j runs while softmax j+1 .. j+pb-1 are already exponentiating, so a fast softmax warp can run
-// pb tiles ahead of the slowest one before it has to wait — which matters because for d = 40 this kernel is bound by
-// the exp (MUFU) rate and by instruction issue, not by the MMAs (16 exps per 96 MMA-FLOPs).
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%2] = Q K_j^T (M128 x N<=64 x K=d),
+//             O_h (+)= P_h V_h for the two 32-row halves h of the kv tile (M128 x N=d_pad x K=32 each, V consumed
+//             MN-major straight from its TMA tile)
+//   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane; the two warps of a lane quarter
+//             take the two 32-column halves of the kv tile.
+// The two halves of a row are INDEPENDENT online-softmax streams: each has its own running maximum and its own
+// accumulator (O_a for kv rows 0-31 of every tile, O_b for rows 32-63), merged once at the end
+//   O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)),   m = max(m_a, m_b).
+// That removes the per-tile cross-warp vote of a shared maximum (a 64-thread named barrier per tile cost 6 % of the
+// exp rate in isolation, tools/xu_probe.cu); the only per-tile agreement left is a warp-local __any_sync.
 // Softmax is single pass ("lazy max"): P = exp2(S*scale - m_used) uses the running maximum of earlier tiles; the
 // maximum of the produced P values is tracked on the packed 16-bit pairs (3-input VHMNMX), and only if it exceeds 2^8
-// (P would leave fp16's comfortable range) is the tile redone with an exact new maximum after rescaling O in TMEM — a
-// vote between the two warps of a row quarter, rare after the first tile.  S*scale - m is a packed FFMA2, each S
-// element is read from TMEM once, the TMEM load of the next 16 columns is in flight while the current 16 are
-// exponentiated, and with a ones column in V (v_ones_col) the row sums come out of the P.V MMA instead of CUDA-core
-// adds.
+// for some lane of the warp (P would leave fp16's comfortable range) is the tile redone with an exact new maximum
+// after rescaling the warp's rows of O_h in TMEM — rare after the first tile.  S*scale - m is a packed FFMA2, each S
+// element is read from TMEM once (one 32-column load per thread and tile), and with a ones column in V (v_ones_col)
+// the row sums l_a, l_b come out of the P.V MMAs instead of CUDA-core adds.
+//
+// TMEM: S0 @ +0, S1 @ +64 (64 fp32 columns each), O_a @ +128, O_b @ +128 + d_pad.  d_pad == 64: 256 columns and
+// ~100 KB shared memory, two CTAs per SM.
 //
 // mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
 //   o_full[pb] P.V of tile j commits to o_full[j%pb].  Every softmax thread waits for tile j-pb on o_full[j%pb] before
 //              it overwrites P[j%pb] (S[j] being ready proves nothing about P.V of that tile), so it observes every
 //              phase of every o_full barrier; the rare-path wait for tile j-1 and the final wait are therefore at most
-//              one phase behind, and P.V of tile j cannot complete before the waiter itself has arrived on p_full.
-//   s_full[sb] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
-// Waits in the softmax loop use try_wait with a suspend hint: a polling loop without it steals issue slots from the
-// warps doing the exponentials (measured: a polling TMA producer cost 25 % of this kernel's time).
+//              one phase behind, and P.V of tile j cannot complete before the waiter's warp has arrived on p_full.
+//   s_full[2] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
+// All waits carry a suspend hint: a polling loop without it steals issue slots from the warps doing the exponentials
+// (measured: a polling TMA producer cost 25 % of this kernel's time).
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -49,11 +52,11 @@ constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
 constexpr int kAttnThreads = 64 + kSoftmaxThreads;
 constexpr int kQTile = 128;
 constexpr int kKv = 64;                              // kv rows per tile
+constexpr int kSBufs = 2;                            // S buffers in TMEM
 constexpr uint32_t kQChunkBytes = kQTile * 128;      // 128 rows x 64 halfs
 constexpr uint32_t kKvChunkBytes = kKv * 128;        // 64 rows x 64 halfs
 constexpr uint32_t kPBytes = kQTile * kKv * 2;       // one K-major SWIZZLE_128B atom: 128 rows x 64 halfs
 constexpr int kMaxRing = 4;
-constexpr int kMaxSBufs = 3;
 constexpr int kMaxPBufs = 3;
 
 struct AttnParams {
@@ -61,11 +64,10 @@ struct AttnParams {
   int d16;           // d rounded up to 16 (MMA K of Q.K^T; O columns that carry data)
   int dpv;           // MMA N of P.V = d_pad (whole 64-wide MN-major swizzle atoms; pad columns of V are zero)
   int chunks;        // d_pad / 64
-  int s_bufs;        // S buffers in TMEM (2 or 3); O lives behind them at column s_bufs * 64
   int p_bufs;        // P buffers in shared memory (2 or 3)
   int k_stages, v_stages;  // K / V ring depths (<= kMaxRing)
   int tmem_cols;
-  int l_col;         // >= 0: V carries a ones column at l_col (== d) and O[:, l_col] is the softmax denominator
+  int l_col;         // >= 0: V carries a ones column at l_col (== d) and O_h[:, l_col] is the softmax denominator
   int resc_cols;     // O columns touched by a rescale (multiple of 16, covers l_col)
   float scale_log2;  // softmax scale * log2(e)
   void* O;
@@ -77,10 +79,11 @@ struct __align__(16) AttnShared {
   uint64_t q_full;
   uint64_t k_full[kMaxRing], k_empty[kMaxRing];
   uint64_t v_full[kMaxRing], v_empty[kMaxRing];
-  uint64_t s_full[kMaxSBufs], p_full[kMaxPBufs], o_full[kMaxPBufs];
+  uint64_t s_full[kSBufs], p_full[kMaxPBufs], o_full[kMaxPBufs];
   uint32_t tmem_base;
   uint32_t pad;
-  float xch[2][kQTile];  // row maxima / sums exchanged between the two column halves
+  float xm[2][kQTile];  // final merge: running maxima / row sums of the two column halves
+  float xl[2][kQTile];
 };
 
 template <bool kBf16>
@@ -108,20 +111,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void pair_bar_sync(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
 }
-__device__ __forceinline__ bool pair_bar_or(int quarter, bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %1, 0;\n\t"
-      "bar.red.or.pred p, %2, 64, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(out)
-      : "r"(static_cast<uint32_t>(pred)), "r"(quarter + 1)
-      : "memory");
-  return out != 0;
-}
 
 // maximum of my 32 columns [col0, col0+32) of the S tile (raw logits); kv columns >= nvalid ignored
 template <bool kFull>
@@ -130,9 +119,8 @@ __device__ __forceinline__ float half_row_max(uint32_t tmem_row, int col0, int n
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const int cbase = col0 + s * 16;
-    if (!kFull && cbase >= nvalid) break;
     uint32_t v[16];
-    tmem_ld_x16(tmem_row + cbase, v);
+    tmem_ld_x16(tmem_row + cbase, v);  // warp-collective: never skipped, masked instead
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
@@ -188,59 +176,7 @@ __device__ __forceinline__ float h2_hmax(uint32_t v) {
 // P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
 constexpr float kPRedo = 256.0f;
 
-// exponentiate 16 columns, track the maximum of the produced P values (packed, 16-bit) / their sum, and write them as
-// two 16-byte chunks of the swizzled P atom.  p_row = shared-space address of my row of the P buffer, rx = row & 7
-// (the 128-byte swizzle phase); scale2 / negm2 = (scale_log2, scale_log2) / (-m_used, -m_used) packed for FFMA2.
-template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ void softmax16(const uint32_t (&v)[16], uint32_t p_row, uint32_t rx, int cbase, int nvalid,
-                                          uint64_t scale2, uint64_t negm2, uint32_t& pmax, float& lsum) {
-  uint32_t pk[8];
-  float acc = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; i += 2) {
-    float xa, xb;
-    ffma2(xa, xb, v[i], v[i + 1], scale2, negm2);
-    float ea = fast_exp2(xa);
-    float eb = fast_exp2(xb);
-    if (!kFull) {
-      if (cbase + i >= nvalid) ea = 0.f;
-      if (cbase + i + 1 >= nvalid) eb = 0.f;
-    }
-    if constexpr (kSum) acc += ea + eb;
-    pk[i >> 1] = pack_h2<kBf16>(ea, eb);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) pmax = max3_h2<kBf16>(pmax, pk[i], pk[i + 1]);
-  if constexpr (kSum) lsum += acc;
-  const uint32_t chunk16 = static_cast<uint32_t>(cbase >> 3);  // 8 halfs per 16-byte chunk
-  sts128(p_row + ((chunk16 ^ rx) << 4), pk[0], pk[1], pk[2], pk[3]);
-  sts128(p_row + (((chunk16 + 1) ^ rx) << 4), pk[4], pk[5], pk[6], pk[7]);
-}
-
-// One pass over my 32 columns: the TMEM load of the second 16 is in flight while the first 16 are processed.
-// Returns true when some P value left the comfortable range (the caller votes on a redo).
-template <bool kFull, bool kBf16, bool kSum>
-__device__ __forceinline__ bool softmax_half(uint32_t tmem_row, uint32_t p_row, uint32_t rx, int col0, int nvalid,
-                                             float scale_log2, float m_used, float& lsum) {
-  uint32_t va[16], vb[16];
-  tmem_ld_x16(tmem_row + col0, va);
-  const uint64_t scale2 = pack_f2(__float_as_uint(scale_log2), __float_as_uint(scale_log2));
-  const uint64_t negm2 = pack_f2(__float_as_uint(-m_used), __float_as_uint(-m_used));
-  uint32_t pmax = 0u;
-  tmem_ld_wait();
-  tmem_ld_x16(tmem_row + col0 + 16, vb);
-  softmax16<kFull, kBf16, kSum>(va, p_row, rx, col0, nvalid, scale2, negm2, pmax, lsum);
-  tmem_ld_wait();
-  softmax16<kFull, kBf16, kSum>(vb, p_row, rx, col0 + 16, nvalid, scale2, negm2, pmax, lsum);
-  return h2_hmax<kBf16>(pmax) > kPRedo;
-}
-
-#ifndef B200SD_ATTN_PREFETCH
-#define B200SD_ATTN_PREFETCH 0
-#endif
-
-// 32 columns at once from registers (loaded earlier, so the TMEM latency is hidden): P values packed into pk[16].
-// Returns true when some P value left the comfortable range.
+// my 32 columns of one S tile -> P values packed into pk[16]; returns true when some P value left the comfortable range
 template <bool kFull, bool kBf16, bool kSum>
 __device__ __forceinline__ bool softmax32(const uint32_t (&v)[32], uint32_t (&pk)[16], int col0, int nvalid,
                                           float scale_log2, float m_used, float& lsum) {
@@ -269,6 +205,7 @@ __device__ __forceinline__ bool softmax32(const uint32_t (&v)[32], uint32_t (&pk
   if constexpr (kSum) lsum += acc;
   return fmaxf(h2_hmax<kBf16>(pm0), h2_hmax<kBf16>(pm1)) > kPRedo;
 }
+// four 16-byte chunks of my row of the swizzled P atom; p_row = shared-space address of the row, rx = row & 7
 __device__ __forceinline__ void p_store32(const uint32_t (&pk)[16], uint32_t p_row, uint32_t rx, int col0) {
   const uint32_t chunk0 = static_cast<uint32_t>(col0 >> 3);  // 8 halfs per 16-byte chunk
 #pragma unroll
@@ -280,138 +217,52 @@ template <bool kBf16, bool kSum>
 __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_base,
                                               int warp, int lane, int q0, int head, int b, int nkv) {
   const int quarter = warp & 3;
-  const int half = (warp - 2) >> 2;   // which 32-column half of the kv tile is mine
+  const int half = (warp - 2) >> 2;   // which 32-column half of the kv tile (and which accumulator) is mine
   const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
   const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-  const uint32_t o_row = tmem_base + static_cast<uint32_t>(p.s_bufs * kKv) + lane_base;
+  const uint32_t oa_row = tmem_base + static_cast<uint32_t>(kSBufs * kKv) + lane_base;
+  const uint32_t ob_row = oa_row + static_cast<uint32_t>(p.dpv);
+  const uint32_t o_row = half == 0 ? oa_row : ob_row;  // the accumulator my P values feed
   const uint32_t p_row0 = smem_u32(sP) + static_cast<uint32_t>(r) * 128u;
   const uint32_t rx = static_cast<uint32_t>(r) & 7u;
   const uint32_t a_s_full = smem_u32(&sh->s_full[0]);
   const uint32_t a_p_full = smem_u32(&sh->p_full[0]);
   const uint32_t a_o_full = smem_u32(&sh->o_full[0]);
   const int col0 = half * 32;
-  const int s_bufs = p.s_bufs, p_bufs = p.p_bufs, skv = p.Skv;
+  const int p_bufs = p.p_bufs, skv = p.Skv;
   const float scale_log2 = p.scale_log2;
-  float m_used = -INFINITY;  // scaled log2 domain
+  float m_used = -INFINITY;  // scaled log2 domain; running maximum of MY half of the row
   float l = 0.f;
-  int sb = 0, pb = 0;        // S / P buffer of tile j and the parities of their current barrier phases
-  uint32_t s_par = 0, p_par = 0;
-#if B200SD_ATTN_PREFETCH
-  // Software-pipelined variant: the 32 S values of tile j+1 are requested from TMEM as soon as tile j's have been
-  // exponentiated, so the s_full wait and the TMEM round trip overlap the vote / proxy fence / arrive of tile j.
-  {
-    uint32_t v[32];
-    mbar_wait_a(a_s_full, 0u, 17);
-    tc_fence_after();
-    {
-      const int nvalid0 = min(kKv, skv);
-      const uint32_t s_row0 = tmem_base + lane_base;
-      const float mx = nvalid0 == kKv ? half_row_max<true>(s_row0, col0, nvalid0) : half_row_max<false>(s_row0, col0, nvalid0);
-      sh->xch[half][r] = mx;
-      pair_bar_sync(quarter);
-      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * scale_log2;
-      tmem_ld_x32(s_row0 + col0, v);
-    }
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = min(kKv, skv - j * kKv);
-      const bool full = nvalid == kKv;
-      const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
-      const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
-      int sb_n = sb + 1;
-      uint32_t s_par_n = s_par;
-      if (sb_n == s_bufs) {
-        sb_n = 0;
-        s_par_n ^= 1u;
-      }
-      const uint32_t s_row_n = tmem_base + static_cast<uint32_t>(sb_n * kKv) + lane_base;
-      uint32_t pk[16];
-      float lsum = 0.f;
-      tmem_ld_wait();
-      const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
-                             : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-      if (j + 1 < nkv) {  // v is dead: fetch the next tile's S into it
-        mbar_wait_a(a_s_full + sb_n * 8, s_par_n, 17);
-        tc_fence_after();
-        tmem_ld_x32(s_row_n + col0, v);
-      }
-      // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
-      if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
-      p_store32(pk, p_row, rx, col0);
-      if (pair_bar_or(quarter, over)) {
-        // rare path: the running maximum moved by more than 2^8 for some row of this quarter
-        tmem_ld_wait();  // drain the prefetch; v is refilled below
-        const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
-        sh->xch[half][r] = mx * scale_log2;
-        pair_bar_sync(quarter);
-        const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
-        const float alpha = fast_exp2(m_used - m_new);
-        if (j > 0) {
-          mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
-          tc_fence_after();
-          for (int c = half; c < p.resc_cols / 16; c += 2) {
-            uint32_t o[16];
-            tmem_ld_x16(o_row + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x16(o_row + c * 16, o);
-          }
-          tmem_st_wait();
-        }
-        l *= alpha;
-        m_used = m_new;
-        lsum = 0.f;
-        tmem_ld_x32(s_row + col0, v);
-        tmem_ld_wait();
-        if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-        else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-        p_store32(pk, p_row, rx, col0);
-        if (j + 1 < nkv) tmem_ld_x32(s_row_n + col0, v);
-      }
-      l += lsum;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
-      sb = sb_n;
-      s_par = s_par_n;
-      if (++pb == p_bufs) {
-        pb = 0;
-        p_par ^= 1u;
-      }
-    }
-  }
-#else
+  int pb = 0;                // P buffer of tile j and the parity of its current barrier phase
+  uint32_t p_par = 0;
   for (int j = 0; j < nkv; ++j) {
+    const int sb = j & 1;
     const int nvalid = min(kKv, skv - j * kKv);
     const bool full = nvalid == kKv;
     const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
     const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
-    mbar_wait_a(a_s_full + sb * 8, s_par, 17);
+    mbar_wait_a(a_s_full + sb * 8, (j >> 1) & 1, 17);
+    tc_fence_after();
+    if (j == 0) m_used = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
+    uint32_t v[32], pk[16];
+    tmem_ld_x32(s_row + col0, v);
+    tmem_ld_wait();
+    float lsum = 0.f;
+    const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
+                           : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
     // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
     if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
-    tc_fence_after();
-    if (j == 0) {
-      const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
-      sh->xch[half][r] = mx;
-      pair_bar_sync(quarter);
-      m_used = fmaxf(sh->xch[0][r], sh->xch[1][r]) * scale_log2;
-    }
-    float lsum = 0.f;
-    const bool over = full ? softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum)
-                           : softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
-    if (pair_bar_or(quarter, over)) {
-      // rare path: the running maximum moved by more than 2^8 for some row of this quarter
-      const float mx = full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid);
-      sh->xch[half][r] = mx * scale_log2;
-      pair_bar_sync(quarter);
-      const float m_new = fmax3(m_used, sh->xch[0][r], sh->xch[1][r]);
+    if (__any_sync(0xffffffffu, over)) {
+      // rare path (warp-uniform, the TMEM accesses are warp-collective): some row of this warp saw its maximum move
+      // by more than 2^8.  Lanes that did not overflow run it with alpha ~ 1.
+      const float mx = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
+      const float m_new = fmaxf(m_used, mx);
       const float alpha = fast_exp2(m_used - m_new);
       if (j > 0) {
-        // P.V of the previous tile must have landed in O
+        // P.V of the previous tile must have landed in O_h
         mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
         tc_fence_after();
-        for (int c = half; c < p.resc_cols / 16; c += 2) {
+        for (int c = 0; c < p.resc_cols / 16; ++c) {
           uint32_t o[16];
           tmem_ld_x16(o_row + c * 16, o);
           tmem_ld_wait();
@@ -424,33 +275,27 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
       l *= alpha;
       m_used = m_new;
       lsum = 0.f;
-      if (full) softmax_half<true, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
-      else      softmax_half<false, kBf16, kSum>(s_row, p_row, rx, col0, nvalid, scale_log2, m_used, lsum);
+      tmem_ld_x32(s_row + col0, v);
+      tmem_ld_wait();
+      if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+      else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
     }
+    p_store32(pk, p_row, rx, col0);
     l += lsum;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
-    if (++sb == s_bufs) {
-      sb = 0;
-      s_par ^= 1u;
-    }
     if (++pb == p_bufs) {
       pb = 0;
       p_par ^= 1u;
     }
   }
-#endif
-  // ---- epilogue: O / l -> global (the pair splits the 16-column chunks of O) ----
+  // ---- epilogue: merge the two halves of every row, O / l -> global (the pair splits the 16-column chunks) ----
   mbar_wait_a(a_o_full + ((nkv - 1) % p_bufs) * 8, ((nkv - 1) / p_bufs) & 1, 19);
   tc_fence_after();
-  if constexpr (kSum) {
-    pair_bar_sync(quarter);  // both threads of every pair are past their last xch read
-    sh->xch[half][r] = l;
-    pair_bar_sync(quarter);
-    l = sh->xch[0][r] + sh->xch[1][r];
-  } else {
+  const bool has_b = skv > 32;  // kv rows 32-63 never exist when Skv <= 32: O_b was never written
+  if constexpr (!kSum) {
     uint32_t o[16];
     tmem_ld_x16(o_row + (p.l_col / 16) * 16, o);
     tmem_ld_wait();
@@ -459,19 +304,37 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
     for (int i = 0; i < 16; ++i)
       if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
   }
-  const float inv_l = 1.0f / l;
+  if (half == 1 && !has_b) {
+    l = 0.f;
+    m_used = -INFINITY;
+  }
+  sh->xm[half][r] = m_used;
+  sh->xl[half][r] = l;
+  pair_bar_sync(quarter);
+  const float m_o = sh->xm[half ^ 1][r], l_o = sh->xl[half ^ 1][r];
+  const float m = fmaxf(m_used, m_o);
+  const float a_me = fast_exp2(m_used - m), a_ot = fast_exp2(m_o - m);  // 2^(-inf) = 0 for an empty half
+  const float inv_l = 1.0f / (l * a_me + l_o * a_ot);
+  const float wa = (half == 0 ? a_me : a_ot) * inv_l, wb = (half == 0 ? a_ot : a_me) * inv_l;
   const int srow = q0 + r;
   const bool valid = srow < p.Sq;
   uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
                   ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
   for (int c = half; c < p.d16 / 16; c += 2) {
-    uint32_t o[16];
-    tmem_ld_x16(o_row + c * 16, o);
+    uint32_t oa[16], ob[16];
+    tmem_ld_x16(oa_row + c * 16, oa);
+    tmem_ld_x16(ob_row + c * 16, ob);
     tmem_ld_wait();
     uint32_t h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      h[i] = pack_h2<kBf16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+    for (int i = 0; i < 8; ++i) {
+      float x0 = __uint_as_float(oa[2 * i]) * wa, x1 = __uint_as_float(oa[2 * i + 1]) * wa;
+      if (has_b) {
+        x0 = fmaf(__uint_as_float(ob[2 * i]), wb, x0);
+        x1 = fmaf(__uint_as_float(ob[2 * i + 1]), wb, x1);
+      }
+      h[i] = pack_h2<kBf16>(x0, x1);
+    }
     if (valid) {
       if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
       if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
@@ -511,7 +374,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&sh->v_full[s], 1);
       mbar_init(&sh->v_empty[s], 1);
     }
-    for (int s = 0; s < kMaxSBufs; ++s) mbar_init(&sh->s_full[s], 1);
+    for (int s = 0; s < kSBufs; ++s) mbar_init(&sh->s_full[s], 1);
     for (int s = 0; s < kMaxPBufs; ++s) {
       mbar_init(&sh->p_full[s], kSoftmaxWarps);
       mbar_init(&sh->o_full[s], 1);
@@ -522,14 +385,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = sh->tmem_base;  // S buffers (64 fp32 columns each) at +0, +64[, +128]; O behind them
-  const uint32_t tmem_O = tmem_base + static_cast<uint32_t>(p.s_bufs * kKv);
+  const uint32_t tmem_base = sh->tmem_base;  // S0 @ +0, S1 @ +64, O_a @ +128, O_b @ +128 + dpv
+  const uint32_t tmem_Oa = tmem_base + static_cast<uint32_t>(kSBufs * kKv);
+  const uint32_t tmem_Ob = tmem_Oa + static_cast<uint32_t>(p.dpv);
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     // Loads go out in exactly the order the MMA thread consumes (and therefore frees) tiles:
-    //   K_0 .. K_{sb-1},  then  V_j, K_{j+sb}  for j = 0, 1, ...   so a blocking wait never holds back a tile that is
-    // needed earlier than the one being waited for.
+    //   K_0, K_1,  then  V_j, K_{j+2}  for j = 0, 1, ...   so a blocking wait never holds back a tile that is needed
+    // earlier than the one being waited for.
     if (lane == 0) {
       int kj = 0, k_st = 0, v_st = 0;
       uint32_t k_par = 0, v_par = 0;
@@ -546,7 +410,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       mbar_arrive_expect_tx(&sh->q_full, q_bytes);
       for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
-      for (int i = 0; i < p.s_bufs && i < nkv; ++i) load_k();
+      for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&sh->v_empty[v_st], v_par ^ 1u, 12);
         mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
@@ -565,9 +429,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool bf = p.is_bf16 != 0;
       const int ksteps_qk = p.d16 / 16;
       const uint32_t aQ = smem_u32(sQ);
-      int qj = 0, q_sb = 0, q_ks = 0;  // next Q.K^T: tile, S buffer, K ring slot (+ parity of its k_full phase)
+      int qj = 0, q_ks = 0;  // next Q.K^T: tile, K ring slot (+ parity of its k_full phase)
       uint32_t q_kpar = 0;
-      auto issue_qk = [&]() {  // S[q_sb] = Q K_qj^T
+      auto issue_qk = [&]() {  // S[qj & 1] = Q K_qj^T
+        const int q_sb = qj & 1;
         const int nvalid = min(kKv, p.Skv - qj * kKv);
         const int n16 = (nvalid + 15) & ~15;
         mbar_wait(&sh->k_full[q_ks], q_kpar, 14);
@@ -583,20 +448,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(&sh->k_empty[q_ks]);
         umma_commit(&sh->s_full[q_sb]);
         ++qj;
-        if (++q_sb == p.s_bufs) q_sb = 0;
         if (++q_ks == p.k_stages) {
           q_ks = 0;
           q_kpar ^= 1u;
         }
       };
       mbar_wait(&sh->q_full, 0, 13);
-      for (int i = 0; i < p.s_bufs && i < nkv; ++i) issue_qk();
+      for (int i = 0; i < kSBufs && i < nkv; ++i) issue_qk();
       int vs = 0, pb = 0;
       uint32_t v_par = 0, p_par = 0;
       for (int j = 0; j < nkv; ++j) {
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
-        // ---- O (+)= P_j V_j ----
+        // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
         mbar_wait(&sh->p_full[pb], p_par, 15);
         mbar_wait(&sh->v_full[vs], v_par, 16);
         tc_fence_after();
@@ -608,8 +472,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int k = 0; k < ksteps_pv; ++k) {
             const uint32_t offP = static_cast<uint32_t>(k) * 32u;    // 16 halfs inside the 128-byte swizzle row
             const uint32_t offV = static_cast<uint32_t>(k) * 2048u;  // 16 kv rows x 128 B
-            umma_f16_ss(tmem_O, make_sdesc_sw128(aP + offP, 16, 1024), make_sdesc_sw128(aV + offV, kKvChunkBytes, 1024),
-                        idesc, (j | k) != 0 ? 1u : 0u);
+            const bool first = j == 0 && (k & 1) == 0;               // first MMA into this accumulator
+            umma_f16_ss(k < 2 ? tmem_Oa : tmem_Ob, make_sdesc_sw128(aP + offP, 16, 1024),
+                        make_sdesc_sw128(aV + offV, kKvChunkBytes, 1024), idesc, first ? 0u : 1u);
           }
           umma_commit(&sh->v_empty[vs]);
           umma_commit(&sh->o_full[pb]);
@@ -622,7 +487,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pb = 0;
           p_par ^= 1u;
         }
-        // ---- softmax j has released its S buffer: refill it s_bufs tiles ahead ----
+        // ---- softmax j has released its S buffer: refill it two tiles ahead ----
         if (qj < nkv) issue_qk();
       }
     }
@@ -649,11 +514,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
 
-// tuning overrides for experiments: B200SD_ATTN_SBUFS=2|3, B200SD_ATTN_RING="k,v" (ring depths, 1..4 each)
-static void attn_env(int* s_bufs, int* p_bufs, int* k_st, int* v_st) {
-  static int cached = 0, e_sb = 0, e_pb = 0, e_k = 0, e_v = 0;
+// tuning overrides for experiments: B200SD_ATTN_PBUFS=2|3, B200SD_ATTN_RING="k,v" (ring depths, 1..4 each)
+static void attn_env(int* p_bufs, int* k_st, int* v_st) {
+  static int cached = 0, e_pb = 0, e_k = 0, e_v = 0;
   if (!cached) {
-    if (const char* s = std::getenv("B200SD_ATTN_SBUFS")) e_sb = std::atoi(s);
     if (const char* s = std::getenv("B200SD_ATTN_PBUFS")) e_pb = std::atoi(s);
     if (const char* s = std::getenv("B200SD_ATTN_RING")) {
       e_k = std::atoi(s);
@@ -663,7 +527,6 @@ static void attn_env(int* s_bufs, int* p_bufs, int* k_st, int* v_st) {
     }
     cached = 1;
   }
-  *s_bufs = e_sb;
   *p_bufs = e_pb;
   *k_st = e_k;
   *v_st = e_v;
@@ -673,7 +536,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
                  long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int v_ones_col,
                  int is_bf16, cudaStream_t stream) {
   if (B <= 0 || heads <= 0 || Sq <= 0) return B200SD_OK;
-  if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 64 != 0 || d_pad < d || d > 240) return B200SD_ERR_INVALID;
+  if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 64 != 0 || d_pad < d) return B200SD_ERR_INVALID;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return B200SD_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
        reinterpret_cast<uintptr_t>(O)) & 15)
@@ -702,16 +565,14 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
   p.dpv = d_pad;
-  if (p.dpv > 256) return B200SD_ERR_UNSUPPORTED;
+  // TMEM: two S buffers + one accumulator per kv-tile half.  d_pad 64 -> 256 columns (two CTAs per SM), up to 192 -> 512
+  if (kSBufs * kKv + 2 * p.dpv > 512) return B200SD_ERR_UNSUPPORTED;
   if (v_ones_col && d >= d_pad) return B200SD_ERR_INVALID;  // needs a free pad column
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
-  int e_sb, e_pb, e_k, e_v;
-  attn_env(&e_sb, &e_pb, &e_k, &e_v);
-  // three S buffers when they fit next to O in 256 TMEM columns (d_pad == 64: two CTAs per SM stay possible)
-  p.s_bufs = (3 * kKv + p.dpv <= 256) ? 3 : 2;
-  if (e_sb == 2 || (e_sb == 3 && 3 * kKv + p.dpv <= 512)) p.s_bufs = e_sb;
-  p.tmem_cols = (p.s_bufs * kKv + p.dpv <= 256) ? 256 : 512;
+  p.tmem_cols = (kSBufs * kKv + 2 * p.dpv <= 256) ? 256 : 512;
+  int e_pb, e_k, e_v;
+  attn_env(&e_pb, &e_k, &e_v);
   // shared memory: Q + p_bufs P atoms + K/V rings.  Three P buffers and a K 3 / V 2 ring when that keeps two CTAs per
   // SM (d_pad == 64) or simply fits (one CTA per SM), otherwise two and 2 / 2.
   const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
