@@ -47,6 +47,9 @@ typedef struct b200sd_epilogue {
 
 /* library / build identification: returns a static string "b200sd <version> sm_100a" */
 const char* b200sd_version(void);
+/* debug: a device buffer of 16 x 64 int64 that one CTA of every later b200sd_attention launch fills with clock64()
+ * stamps of its per-tile pipeline events (tools/attn_trace.py); NULL switches it off (default). */
+int b200sd_debug_attention_trace(void* device_buffer);
 
 /* ---- tensor-core ops (tcgen05 + TMA) ----------------------------------------------------------- */
 

@@ -73,6 +73,7 @@ struct AttnParams {
   void* O;
   long long ldo;
   int is_bf16;
+  long long* trace;  // debug: clock64 timeline of one CTA ([16 events][nkv]), or null
 };
 
 struct __align__(16) AttnShared {
@@ -176,6 +177,10 @@ __device__ __forceinline__ float h2_hmax(uint32_t v) {
 // P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
 constexpr float kPRedo = 256.0f;
 
+// debug timeline (b200sd_debug_attention_trace): CTA (3, 2, 1) stamps per-tile events of softmax warp 2 and the MMA thread
+#define ATTN_TRACE(ev, j) \
+  do { if (trace) trace[(ev) * 64 + ((j) & 63)] = clock64(); } while (0)
+
 // my 32 columns of one S tile -> P values packed into pk[16]; returns true when some P value left the comfortable range
 template <bool kFull, bool kBf16, bool kSum>
 __device__ __forceinline__ bool softmax32(const uint32_t (&v)[32], uint32_t (&pk)[16], int col0, int nvalid,
@@ -231,6 +236,7 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
   const int col0 = half * 32;
   const int p_bufs = p.p_bufs, skv = p.Skv;
   const float scale_log2 = p.scale_log2;
+  long long* trace = (p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1 && warp == 2 && lane == 0) ? p.trace : nullptr;
   float m_used = -INFINITY;  // scaled log2 domain; running maximum of MY half of the row
   float l = 0.f;
   int pb = 0;                // P buffer of tile j and the parity of its current barrier phase
@@ -241,17 +247,22 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
     const bool full = nvalid == kKv;
     const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
     const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
+    ATTN_TRACE(0, j);
     mbar_wait_a(a_s_full + sb * 8, (j >> 1) & 1, 17);
     tc_fence_after();
+    ATTN_TRACE(1, j);
     if (j == 0) m_used = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
     uint32_t v[32], pk[16];
     tmem_ld_x32(s_row + col0, v);
     tmem_ld_wait();
+    ATTN_TRACE(2, j);
     float lsum = 0.f;
     const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
                            : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
     // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
+    ATTN_TRACE(3, j);
     if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
+    ATTN_TRACE(4, j);
     if (__any_sync(0xffffffffu, over)) {
       // rare path (warp-uniform, the TMEM accesses are warp-collective): some row of this warp saw its maximum move
       // by more than 2^8.  Lanes that did not overflow run it with alpha ~ 1.
@@ -282,9 +293,11 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
     }
     p_store32(pk, p_row, rx, col0);
     l += lsum;
+    ATTN_TRACE(5, j);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncwarp();
+    ATTN_TRACE(6, j);
     if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
     if (++pb == p_bufs) {
       pb = 0;
@@ -426,6 +439,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ---------------------------------------
     if (lane == 0) {
+      long long* trace = (p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1) ? p.trace : nullptr;
       const bool bf = p.is_bf16 != 0;
       const int ksteps_qk = p.d16 / 16;
       const uint32_t aQ = smem_u32(sQ);
@@ -435,8 +449,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int q_sb = qj & 1;
         const int nvalid = min(kKv, p.Skv - qj * kKv);
         const int n16 = (nvalid + 15) & ~15;
+        ATTN_TRACE(11, qj);
         mbar_wait(&sh->k_full[q_ks], q_kpar, 14);
         tc_fence_after();
+        ATTN_TRACE(12, qj);
         const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
         const uint32_t aK = smem_u32(sK + q_ks * kv_bytes);
         for (int k = 0; k < ksteps_qk; ++k) {
@@ -447,6 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         umma_commit(&sh->k_empty[q_ks]);
         umma_commit(&sh->s_full[q_sb]);
+        ATTN_TRACE(13, qj);
         ++qj;
         if (++q_ks == p.k_stages) {
           q_ks = 0;
@@ -461,9 +478,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int nvalid = min(kKv, p.Skv - j * kKv);
         const int n16 = (nvalid + 15) & ~15;
         // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
+        ATTN_TRACE(7, j);
         mbar_wait(&sh->p_full[pb], p_par, 15);
+        ATTN_TRACE(8, j);
         mbar_wait(&sh->v_full[vs], v_par, 16);
         tc_fence_after();
+        ATTN_TRACE(9, j);
         {
           const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
           const uint32_t aP = smem_u32(sP + pb * kPBytes);
@@ -478,6 +498,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           umma_commit(&sh->v_empty[vs]);
           umma_commit(&sh->o_full[pb]);
+          ATTN_TRACE(10, j);
         }
         if (++vs == p.v_stages) {
           vs = 0;
@@ -511,6 +532,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+static long long* g_attn_trace = nullptr;
 static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
 
@@ -564,6 +586,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.chunks = d_pad / 64;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
+  p.trace = g_attn_trace;
   p.dpv = d_pad;
   // TMEM: two S buffers + one accumulator per kv-tile half.  d_pad 64 -> 256 columns (two CTAs per SM), up to 192 -> 512
   if (kSBufs * kKv + 2 * p.dpv > 512) return B200SD_ERR_UNSUPPORTED;
@@ -615,3 +638,9 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
 }
 
 }  // namespace b200sd
+
+// debug hook: device buffer of 16 * 64 int64 that CTA (3, 2, 1) of later attention launches fills with clock64 stamps
+extern "C" int b200sd_debug_attention_trace(void* device_buffer) {
+  b200sd::g_attn_trace = static_cast<long long*>(device_buffer);
+  return B200SD_OK;
+}

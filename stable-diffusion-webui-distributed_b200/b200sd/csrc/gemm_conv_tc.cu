@@ -22,6 +22,7 @@
 // ldm ResBlock conv3x3 / skip 1x1, Up/Downsample conv, SpatialTransformer proj_in/out, CrossAttention
 // to_q/k/v/out, FeedForward GEGLU + out, AutoencoderKL decoder convs (SURVEY.md §8 a-ext x1,x2,x5,x7,x8,x9,x11).
 #include <math.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
@@ -304,82 +305,117 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // Converged warp, one elected issuing lane (see the MMA issuer below); the (tap, channel-block) position of the
+    // conv K loop is advanced by counters — a division per k-block on this single thread was as slow as the MMAs.
+    {
+      const bool leader = elect_one();
+      const uint32_t bar0 = warp_uniform(smem_u32(bars));
+      const uint32_t a_full = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, full));
+      const uint32_t a_empty = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, empty));
+      const int nkb = p.num_k_blocks, nstages = p.num_stages, cblocks = p.cblocks;
+      const bool conv = p.mode == 1, taps9 = p.taps == 9;
+      const uint32_t tx_bytes = (kPair ? 2u : 1u) * (p.a_bytes + p.b_bytes);
       int stage = 0;
       uint32_t phase = 0;
       for (int item = first_item; item < num_items; item += item_step) {
         const int n_tile = item % p.num_n_tiles;
         const int m_tile = kPair ? 2 * (item / p.num_n_tiles) + rank : item / p.num_n_tiles;
         int cx = 0, cy = 0, cn = 0;
-        if (p.mode == 1) {
+        if (conv) {
           const int tx = m_tile % p.tiles_x;
           const int ty = (m_tile / p.tiles_x) % p.tiles_y;
           cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn;
           cx = tx * p.bw * p.stride - p.pad;
           cy = ty * p.bh * p.stride - p.pad;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1u, 1);
-          uint8_t* sA = smem + static_cast<size_t>(stage) * stage_bytes;
-          uint8_t* sB = sA + 16384;
-          int tap = 0, cb = kb, dy = 0, dx = 0;
-          if (p.mode == 1) {
-            tap = kb / p.cblocks;
-            cb = kb - tap * p.cblocks;
-            dy = (p.taps == 9) ? tap / 3 : 0;
-            dx = (p.taps == 9) ? tap - dy * 3 : 0;
+        const int b_row = n_tile * p.block_n + (kPair ? rank * bn_local : 0);
+        const int a_row = m_tile * kBlockM;
+        int cb = 0, dx = 0, dy = 0;  // conv: channel block within the tap, tap offsets
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_a(a_empty + static_cast<uint32_t>(stage) * 8u, phase ^ 1u, 1);
+          if (leader) {
+            uint8_t* sA = smem + static_cast<size_t>(stage) * stage_bytes;
+            uint8_t* sB = sA + 16384;
+            uint64_t* full_bar = &bars->full[stage];
+            if constexpr (kPair) {
+              // both CTAs' bytes land on the LEADER's barrier; only the leader arms it (for the bytes of both)
+              const uint32_t lead_bar = mapa_u32(a_full + static_cast<uint32_t>(stage) * 8u, 0);
+              if (rank == 0) mbar_arrive_expect_tx(full_bar, tx_bytes);
+              if (!conv) tma_load_2d_pair(sA, &tmA, lead_bar, kb * kBlockK, a_row);
+              else tma_load_4d_pair(sA, &tmA, lead_bar, cb * kBlockK, cx + dx, cy + dy, cn);
+              tma_load_2d_pair(sB, &tmB, lead_bar, kb * kBlockK, b_row);
+            } else {
+              mbar_arrive_expect_tx(full_bar, tx_bytes);
+              if (!conv) tma_load_2d(sA, &tmA, full_bar, kb * kBlockK, a_row);
+              else tma_load_4d(sA, &tmA, full_bar, cb * kBlockK, cx + dx, cy + dy, cn);
+              tma_load_2d(sB, &tmB, full_bar, kb * kBlockK, b_row);
+            }
           }
-          if constexpr (kPair) {
-            // both CTAs' bytes land on the LEADER's barrier; only the leader arms it (for the bytes of both)
-            const uint32_t lead_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (p.a_bytes + p.b_bytes));
-            if (p.mode == 0) tma_load_2d_pair(sA, &tmA, lead_bar, kb * kBlockK, m_tile * kBlockM);
-            else tma_load_4d_pair(sA, &tmA, lead_bar, cb * kBlockK, cx + dx, cy + dy, cn);
-            tma_load_2d_pair(sB, &tmB, lead_bar, kb * kBlockK, n_tile * p.block_n + rank * bn_local);
-          } else {
-            mbar_arrive_expect_tx(&bars->full[stage], p.a_bytes + p.b_bytes);
-            if (p.mode == 0) tma_load_2d(sA, &tmA, &bars->full[stage], kb * kBlockK, m_tile * kBlockM);
-            else tma_load_4d(sA, &tmA, &bars->full[stage], cb * kBlockK, cx + dx, cy + dy, cn);
-            tma_load_2d(sB, &tmB, &bars->full[stage], kb * kBlockK, n_tile * p.block_n);
+          if (++cb == cblocks) {  // next tap (1x1 convs have a single tap: dx, dy never move)
+            cb = 0;
+            if (taps9 && ++dx == 3) { dx = 0; ++dy; }
           }
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (leader CTA only in pair mode) --
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loop converged (waits included) and one elected lane issues: every operand of the
+    // tcgen05 instructions is then provably warp-uniform, so they compile to bare UTCHMMA / UTCBAR with uniform-register
+    // descriptors — no per-instruction broadcast loop — and the descriptors advance by one add per operand.
+    if (rank == 0) {
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_f16(kPair ? 2 * kBlockM : kBlockM, p.block_n, p.is_bf16 != 0, false, false);
+      const uint32_t tmem0 = warp_uniform(tmem_base);
+      const uint32_t smem0 = warp_uniform(smem_u32(smem));
+      const uint32_t bar0 = warp_uniform(smem_u32(bars));
+      const uint32_t a_full = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, full));
+      const uint32_t a_empty = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, empty));
+      const uint32_t a_tfull = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, tmem_full));
+      const uint32_t a_tempty = bar0 + static_cast<uint32_t>(offsetof(GemmBarriers, tmem_empty));
+      const uint32_t hi = sdesc_hi_sw128(1024);
+      const uint32_t lo0 = sdesc_lo(smem0, 16);         // A of stage 0; B sits 16 KB (1024 descriptor units) behind it
+      const uint32_t lo_step = stage_bytes >> 4;
+      const int nkb = p.num_k_blocks, nstages = p.num_stages;
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, lo = lo0;
       int it = 0;
       for (int item = first_item; item < num_items; item += item_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1u, 2);
+        const uint32_t acc = static_cast<uint32_t>(it) & 1u;
+        mbar_wait_a(a_tempty + acc * 8u, ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u, 2);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&bars->full[stage], phase, 3);
+        const uint32_t tmem_acc = tmem0 + acc * kAccStride;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_a(a_full + static_cast<uint32_t>(stage) * 8u, phase, 3);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sB = sA + 16384u;
+          if (leader) {
+            if constexpr (kPair) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_sdesc_sw128(sA + k * (kUmmaK * 2), 16, 1024);
-            const uint64_t db = make_sdesc_sw128(sB + k * (kUmmaK * 2), 16, 1024);
-            if constexpr (kPair) umma_f16_ss_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t da = (static_cast<uint64_t>(hi) << 32) | (lo + 2u * k);
+                const uint64_t db = (static_cast<uint64_t>(hi) << 32) | (lo + 1024u + 2u * k);
+                umma_f16_ss_pair(tmem_acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit_pair(&bars->empty[stage]);  // smem slot free (in both CTAs) once these MMAs retire
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_f16_ss_lh(tmem_acc, lo + 2u * k, hi, lo + 1024u + 2u * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_commit_a(a_empty + static_cast<uint32_t>(stage) * 8u);
+            }
           }
-          // smem slot free (in both CTAs) once these MMAs retire
-          if constexpr (kPair) umma_commit_pair(&bars->empty[stage]);
-          else umma_commit(&bars->empty[stage]);
-          if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+          lo += lo_step;
+          if (++stage == nstages) { stage = 0; phase ^= 1u; lo = lo0; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (kPair) umma_commit_pair(&bars->tmem_full[acc]);
-        else umma_commit(&bars->tmem_full[acc]);
+        if (leader) {
+          if constexpr (kPair) umma_commit_pair(&bars->tmem_full[acc]);
+          else umma_commit_a(a_tfull + acc * 8u);
+        }
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------- epilogue warps -----------------------------

@@ -215,6 +215,38 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   return d;
 }
 
+// Lean forms for the MMA-issue loops.  One thread issues every tcgen05.mma of a CTA, and under contention with the
+// math warps of its SM sub-partition it retires roughly one instruction per 7 clocks, so every instruction in that loop
+// is on the kernel's critical path (measured with tools/attn_trace.py: ~160 clocks per issued MMA before this).
+// The 64-bit descriptor is (lo, hi): lo = addr>>4 | (LBO>>4)<<16 advances by plain adds (shared addresses stay below
+// 2^18, no carry into the LBO field), hi = SBO>>4 | version 1 (bit 14) | SWIZZLE_128B (2 << 29) is a constant.
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t sdesc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ void umma_f16_ss_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// a value every lane of a converged warp holds identically, made provably warp-uniform for the compiler (tcgen05
+// operands live in uniform registers; a value loaded from shared memory otherwise costs a broadcast loop per use)
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05.ld / st: 32 lanes x 32 bit, N consecutive columns; thread i of the warp <-> TMEM lane
 // (warp_id % 4) * 32 + i.  taddr = (lane << 16) | column.
