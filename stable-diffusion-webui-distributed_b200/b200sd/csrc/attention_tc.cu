@@ -40,6 +40,7 @@
 //   s_full[2] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
 // All waits carry a suspend hint: a polling loop without it steals issue slots from the warps doing the exponentials
 // (measured: a polling TMA producer cost 25 % of this kernel's time).
+#include <cstddef>
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -399,119 +400,161 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;  // S0 @ +0, S1 @ +64, O_a @ +128, O_b @ +128 + dpv
-  const uint32_t tmem_Oa = tmem_base + static_cast<uint32_t>(kSBufs * kKv);
-  const uint32_t tmem_Ob = tmem_Oa + static_cast<uint32_t>(p.dpv);
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
     // Loads go out in exactly the order the MMA thread consumes (and therefore frees) tiles:
     //   K_0, K_1,  then  V_j, K_{j+2}  for j = 0, 1, ...   so a blocking wait never holds back a tile that is needed
-    // earlier than the one being waited for.
-    if (lane == 0) {
-      int kj = 0, k_st = 0, v_st = 0;
-      uint32_t k_par = 0, v_par = 0;
-      auto load_k = [&]() {
-        mbar_wait(&sh->k_empty[k_st], k_par ^ 1u, 11);
+    // earlier than the one being waited for.  The warp stays converged (all lanes wait) and one elected lane issues, so
+    // the TMA instructions take warp-uniform operands without a per-instruction broadcast loop.
+    const bool leader = elect_one();
+    const uint32_t bar0 = warp_uniform(smem_u32(sh));
+    const uint32_t a_k_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_empty));
+    const uint32_t a_v_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_empty));
+    const int k_stages = p.k_stages, v_stages = p.v_stages, chunks = p.chunks;
+    int kj = 0, k_st = 0, v_st = 0;
+    uint32_t k_par = 0, v_par = 0;
+    auto load_k = [&]() {
+      mbar_wait_a(a_k_empty + static_cast<uint32_t>(k_st) * 8u, k_par ^ 1u, 11);
+      if (leader) {
         mbar_arrive_expect_tx(&sh->k_full[k_st], kv_bytes);
-        for (int c = 0; c < p.chunks; ++c)
+        for (int c = 0; c < chunks; ++c)
           tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[k_st], col0 + c * 64, kj * kKv, b);
-        ++kj;
-        if (++k_st == p.k_stages) {
-          k_st = 0;
-          k_par ^= 1u;
-        }
-      };
-      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
-      for (int c = 0; c < p.chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
-      for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&sh->v_empty[v_st], v_par ^ 1u, 12);
-        mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
-        for (int c = 0; c < p.chunks; ++c)
-          tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
-        if (++v_st == p.v_stages) {
-          v_st = 0;
-          v_par ^= 1u;
-        }
-        if (kj < nkv) load_k();
       }
+      ++kj;
+      if (++k_st == k_stages) {
+        k_st = 0;
+        k_par ^= 1u;
+      }
+    };
+    if (leader) {
+      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
+      for (int c = 0; c < chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
     }
+    for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait_a(a_v_empty + static_cast<uint32_t>(v_st) * 8u, v_par ^ 1u, 12);
+      if (leader) {
+        mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
+        for (int c = 0; c < chunks; ++c)
+          tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
+      }
+      if (++v_st == v_stages) {
+        v_st = 0;
+        v_par ^= 1u;
+      }
+      if (kj < nkv) load_k();
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ---------------------------------------
-    if (lane == 0) {
-      long long* trace = (p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1) ? p.trace : nullptr;
-      const bool bf = p.is_bf16 != 0;
-      const int ksteps_qk = p.d16 / 16;
-      const uint32_t aQ = smem_u32(sQ);
-      int qj = 0, q_ks = 0;  // next Q.K^T: tile, K ring slot (+ parity of its k_full phase)
-      uint32_t q_kpar = 0;
-      auto issue_qk = [&]() {  // S[qj & 1] = Q K_qj^T
-        const int q_sb = qj & 1;
-        const int nvalid = min(kKv, p.Skv - qj * kKv);
-        const int n16 = (nvalid + 15) & ~15;
-        ATTN_TRACE(11, qj);
-        mbar_wait(&sh->k_full[q_ks], q_kpar, 14);
-        tc_fence_after();
-        ATTN_TRACE(12, qj);
-        const uint32_t idesc = make_idesc_f16(128, n16, bf, false, false);
-        const uint32_t aK = smem_u32(sK + q_ks * kv_bytes);
+    // One elected lane issues every tcgen05.mma of the CTA.  Under contention with the softmax warps of its SM
+    // sub-partition that lane retires about one instruction per 7 clocks, and before this loop was made lean (converged
+    // warp -> warp-uniform operands -> bare UTCHMMA; descriptors advanced by adds) its ~250 instructions per kv tile
+    // WERE the kernel's critical path (tools/attn_trace.py: 655 clocks to issue 4 MMAs + 2 commits).
+    const bool leader = elect_one();
+    long long* trace = (leader && p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1) ? p.trace : nullptr;
+    const bool bf = p.is_bf16 != 0;
+    const int ksteps_qk = p.d16 / 16, k_stages = p.k_stages, v_stages = p.v_stages, p_bufs = p.p_bufs, skv = p.Skv;
+    const uint32_t tm_S = warp_uniform(tmem_base);
+    const uint32_t tm_Oa = tm_S + static_cast<uint32_t>(kSBufs * kKv), tm_Ob = tm_Oa + static_cast<uint32_t>(p.dpv);
+    const uint32_t bar0 = warp_uniform(smem_u32(sh));
+    const uint32_t a_k_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_full));
+    const uint32_t a_k_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_empty));
+    const uint32_t a_v_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_full));
+    const uint32_t a_v_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_empty));
+    const uint32_t a_s_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, s_full));
+    const uint32_t a_p_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, p_full));
+    const uint32_t a_o_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, o_full));
+    const uint32_t a_q_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, q_full));
+    // descriptor low words (address >> 4 | LBO field); the high word (SBO 1024, version, SWIZZLE_128B) is one constant
+    const uint32_t s0 = warp_uniform(smem_u32(sQ));
+    const uint32_t hi = sdesc_hi_sw128(1024);
+    const uint32_t q_lo = sdesc_lo(s0, 16);
+    const uint32_t p_lo0 = sdesc_lo(s0 + q_bytes, 16);
+    const uint32_t k_lo0 = sdesc_lo(s0 + q_bytes + static_cast<uint32_t>(p_bufs) * kPBytes, 16);
+    const uint32_t v_lo0 = sdesc_lo(s0 + q_bytes + static_cast<uint32_t>(p_bufs) * kPBytes + static_cast<uint32_t>(k_stages) * kv_bytes,
+                                    kKvChunkBytes);  // V is consumed MN-major: LBO = distance between 64-wide chunks
+    const uint32_t kv_step = kv_bytes >> 4;
+    const uint32_t idesc_qk_full = make_idesc_f16(128, kKv, bf, false, false);
+    const uint32_t idesc_pv = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
+    int qj = 0, q_ks = 0;  // next Q.K^T: tile, K ring slot (+ parity of its k_full phase)
+    uint32_t q_kpar = 0, k_lo = k_lo0;
+    auto issue_qk = [&]() {  // S[qj & 1] = Q K_qj^T
+      const uint32_t q_sb = static_cast<uint32_t>(qj) & 1u;
+      const int nvalid = min(kKv, skv - qj * kKv);
+      ATTN_TRACE(11, qj);
+      mbar_wait_a(a_k_full + static_cast<uint32_t>(q_ks) * 8u, q_kpar, 14);
+      tc_fence_after();
+      ATTN_TRACE(12, qj);
+      if (leader) {
+        const uint32_t idesc = nvalid == kKv ? idesc_qk_full : make_idesc_f16(128, (nvalid + 15) & ~15, bf, false, false);
+        const uint32_t d_tmem = tm_S + q_sb * kKv;
         for (int k = 0; k < ksteps_qk; ++k) {
-          const uint32_t offq = static_cast<uint32_t>(k >> 2) * kQChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
-          const uint32_t offk = static_cast<uint32_t>(k >> 2) * kKvChunkBytes + static_cast<uint32_t>(k & 3) * 32u;
-          umma_f16_ss(tmem_base + static_cast<uint32_t>(q_sb * kKv), make_sdesc_sw128(aQ + offq, 16, 1024),
-                      make_sdesc_sw128(aK + offk, 16, 1024), idesc, k != 0 ? 1u : 0u);
+          const uint32_t ch = static_cast<uint32_t>(k) >> 2, in = (static_cast<uint32_t>(k) & 3u) * 2u;
+          umma_f16_ss_lh(d_tmem, q_lo + ch * (kQChunkBytes >> 4) + in, hi, k_lo + ch * (kKvChunkBytes >> 4) + in, hi, idesc,
+                         k != 0 ? 1u : 0u);
         }
-        umma_commit(&sh->k_empty[q_ks]);
-        umma_commit(&sh->s_full[q_sb]);
-        ATTN_TRACE(13, qj);
-        ++qj;
-        if (++q_ks == p.k_stages) {
-          q_ks = 0;
-          q_kpar ^= 1u;
-        }
-      };
-      mbar_wait(&sh->q_full, 0, 13);
-      for (int i = 0; i < kSBufs && i < nkv; ++i) issue_qk();
-      int vs = 0, pb = 0;
-      uint32_t v_par = 0, p_par = 0;
-      for (int j = 0; j < nkv; ++j) {
-        const int nvalid = min(kKv, p.Skv - j * kKv);
-        const int n16 = (nvalid + 15) & ~15;
-        // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
-        ATTN_TRACE(7, j);
-        mbar_wait(&sh->p_full[pb], p_par, 15);
-        ATTN_TRACE(8, j);
-        mbar_wait(&sh->v_full[vs], v_par, 16);
-        tc_fence_after();
-        ATTN_TRACE(9, j);
-        {
-          const uint32_t idesc = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
-          const uint32_t aP = smem_u32(sP + pb * kPBytes);
-          const uint32_t aV = smem_u32(sV + vs * kv_bytes);
-          const int ksteps_pv = n16 / 16;
-          for (int k = 0; k < ksteps_pv; ++k) {
-            const uint32_t offP = static_cast<uint32_t>(k) * 32u;    // 16 halfs inside the 128-byte swizzle row
-            const uint32_t offV = static_cast<uint32_t>(k) * 2048u;  // 16 kv rows x 128 B
-            const bool first = j == 0 && (k & 1) == 0;               // first MMA into this accumulator
-            umma_f16_ss(k < 2 ? tmem_Oa : tmem_Ob, make_sdesc_sw128(aP + offP, 16, 1024),
-                        make_sdesc_sw128(aV + offV, kKvChunkBytes, 1024), idesc, first ? 0u : 1u);
-          }
-          umma_commit(&sh->v_empty[vs]);
-          umma_commit(&sh->o_full[pb]);
-          ATTN_TRACE(10, j);
-        }
-        if (++vs == p.v_stages) {
-          vs = 0;
-          v_par ^= 1u;
-        }
-        if (++pb == p.p_bufs) {
-          pb = 0;
-          p_par ^= 1u;
-        }
-        // ---- softmax j has released its S buffer: refill it two tiles ahead ----
-        if (qj < nkv) issue_qk();
+        umma_commit_a(a_k_empty + static_cast<uint32_t>(q_ks) * 8u);
+        umma_commit_a(a_s_full + q_sb * 8u);
       }
+      ATTN_TRACE(13, qj);
+      ++qj;
+      k_lo += kv_step;
+      if (++q_ks == k_stages) {
+        q_ks = 0;
+        q_kpar ^= 1u;
+        k_lo = k_lo0;
+      }
+    };
+    mbar_wait_a(a_q_full, 0, 13);
+    for (int i = 0; i < kSBufs && i < nkv; ++i) issue_qk();
+    int vs = 0, pb = 0;
+    uint32_t v_par = 0, p_par = 0, v_lo = v_lo0, p_lo = p_lo0;
+    for (int j = 0; j < nkv; ++j) {
+      const int nvalid = min(kKv, skv - j * kKv);
+      // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
+      ATTN_TRACE(7, j);
+      mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
+      ATTN_TRACE(8, j);
+      mbar_wait_a(a_v_full + static_cast<uint32_t>(vs) * 8u, v_par, 16);
+      tc_fence_after();
+      ATTN_TRACE(9, j);
+      if (leader) {
+        const uint32_t acc = j != 0 ? 1u : 0u;  // the first MMA into each accumulator overwrites it
+        if (nvalid == kKv) {
+          // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units apart);
+          // the two accumulators alternate so that consecutive MMAs never depend on each other
+          umma_f16_ss_lh(tm_Oa, p_lo + 0u, hi, v_lo + 0u, hi, idesc_pv, acc);
+          umma_f16_ss_lh(tm_Ob, p_lo + 4u, hi, v_lo + 256u, hi, idesc_pv, acc);
+          umma_f16_ss_lh(tm_Oa, p_lo + 2u, hi, v_lo + 128u, hi, idesc_pv, 1u);
+          umma_f16_ss_lh(tm_Ob, p_lo + 6u, hi, v_lo + 384u, hi, idesc_pv, 1u);
+        } else {
+          const int ksteps_pv = ((nvalid + 15) & ~15) / 16;
+          for (int k = 0; k < ksteps_pv; ++k)
+            umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
+                           (k & 1) == 0 ? acc : 1u);
+        }
+        umma_commit_a(a_v_empty + static_cast<uint32_t>(vs) * 8u);
+        umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
+      }
+      ATTN_TRACE(10, j);
+      v_lo += kv_step;
+      if (++vs == v_stages) {
+        vs = 0;
+        v_par ^= 1u;
+        v_lo = v_lo0;
+      }
+      p_lo += kPBytes >> 4;
+      if (++pb == p_bufs) {
+        pb = 0;
+        p_par ^= 1u;
+        p_lo = p_lo0;
+      }
+      // ---- softmax j has released its S buffer: refill it two tiles ahead ----
+      if (qj < nkv) issue_qk();
     }
+    __syncwarp();
   } else {
     const bool sum_here = p.l_col < 0;
     if (p.is_bf16) {
