@@ -33,10 +33,12 @@
 // ~100 KB shared memory, two CTAs per SM.
 //
 // mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
-//   o_full[pb] P.V of tile j commits to o_full[j%pb].  Every softmax thread waits for tile j-pb on o_full[j%pb] before
-//              it overwrites P[j%pb] (S[j] being ready proves nothing about P.V of that tile), so it observes every
-//              phase of every o_full barrier; the rare-path wait for tile j-1 and the final wait are therefore at most
-//              one phase behind, and P.V of tile j cannot complete before the waiter's warp has arrived on p_full.
+//   o_full[pb] P.V of tile j commits to o_full[j%pb].  One thread issues all MMAs in the order ... P.V(j-2), Q.K(j),
+//              P.V(j-1), Q.K(j+1) ... and the tensor pipe completes them in order, so "S[j] is ready" (which every softmax
+//              thread observes before touching tile j) already proves that P.V of tiles <= j-2 has completed: P[j%pb]
+//              (pb >= 2) is free without a wait of its own, and the rare-path wait for tile j-1 / the final wait can be at
+//              most one phase behind their barrier (the phase before belongs to a tile <= j-3).  P.V of tile j cannot
+//              complete before the waiter's own warp has arrived on p_full.
 //   s_full[2] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
 // All waits carry a suspend hint: a polling loop without it steals issue slots from the warps doing the exponentials
 // (measured: a polling TMA producer cost 25 % of this kernel's time).
@@ -260,9 +262,8 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
     float lsum = 0.f;
     const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
                            : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-    // P[pb] was last read by P.V of tile j - p_bufs (issued that many softmax tiles ago, normally long complete)
+    // P[pb] was last read by P.V of tile j - p_bufs <= j - 2, complete because S[j] is (see the header)
     ATTN_TRACE(3, j);
-    if (j >= p_bufs) mbar_wait_a(a_o_full + pb * 8, p_par ^ 1u, 20);
     ATTN_TRACE(4, j);
     if (__any_sync(0xffffffffu, over)) {
       // rare path (warp-uniform, the TMEM accesses are warp-collective): some row of this warp saw its maximum move
@@ -490,10 +491,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (leader) {
         const uint32_t idesc = nvalid == kKv ? idesc_qk_full : make_idesc_f16(128, (nvalid + 15) & ~15, bf, false, false);
         const uint32_t d_tmem = tm_S + q_sb * kKv;
-        for (int k = 0; k < ksteps_qk; ++k) {
-          const uint32_t ch = static_cast<uint32_t>(k) >> 2, in = (static_cast<uint32_t>(k) & 3u) * 2u;
-          umma_f16_ss_lh(d_tmem, q_lo + ch * (kQChunkBytes >> 4) + in, hi, k_lo + ch * (kKvChunkBytes >> 4) + in, hi, idesc,
-                         k != 0 ? 1u : 0u);
+        if (ksteps_qk == 3) {  // d = 40: the shape that dominates; straight-line issue
+          umma_f16_ss_lh(d_tmem, q_lo, hi, k_lo, hi, idesc, 0u);
+          umma_f16_ss_lh(d_tmem, q_lo + 2u, hi, k_lo + 2u, hi, idesc, 1u);
+          umma_f16_ss_lh(d_tmem, q_lo + 4u, hi, k_lo + 4u, hi, idesc, 1u);
+        } else {
+          for (int k = 0; k < ksteps_qk; ++k) {
+            const uint32_t ch = static_cast<uint32_t>(k) >> 2, in = (static_cast<uint32_t>(k) & 3u) * 2u;
+            umma_f16_ss_lh(d_tmem, q_lo + ch * (kQChunkBytes >> 4) + in, hi, k_lo + ch * (kKvChunkBytes >> 4) + in, hi,
+                           idesc, k != 0 ? 1u : 0u);
+          }
         }
         umma_commit_a(a_k_empty + static_cast<uint32_t>(q_ks) * 8u);
         umma_commit_a(a_s_full + q_sb * 8u);
