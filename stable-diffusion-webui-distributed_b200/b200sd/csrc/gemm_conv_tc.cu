@@ -82,6 +82,62 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// The same GELU on two values at once with Blackwell's packed fp32 pipe (FMUL2 / FFMA2 / FADD2): the GEGLU epilogue is
+// bound by instruction issue (8 epilogue warps must evaluate 128 x 128 GELUs per tile in the ~2560 clocks its MMAs
+// take), and the packed form needs ~12 instead of ~22 instructions per element.
+struct F2 {
+  uint64_t v;
+};
+__device__ __forceinline__ F2 f2(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_get(F2 x, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ F2 gelu_erf2(F2 x) {
+  float x0, x1;
+  f2_get(x, x0, x1);
+  const F2 z = f2_mul(f2(fabsf(x0), fabsf(x1)), f2(0.70710678118654752440f, 0.70710678118654752440f));
+  const F2 d = f2_fma(f2(0.3275911f, 0.3275911f), z, f2(1.0f, 1.0f));
+  float d0, d1;
+  f2_get(d, d0, d1);
+  const F2 t = f2(rcp_approx(d0), rcp_approx(d1));
+  // -(a1 t + a2 t^2 + ... + a5 t^5): coefficients negated so that erf_abs = 1 + (-poly t) e is a single FFMA2
+  F2 poly = f2_fma(f2(-1.061405429f, -1.061405429f), t, f2(1.453152027f, 1.453152027f));
+  poly = f2_fma(poly, t, f2(-1.421413741f, -1.421413741f));
+  poly = f2_fma(poly, t, f2(0.284496736f, 0.284496736f));
+  poly = f2_fma(poly, t, f2(-0.254829592f, -0.254829592f));
+  const F2 npt = f2_mul(poly, t);
+  const F2 arg = f2_mul(f2_mul(z, z), f2(-1.4426950408889634f, -1.4426950408889634f));  // exp(-z^2) = 2^(-z^2 log2 e)
+  float a0, a1;
+  f2_get(arg, a0, a1);
+  const F2 erf_abs = f2_fma(npt, f2(fast_exp2(a0), fast_exp2(a1)), f2(1.0f, 1.0f));
+  float e0, e1;
+  f2_get(erf_abs, e0, e1);
+  const F2 h = f2_fma(f2(0.5f, 0.5f), f2(copysignf(e0, x0), copysignf(e1, x1)), f2(0.5f, 0.5f));
+  return f2_mul(x, h);
+}
+
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   if constexpr (kBf16) {
@@ -197,10 +253,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       for (int j = 0; j < 32; j += 4) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + j));
-        f[j] *= gelu_erf(__uint_as_float(g[j]) + b.x);
-        f[j + 1] *= gelu_erf(__uint_as_float(g[j + 1]) + b.y);
-        f[j + 2] *= gelu_erf(__uint_as_float(g[j + 2]) + b.z);
-        f[j + 3] *= gelu_erf(__uint_as_float(g[j + 3]) + b.w);
+        const F2 y01 = f2_mul(f2(f[j], f[j + 1]),
+                              gelu_erf2(f2_add(f2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), f2(b.x, b.y))));
+        const F2 y23 = f2_mul(f2(f[j + 2], f[j + 3]),
+                              gelu_erf2(f2_add(f2(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), f2(b.z, b.w))));
+        f2_get(y01, f[j], f[j + 1]);
+        f2_get(y23, f[j + 2], f[j + 3]);
       }
     }
     if (p.has_residual) {

@@ -144,11 +144,18 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     return out
 
 
+_GN_FLOATS = {}
+
+
 def groupnorm_stats_floats(nb: int, hw: int, c: int, groups: int) -> int:
     """fp32 elements a `stats` buffer for groupnorm() must hold (results + the reduction's scratch)"""
-    n = int(_lib.lib().b200sd_groupnorm_stats_floats(nb, hw, c, groups))
-    if n < 0:
-        raise _lib.B200SDError(f"groupnorm: unsupported shape C={c}")
+    key = (nb, hw, c, groups)
+    n = _GN_FLOATS.get(key)
+    if n is None:
+        n = int(_lib.lib().b200sd_groupnorm_stats_floats(nb, hw, c, groups))
+        if n < 0:
+            raise _lib.B200SDError(f"groupnorm: unsupported shape C={c}")
+        _GN_FLOATS[key] = n
     return n
 
 
