@@ -184,9 +184,12 @@ class LocalGPUWorker(Worker):
             if eng.interrupted:
                 break
         images = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
-        host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
-        host.copy_(images, non_blocking=True)
-        torch.cuda.current_stream(images.device).synchronize()
+        if images.device.type == "cuda":
+            host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
+            host.copy_(images, non_blocking=True)
+            torch.cuda.current_stream(images.device).synchronize()
+        else:  # an engine double in the host-logic tests; the real engine refuses non-CUDA devices
+            host = images.to(torch.uint8).contiguous()
         n = host.shape[0]
         seeds = [seed + i for i in range(n)]
         subseeds = [subseed + i for i in range(n)]

@@ -106,6 +106,30 @@ def test_worker_img2img_request(env):
     assert torch.equal(r["tensors"], direct)  # two runs of the same request are bit-identical (deterministic kernels)
 
 
+def test_rest_worker_serves_the_executor(env):
+    """SURVEY §8 f1 on a GPU: POST /sdapi/v1/txt2img -> LocalGPUWorker -> SDEngine; the PNGs decode to exactly the images
+    a direct engine call produces (PNG is lossless, the kernels are deterministic)."""
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    import base64, io
+    import numpy as np
+    from fastapi.testclient import TestClient
+    from PIL import Image
+    from b200sd.factory import synthetic_tokens
+    from server.sdapi import create_app
+    c = TestClient(create_app(lambda device: eng, [0]))
+    mem = c.get("/sdapi/v1/memory").json()
+    assert mem["cuda"]["system"]["total"] > mem["cuda"]["system"]["free"] > 0
+    payload = {"prompt": "rest probe", "negative_prompt": "", "seed": 5, "subseed": 1, "batch_size": 2, "n_iter": 1, "steps": 5,
+               "width": 64, "height": 64, "sampler_name": "DDIM", "cfg_scale": 6.0}
+    r = c.post("/sdapi/v1/txt2img", json=payload)
+    assert r.status_code == 200
+    got = torch.stack([torch.from_numpy(np.array(Image.open(io.BytesIO(base64.b64decode(s))))) for s in r.json()["images"]])
+    vocab = eng.clip_cfg.vocab
+    direct = eng.txt2img(synthetic_tokens(["rest probe"] * 2, vocab), synthetic_tokens([""] * 2, vocab), 5, steps=5,
+                         cfg_scale=6.0, height=64, width=64, sampler="DDIM").cpu()
+    assert torch.equal(got, direct)
+
+
 def test_device_failure_marks_worker_unavailable(env):
     processing, mscripts, DistributedScript, eng, State, sh = env
 
