@@ -223,7 +223,6 @@ def main():
     seed0 = 1000 + rank * b   # global image index -> seed (reference: seed + images owned by earlier jobs)
     x_T = E.per_image_noise(seed0, b, (4, HW, HW))[0]
     tokens_d, neg_d, x_T_d = tokens.to(dev), neg.to(dev), x_T.to(dev)
-    gathered = torch.empty((world * b, HW * 8, HW * 8, 3), device=dev, dtype=torch.uint8) if world > 1 else None
 
     def step_device():
         cond = eng.encode_prompts(tokens_d)
