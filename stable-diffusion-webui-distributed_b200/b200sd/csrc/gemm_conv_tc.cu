@@ -57,6 +57,8 @@ struct GemmKernelParams {
   int flags;                       // B200SD_EPI_*
   int is_bf16;
   int pair;                        // 1: launched as CTA pairs (tcgen05 cta_group::2, 256-row tiles)
+  int d_bufs;                      // output staging buffers per epilogue group (2, or 3 so a TMA store may still be
+                                   // reading its buffer while the next chunk is staged)
 };
 
 struct __align__(8) GemmBarriers {
@@ -187,7 +189,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
                                               GemmBarriers* bars, uint8_t* stage_d, uint8_t* stage_r,
                                               uint64_t* tmem_full_bar, uint32_t full_parity, uint32_t tmem_acc,
                                               int m_tile, int n_tile, int quarter, int group, int lane,
-                                              uint32_t (&uses)[2], uint32_t& chunk_count) {
+                                              uint32_t (&uses)[2], uint32_t& chunk_count, uint32_t& d_slot) {
   const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
   const bool leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
   const TileCoord tc = tile_coord(p, m_tile);
@@ -195,7 +197,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
   const int out_bn = geglu ? p.block_n / 2 : p.block_n;
   const int nchunks = out_bn / kChunkCols;
   const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-  uint8_t* my_d = stage_d + group * 2 * kStageTileBytes;
+  uint8_t* my_d = stage_d + group * p.d_bufs * kStageTileBytes;
   uint8_t* my_r = stage_r + group * 2 * kStageTileBytes;
 
   auto load_residual = [&](int buf, int c) {  // leader only
@@ -281,7 +283,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
     }
-    uint8_t* dt = my_d + buf * kStageTileBytes;
+    uint8_t* dt = my_d + d_slot * kStageTileBytes;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 o;
@@ -292,7 +294,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       *reinterpret_cast<uint4*>(dt + sw64_offset(r, q)) = o;
     }
     fence_proxy_async_smem();          // my staging writes (and residual reads) -> visible / ordered for the async proxy
-    if (leader) bulk_wait_read<0>();   // the previous chunk's store has finished reading the OTHER staging buffer
+    // before chunk i+1 is staged into the buffer after this one, the store that last read THAT buffer must be done:
+    // with two buffers that is the previous store (wait for all), with three the one before it (one may stay in flight)
+    if (leader) {
+      if (p.d_bufs == 3) bulk_wait_read<1>();
+      else bulk_wait_read<0>();
+    }
     group_bar_sync(group);
     if (leader) {
       const int col = n_tile * out_bn + c * kChunkCols;
@@ -301,6 +308,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       bulk_commit();
       if (p.has_residual && c + 4 < nchunks) load_residual(buf, c + 4);  // everyone is past reading this buffer
     }
+    if (++d_slot == static_cast<uint32_t>(p.d_bufs)) d_slot = 0;
   }
   chunk_count = base + ci;
 }
@@ -321,7 +329,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int bn_local = kPair ? p.block_n / 2 : p.block_n;  // B rows staged by this CTA
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(bn_local) * 128u;
   uint8_t* stage_d = smem + static_cast<size_t>(p.num_stages) * stage_bytes;
-  uint8_t* stage_r = stage_d + kStagingBytes;
+  uint8_t* stage_r = stage_d + static_cast<size_t>(p.d_bufs) * 2 * kStageTileBytes;
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_r + (p.has_residual ? kStagingBytes : 0));
 
   const int warp = threadIdx.x >> 5;
@@ -480,7 +488,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;      // TMEM lane quarter this warp may access
     const int group = (warp - 2) >> 2;  // warps 2-5 / 6-9: chunks group, group+2, ...
     uint32_t uses[2] = {0u, 0u};
-    uint32_t chunk_count = 0u;
+    uint32_t chunk_count = 0u, d_slot = 0u;
     int it = 0;
     for (int item = first_item; item < num_items; item += item_step, ++it) {
       const int acc = it & 1;
@@ -490,10 +498,10 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
       if (p.is_bf16)
         epilogue_tile<true>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                            n_tile, quarter, group, lane, uses, chunk_count);
+                            n_tile, quarter, group, lane, uses, chunk_count, d_slot);
       else
         epilogue_tile<false>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                             n_tile, quarter, group, lane, uses, chunk_count);
+                             n_tile, quarter, group, lane, uses, chunk_count, d_slot);
       tc_fence_before();
       // the MMA issuer (leader CTA) may overwrite this accumulator once BOTH CTAs have drained theirs
       // one (possibly remote) arrival per warp: 256 remote arrivals per tile cost more than a short tile's MMAs
@@ -577,7 +585,20 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
                   GemmKernelParams& p, int max_ctas, cudaStream_t stream) {
   const int bn_local = p.pair ? p.block_n / 2 : p.block_n;
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(bn_local) * 128u;
-  const int staging = static_cast<int>(kStagingBytes) * (p.has_residual ? 2 : 1);
+  // Output staging: a third buffer per epilogue group lets the TMA store of chunk i-1 keep reading while chunk i is
+  // staged (with two, every chunk waits for the previous store's shared-memory read).  It pays for short-K tiles, whose
+  // epilogue is not hidden behind a long MMA phase — as long as the operand ring keeps at least 3 stages.
+  static int dbufs_env = -1;  // experiment knob: B200SD_GEMM_DBUFS = 2 | 3
+  if (dbufs_env < 0) {
+    const char* e = getenv("B200SD_GEMM_DBUFS");
+    dbufs_env = e ? atoi(e) : 0;
+  }
+  const int fixed = 1024 /*align*/ + static_cast<int>(sizeof(GemmBarriers)) + 64 +
+                    (p.has_residual ? static_cast<int>(kStagingBytes) : 0);
+  const int stages3 = (g_max_smem - fixed - 6 * static_cast<int>(kStageTileBytes)) / static_cast<int>(stage_bytes);
+  p.d_bufs = (p.num_k_blocks <= 24 && stages3 >= 3) ? 3 : 2;
+  if (dbufs_env == 2 || dbufs_env == 3) p.d_bufs = dbufs_env;
+  const int staging = p.d_bufs * 2 * static_cast<int>(kStageTileBytes) + (p.has_residual ? static_cast<int>(kStagingBytes) : 0);
   const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
