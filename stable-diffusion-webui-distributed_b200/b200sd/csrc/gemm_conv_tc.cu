@@ -586,18 +586,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   const int bn_local = p.pair ? p.block_n / 2 : p.block_n;
   const uint32_t stage_bytes = 16384u + static_cast<uint32_t>(bn_local) * 128u;
   // Output staging: a third buffer per epilogue group lets the TMA store of chunk i-1 keep reading while chunk i is
-  // staged (with two, every chunk waits for the previous store's shared-memory read).  It pays for short-K tiles, whose
-  // epilogue is not hidden behind a long MMA phase — as long as the operand ring keeps at least 3 stages.
-  static int dbufs_env = -1;  // experiment knob: B200SD_GEMM_DBUFS = 2 | 3
+  // staged (with two, every chunk waits for the previous store's shared-memory read).  Measured (tools/gemm_sweep.py,
+  // K = 320 / 1280 linears): no gain — those GEMMs sit at 70-85 % of their HBM roofline, not on the store latency — so
+  // two buffers stay the default and B200SD_GEMM_DBUFS=3 remains an experiment knob.
+  static int dbufs_env = -1;
   if (dbufs_env < 0) {
     const char* e = getenv("B200SD_GEMM_DBUFS");
     dbufs_env = e ? atoi(e) : 0;
   }
-  const int fixed = 1024 /*align*/ + static_cast<int>(sizeof(GemmBarriers)) + 64 +
-                    (p.has_residual ? static_cast<int>(kStagingBytes) : 0);
-  const int stages3 = (g_max_smem - fixed - 6 * static_cast<int>(kStageTileBytes)) / static_cast<int>(stage_bytes);
-  p.d_bufs = (p.num_k_blocks <= 24 && stages3 >= 3) ? 3 : 2;
-  if (dbufs_env == 2 || dbufs_env == 3) p.d_bufs = dbufs_env;
+  p.d_bufs = dbufs_env == 3 ? 3 : 2;
   const int staging = p.d_bufs * 2 * static_cast<int>(kStageTileBytes) + (p.has_residual ? static_cast<int>(kStagingBytes) : 0);
   const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);

@@ -194,12 +194,14 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
   for (; p < p1; p += PY) emit(__ldg(reinterpret_cast<const uint4*>(xb + p * rx)), p);
 }
 
-// One warp per row, VPT 16-byte vectors per lane (C <= 256 * VPT); gamma/beta staged in smem once per CTA;
+// LPR lanes (a power of two, 4..32) share one row and 32/LPR rows share a warp, so every lane carries data whatever C is
+// (C = 320 is 40 vectors: 8 lanes x 5, four rows per warp — one row per warp would leave 3/8 of the load slots empty);
+// VPT 16-byte vectors per lane, all in flight before the first reduction; gamma/beta staged in smem once per CTA;
 // persistent CTAs stride over rows so the staging is amortised and many rows are in flight per SM.
 template <bool kBf16, int VPT>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy, int rows, int C,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int lpr) {
   extern __shared__ float gb[];  // gamma[C], beta[C]
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     gb[i] = gamma[i];
@@ -207,42 +209,49 @@ layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restri
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int sub = lane & (lpr - 1);   // my position among the lanes of my row
+  const int rpw = 32 / lpr;           // rows per warp
+  const int wrow = lane / lpr;        // which of the warp's rows is mine
   const int warps_per_cta = blockDim.x >> 5;
   const int nvec = C / 8;
   const float inv_c = 1.0f / static_cast<float>(C);
-  for (int row = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_cta) {
-    const uint8_t* xr = X + static_cast<long long>(row) * ldx * 2;
-    uint8_t* yr = Y + static_cast<long long>(row) * ldy * 2;
+  const int row_step = gridDim.x * warps_per_cta * rpw;
+  for (int row0 = (blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * rpw; row0 < rows; row0 += row_step) {
+    const int row = row0 + wrow;
+    const bool live = row < rows;     // whole-warp shuffles below: dead rows just carry zeros
+    const uint8_t* xr = X + static_cast<long long>(live ? row : 0) * ldx * 2;
+    uint8_t* yr = Y + static_cast<long long>(live ? row : 0) * ldy * 2;
     float f[VPT][8];
     float sum = 0.f;
 #pragma unroll
     for (int it = 0; it < VPT; ++it) {
-      const int vec = it * 32 + lane;
-      if (vec < nvec) {
+      const int vec = it * lpr + sub;
+      if (live && vec < nvec) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long long>(vec) * 16));
         unpack8<kBf16>(u, f[it]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) sum += f[it][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[it][i] = 0.f;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum * inv_c;
     float var = 0.f;
 #pragma unroll
     for (int it = 0; it < VPT; ++it) {
-      if (it * 32 + lane < nvec) {
+      if (it * lpr + sub < nvec) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const float d = f[it][i] - mean; var = fmaf(d, d, var); }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    for (int o = lpr >> 1; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = rsqrtf(var * inv_c + eps);
 #pragma unroll
     for (int it = 0; it < VPT; ++it) {
-      const int vec = it * 32 + lane;
-      if (vec < nvec) {
+      const int vec = it * lpr + sub;
+      if (live && vec < nvec) {
         float o8[8];
         const float4 g0 = *reinterpret_cast<const float4*>(gb + vec * 8);
         const float4 g1 = *reinterpret_cast<const float4*>(gb + vec * 8 + 4);
@@ -277,15 +286,15 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
 }
 
 template <bool kBf16>
-static void launch_ln(int vpt, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx, uint8_t* Y,
+static void launch_ln(int vpt, int lpr, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx, uint8_t* Y,
                       long long ldy, int rows, int C, const float* gamma, const float* beta, float eps) {
   switch (vpt) {
-    case 1: layernorm_kernel<kBf16, 1><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
-    case 2: layernorm_kernel<kBf16, 2><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
-    case 3: layernorm_kernel<kBf16, 3><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
-    case 4: layernorm_kernel<kBf16, 4><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
-    case 5: layernorm_kernel<kBf16, 5><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
-    default: layernorm_kernel<kBf16, 8><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 1: layernorm_kernel<kBf16, 1><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 2: layernorm_kernel<kBf16, 2><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 3: layernorm_kernel<kBf16, 3><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 4: layernorm_kernel<kBf16, 4><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 5: layernorm_kernel<kBf16, 5><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    default: layernorm_kernel<kBf16, 8><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
   }
 }
 
@@ -349,17 +358,22 @@ extern "C" int b200sd_layernorm(const void* X, long long ldx, void* Y, long long
   if (C % 8 != 0 || C > 2048 || ldx % 8 != 0 || ldy % 8 != 0 ||
       ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15))
     return B200SD_ERR_INVALID;
-  const int vpt = (C / 8 + 31) / 32;
-  const int warps_per_block = 8;
-  int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  // lanes per row: the fewest (power of two >= 4) that keep the per-lane vector count at 5 or below
+  const int nvec = C / 8;
+  int lpr = 4;
+  while (lpr < 32 && (nvec + lpr - 1) / lpr > 5) lpr <<= 1;
+  int vpt = (nvec + lpr - 1) / lpr;
+  if (vpt > 5) vpt = 8;
+  const int rows_per_block = 8 * (32 / lpr);
+  int blocks = (rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 148 * 8) blocks = 148 * 8;
   const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
-    launch_ln<true>(vpt, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
+    launch_ln<true>(vpt, lpr, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
                     gamma, beta, eps);
   else
-    launch_ln<false>(vpt, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
+    launch_ln<false>(vpt, lpr, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
                      gamma, beta, eps);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
