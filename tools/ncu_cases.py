@@ -29,6 +29,12 @@ def main():
         plan.table[:1].copy_(eng.temb.table(torch.tensor([651.0])))
         ops.pack_unet_input(torch.randn((nb // 2, 4096, 4), device="cuda"), plan.unet.xin, 1.0)
         fn = lambda: plan.step_ddim(7.0)  # noqa: E731
+    elif case == "vae":
+        from b200sd import config as C, engine as E, synth
+        cfgs = (C.SD15_UNET, C.SD15_VAE, C.SD15_CLIP)
+        eng = E.SDEngine(synth.make_state_dict(*cfgs, seed=0), *cfgs, device="cuda:0", use_graphs=False)
+        lat = torch.randn((nb // 2, 4096, 4), device="cuda") * 0.18215
+        fn = lambda: eng.decode(lat, 64, 64)  # noqa: E731
     elif case == "conv":
         x, w, o = rnd(nb, 64, 64, 320), rnd(320, 2880, scale=0.02), torch.empty((nb * 4096, 320), device="cuda", dtype=torch.half)
         b = torch.randn(320, device="cuda")
