@@ -33,12 +33,13 @@
 // ~100 KB shared memory, two CTAs per SM.
 //
 // mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
-//   o_full[pb] P.V of tile j commits to o_full[j%pb].  One thread issues all MMAs in the order ... P.V(j-2), Q.K(j),
-//              P.V(j-1), Q.K(j+1) ... and the tensor pipe completes them in order, so "S[j] is ready" (which every softmax
-//              thread observes before touching tile j) already proves that P.V of tiles <= j-2 has completed: P[j%pb]
-//              (pb >= 2) is free without a wait of its own, and the rare-path wait for tile j-1 / the final wait can be at
-//              most one phase behind their barrier (the phase before belongs to a tile <= j-3).  P.V of tile j cannot
-//              complete before the waiter's own warp has arrived on p_full.
+//   o_full[pb] P.V of tile j commits to o_full[j%pb].  One thread issues all MMAs in the order ... Q.K(j), P.V(j-2),
+//              Q.K(j+1), P.V(j-1) ... (Q.K first: S is what the softmax warps wait for) and a commit fires when ALL MMAs
+//              issued before it have completed, so "S[j] is ready" (which every softmax thread observes before touching
+//              tile j) already proves that P.V of tiles <= j-3 has completed: P[j%3] is free without a wait of its own
+//              (hence three P buffers), and the rare-path wait for tile j-1 / the final wait can be at most one phase
+//              behind their barrier (the phase before belongs to tile j-4).  P.V of tile j cannot complete before the
+//              waiter's own warp has arrived on p_full.
 //   s_full[2] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
 // All waits carry a suspend hint: a polling loop without it steals issue slots from the warps doing the exponentials
 // (measured: a polling TMA producer cost 25 % of this kernel's time).
@@ -179,6 +180,11 @@ __device__ __forceinline__ float h2_hmax(uint32_t v) {
 
 // P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
 constexpr float kPRedo = 256.0f;
+
+// 1: per kv tile the MMA thread issues Q.K of tile j+2 before P.V of tile j (needs 3 P buffers, see the header)
+#ifndef B200SD_ATTN_QK_FIRST
+#define B200SD_ATTN_QK_FIRST 1
+#endif
 
 // debug timeline (b200sd_debug_attention_trace): CTA (3, 2, 1) stamps per-tile events of softmax warp 2 and the MMA thread
 #define ATTN_TRACE(ev, j) \
@@ -434,6 +440,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
     for (int j = 0; j < nkv; ++j) {
+#if B200SD_ATTN_QK_FIRST
+      if (kj < nkv) load_k();  // consumption order: K_{j+2} (Q.K of tile j+2) before V_j (P.V of tile j)
+#endif
       mbar_wait_a(a_v_empty + static_cast<uint32_t>(v_st) * 8u, v_par ^ 1u, 12);
       if (leader) {
         mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
@@ -444,7 +453,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         v_st = 0;
         v_par ^= 1u;
       }
+#if !B200SD_ATTN_QK_FIRST
       if (kj < nkv) load_k();
+#endif
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -520,10 +531,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t v_par = 0, p_par = 0, v_lo = v_lo0, p_lo = p_lo0;
     for (int j = 0; j < nkv; ++j) {
       const int nvalid = min(kKv, skv - j * kKv);
-      // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
       ATTN_TRACE(7, j);
       mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
       ATTN_TRACE(8, j);
+#if B200SD_ATTN_QK_FIRST
+      // ---- softmax j has released its S buffer: refill it two tiles ahead, BEFORE this tile's P.V — S is what the
+      // softmax warps wait for next; O is not read until the end ----
+      if (qj < nkv) issue_qk();
+#endif
+      // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
       mbar_wait_a(a_v_full + static_cast<uint32_t>(vs) * 8u, v_par, 16);
       tc_fence_after();
       ATTN_TRACE(9, j);
@@ -558,8 +574,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         p_par ^= 1u;
         p_lo = p_lo0;
       }
+#if !B200SD_ATTN_QK_FIRST
       // ---- softmax j has released its S buffer: refill it two tiles ahead ----
       if (qj < nkv) issue_qk();
+#endif
     }
     __syncwarp();
   } else {
@@ -655,6 +673,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
                             ? half_sm : static_cast<size_t>(g_attn_max_smem);
   p.p_bufs = (base + 3 * kPBytes + 4 * kvt <= budget) ? 3 : 2;
   if (e_pb == 2 || e_pb == 3) p.p_bufs = e_pb;
+  if (B200SD_ATTN_QK_FIRST) p.p_bufs = 3;  // required for the P-buffer reuse argument in that issue order
   const size_t fixed = base + static_cast<size_t>(p.p_bufs) * kPBytes;
   p.k_stages = (fixed + 5 * kvt <= budget) ? 3 : 2;
   p.v_stages = 2;
