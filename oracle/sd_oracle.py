@@ -412,6 +412,18 @@ def sample_euler_a(unet, x_T, cond, uncond, steps: int, cfg_scale: float, noises
     return x
 
 
+def sample_euler(unet, x_T, cond, uncond, steps: int, cfg_scale: float):
+    """k-diffusion sample_euler with s_churn = 0 (sdwui "Euler"): d = (x - denoised) / sigma = eps,
+    x += d * (sigma_next - sigma) on the same CompVisDenoiser sigmas as Euler a."""
+    coefs = euler_a_coefficients(steps)
+    x = x_T * coefs[0][1]
+    for i, (t, s, down, up, c_in, _) in enumerate(coefs):
+        sn = math.sqrt(down * down + up * up)
+        e = cfg_eps(unet, x * c_in, t, cond, uncond, cfg_scale)
+        x = x + e * (sn - s)
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ images / rng
 def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0) -> torch.Tensor:
     """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k."""

@@ -90,6 +90,16 @@ def euler_a_plan(steps: int):
     return t_out, rows, float(sig[0])
 
 
+def euler_plan(steps: int):
+    """k-diffusion sample_euler (s_churn = 0) on the same sigmas: the ancestral step with sigma_up = 0, i.e.
+    sigma_down = sigma_next and no noise — same coefficient rows, same kernel."""
+    t_out, rows, sigma0 = euler_a_plan(steps)
+    for i, r in enumerate(rows):
+        sn = (r[1] ** 2 + r[2] ** 2) ** 0.5   # sigma_next = sqrt(down^2 + up^2)
+        rows[i] = [r[0], sn, 0.0, r[3]]
+    return t_out, rows, sigma0
+
+
 def per_image_noise(seed: int, n: int, shape, draws: int = 1) -> torch.Tensor:
     """sdwui ImageRNG with randn_source = 'CPU': image k owns torch.Generator('cpu').manual_seed(seed + k);
     `draws` successive tensors per image (x_T, then ancestral noises).  Returns [draws, n, *shape] fp32 (host)."""
@@ -129,6 +139,11 @@ class Plan:
         ops.select_step(self.table, self.step, self.unet.cur_bias)
         self.unet.run()
         ops.cfg_euler_a_step(self.unet.eps, self.x, self.noise, self.unet.xin, cfg_scale, self.coef, self.step)
+
+    def step_euler(self, cfg_scale: float):  # sigma_up == 0 in every coefficient row: the kernel needs no noise
+        ops.select_step(self.table, self.step, self.unet.cur_bias)
+        self.unet.run()
+        ops.cfg_euler_a_step(self.unet.eps, self.x, None, self.unet.xin, cfg_scale, self.coef, self.step)
 
 
 class SDEngine:
@@ -212,6 +227,10 @@ class SDEngine:
                 if noises is None:
                     raise ValueError("Euler a needs the per-image ancestral noises")
                 plan.noise = noises.to(self.device, torch.float32).permute(0, 1, 3, 4, 2).reshape(len(rows), b, h * w, 4).contiguous()
+            elif sampler == "Euler":
+                ts, rows, sigma0 = euler_plan(steps)
+                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
             else:
                 raise ValueError(f"sampler {sampler!r} is not implemented on the local executor")
             n_evals = len(ts)

@@ -23,7 +23,7 @@ from modules.shared import state as master_state
 from .shared import logger
 from .worker import InvalidWorkerResponse, State, Worker
 
-SUPPORTED_SAMPLERS = ("DDIM", "Euler a")
+SUPPORTED_SAMPLERS = ("DDIM", "Euler a", "Euler")
 
 
 class LocalGPUWorker(Worker):

@@ -180,6 +180,26 @@ def test_img2img_parity(mods, size, b, px, steps):
     assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
 
 
+def test_euler_parity_tiny(mods):
+    """sdwui "Euler" (k-diffusion sample_euler, s_churn 0) through the worker-facing txt2img call"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b, hw, steps = 2, 16, 6
+    tok = O.random_prompt_tokens(b, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    x_T = O.per_image_noise(2100, b, (4, hw, hw))
+    cond32 = O.clip_text_encode(dsd, cfgs[2], tok.cuda())
+    unc32 = O.clip_text_encode(dsd, cfgs[2], neg.cuda())
+    with torch.no_grad():
+        ref = O.sample_euler(lambda x, t, c: O.unet_forward(dsd, cfgs[0], x, t, c), x_T.cuda(), cond32, unc32, steps, 7.0)
+    got_u8 = eng.txt2img(tok, neg, seed=2100, steps=steps, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler="Euler")
+    torch.cuda.synchronize()
+    z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel = float((z - ref).abs().max() / ref.abs().max())
+    _record("euler tiny", z_rel_max=rel)
+    assert rel <= 3e-2 and got_u8.shape == (b, hw * 8, hw * 8, 3)
+
+
 def test_euler_a_parity_tiny(mods):
     C, E, S, O = mods
     cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")

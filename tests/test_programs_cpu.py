@@ -101,6 +101,25 @@ def test_sample_matches_oracle_euler_a(env):
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
 
 
+def test_sample_matches_oracle_euler(env):
+    """sdwui "Euler" = k-diffusion sample_euler with s_churn 0: the ancestral kernel with sigma_up = 0 rows, no noise"""
+    C, E, O, cfgs, sd, eng = env
+    b, hw, steps = 2, 8, 5
+    ts, rows, s0 = E.euler_plan(steps)
+    ts_a, rows_a, s0_a = E.euler_a_plan(steps)
+    assert ts == ts_a and s0 == s0_a and all(r[2] == 0.0 for r in rows)
+    assert all(abs(r[1] ** 2 - (ra[1] ** 2 + ra[2] ** 2)) < 1e-9 for r, ra in zip(rows, rows_a))
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    nz = E.per_image_noise(3000, b, (4, hw, hw), 1)
+    with torch.no_grad():
+        ref = O.sample_euler(lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c), nz[0], cond, unc, steps, 7.0)
+    lat = eng.sample(cond, unc, nz[0], steps, 7.0, "Euler")
+    z = lat.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
 def test_img2img_matches_oracle(env):
     """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
     C, E, O, cfgs, sd, eng = env
