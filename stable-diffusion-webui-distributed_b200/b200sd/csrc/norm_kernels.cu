@@ -274,11 +274,12 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
   if (py < 1) py = 1;
   if (py > HW) py = HW;
   block = dim3(vx, py, 1);
-  // ~2 waves of (up to) 4 resident CTAs per SM over the whole grid; a CTA owns a multiple of py*unroll pixels
-  int want = (148 * 8 + NB - 1) / NB;
-  int ppc = (HW + want - 1) / want;
+  // A CTA owns ~48 KB of one image (a multiple of py*unroll pixels).  The split depends on the image's shape only,
+  // NOT on how many images are in the batch: the partial sums of an image — and therefore every bit of its result —
+  // are the same whether it is processed alone, in a batch of 32, or on another GPU of a sharded request.
+  (void)NB;
   const int quantum = py * kGnUnroll;
-  ppc = ((ppc + quantum - 1) / quantum) * quantum;
+  int ppc = (48 * 1024 / (2 * C) + quantum - 1) / quantum * quantum;
   if (ppc < quantum) ppc = quantum;
   pix_per_cta = ppc;
   grid = dim3((HW + ppc - 1) / ppc, NB, 1);

@@ -155,6 +155,24 @@ def test_sd15_sampler_is_bit_reproducible(mods):
     assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
 
 
+@pytest.mark.parametrize("size,px", [("tiny", 128), ("sd15", 512)])
+def test_images_do_not_depend_on_their_batch(mods, size, px):
+    """image k is a function of (prompt, seed + k) only — the premise of sharding a request's batch over
+    workers.  Here it holds bit for bit: no kernel's reduction order for one image depends on the other images of the
+    launch (GroupNorm's CTA split is per image shape, GEMM K loops and attention rows are per element), so the last two
+    images of a batch of 5 equal a batch of 2 started at seed + 3."""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, size)
+    tok = O.random_prompt_tokens(1, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(1, vocab_hi=vocab_hi)
+    eng.use_graphs = True
+    five = eng.txt2img(tok.expand(5, -1), neg.expand(5, -1), seed=300, steps=6, cfg_scale=7.0, height=px, width=px).clone()
+    two = eng.txt2img(tok.expand(2, -1), neg.expand(2, -1), seed=303, steps=6, cfg_scale=7.0, height=px, width=px).clone()
+    eng.use_graphs = False
+    torch.cuda.synchronize()
+    assert torch.equal(five[3:], two)
+
+
 @pytest.mark.parametrize("size,b,px,steps", [("tiny", 3, 64, 8), ("sd15", 2, 512, 20)])
 def test_img2img_parity(mods, size, b, px, steps):
     """config C3: VAE encode (posterior mean) + noise to t_enc + DDIM remainder + decode, vs the fp32 oracle."""
