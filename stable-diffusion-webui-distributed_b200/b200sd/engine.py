@@ -7,6 +7,7 @@ exchange; results meet once, at the end (bench: one NCCL all-gather; plugin path
 """
 import contextlib
 import math
+import threading
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -18,6 +19,7 @@ from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
 from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
 
 MAX_STEPS = 256
+_CAPTURE_LOCK = threading.Lock()  # CUDA graph captures are serialised across the per-device worker threads
 
 
 # ------------------------------------------------------------------------------------------------ schedules
@@ -198,10 +200,14 @@ class SDEngine:
                 fn()
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
-            l0 = ops.LAUNCHES
-            with torch.cuda.graph(g):
-                fn()
-            plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
+            # One LocalGPUWorker thread per device may be building its graphs at the same time: capture one at a time,
+            # and in thread-local error mode so that another thread's allocations / launches on ITS device do not
+            # invalidate this capture (the default "global" mode does).
+            with _CAPTURE_LOCK:
+                l0 = ops.LAUNCHES
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    fn()
+                plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
             plan.graphs[name] = g
             plan.x.copy_(saved[0]); plan.step.copy_(saved[1]); plan.unet.xin.copy_(saved[2])
         return plan.graphs[name]
@@ -273,10 +279,11 @@ class SDEngine:
                         vae.run()
                         torch.cuda.current_stream().synchronize()
                         g = torch.cuda.CUDAGraph()
-                        l0 = ops.LAUNCHES
-                        with torch.cuda.graph(g):
-                            vae.run()
-                        plan.graph_launches["vae"] = ops.LAUNCHES - l0
+                        with _CAPTURE_LOCK:
+                            l0 = ops.LAUNCHES
+                            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                                vae.run()
+                            plan.graph_launches["vae"] = ops.LAUNCHES - l0
                         plan.graphs["vae"] = g
                     plan.graphs["vae"].replay()
                     self.graph_replayed_launches += plan.graph_launches["vae"]
