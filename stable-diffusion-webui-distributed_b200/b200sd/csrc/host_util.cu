@@ -4,16 +4,16 @@
 namespace b200sd {
 
 PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static with an initialiser: C++11 makes this thread-safe (one LocalGPUWorker thread per device may
+  // reach it at the same time)
+  static const PFN_encodeTiled fn = []() -> PFN_encodeTiled {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
         qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return nullptr;
+  }();
   return fn;
 }
 

@@ -215,7 +215,7 @@ def test_euler_parity_tiny(mods):
     z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
     rel = float((z - ref).abs().max() / ref.abs().max())
     _record("euler tiny", z_rel_max=rel)
-    assert rel <= 3e-2 and got_u8.shape == (b, hw * 8, hw * 8, 3)
+    assert rel <= 3e-2 and got_u8.shape[0] == b and got_u8.dtype == torch.uint8
 
 
 def test_euler_a_parity_tiny(mods):
