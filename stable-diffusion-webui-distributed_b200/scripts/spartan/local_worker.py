@@ -185,9 +185,13 @@ class LocalGPUWorker(Worker):
                 break
         images = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
         if images.device.type == "cuda":
-            host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
-            host.copy_(images, non_blocking=True)
-            torch.cuda.current_stream(images.device).synchronize()
+            # this thread's current device is cuda:0 whatever device the worker drives: allocate the pinned buffer and
+            # issue the copy under the worker's own device, so the host allocator's bookkeeping (events on the copy
+            # stream) belongs to one device
+            with torch.cuda.device(images.device):
+                host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
+                host.copy_(images, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         else:  # an engine double in the host-logic tests; the real engine refuses non-CUDA devices
             host = images.to(torch.uint8).contiguous()
         n = host.shape[0]
