@@ -119,7 +119,7 @@ class LocalGPUWorker(Worker):
         except Exception as e:
             self.response = None
             if self._is_device_failure(e):
-                logger.error(f"'{self.label}' ({self.device}) failed: {e}")
+                logger.error(f"'{self.label}' ({self.device}) failed: {e}", exc_info=logger.isEnabledFor(10))
                 self.set_state(State.UNAVAILABLE)
                 return
             self.set_state(State.IDLE)
