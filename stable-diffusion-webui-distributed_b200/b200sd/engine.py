@@ -172,8 +172,17 @@ class SDEngine:
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
         self.encoders: Dict[Tuple[int, int, int], VAEEncoderProgram] = {}
         self.interrupted = False
+        self._cap_stream = None
         self.last_unet_evals = 0
         self.graph_replayed_launches = 0   # b200sd kernels launched through graph replays (bench.py gpu_launches)
+
+    def _capture_stream(self):
+        """torch.cuda.graph's default capture stream is ONE process-wide stream, created on whichever device captured
+        first — a second engine on another device would capture (and then run) its kernels on that other device.
+        Every engine captures on a stream of its own device."""
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device)
+        return self._cap_stream
 
     def plan(self, b: int, h: int, w: int) -> Plan:
         key = (b, h, w)
@@ -205,7 +214,7 @@ class SDEngine:
             # invalidate this capture (the default "global" mode does).
             with _CAPTURE_LOCK:
                 l0 = ops.LAUNCHES
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode="thread_local"):
                     fn()
                 plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
             plan.graphs[name] = g
@@ -281,7 +290,7 @@ class SDEngine:
                         g = torch.cuda.CUDAGraph()
                         with _CAPTURE_LOCK:
                             l0 = ops.LAUNCHES
-                            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                            with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode="thread_local"):
                                 vae.run()
                             plan.graph_launches["vae"] = ops.LAUNCHES - l0
                         plan.graphs["vae"] = g
