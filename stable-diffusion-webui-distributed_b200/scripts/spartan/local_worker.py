@@ -185,16 +185,10 @@ class LocalGPUWorker(Worker):
                 break
         images = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
         if images.device.type == "cuda":
-            # Device 0 keeps the pinned fast lane.  For the other devices of a multi-GPU process the reply is freed later
-            # by the collector thread (whose current device is cuda:0), and releasing a pinned block whose stream
-            # bookkeeping belongs to another device aborted the process (torch 2.11, measured on a 2 x B200 box):
-            # a pageable copy costs ~3 ms per 32 images and is always safe.
-            if images.device.index in (0, None):
+            with torch.cuda.device(images.device):  # this thread's current device is cuda:0 whatever the worker drives
                 host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
                 host.copy_(images, non_blocking=True)
-                torch.cuda.current_stream(images.device).synchronize()
-            else:
-                host = images.cpu()
+                torch.cuda.current_stream().synchronize()
         else:  # an engine double in the host-logic tests; the real engine refuses non-CUDA devices
             host = images.to(torch.uint8).contiguous()
         n = host.shape[0]
