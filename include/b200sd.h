@@ -134,6 +134,9 @@ int b200sd_image_to_nhwc(const unsigned char* img, void* out, long long pitch, i
  * (AutoencoderKL.encode(...).mean * scale_factor) */
 int b200sd_unpack_latent(const void* moments, long long pitch, float* x, int B, int HW, float scale, int dtype,
                          void* stream);
+/* hires fix, "Latent" upscaler: fp32 NHWC latents [B,H*W,4] -> [B,Ho*Wo,4], bilinear, half-pixel centres, no antialias
+ * (torch.nn.functional.interpolate(mode="bilinear") in sdwui StableDiffusionProcessingTxt2Img.sample_hr_pass) */
+int b200sd_resize_latent_bilinear(const float* x, float* y, int B, int H, int W, int Ho, int Wo, void* stream);
 
 #ifdef __cplusplus
 }

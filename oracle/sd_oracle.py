@@ -501,6 +501,32 @@ def ddim_img2img_coefficients(steps: int, denoising_strength: float):
     return math.sqrt(a_start), math.sqrt(1.0 - a_start), rows
 
 
+def txt2img_hires(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, steps: int = 20,
+                  cfg_scale: float = 7.0, height: int = 512, width: int = 512, hr_scale: float = 2.0, hr_steps: int = 0,
+                  denoising_strength: float = 0.7, device="cpu"):
+    """sdwui hires fix with the "Latent" upscaler (processing.py StableDiffusionProcessingTxt2Img.sample_hr_pass):
+    DDIM first pass -> F.interpolate(bilinear, antialias=False) of the latents -> fresh per-image noise of the large shape
+    from the same seeds -> DDIM img2img from t_enc -> decode.  Returns (uint8 images, final latents)."""
+    b = tokens.shape[0]
+    h, w = height // 8, width // 8
+    h2, w2 = int(height * hr_scale) // 8, int(width * hr_scale) // 8
+    dsd = {k: v.to(device) for k, v in sd.items()}
+    cond = clip_text_encode(dsd, clip_cfg, tokens.to(device))
+    uncond = clip_text_encode(dsd, clip_cfg, neg_tokens.to(device))
+    unet = lambda a, tt, c: unet_forward(dsd, unet_cfg, a, tt, c)  # noqa: E731
+    x = sample_ddim(unet, per_image_noise(seed, b, (4, h, w)).to(device), cond, uncond, steps, cfg_scale)
+    up = torch.nn.functional.interpolate(x, size=(h2, w2), mode="bilinear", antialias=False)
+    noise = per_image_noise(seed, b, (4, h2, w2)).to(device)
+    sa, s1a, rows = ddim_img2img_coefficients(hr_steps or steps, denoising_strength)
+    x = up * sa + noise * s1a
+    for (t, c_sa, c_s1a, c_sap, c_s1ap) in rows:
+        e = cfg_eps(unet, x, t, cond, uncond, cfg_scale)
+        x0 = (x - c_s1a * e) / c_sa
+        x = c_sap * x0 + c_s1ap * e
+    dec = vae_decode(dsd, vae_cfg, x / vae_cfg.scale_factor)
+    return to_uint8(dec), x
+
+
 def img2img(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, init_u8: torch.Tensor,
             denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, device="cpu"):
     """End-to-end img2img oracle: encode (posterior MEAN, see vae_encode_mean) -> noise to t_enc -> DDIM -> decode."""

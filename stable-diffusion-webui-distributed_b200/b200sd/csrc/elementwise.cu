@@ -240,6 +240,26 @@ __global__ void unpack_latent_kernel(const void* m, long long pitch, float4* x, 
                      load1<kBf16>(m, i * pitch + 2) * scale, load1<kBf16>(m, i * pitch + 3) * scale);
 }
 
+// bilinear resize of NHWC fp32 latents [B, H*W, 4] -> [B, Ho*Wo, 4], half-pixel centres (align_corners = False), no
+// antialiasing: torch.nn.functional.interpolate(mode="bilinear") as sdwui's "Latent" hires upscaler calls it
+__global__ void resize_latent_bilinear_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W,
+                                              int Ho, int Wo) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long n = static_cast<long long>(B) * Ho * Wo;
+  if (i >= n) return;
+  const int xo = static_cast<int>(i % Wo), yo = static_cast<int>((i / Wo) % Ho), b = static_cast<int>(i / (static_cast<long long>(Wo) * Ho));
+  const float sy = fmaxf((yo + 0.5f) * (static_cast<float>(H) / Ho) - 0.5f, 0.f);
+  const float sx = fmaxf((xo + 0.5f) * (static_cast<float>(W) / Wo) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), H - 1), x0 = min(static_cast<int>(sx), W - 1);
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float4* img = x + static_cast<long long>(b) * H * W;
+  const float4 a = img[y0 * W + x0], c = img[y0 * W + x1], d = img[y1 * W + x0], e = img[y1 * W + x1];
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  y[i] = make_float4(w00 * a.x + w01 * c.x + w10 * d.x + w11 * e.x, w00 * a.y + w01 * c.y + w10 * d.y + w11 * e.y,
+                     w00 * a.z + w01 * c.z + w10 * d.z + w11 * e.z, w00 * a.w + w01 * c.w + w10 * d.w + w11 * e.w);
+}
+
 }  // namespace b200sd
 
 using namespace b200sd;
@@ -380,5 +400,15 @@ extern "C" int b200sd_quantize_u8(const void* img, long long pitch, unsigned cha
   const int blocks = static_cast<int>((n + 255) / 256);
   if (dtype == B200SD_BF16) quantize_u8_kernel<true><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
   else quantize_u8_kernel<false><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_resize_latent_bilinear(const float* x, float* y, int B, int H, int W, int Ho, int Wo, void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if (H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15))
+    return B200SD_ERR_INVALID;
+  const long long n = static_cast<long long>(B) * Ho * Wo;
+  resize_latent_bilinear_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, Ho, Wo);
   RET_LAUNCH();
 }

@@ -341,6 +341,31 @@ class SDEngine:
         return self.decode(lat, h, w)
 
     @torch.no_grad()
+    def txt2img_hires(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20,
+                      cfg_scale: float = 7.0, height: int = 512, width: int = 512, hr_scale: float = 2.0,
+                      hr_steps: int = 0, denoising_strength: float = 0.7, sampler: str = "DDIM") -> torch.Tensor:
+        """txt2img with sdwui's hires fix and the "Latent" upscaler (StableDiffusionProcessingTxt2Img.sample /
+        sample_hr_pass): first pass at (height, width), bilinear resize of the latents to hr_scale x, a fresh per-image
+        noise of the large shape from the same seeds, then DDIM img2img from t_enc with `hr_steps` (0 = `steps`)
+        timesteps, decode at the large size.  Returns uint8 [b, H*hr, W*hr, 3] on device."""
+        b = tokens.shape[0]
+        h, w = height // 8, width // 8
+        h2, w2 = int(height * hr_scale) // 8, int(width * hr_scale) // 8
+        cond = self.encode_prompts(tokens)
+        uncond = self.encode_prompts(neg_tokens)
+        draws = 1 + (steps if sampler == "Euler a" else 0)
+        nz = per_image_noise(seed, b, (4, h, w), draws)
+        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None)
+        with self._ctx():
+            up = torch.empty((b, h2 * w2, 4), device=self.device, dtype=torch.float32)
+            ops.resize_latent_bilinear(lat.contiguous(), up, h, w, h2, w2)
+        noise = per_image_noise(seed, b, (4, h2, w2))[0].to(self.device)
+        sa, s1a, ts, rows = ddim_img2img_plan(hr_steps or steps, denoising_strength)
+        init = up.reshape(b, h2, w2, 4).permute(0, 3, 1, 2)
+        lat2 = self.sample(cond, uncond, init * sa + noise * s1a, hr_steps or steps, cfg_scale, "DDIM", schedule=(ts, rows))
+        return self.decode(lat2, h2, w2)
+
+    @torch.no_grad()
     def txt2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20, cfg_scale: float = 7.0,
                 height: int = 512, width: int = 512, sampler: str = "DDIM") -> torch.Tensor:
         """Whole request for this engine's share: returns uint8 [b, H, W, 3] on device."""

@@ -301,3 +301,14 @@ def quantize_u8(img: torch.Tensor, out: torch.Tensor):
     check(rc, "b200sd_quantize_u8")
     _count()
     return out
+
+
+def resize_latent_bilinear(x: torch.Tensor, y: torch.Tensor, h: int, w: int, ho: int, wo: int):
+    """x fp32 [B, h*w, 4] -> y fp32 [B, ho*wo, 4] (F.interpolate bilinear, align_corners=False, no antialias)"""
+    b = x.shape[0]
+    assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.is_contiguous() and y.is_contiguous()
+    assert x.shape == (b, h * w, 4) and y.shape == (b, ho * wo, 4)
+    rc = _lib.lib().b200sd_resize_latent_bilinear(_p(x), _p(y), b, h, w, ho, wo, _stream())
+    check(rc, "b200sd_resize_latent_bilinear")
+    _count()
+    return y

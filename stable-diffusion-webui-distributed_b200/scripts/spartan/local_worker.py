@@ -177,6 +177,18 @@ class LocalGPUWorker(Worker):
             if init_u8 is not None:
                 u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
                                  cfg_scale=cfg_scale)
+            elif payload.get("enable_hr"):
+                # hires fix (reference eta_hr, worker.py:205): second pass at hr_scale x with the "Latent" upscaler
+                upscaler = payload.get("hr_upscaler") or "Latent"
+                if upscaler != "Latent":
+                    logger.warning(f"hires upscaler '{upscaler}' is not implemented on worker {self.label}: using 'Latent'")
+                hr_scale = float(payload.get("hr_scale") or 2.0)
+                if payload.get("hr_resize_x") and payload.get("hr_resize_y"):
+                    hr_scale = float(payload["hr_resize_x"]) / width
+                u8 = eng.txt2img_hires(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
+                                       width=width, hr_scale=hr_scale,
+                                       hr_steps=int(payload.get("hr_second_pass_steps") or 0),
+                                       denoising_strength=float(payload.get("denoising_strength") or 0.7), sampler=sampler)
             else:
                 u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
                                  width=width, sampler=sampler)

@@ -183,7 +183,14 @@ def unpack_latent(moments, x, scale):
     return x
 
 
-ALL = ["linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
+def resize_latent_bilinear(x, y, h, w, ho, wo):
+    b = x.shape[0]
+    t = F.interpolate(x.reshape(b, h, w, 4).permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", antialias=False)
+    y.copy_(t.permute(0, 2, 3, 1).reshape(b, ho * wo, 4))
+    return y
+
+
+ALL = ["resize_latent_bilinear", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
        "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step",
        "quantize_u8", "image_to_nhwc", "unpack_latent"]
 

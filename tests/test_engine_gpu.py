@@ -198,6 +198,25 @@ def test_img2img_parity(mods, size, b, px, steps):
     assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
 
 
+def test_hires_fix_parity_tiny(mods):
+    """hires fix, "Latent" upscaler (bilinear latent resize kernel + DDIM img2img second pass)"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b = 2
+    tok = O.random_prompt_tokens(b, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    with torch.no_grad():
+        ref_u8, ref_x = O.txt2img_hires(dsd, *cfgs, tok, neg, seed=900, steps=6, cfg_scale=7.0, height=64, width=64,
+                                        hr_scale=2.0, hr_steps=8, denoising_strength=0.7, device="cuda")
+    got = eng.txt2img_hires(tok, neg, seed=900, steps=6, cfg_scale=7.0, height=64, width=64, hr_scale=2.0, hr_steps=8,
+                            denoising_strength=0.7)
+    torch.cuda.synchronize()
+    du8 = (got.int() - ref_u8.int()).abs().float()
+    _record("hires tiny", u8_mean=float(du8.mean()), u8_max=float(du8.max()), u8_exact=float((du8 == 0).float().mean()))
+    assert got.shape == ref_u8.shape
+    assert float(du8.mean()) <= 1.5 and float((du8 <= 2).float().mean()) >= 0.97
+
+
 def test_euler_parity_tiny(mods):
     """sdwui "Euler" (k-diffusion sample_euler, s_churn 0) through the worker-facing txt2img call"""
     C, E, S, O = mods

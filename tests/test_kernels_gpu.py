@@ -411,3 +411,15 @@ def test_quantize_u8(ops):
     torch.cuda.synchronize()
     ref = (255.0 * ((img[..., :3].float() + 1.0) * 0.5).clamp(0, 1)).to(torch.uint8)
     assert torch.equal(out, ref)
+
+
+
+def test_resize_latent_bilinear(ops):
+    """F.interpolate(mode="bilinear", antialias=False) on NHWC fp32 latents, integer and fractional scales"""
+    g = _gen(77)
+    for (b, h, w, ho, wo) in [(2, 8, 8, 16, 16), (3, 16, 12, 24, 18), (1, 64, 64, 96, 128)]:
+        x = torch.randn((b, h * w, 4), generator=g, device="cuda")
+        y = torch.empty((b, ho * wo, 4), device="cuda")
+        ops.resize_latent_bilinear(x, y, h, w, ho, wo)
+        ref = F.interpolate(x.reshape(b, h, w, 4).permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", antialias=False)
+        assert torch.allclose(y.reshape(b, ho, wo, 4).permute(0, 3, 1, 2), ref, atol=1e-5, rtol=1e-5)

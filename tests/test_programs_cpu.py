@@ -120,6 +120,22 @@ def test_sample_matches_oracle_euler(env):
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
 
 
+def test_hires_fix_matches_oracle(env):
+    """first pass -> bilinear latent resize -> DDIM img2img from t_enc at the large size -> decode"""
+    C, E, O, cfgs, sd, eng = env
+    b = 2
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    with torch.no_grad():
+        ref_u8, ref_x = O.txt2img_hires(sd, *cfgs, tok, neg, seed=77, steps=5, cfg_scale=7.0, height=64, width=64,
+                                        hr_scale=2.0, hr_steps=6, denoising_strength=0.6)
+    got = eng.txt2img_hires(tok, neg, seed=77, steps=5, cfg_scale=7.0, height=64, width=64, hr_scale=2.0, hr_steps=6,
+                            denoising_strength=0.6)
+    assert got.shape == ref_u8.shape and eng.last_unet_evals == int(0.6 * 6) - 1
+    d = (got.int() - ref_u8.int()).abs()
+    assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
+
+
 def test_img2img_matches_oracle(env):
     """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
     C, E, O, cfgs, sd, eng = env
