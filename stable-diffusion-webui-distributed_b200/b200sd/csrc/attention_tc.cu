@@ -78,10 +78,15 @@ struct AttnParams {
   long long ldo;
   int is_bf16;
   long long* trace;  // debug: clock64 timeline of one CTA ([16 events][nkv]), or null
+  int resident;      // 1: K / V fit in shared memory (Skv <= 128): loaded once, the CTA walks `qpc` Q tiles
+  int qpc;           // Q tiles per CTA (1 in ring mode)
+  int q_bufs;        // Q buffers in shared memory (2 in resident mode: the next Q tile is prefetched)
+  int num_q_tiles;
 };
 
 struct __align__(16) AttnShared {
-  uint64_t q_full;
+  uint64_t q_full[2], q_empty[2];
+  uint64_t o_free;  // resident mode: the epilogue of a Q tile has read both accumulators
   uint64_t k_full[kMaxRing], k_empty[kMaxRing];
   uint64_t v_full[kMaxRing], v_empty[kMaxRing];
   uint64_t s_full[kSBufs], p_full[kMaxPBufs], o_full[kMaxPBufs];
@@ -181,14 +186,22 @@ __device__ __forceinline__ float h2_hmax(uint32_t v) {
 // P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
 constexpr float kPRedo = 256.0f;
 
-// 1: per kv tile the MMA thread issues Q.K of tile j+2 before P.V of tile j (needs 3 P buffers, see the header)
-#ifndef B200SD_ATTN_QK_FIRST
-#define B200SD_ATTN_QK_FIRST 1
-#endif
 
-// debug timeline (b200sd_debug_attention_trace): CTA (3, 2, 1) stamps per-tile events of softmax warp 2 and the MMA thread
+
+// debug timeline (b200sd_debug_attention_trace; build with -DB200SD_ATTN_TRACE_ENABLE=1): CTA (3, 2, 1) stamps per-tile
+// events of softmax warp 2 and the MMA thread.  Compiled out by default: the trace pointer costs two registers in a
+// kernel that sits exactly at its register cap.
+#ifndef B200SD_ATTN_TRACE_ENABLE
+#define B200SD_ATTN_TRACE_ENABLE 0
+#endif
+#if B200SD_ATTN_TRACE_ENABLE
 #define ATTN_TRACE(ev, j) \
   do { if (trace) trace[(ev) * 64 + ((j) & 63)] = clock64(); } while (0)
+#define ATTN_TRACE_PTR(cond) long long* trace = (cond) ? p.trace : nullptr
+#else
+#define ATTN_TRACE(ev, j) do { } while (0)
+#define ATTN_TRACE_PTR(cond) do { } while (0)
+#endif
 
 // my 32 columns of one S tile -> P values packed into pk[16]; returns true when some P value left the comfortable range
 template <bool kFull, bool kBf16, bool kSum>
@@ -229,7 +242,7 @@ __device__ __forceinline__ void p_store32(const uint32_t (&pk)[16], uint32_t p_r
 
 template <bool kBf16, bool kSum>
 __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* sh, uint8_t* sP, uint32_t tmem_base,
-                                              int warp, int lane, int q0, int head, int b, int nkv) {
+                                              int warp, int lane, int first_qt, int n_items, int head, int b, int nkv) {
   const int quarter = warp & 3;
   const int half = (warp - 2) >> 2;   // which 32-column half of the kv tile (and which accumulator) is mine
   const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
@@ -242,124 +255,135 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
   const uint32_t a_s_full = smem_u32(&sh->s_full[0]);
   const uint32_t a_p_full = smem_u32(&sh->p_full[0]);
   const uint32_t a_o_full = smem_u32(&sh->o_full[0]);
+  const uint32_t a_o_free = smem_u32(&sh->o_free);
   const int col0 = half * 32;
   const int p_bufs = p.p_bufs, skv = p.Skv;
   const float scale_log2 = p.scale_log2;
-  long long* trace = (p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1 && warp == 2 && lane == 0) ? p.trace : nullptr;
-  float m_used = -INFINITY;  // scaled log2 domain; running maximum of MY half of the row
-  float l = 0.f;
-  int pb = 0;                // P buffer of tile j and the parity of its current barrier phase
+  const bool has_b = skv > 32;  // kv rows 32-63 never exist when Skv <= 32: O_b is never written
+  ATTN_TRACE_PTR(p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1 && warp == 2 && lane == 0);
+  // The kv tiles of all the CTA's Q tiles ("items") form ONE stream t = 0, 1, ...: S / P buffers and barrier phases
+  // simply continue across items.
+  int t = 0;
+  int pb = 0;                // P buffer of tile t and the parity of its current barrier phase
   uint32_t p_par = 0;
-  for (int j = 0; j < nkv; ++j) {
-    const int sb = j & 1;
-    const int nvalid = min(kKv, skv - j * kKv);
-    const bool full = nvalid == kKv;
-    const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
-    const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
-    ATTN_TRACE(0, j);
-    mbar_wait_a(a_s_full + sb * 8, (j >> 1) & 1, 17);
-    tc_fence_after();
-    ATTN_TRACE(1, j);
-    if (j == 0) m_used = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
-    uint32_t v[32], pk[16];
-    tmem_ld_x32(s_row + col0, v);
-    tmem_ld_wait();
-    ATTN_TRACE(2, j);
-    float lsum = 0.f;
-    const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
-                           : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-    // P[pb] was last read by P.V of tile j - p_bufs <= j - 2, complete because S[j] is (see the header)
-    ATTN_TRACE(3, j);
-    ATTN_TRACE(4, j);
-    if (__any_sync(0xffffffffu, over)) {
-      // rare path (warp-uniform, the TMEM accesses are warp-collective): some row of this warp saw its maximum move
-      // by more than 2^8.  Lanes that did not overflow run it with alpha ~ 1.
-      const float mx = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
-      const float m_new = fmaxf(m_used, mx);
-      const float alpha = fast_exp2(m_used - m_new);
-      if (j > 0) {
-        // P.V of the previous tile must have landed in O_h
-        mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
-        tc_fence_after();
-        for (int c = 0; c < p.resc_cols / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld_x16(o_row + c * 16, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x16(o_row + c * 16, o);
-        }
-        tmem_st_wait();
-      }
-      l *= alpha;
-      m_used = m_new;
-      lsum = 0.f;
+  for (int it = 0; it < n_items; ++it) {
+    const int q0 = (first_qt + it) * kQTile;
+    float m_used = -INFINITY;  // scaled log2 domain; running maximum of MY half of the row
+    float l = 0.f;
+    for (int j = 0; j < nkv; ++j, ++t) {
+      const int sb = t & 1;
+      const int nvalid = min(kKv, skv - j * kKv);
+      const bool full = nvalid == kKv;
+      const uint32_t s_row = tmem_base + static_cast<uint32_t>(sb * kKv) + lane_base;
+      const uint32_t p_row = p_row0 + static_cast<uint32_t>(pb) * kPBytes;
+      ATTN_TRACE(0, t);
+      mbar_wait_a(a_s_full + sb * 8, (static_cast<uint32_t>(t) >> 1) & 1u, 17);
+      tc_fence_after();
+      ATTN_TRACE(1, t);
+      if (j == 0) m_used = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
+      uint32_t v[32], pk[16];
       tmem_ld_x32(s_row + col0, v);
       tmem_ld_wait();
-      if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
-      else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+      ATTN_TRACE(2, t);
+      float lsum = 0.f;
+      const bool over = full ? softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum)
+                             : softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+      // P[pb] was last read by P.V of tile t - p_bufs, complete because S[t] is (see the header)
+      ATTN_TRACE(3, t);
+      if (__any_sync(0xffffffffu, over)) {
+        // rare path (warp-uniform, the TMEM accesses are warp-collective): some row of this warp saw its maximum move
+        // by more than 2^8.  Lanes that did not overflow run it with alpha ~ 1.
+        const float mx = (full ? half_row_max<true>(s_row, col0, nvalid) : half_row_max<false>(s_row, col0, nvalid)) * scale_log2;
+        const float m_new = fmaxf(m_used, mx);
+        const float alpha = fast_exp2(m_used - m_new);
+        if (j > 0) {
+          // P.V of the previous tile must have landed in O_h
+          mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 18);
+          tc_fence_after();
+          for (int c = 0; c < p.resc_cols / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_x16(o_row + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x16(o_row + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m_used = m_new;
+        lsum = 0.f;
+        tmem_ld_x32(s_row + col0, v);
+        tmem_ld_wait();
+        if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+        else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
+      }
+      p_store32(pk, p_row, rx, col0);
+      l += lsum;
+      ATTN_TRACE(5, t);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      ATTN_TRACE(6, t);
+      if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
+      if (++pb == p_bufs) {
+        pb = 0;
+        p_par ^= 1u;
+      }
     }
-    p_store32(pk, p_row, rx, col0);
-    l += lsum;
-    ATTN_TRACE(5, j);
-    fence_proxy_async_smem();
+    // ---- epilogue of this Q tile: merge the two halves of every row, O / l -> global (the pair splits the chunks) ----
+    mbar_wait_a(a_o_full + (pb == 0 ? p_bufs - 1 : pb - 1) * 8, pb == 0 ? p_par ^ 1u : p_par, 19);  // P.V of tile t-1
+    tc_fence_after();
+    if constexpr (!kSum) {
+      uint32_t o[16];
+      tmem_ld_x16(o_row + (p.l_col / 16) * 16, o);
+      tmem_ld_wait();
+      l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
+    }
+    if (half == 1 && !has_b) {
+      l = 0.f;
+      m_used = -INFINITY;
+    }
+    if (it > 0) pair_bar_sync(quarter);  // my partner has read the previous Q tile's exchange values
+    sh->xm[half][r] = m_used;
+    sh->xl[half][r] = l;
+    pair_bar_sync(quarter);
+    const float m_o = sh->xm[half ^ 1][r], l_o = sh->xl[half ^ 1][r];
+    const float m = fmaxf(m_used, m_o);
+    const float a_me = fast_exp2(m_used - m), a_ot = fast_exp2(m_o - m);  // 2^(-inf) = 0 for an empty half
+    const float inv_l = 1.0f / (l * a_me + l_o * a_ot);
+    const float wa = (half == 0 ? a_me : a_ot) * inv_l, wb = (half == 0 ? a_ot : a_me) * inv_l;
+    const int srow = q0 + r;
+    const bool valid = srow < p.Sq;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
+                    ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
+    for (int c = half; c < p.d16 / 16; c += 2) {
+      uint32_t oa[16], ob[16];
+      tmem_ld_x16(oa_row + c * 16, oa);
+      tmem_ld_x16(ob_row + c * 16, ob);
+      tmem_ld_wait();
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x0 = __uint_as_float(oa[2 * i]) * wa, x1 = __uint_as_float(oa[2 * i + 1]) * wa;
+        if (has_b) {
+          x0 = fmaf(__uint_as_float(ob[2 * i]), wb, x0);
+          x1 = fmaf(__uint_as_float(ob[2 * i + 1]), wb, x1);
+        }
+        h[i] = pack_h2<kBf16>(x0, x1);
+      }
+      if (valid) {
+        if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+      }
+    }
+    // the accumulators may be overwritten by the next Q tile's first P.V
     tc_fence_before();
     __syncwarp();
-    ATTN_TRACE(6, j);
-    if (lane == 0) mbar_arrive_a(a_p_full + pb * 8);  // one arrival per warp
-    if (++pb == p_bufs) {
-      pb = 0;
-      p_par ^= 1u;
-    }
-  }
-  // ---- epilogue: merge the two halves of every row, O / l -> global (the pair splits the 16-column chunks) ----
-  mbar_wait_a(a_o_full + ((nkv - 1) % p_bufs) * 8, ((nkv - 1) / p_bufs) & 1, 19);
-  tc_fence_after();
-  const bool has_b = skv > 32;  // kv rows 32-63 never exist when Skv <= 32: O_b was never written
-  if constexpr (!kSum) {
-    uint32_t o[16];
-    tmem_ld_x16(o_row + (p.l_col / 16) * 16, o);
-    tmem_ld_wait();
-    l = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i == (p.l_col & 15)) l = __uint_as_float(o[i]);
-  }
-  if (half == 1 && !has_b) {
-    l = 0.f;
-    m_used = -INFINITY;
-  }
-  sh->xm[half][r] = m_used;
-  sh->xl[half][r] = l;
-  pair_bar_sync(quarter);
-  const float m_o = sh->xm[half ^ 1][r], l_o = sh->xl[half ^ 1][r];
-  const float m = fmaxf(m_used, m_o);
-  const float a_me = fast_exp2(m_used - m), a_ot = fast_exp2(m_o - m);  // 2^(-inf) = 0 for an empty half
-  const float inv_l = 1.0f / (l * a_me + l_o * a_ot);
-  const float wa = (half == 0 ? a_me : a_ot) * inv_l, wb = (half == 0 ? a_ot : a_me) * inv_l;
-  const int srow = q0 + r;
-  const bool valid = srow < p.Sq;
-  uint8_t* orow = reinterpret_cast<uint8_t*>(p.O) +
-                  ((static_cast<long long>(b) * p.Sq + (valid ? srow : 0)) * p.ldo + static_cast<long long>(head) * p.d) * 2;
-  for (int c = half; c < p.d16 / 16; c += 2) {
-    uint32_t oa[16], ob[16];
-    tmem_ld_x16(oa_row + c * 16, oa);
-    tmem_ld_x16(ob_row + c * 16, ob);
-    tmem_ld_wait();
-    uint32_t h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float x0 = __uint_as_float(oa[2 * i]) * wa, x1 = __uint_as_float(oa[2 * i + 1]) * wa;
-      if (has_b) {
-        x0 = fmaf(__uint_as_float(ob[2 * i]), wb, x0);
-        x1 = fmaf(__uint_as_float(ob[2 * i + 1]), wb, x1);
-      }
-      h[i] = pack_h2<kBf16>(x0, x1);
-    }
-    if (valid) {
-      if (c * 16 + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32) = make_uint4(h[0], h[1], h[2], h[3]);
-      if (c * 16 + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c * 32 + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-    }
+    if (lane == 0) mbar_arrive_a(a_o_free);
   }
 }
 
@@ -370,25 +394,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t q_bytes = static_cast<uint32_t>(p.chunks) * kQChunkBytes;
   const uint32_t kv_bytes = static_cast<uint32_t>(p.chunks) * kKvChunkBytes;
-  uint8_t* sQ = smem;
-  uint8_t* sP = sQ + q_bytes;  // p_bufs x 16 KB
+  uint8_t* sQ = smem;                                   // q_bufs x (128 rows x d_pad)
+  uint8_t* sP = sQ + static_cast<size_t>(p.q_bufs) * q_bytes;  // p_bufs x 16 KB
   uint8_t* sK = sP + p.p_bufs * kPBytes;
   uint8_t* sV = sK + p.k_stages * kv_bytes;
   AttnShared* sh = reinterpret_cast<AttnShared*>(sV + p.v_stages * kv_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQTile;
+  const int first_qt = blockIdx.x * p.qpc;               // this CTA's Q tiles: first_qt .. first_qt + n_items - 1
+  const int n_items = min(p.qpc, p.num_q_tiles - first_qt);
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int nkv = (p.Skv + kKv - 1) / kKv;
   const int col0 = head * p.d_pad;
+  const bool resident = p.resident != 0;                  // K / V of this (batch, head) stay in shared memory
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(&sh->q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sh->q_full[s], 1);
+      mbar_init(&sh->q_empty[s], 1);
+    }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&sh->k_full[s], 1);
       mbar_init(&sh->k_empty[s], 1);
@@ -400,6 +429,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&sh->p_full[s], kSoftmaxWarps);
       mbar_init(&sh->o_full[s], 1);
     }
+    mbar_init(&sh->o_free, kSoftmaxWarps);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&sh->tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -410,52 +440,78 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    // Loads go out in exactly the order the MMA thread consumes (and therefore frees) tiles:
-    //   K_0, K_1,  then  V_j, K_{j+2}  for j = 0, 1, ...   so a blocking wait never holds back a tile that is needed
-    // earlier than the one being waited for.  The warp stays converged (all lanes wait) and one elected lane issues, so
-    // the TMA instructions take warp-uniform operands without a per-instruction broadcast loop.
+    // The warp stays converged (all lanes wait) and one elected lane issues, so the TMA instructions take warp-uniform
+    // operands without a per-instruction broadcast loop.
     const bool leader = elect_one();
     const uint32_t bar0 = warp_uniform(smem_u32(sh));
     const uint32_t a_k_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_empty));
     const uint32_t a_v_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_empty));
+    const uint32_t a_q_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, q_empty));
     const int k_stages = p.k_stages, v_stages = p.v_stages, chunks = p.chunks;
-    int kj = 0, k_st = 0, v_st = 0;
-    uint32_t k_par = 0, v_par = 0;
-    auto load_k = [&]() {
-      mbar_wait_a(a_k_empty + static_cast<uint32_t>(k_st) * 8u, k_par ^ 1u, 11);
+    if (resident) {
+      // K / V (at most two tiles each) are loaded once; Q tiles stream through two buffers, one tile ahead
       if (leader) {
-        mbar_arrive_expect_tx(&sh->k_full[k_st], kv_bytes);
-        for (int c = 0; c < chunks; ++c)
-          tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[k_st], col0 + c * 64, kj * kKv, b);
+        for (int j = 0; j < nkv; ++j) {
+          mbar_arrive_expect_tx(&sh->k_full[j], kv_bytes);
+          for (int c = 0; c < chunks; ++c)
+            tma_load_3d(sK + j * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[j], col0 + c * 64, j * kKv, b);
+        }
       }
-      ++kj;
-      if (++k_st == k_stages) {
-        k_st = 0;
-        k_par ^= 1u;
+      for (int it = 0; it < n_items; ++it) {
+        const int qs = it & 1;
+        mbar_wait_a(a_q_empty + static_cast<uint32_t>(qs) * 8u, ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u, 10);
+        if (leader) {
+          mbar_arrive_expect_tx(&sh->q_full[qs], q_bytes);
+          for (int c = 0; c < chunks; ++c)
+            tma_load_3d(sQ + qs * q_bytes + c * kQChunkBytes, &tmQ, &sh->q_full[qs], col0 + c * 64,
+                        (first_qt + it) * kQTile, b);
+          if (it == 0) {
+            for (int j = 0; j < nkv; ++j) {
+              mbar_arrive_expect_tx(&sh->v_full[j], kv_bytes);
+              for (int c = 0; c < chunks; ++c)
+                tma_load_3d(sV + j * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[j], col0 + c * 64, j * kKv, b);
+            }
+          }
+        }
       }
-    };
-    if (leader) {
-      mbar_arrive_expect_tx(&sh->q_full, q_bytes);
-      for (int c = 0; c < chunks; ++c) tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full, col0 + c * 64, q0, b);
-    }
-    for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
-    for (int j = 0; j < nkv; ++j) {
-#if B200SD_ATTN_QK_FIRST
-      if (kj < nkv) load_k();  // consumption order: K_{j+2} (Q.K of tile j+2) before V_j (P.V of tile j)
-#endif
-      mbar_wait_a(a_v_empty + static_cast<uint32_t>(v_st) * 8u, v_par ^ 1u, 12);
+    } else {
+      // Ring mode (one Q tile per CTA).  Loads go out in exactly the order the MMA thread consumes (and therefore frees)
+      // tiles: K_0, K_1, then K_{j+2}, V_j for j = 0, 1, ... so a blocking wait never holds back a tile that is needed
+      // earlier than the one being waited for.
+      int kj = 0, k_st = 0, v_st = 0;
+      uint32_t k_par = 0, v_par = 0;
+      auto load_k = [&]() {
+        mbar_wait_a(a_k_empty + static_cast<uint32_t>(k_st) * 8u, k_par ^ 1u, 11);
+        if (leader) {
+          mbar_arrive_expect_tx(&sh->k_full[k_st], kv_bytes);
+          for (int c = 0; c < chunks; ++c)
+            tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[k_st], col0 + c * 64, kj * kKv, b);
+        }
+        ++kj;
+        if (++k_st == k_stages) {
+          k_st = 0;
+          k_par ^= 1u;
+        }
+      };
       if (leader) {
-        mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
+        mbar_arrive_expect_tx(&sh->q_full[0], q_bytes);
         for (int c = 0; c < chunks; ++c)
-          tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
+          tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full[0], col0 + c * 64, first_qt * kQTile, b);
       }
-      if (++v_st == v_stages) {
-        v_st = 0;
-        v_par ^= 1u;
+      for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
+      for (int j = 0; j < nkv; ++j) {
+        if (kj < nkv) load_k();  // consumption order: K_{j+2} (Q.K of tile j+2) before V_j (P.V of tile j)
+        mbar_wait_a(a_v_empty + static_cast<uint32_t>(v_st) * 8u, v_par ^ 1u, 12);
+        if (leader) {
+          mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
+          for (int c = 0; c < chunks; ++c)
+            tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
+        }
+        if (++v_st == v_stages) {
+          v_st = 0;
+          v_par ^= 1u;
+        }
       }
-#if !B200SD_ATTN_QK_FIRST
-      if (kj < nkv) load_k();
-#endif
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -464,10 +520,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // sub-partition that lane retires about one instruction per 7 clocks, and before this loop was made lean (converged
     // warp -> warp-uniform operands -> bare UTCHMMA; descriptors advanced by adds) its ~250 instructions per kv tile
     // WERE the kernel's critical path (tools/attn_trace.py: 655 clocks to issue 4 MMAs + 2 commits).
+    // The kv tiles of all the CTA's Q tiles form one stream t = 0 .. T-1 (tile t: item t / nkv, kv tile t % nkv).
     const bool leader = elect_one();
-    long long* trace = (leader && p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1) ? p.trace : nullptr;
+    ATTN_TRACE_PTR(leader && p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1);
     const bool bf = p.is_bf16 != 0;
+    const bool qk_first = !resident;  // ring mode: Q.K(t+2) before P.V(t) (three P buffers); resident mode: after
     const int ksteps_qk = p.d16 / 16, k_stages = p.k_stages, v_stages = p.v_stages, p_bufs = p.p_bufs, skv = p.Skv;
+    const int T = n_items * nkv;
     const uint32_t tm_S = warp_uniform(tmem_base);
     const uint32_t tm_Oa = tm_S + static_cast<uint32_t>(kSBufs * kKv), tm_Ob = tm_Oa + static_cast<uint32_t>(p.dpv);
     const uint32_t bar0 = warp_uniform(smem_u32(sh));
@@ -479,29 +538,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t a_p_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, p_full));
     const uint32_t a_o_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, o_full));
     const uint32_t a_q_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, q_full));
+    const uint32_t a_q_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, q_empty));
+    const uint32_t a_o_free = bar0 + static_cast<uint32_t>(offsetof(AttnShared, o_free));
     // descriptor low words (address >> 4 | LBO field); the high word (SBO 1024, version, SWIZZLE_128B) is one constant
     const uint32_t s0 = warp_uniform(smem_u32(sQ));
     const uint32_t hi = sdesc_hi_sw128(1024);
-    const uint32_t q_lo = sdesc_lo(s0, 16);
-    const uint32_t p_lo0 = sdesc_lo(s0 + q_bytes, 16);
-    const uint32_t k_lo0 = sdesc_lo(s0 + q_bytes + static_cast<uint32_t>(p_bufs) * kPBytes, 16);
-    const uint32_t v_lo0 = sdesc_lo(s0 + q_bytes + static_cast<uint32_t>(p_bufs) * kPBytes + static_cast<uint32_t>(k_stages) * kv_bytes,
+    const uint32_t q_lo0 = sdesc_lo(s0, 16);
+    const uint32_t q_all = static_cast<uint32_t>(p.q_bufs) * q_bytes;
+    const uint32_t p_lo0 = sdesc_lo(s0 + q_all, 16);
+    const uint32_t k_lo0 = sdesc_lo(s0 + q_all + static_cast<uint32_t>(p_bufs) * kPBytes, 16);
+    const uint32_t v_lo0 = sdesc_lo(s0 + q_all + static_cast<uint32_t>(p_bufs) * kPBytes + static_cast<uint32_t>(k_stages) * kv_bytes,
                                     kKvChunkBytes);  // V is consumed MN-major: LBO = distance between 64-wide chunks
     const uint32_t kv_step = kv_bytes >> 4;
     const uint32_t idesc_qk_full = make_idesc_f16(128, kKv, bf, false, false);
     const uint32_t idesc_pv = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
-    int qj = 0, q_ks = 0;  // next Q.K^T: tile, K ring slot (+ parity of its k_full phase)
-    uint32_t q_kpar = 0, k_lo = k_lo0;
-    auto issue_qk = [&]() {  // S[qj & 1] = Q K_qj^T
-      const uint32_t q_sb = static_cast<uint32_t>(qj) & 1u;
-      const int nvalid = min(kKv, skv - qj * kKv);
-      ATTN_TRACE(11, qj);
-      mbar_wait_a(a_k_full + static_cast<uint32_t>(q_ks) * 8u, q_kpar, 14);
+    int qk_t = 0, qk_item = 0, qk_j = 0, q_ks = 0;  // next Q.K: stream index, item, kv tile, K ring slot (ring mode)
+    uint32_t q_kpar = 0, k_lo_ring = k_lo0;
+    auto issue_qk = [&]() {  // S[qk_t & 1] = Q_item K_j^T
+      const uint32_t q_sb = static_cast<uint32_t>(qk_t) & 1u;
+      const uint32_t qs = resident ? (static_cast<uint32_t>(qk_item) & 1u) : 0u;
+      const int nvalid = min(kKv, skv - qk_j * kKv);
+      ATTN_TRACE(11, qk_t);
+      if (qk_j == 0) mbar_wait_a(a_q_full + qs * 8u, resident ? ((static_cast<uint32_t>(qk_item) >> 1) & 1u) : 0u, 13);
+      const uint32_t kslot = resident ? static_cast<uint32_t>(qk_j) : static_cast<uint32_t>(q_ks);
+      const uint32_t k_lo = resident ? k_lo0 + kslot * kv_step : k_lo_ring;
+      mbar_wait_a(a_k_full + kslot * 8u, resident ? 0u : q_kpar, 14);
       tc_fence_after();
-      ATTN_TRACE(12, qj);
+      ATTN_TRACE(12, qk_t);
       if (leader) {
         const uint32_t idesc = nvalid == kKv ? idesc_qk_full : make_idesc_f16(128, (nvalid + 15) & ~15, bf, false, false);
         const uint32_t d_tmem = tm_S + q_sb * kKv;
+        const uint32_t q_lo = q_lo0 + qs * (q_bytes >> 4);
         if (ksteps_qk == 3) {  // d = 40: the shape that dominates; straight-line issue
           umma_f16_ss_lh(d_tmem, q_lo, hi, k_lo, hi, idesc, 0u);
           umma_f16_ss_lh(d_tmem, q_lo + 2u, hi, k_lo + 2u, hi, idesc, 1u);
@@ -513,38 +580,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                            idesc, k != 0 ? 1u : 0u);
           }
         }
-        umma_commit_a(a_k_empty + static_cast<uint32_t>(q_ks) * 8u);
+        if (!resident) umma_commit_a(a_k_empty + kslot * 8u);
+        else if (qk_j == nkv - 1) umma_commit_a(a_q_empty + qs * 8u);  // this Q buffer may be refilled
         umma_commit_a(a_s_full + q_sb * 8u);
       }
-      ATTN_TRACE(13, qj);
-      ++qj;
-      k_lo += kv_step;
-      if (++q_ks == k_stages) {
-        q_ks = 0;
-        q_kpar ^= 1u;
-        k_lo = k_lo0;
+      ATTN_TRACE(13, qk_t);
+      ++qk_t;
+      if (++qk_j == nkv) {
+        qk_j = 0;
+        ++qk_item;
+      }
+      if (!resident) {
+        k_lo_ring += kv_step;
+        if (++q_ks == k_stages) {
+          q_ks = 0;
+          q_kpar ^= 1u;
+          k_lo_ring = k_lo0;
+        }
       }
     };
-    mbar_wait_a(a_q_full, 0, 13);
-    for (int i = 0; i < kSBufs && i < nkv; ++i) issue_qk();
-    int vs = 0, pb = 0;
-    uint32_t v_par = 0, p_par = 0, v_lo = v_lo0, p_lo = p_lo0;
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = min(kKv, skv - j * kKv);
-      ATTN_TRACE(7, j);
+    for (int i = 0; i < kSBufs && i < T; ++i) issue_qk();
+    int vs = 0, pb = 0, pv_item = 0, pv_j = 0;
+    uint32_t v_par = 0, p_par = 0, v_lo_ring = v_lo0, p_lo = p_lo0;
+    for (int t = 0; t < T; ++t) {
+      const int nvalid = min(kKv, skv - pv_j * kKv);
+      ATTN_TRACE(7, t);
       mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
-      ATTN_TRACE(8, j);
-#if B200SD_ATTN_QK_FIRST
-      // ---- softmax j has released its S buffer: refill it two tiles ahead, BEFORE this tile's P.V — S is what the
-      // softmax warps wait for next; O is not read until the end ----
-      if (qj < nkv) issue_qk();
-#endif
+      ATTN_TRACE(8, t);
+      // softmax t has released its S buffer: refill it two tiles ahead.  In ring mode BEFORE this tile's P.V — S is what
+      // the softmax warps wait for next, O is not read until the end.
+      if (qk_first && qk_t < T) issue_qk();
       // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
-      mbar_wait_a(a_v_full + static_cast<uint32_t>(vs) * 8u, v_par, 16);
+      if (pv_j == 0 && pv_item > 0)  // the previous Q tile's epilogue has read the accumulators this P.V overwrites
+        mbar_wait_a(a_o_free, (static_cast<uint32_t>(pv_item) - 1u) & 1u, 21);
+      const uint32_t vslot = resident ? static_cast<uint32_t>(pv_j) : static_cast<uint32_t>(vs);
+      const uint32_t v_lo = resident ? v_lo0 + vslot * kv_step : v_lo_ring;
+      mbar_wait_a(a_v_full + vslot * 8u, resident ? 0u : v_par, 16);
       tc_fence_after();
-      ATTN_TRACE(9, j);
+      ATTN_TRACE(9, t);
       if (leader) {
-        const uint32_t acc = j != 0 ? 1u : 0u;  // the first MMA into each accumulator overwrites it
+        const uint32_t acc = pv_j != 0 ? 1u : 0u;  // the first MMA of a Q tile into each accumulator overwrites it
         if (nvalid == kKv) {
           // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units apart);
           // the two accumulators alternate so that consecutive MMAs never depend on each other
@@ -558,15 +633,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
                            (k & 1) == 0 ? acc : 1u);
         }
-        umma_commit_a(a_v_empty + static_cast<uint32_t>(vs) * 8u);
+        if (!resident) umma_commit_a(a_v_empty + vslot * 8u);
         umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
       }
-      ATTN_TRACE(10, j);
-      v_lo += kv_step;
-      if (++vs == v_stages) {
-        vs = 0;
-        v_par ^= 1u;
-        v_lo = v_lo0;
+      ATTN_TRACE(10, t);
+      if (!resident) {
+        v_lo_ring += kv_step;
+        if (++vs == v_stages) {
+          vs = 0;
+          v_par ^= 1u;
+          v_lo_ring = v_lo0;
+        }
       }
       p_lo += kPBytes >> 4;
       if (++pb == p_bufs) {
@@ -574,20 +651,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         p_par ^= 1u;
         p_lo = p_lo0;
       }
-#if !B200SD_ATTN_QK_FIRST
-      // ---- softmax j has released its S buffer: refill it two tiles ahead ----
-      if (qj < nkv) issue_qk();
-#endif
+      if (++pv_j == nkv) {
+        pv_j = 0;
+        ++pv_item;
+      }
+      if (!qk_first && qk_t < T) issue_qk();
     }
     __syncwarp();
   } else {
     const bool sum_here = p.l_col < 0;
     if (p.is_bf16) {
-      if (sum_here) softmax_warps<true, true>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
-      else          softmax_warps<true, false>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
+      if (sum_here) softmax_warps<true, true>(p, sh, sP, tmem_base, warp, lane, first_qt, n_items, head, b, nkv);
+      else          softmax_warps<true, false>(p, sh, sP, tmem_base, warp, lane, first_qt, n_items, head, b, nkv);
     } else {
-      if (sum_here) softmax_warps<false, true>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
-      else          softmax_warps<false, false>(p, sh, sP, tmem_base, warp, lane, q0, head, b, nkv);
+      if (sum_here) softmax_warps<false, true>(p, sh, sP, tmem_base, warp, lane, first_qt, n_items, head, b, nkv);
+      else          softmax_warps<false, false>(p, sh, sP, tmem_base, warp, lane, first_qt, n_items, head, b, nkv);
     }
   }
 
@@ -664,22 +742,53 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.tmem_cols = (kSBufs * kKv + 2 * p.dpv <= 256) ? 256 : 512;
   int e_pb, e_k, e_v;
   attn_env(&e_pb, &e_k, &e_v);
-  // shared memory: Q + p_bufs P atoms + K/V rings.  Three P buffers and a K 3 / V 2 ring when that keeps two CTAs per
-  // SM (d_pad == 64) or simply fits (one CTA per SM), otherwise two and 2 / 2.
+  const int nkv = (Skv + kKv - 1) / kKv;
+  p.num_q_tiles = (Sq + kQTile - 1) / kQTile;
   const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
-  const size_t base = 1024 + static_cast<size_t>(p.chunks) * kQChunkBytes + sizeof(AttnShared) + 64;
-  const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
-  const size_t budget = (p.tmem_cols <= 256 && base + 2 * kPBytes + 4 * kvt <= half_sm)
-                            ? half_sm : static_cast<size_t>(g_attn_max_smem);
-  p.p_bufs = (base + 3 * kPBytes + 4 * kvt <= budget) ? 3 : 2;
-  if (e_pb == 2 || e_pb == 3) p.p_bufs = e_pb;
-  if (B200SD_ATTN_QK_FIRST) p.p_bufs = 3;  // required for the P-buffer reuse argument in that issue order
-  const size_t fixed = base + static_cast<size_t>(p.p_bufs) * kPBytes;
-  p.k_stages = (fixed + 5 * kvt <= budget) ? 3 : 2;
-  p.v_stages = 2;
-  if (e_k >= 1 && e_k <= kMaxRing) p.k_stages = e_k;
-  if (e_v >= 1 && e_v <= kMaxRing) p.v_stages = e_v;
-  const size_t smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;
+  const size_t qt = static_cast<size_t>(p.chunks) * kQChunkBytes;
+  static int e_res = -1;  // experiment knob: B200SD_ATTN_RESIDENT=0 disables the resident-K/V mode
+  if (e_res < 0) {
+    const char* e = std::getenv("B200SD_ATTN_RESIDENT");
+    e_res = e ? std::atoi(e) : 1;
+  }
+  p.resident = (nkv <= 2 && e_res != 0) ? 1 : 0;
+  size_t smem;
+  if (p.resident) {
+    // Cross-attention (77 context tokens): K / V of a (batch, head) are two tiles — loaded once per CTA, which then walks
+    // several Q tiles (the next one prefetched into a second Q buffer).  Per-CTA start-up (launch, TMEM allocation,
+    // first loads) dominated the one-tile-per-CTA form: 7 us per CTA for 2 us of work.
+    p.q_bufs = 2;
+    p.p_bufs = 2;  // P.V(t) is issued before Q.K(t+2) in this mode: "S[t] ready" covers P.V of tile t-2
+    p.k_stages = nkv;
+    p.v_stages = nkv;
+    // Q tiles per CTA: as many as keep at least one full wave of CTAs (148) in the grid, at most 8
+    p.qpc = 1;
+    for (int c = 8; c > 1; c >>= 1) {
+      const long long ctas = static_cast<long long>((p.num_q_tiles + c - 1) / c) * heads * B;
+      if (c <= p.num_q_tiles && ctas >= 148) {
+        p.qpc = c;
+        break;
+      }
+    }
+    smem = 1024 + 2 * qt + 2 * kPBytes + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64;
+  } else {
+    // Ring mode.  shared memory: Q + three P atoms (required by the Q.K-first issue order, see the header) + K/V rings,
+    // K 3 / V 2 when that keeps two CTAs per SM (d_pad == 64) or simply fits (one CTA per SM), otherwise 2 / 2.
+    p.q_bufs = 1;
+    p.qpc = 1;
+    p.p_bufs = 3;
+    (void)e_pb;
+    const size_t base = 1024 + qt + sizeof(AttnShared) + 64;
+    const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
+    const size_t budget = (p.tmem_cols <= 256 && base + 3 * kPBytes + 4 * kvt <= half_sm)
+                              ? half_sm : static_cast<size_t>(g_attn_max_smem);
+    const size_t fixed = base + 3 * kPBytes;
+    p.k_stages = (fixed + 5 * kvt <= budget) ? 3 : 2;
+    p.v_stages = 2;
+    if (e_k >= 2 && e_k <= kMaxRing) p.k_stages = e_k;
+    if (e_v >= 2 && e_v <= kMaxRing) p.v_stages = e_v;
+    smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;
+  }
   if (smem > static_cast<size_t>(g_attn_max_smem)) return B200SD_ERR_UNSUPPORTED;
   CUtensorMap tmQ, tmK, tmV;
   const uint32_t es[3] = {1, 1, 1};
@@ -701,7 +810,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     const uint64_t st[2] = {static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(ldv) * 2 * Skv};
     if ((rc = make_tmap_sw128(&tmV, V, 3, dims, st, kvbox, es)) != B200SD_OK) return rc;
   }
-  dim3 grid((Sq + kQTile - 1) / kQTile, heads, B);
+  dim3 grid((p.num_q_tiles + p.qpc - 1) / p.qpc, heads, B);
   attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }

@@ -213,6 +213,8 @@ def _padded_heads(b, s, heads, d, d_pad, g, ones_col=False):
 @pytest.mark.parametrize("b,heads,sq,skv,d", [
     (1, 2, 128, 128, 64), (2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
     (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 256, 77, 160), (1, 10, 1024, 1024, 64), (1, 4, 200, 300, 40),
+    # resident-K/V mode (Skv <= 128) with several Q tiles per CTA: 8, 8, 4, 2 (ragged last Q tile), and short kv
+    (8, 8, 4096, 77, 40), (8, 8, 1024, 128, 40), (8, 8, 1024, 20, 40), (6, 8, 1000, 77, 80), (16, 8, 512, 40, 160),
 ])
 def test_attention(ops, b, heads, sq, skv, d, ones_col):
     g = _gen(sq + skv + d)

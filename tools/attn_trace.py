@@ -1,5 +1,6 @@
 """Per-tile timeline of one attention CTA (clock64 stamps written by the kernel's debug hook): where does a kv tile's
-time go between the softmax warps and the MMA thread?
+time go between the softmax warps and the MMA thread?  Needs a trace-enabled library build:
+    B200SD_NVCC_EXTRA="-DB200SD_ATTN_TRACE_ENABLE=1" python stable-diffusion-webui-distributed_b200/b200sd/build.py --force
 
 events (per kv tile j):
   softmax warp 2, lane 0:  0 loop top   1 S ready (s_full passed)   2 S in registers   3 exp/pack issued
