@@ -752,6 +752,9 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     e_res = e ? std::atoi(e) : 1;
   }
   p.resident = (nkv <= 2 && e_res != 0) ? 1 : 0;
+  if (p.resident && 1024 + 2 * qt + 2 * kPBytes + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64 >
+                        static_cast<size_t>(g_attn_max_smem))
+    p.resident = 0;  // d_pad = 192 with two kv tiles: two Q buffers do not fit, use the ring form
   size_t smem;
   if (p.resident) {
     // Cross-attention (77 context tokens): K / V of a (batch, head) are two tiles — loaded once per CTA, which then walks
