@@ -426,7 +426,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int s = 0; s < kSBufs; ++s) mbar_init(&sh->s_full[s], 1);
     for (int s = 0; s < kMaxPBufs; ++s) {
-      mbar_init(&sh->p_full[s], kSoftmaxWarps);
+      mbar_init(&sh->p_full[s], resident ? kSoftmaxWarps : kSoftmaxWarps + 1);  // ring mode: + the producer's expect_tx
       mbar_init(&sh->o_full[s], 1);
     }
     mbar_init(&sh->o_free, kSoftmaxWarps);
@@ -475,42 +475,60 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     } else {
-      // Ring mode (one Q tile per CTA).  Loads go out in exactly the order the MMA thread consumes (and therefore frees)
-      // tiles: K_0, K_1, then K_{j+2}, V_j for j = 0, 1, ... so a blocking wait never holds back a tile that is needed
-      // earlier than the one being waited for.
-      int kj = 0, k_st = 0, v_st = 0;
-      uint32_t k_par = 0, v_par = 0;
-      auto load_k = [&]() {
-        mbar_wait_a(a_k_empty + static_cast<uint32_t>(k_st) * 8u, k_par ^ 1u, 11);
-        if (leader) {
-          mbar_arrive_expect_tx(&sh->k_full[k_st], kv_bytes);
-          for (int c = 0; c < chunks; ++c)
-            tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->k_full[k_st], col0 + c * 64, kj * kKv, b);
-        }
-        ++kj;
-        if (++k_st == k_stages) {
-          k_st = 0;
-          k_par ^= 1u;
-        }
-      };
+      // Ring mode (one Q tile per CTA).  Q, K_0 and K_1 land on q_full.  After that the operands the MMA thread needs once
+      // the softmax warps have delivered P_t — K_{t+2} for S[t+2] and V_t for P_t.V_t — are loaded as "pair t", and their
+      // bytes are expected on p_full of tile t itself: the barrier the MMA thread waits on anyway then also covers the
+      // loads, and the ring needs no full/empty barriers of its own (every mbarrier operation costs the issuing thread
+      // 150-350 clocks even when it does not block; the MMA thread's instruction stream is the kernel's critical path).
+      //   slots:  K_j in slot j % 3, V_j in slot j % 2.  Pair t overwrites K_{t-1} and V_{t-2}; Q.K of tile t-1 was issued
+      //           before P.V of tile t-3 and a commit covers every MMA its thread issued before it, so o_full(t-2) (or
+      //           o_full(0) for the K tiles used by the two start-up Q.K products) frees both.
+      //   phases: the producer arrives on p_full[t % pb] for tile t only after observing the phase of tile t-pb complete.
+      //           As an extra waiter on o_full / p_full it cannot be lapped: a later phase of either barrier needs
+      //           p_full of a tile this thread has not arrived for yet.
+      const uint32_t a_p_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, p_full));
+      const uint32_t a_o_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, o_full));
+      const int p_bufs = p.p_bufs;
+      const int pre = min(kSBufs, nkv);
       if (leader) {
-        mbar_arrive_expect_tx(&sh->q_full[0], q_bytes);
+        mbar_arrive_expect_tx(&sh->q_full[0], q_bytes + static_cast<uint32_t>(pre) * kv_bytes);
         for (int c = 0; c < chunks; ++c)
           tma_load_3d(sQ + c * kQChunkBytes, &tmQ, &sh->q_full[0], col0 + c * 64, first_qt * kQTile, b);
-      }
-      for (int i = 0; i < kSBufs && i < nkv; ++i) load_k();
-      for (int j = 0; j < nkv; ++j) {
-        if (kj < nkv) load_k();  // consumption order: K_{j+2} (Q.K of tile j+2) before V_j (P.V of tile j)
-        mbar_wait_a(a_v_empty + static_cast<uint32_t>(v_st) * 8u, v_par ^ 1u, 12);
-        if (leader) {
-          mbar_arrive_expect_tx(&sh->v_full[v_st], kv_bytes);
+        for (int j = 0; j < pre; ++j)
           for (int c = 0; c < chunks; ++c)
-            tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->v_full[v_st], col0 + c * 64, j * kKv, b);
+            tma_load_3d(sK + j * kv_bytes + c * kKvChunkBytes, &tmK, &sh->q_full[0], col0 + c * 64, j * kKv, b);
+      }
+      int pb = 0, k_st = pre % k_stages, v_st = 0;   // P buffer of tile t; ring slots of K_{t+2} and V_t
+      int ob = 0, lb = 0;                            // P buffers of tiles t-2 (o_full wait) and t-pb (p_full wait)
+      uint32_t o_par = 0, l_par = 0;
+      for (int t = 0; t < nkv; ++t) {
+        if (t >= 1) {  // slots free: P.V of tile max(t-2, 0) and everything issued before it has completed
+          mbar_wait_a(a_o_full + static_cast<uint32_t>(ob) * 8u, o_par, 11);
+          if (t >= 2 && ++ob == p_bufs) {
+            ob = 0;
+            o_par ^= 1u;
+          }
         }
-        if (++v_st == v_stages) {
-          v_st = 0;
-          v_par ^= 1u;
+        if (t >= p_bufs) {  // p_full[pb] has finished the phase of tile t - p_bufs: my arrival counts for tile t
+          mbar_wait_a(a_p_full + static_cast<uint32_t>(lb) * 8u, l_par, 12);
+          if (++lb == p_bufs) {
+            lb = 0;
+            l_par ^= 1u;
+          }
         }
+        const bool has_k = t + kSBufs < nkv;
+        if (leader) {
+          mbar_arrive_expect_tx(&sh->p_full[pb], has_k ? 2u * kv_bytes : kv_bytes);
+          if (has_k)
+            for (int c = 0; c < chunks; ++c)
+              tma_load_3d(sK + k_st * kv_bytes + c * kKvChunkBytes, &tmK, &sh->p_full[pb], col0 + c * 64,
+                          (t + kSBufs) * kKv, b);
+          for (int c = 0; c < chunks; ++c)
+            tma_load_3d(sV + v_st * kv_bytes + c * kKvChunkBytes, &tmV, &sh->p_full[pb], col0 + c * 64, t * kKv, b);
+        }
+        if (++pb == p_bufs) pb = 0;
+        if (++k_st == k_stages) k_st = 0;
+        if (++v_st == v_stages) v_st = 0;
       }
     }
     __syncwarp();
@@ -559,10 +577,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t qs = resident ? (static_cast<uint32_t>(qk_item) & 1u) : 0u;
       const int nvalid = min(kKv, skv - qk_j * kKv);
       ATTN_TRACE(11, qk_t);
-      if (qk_j == 0) mbar_wait_a(a_q_full + qs * 8u, resident ? ((static_cast<uint32_t>(qk_item) >> 1) & 1u) : 0u, 13);
+      if (resident ? qk_j == 0 : qk_t == 0)  // ring mode: Q, K_0 and K_1 share q_full[0]
+        mbar_wait_a(a_q_full + qs * 8u, resident ? ((static_cast<uint32_t>(qk_item) >> 1) & 1u) : 0u, 13);
       const uint32_t kslot = resident ? static_cast<uint32_t>(qk_j) : static_cast<uint32_t>(q_ks);
       const uint32_t k_lo = resident ? k_lo0 + kslot * kv_step : k_lo_ring;
-      mbar_wait_a(a_k_full + kslot * 8u, resident ? 0u : q_kpar, 14);
+      if (resident) mbar_wait_a(a_k_full + kslot * 8u, 0u, 14);  // ring mode: K_t landed on p_full of tile t - 2
       tc_fence_after();
       ATTN_TRACE(12, qk_t);
       if (leader) {
@@ -580,8 +599,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                            idesc, k != 0 ? 1u : 0u);
           }
         }
-        if (!resident) umma_commit_a(a_k_empty + kslot * 8u);
-        else if (qk_j == nkv - 1) umma_commit_a(a_q_empty + qs * 8u);  // this Q buffer may be refilled
+        if (resident && qk_j == nkv - 1) umma_commit_a(a_q_empty + qs * 8u);  // this Q buffer may be refilled
         umma_commit_a(a_s_full + q_sb * 8u);
       }
       ATTN_TRACE(13, qk_t);
@@ -615,7 +633,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait_a(a_o_free, (static_cast<uint32_t>(pv_item) - 1u) & 1u, 21);
       const uint32_t vslot = resident ? static_cast<uint32_t>(pv_j) : static_cast<uint32_t>(vs);
       const uint32_t v_lo = resident ? v_lo0 + vslot * kv_step : v_lo_ring;
-      mbar_wait_a(a_v_full + vslot * 8u, resident ? 0u : v_par, 16);
+      if (resident) mbar_wait_a(a_v_full + vslot * 8u, 0u, 16);  // ring mode: V_t landed on p_full of tile t
       tc_fence_after();
       ATTN_TRACE(9, t);
       if (leader) {
@@ -633,7 +651,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
                            (k & 1) == 0 ? acc : 1u);
         }
-        if (!resident) umma_commit_a(a_v_empty + vslot * 8u);
         umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
       }
       ATTN_TRACE(10, t);
@@ -775,21 +792,17 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     }
     smem = 1024 + 2 * qt + 2 * kPBytes + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64;
   } else {
-    // Ring mode.  shared memory: Q + three P atoms (required by the Q.K-first issue order, see the header) + K/V rings,
-    // K 3 / V 2 when that keeps two CTAs per SM (d_pad == 64) or simply fits (one CTA per SM), otherwise 2 / 2.
+    // Ring mode.  shared memory: Q + three P atoms (required by the Q.K-first issue order, see the header) + K ring of 3
+    // + V ring of 2: 104 KB for d_pad == 64 (two CTAs per SM), 219 KB for d_pad == 192.
     p.q_bufs = 1;
     p.qpc = 1;
     p.p_bufs = 3;
     (void)e_pb;
-    const size_t base = 1024 + qt + sizeof(AttnShared) + 64;
-    const size_t half_sm = static_cast<size_t>(g_attn_max_smem) / 2 - 1024;
-    const size_t budget = (p.tmem_cols <= 256 && base + 3 * kPBytes + 4 * kvt <= half_sm)
-                              ? half_sm : static_cast<size_t>(g_attn_max_smem);
-    const size_t fixed = base + 3 * kPBytes;
-    p.k_stages = (fixed + 5 * kvt <= budget) ? 3 : 2;
+    (void)e_k;
+    (void)e_v;
+    const size_t fixed = 1024 + qt + sizeof(AttnShared) + 64 + 3 * kPBytes;
+    p.k_stages = 3;  // the producer's slot-reuse argument (see the kernel) is written for exactly this ring: K 3 / V 2 / P 3
     p.v_stages = 2;
-    if (e_k >= 2 && e_k <= kMaxRing) p.k_stages = e_k;
-    if (e_v >= 2 && e_v <= kMaxRing) p.v_stages = e_v;
     smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;
   }
   if (smem > static_cast<size_t>(g_attn_max_smem)) return B200SD_ERR_UNSUPPORTED;
