@@ -617,62 +617,127 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     };
-    for (int i = 0; i < kSBufs && i < T; ++i) issue_qk();
-    int vs = 0, pb = 0, pv_item = 0, pv_j = 0;
-    uint32_t v_par = 0, p_par = 0, v_lo_ring = v_lo0, p_lo = p_lo0;
-    for (int t = 0; t < T; ++t) {
-      const int nvalid = min(kKv, skv - pv_j * kKv);
-      ATTN_TRACE(7, t);
-      mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
-      ATTN_TRACE(8, t);
-      // softmax t has released its S buffer: refill it two tiles ahead.  In ring mode BEFORE this tile's P.V — S is what
-      // the softmax warps wait for next, O is not read until the end.
-      if (qk_first && qk_t < T) issue_qk();
-      // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
-      if (pv_j == 0 && pv_item > 0)  // the previous Q tile's epilogue has read the accumulators this P.V overwrites
-        mbar_wait_a(a_o_free, (static_cast<uint32_t>(pv_item) - 1u) & 1u, 21);
-      const uint32_t vslot = resident ? static_cast<uint32_t>(pv_j) : static_cast<uint32_t>(vs);
-      const uint32_t v_lo = resident ? v_lo0 + vslot * kv_step : v_lo_ring;
-      if (resident) mbar_wait_a(a_v_full + vslot * 8u, 0u, 16);  // ring mode: V_t landed on p_full of tile t
-      tc_fence_after();
-      ATTN_TRACE(9, t);
-      if (leader) {
-        const uint32_t acc = pv_j != 0 ? 1u : 0u;  // the first MMA of a Q tile into each accumulator overwrites it
-        if (nvalid == kKv) {
-          // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units apart);
-          // the two accumulators alternate so that consecutive MMAs never depend on each other
-          umma_f16_ss_lh(tm_Oa, p_lo + 0u, hi, v_lo + 0u, hi, idesc_pv, acc);
-          umma_f16_ss_lh(tm_Ob, p_lo + 4u, hi, v_lo + 256u, hi, idesc_pv, acc);
-          umma_f16_ss_lh(tm_Oa, p_lo + 2u, hi, v_lo + 128u, hi, idesc_pv, 1u);
-          umma_f16_ss_lh(tm_Ob, p_lo + 6u, hi, v_lo + 384u, hi, idesc_pv, 1u);
+    if (!resident) {
+      // ---- ring mode: one Q tile, tiles t = 0 .. nkv-1.  Unrolled by six (the common period of the P ring of 3, the K
+      // ring of 3, the V ring of 2, the S pair and the p_full parity), so every slot address and barrier parity of a step
+      // is a constant: this thread's instruction count per tile bounds the kernel (see the header). ----
+      const int nvalid_last = skv - (nkv - 1) * kKv;
+      const uint32_t idesc_qk_last = make_idesc_f16(128, (nvalid_last + 15) & ~15, bf, false, false);
+      auto qk = [&](int tile, uint32_t q_sb, uint32_t kslot) {  // leader only
+        const uint32_t idesc = tile == nkv - 1 ? idesc_qk_last : idesc_qk_full;
+        const uint32_t d_tmem = tm_S + q_sb * kKv;
+        const uint32_t k_lo = k_lo0 + kslot * kv_step;
+        if (ksteps_qk == 3) {  // d = 40: the shape that dominates; straight-line issue
+          umma_f16_ss_lh(d_tmem, q_lo0, hi, k_lo, hi, idesc, 0u);
+          umma_f16_ss_lh(d_tmem, q_lo0 + 2u, hi, k_lo + 2u, hi, idesc, 1u);
+          umma_f16_ss_lh(d_tmem, q_lo0 + 4u, hi, k_lo + 4u, hi, idesc, 1u);
         } else {
-          const int ksteps_pv = ((nvalid + 15) & ~15) / 16;
-          for (int k = 0; k < ksteps_pv; ++k)
-            umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
-                           (k & 1) == 0 ? acc : 1u);
+          for (int k = 0; k < ksteps_qk; ++k) {
+            const uint32_t ch = static_cast<uint32_t>(k) >> 2, in = (static_cast<uint32_t>(k) & 3u) * 2u;
+            umma_f16_ss_lh(d_tmem, q_lo0 + ch * (kQChunkBytes >> 4) + in, hi, k_lo + ch * (kKvChunkBytes >> 4) + in, hi,
+                           idesc, k != 0 ? 1u : 0u);
+          }
         }
-        umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
+        umma_commit_a(a_s_full + q_sb * 8u);
+      };
+      mbar_wait_a(a_q_full, 0u, 13);  // Q, K_0, K_1
+      tc_fence_after();
+      if (leader) {
+        qk(0, 0u, 0u);
+        if (nkv > 1) qk(1, 1u, 1u);
       }
-      ATTN_TRACE(10, t);
-      if (!resident) {
-        v_lo_ring += kv_step;
-        if (++vs == v_stages) {
-          vs = 0;
-          v_par ^= 1u;
-          v_lo_ring = v_lo0;
+      for (int t0 = 0; t0 < nkv; t0 += 6) {
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int t = t0 + u;
+          if (t >= nkv) break;
+          ATTN_TRACE(7, t);
+          mbar_wait_a(a_p_full + static_cast<uint32_t>(u % 3) * 8u, static_cast<uint32_t>(u / 3), 15);  // P_t, K_{t+2}, V_t
+          tc_fence_after();
+          ATTN_TRACE(8, t);
+          if (leader) {
+            // Q.K of tile t+2 first: S is what the softmax warps wait for next, O is not read until the end
+            if (t + 2 < nkv) qk(t + 2, static_cast<uint32_t>(u & 1), static_cast<uint32_t>((u + 2) % 3));
+            ATTN_TRACE(13, t + 2);
+            const uint32_t p_lo = p_lo0 + static_cast<uint32_t>(u % 3) * (kPBytes >> 4);
+            const uint32_t v_lo = v_lo0 + static_cast<uint32_t>(u & 1) * kv_step;
+            const uint32_t acc = t != 0 ? 1u : 0u;  // the first MMA into each accumulator overwrites it
+            if (t != nkv - 1 || nvalid_last == kKv) {
+              // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units
+              // apart); the two accumulators alternate so that consecutive MMAs never depend on each other
+              umma_f16_ss_lh(tm_Oa, p_lo + 0u, hi, v_lo + 0u, hi, idesc_pv, acc);
+              umma_f16_ss_lh(tm_Ob, p_lo + 4u, hi, v_lo + 256u, hi, idesc_pv, acc);
+              umma_f16_ss_lh(tm_Oa, p_lo + 2u, hi, v_lo + 128u, hi, idesc_pv, 1u);
+              umma_f16_ss_lh(tm_Ob, p_lo + 6u, hi, v_lo + 384u, hi, idesc_pv, 1u);
+            } else {
+              const int ksteps_pv = ((nvalid_last + 15) & ~15) / 16;
+              for (int k = 0; k < ksteps_pv; ++k)
+                umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
+                               (k & 1) == 0 ? acc : 1u);
+            }
+            umma_commit_a(a_o_full + static_cast<uint32_t>(u % 3) * 8u);
+          }
+          ATTN_TRACE(10, t);
         }
       }
-      p_lo += kPBytes >> 4;
-      if (++pb == p_bufs) {
-        pb = 0;
-        p_par ^= 1u;
-        p_lo = p_lo0;
+    } else {
+      for (int i = 0; i < kSBufs && i < T; ++i) issue_qk();
+      int vs = 0, pb = 0, pv_item = 0, pv_j = 0;
+      uint32_t v_par = 0, p_par = 0, v_lo_ring = v_lo0, p_lo = p_lo0;
+      for (int t = 0; t < T; ++t) {
+        const int nvalid = min(kKv, skv - pv_j * kKv);
+        ATTN_TRACE(7, t);
+        mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
+        ATTN_TRACE(8, t);
+        // softmax t has released its S buffer: refill it two tiles ahead.  In ring mode BEFORE this tile's P.V — S is what
+        // the softmax warps wait for next, O is not read until the end.
+        if (qk_first && qk_t < T) issue_qk();
+        // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
+        if (pv_j == 0 && pv_item > 0)  // the previous Q tile's epilogue has read the accumulators this P.V overwrites
+          mbar_wait_a(a_o_free, (static_cast<uint32_t>(pv_item) - 1u) & 1u, 21);
+        const uint32_t vslot = resident ? static_cast<uint32_t>(pv_j) : static_cast<uint32_t>(vs);
+        const uint32_t v_lo = resident ? v_lo0 + vslot * kv_step : v_lo_ring;
+        if (resident) mbar_wait_a(a_v_full + vslot * 8u, 0u, 16);  // ring mode: V_t landed on p_full of tile t
+        tc_fence_after();
+        ATTN_TRACE(9, t);
+        if (leader) {
+          const uint32_t acc = pv_j != 0 ? 1u : 0u;  // the first MMA of a Q tile into each accumulator overwrites it
+          if (nvalid == kKv) {
+            // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units apart);
+            // the two accumulators alternate so that consecutive MMAs never depend on each other
+            umma_f16_ss_lh(tm_Oa, p_lo + 0u, hi, v_lo + 0u, hi, idesc_pv, acc);
+            umma_f16_ss_lh(tm_Ob, p_lo + 4u, hi, v_lo + 256u, hi, idesc_pv, acc);
+            umma_f16_ss_lh(tm_Oa, p_lo + 2u, hi, v_lo + 128u, hi, idesc_pv, 1u);
+            umma_f16_ss_lh(tm_Ob, p_lo + 6u, hi, v_lo + 384u, hi, idesc_pv, 1u);
+          } else {
+            const int ksteps_pv = ((nvalid + 15) & ~15) / 16;
+            for (int k = 0; k < ksteps_pv; ++k)
+              umma_f16_ss_lh(k < 2 ? tm_Oa : tm_Ob, p_lo + 2u * k, hi, v_lo + 128u * k, hi, idesc_pv,
+                             (k & 1) == 0 ? acc : 1u);
+          }
+          umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
+        }
+        ATTN_TRACE(10, t);
+        if (!resident) {
+          v_lo_ring += kv_step;
+          if (++vs == v_stages) {
+            vs = 0;
+            v_par ^= 1u;
+            v_lo_ring = v_lo0;
+          }
+        }
+        p_lo += kPBytes >> 4;
+        if (++pb == p_bufs) {
+          pb = 0;
+          p_par ^= 1u;
+          p_lo = p_lo0;
+        }
+        if (++pv_j == nkv) {
+          pv_j = 0;
+          ++pv_item;
+        }
+        if (!qk_first && qk_t < T) issue_qk();
       }
-      if (++pv_j == nkv) {
-        pv_j = 0;
-        ++pv_item;
-      }
-      if (!qk_first && qk_t < T) issue_qk();
     }
     __syncwarp();
   } else {

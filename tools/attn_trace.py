@@ -39,7 +39,7 @@ def main():
     rel = (t - t0).tolist()
     print("tile |  softmax: top  Srdy  Sreg  exp  Pfree Pstor fence | MMA: waitP  Pfull  Vrdy  PVdone | QK(j): kwait  krdy  issued")
     for j in list(range(0, 6)) + list(range(30, 36)) + list(range(60, 64)):
-        r = [rel[e][j] for e in range(14)]
+        r = [rel[e][j] if e != 4 else 0 for e in range(14)]
         print(f"{j:4d} | " + " ".join(f"{x:7d}" for x in r[:7]) + " | " + " ".join(f"{x:7d}" for x in r[7:11]) + " | " +
               " ".join(f"{x:7d}" for x in r[11:14]))
     # steady-state averages over tiles 16..56
@@ -52,8 +52,7 @@ def main():
     print(f"  wait for S (0->1)                           {avg(lambda j: rel[1][j] - rel[0][j]):8.1f}")
     print(f"  TMEM load of 32 columns (1->2)              {avg(lambda j: rel[2][j] - rel[1][j]):8.1f}")
     print(f"  FFMA2/ex2/pack/max (2->3)                   {avg(lambda j: rel[3][j] - rel[2][j]):8.1f}")
-    print(f"  wait for P buffer (3->4)                    {avg(lambda j: rel[4][j] - rel[3][j]):8.1f}")
-    print(f"  any_sync + P stores (4->5)                  {avg(lambda j: rel[5][j] - rel[4][j]):8.1f}")
+    print(f"  any_sync + P stores (3->5)                  {avg(lambda j: rel[5][j] - rel[3][j]):8.1f}")
     print(f"  proxy fence + syncwarp (5->6)               {avg(lambda j: rel[6][j] - rel[5][j]):8.1f}")
     print(f"  arrive + loop (6->next top)                 {avg(lambda j: rel[0][j + 1] - rel[6][j]):8.1f}")
     print(f"  MMA: wait for P_j (7->8)                    {avg(lambda j: rel[8][j] - rel[7][j]):8.1f}")
@@ -62,7 +61,12 @@ def main():
     print(f"  MMA: issue P.V + commits (9->10)            {avg(lambda j: rel[10][j] - rel[9][j]):8.1f}")
     print(f"  MMA: QK(j+2) K wait (11->12)                {avg(lambda j: rel[12][j + 2] - rel[11][j + 2]):8.1f}")
     print(f"  MMA: issue QK(j+2) + commits (12->13)       {avg(lambda j: rel[13][j + 2] - rel[12][j + 2]):8.1f}")
-    print(f"  QK(j+2) issued -> softmax sees S(j+2) ready {avg(lambda j: rel[1][j + 2] - rel[13][j + 2]):8.1f}  (<= 0: S was ready before it was needed)")
+    print(f"  QK(j+2) issued -> softmax sees S(j+2) ready {avg(lambda j: rel[1][j + 2] - rel[13][j + 2]):8.1f}")
+    print(f"  QK(j+2) issued -> softmax WANTS S(j+2)      {avg(lambda j: rel[0][j + 2] - rel[13][j + 2]):8.1f}  (< 0: the softmax warp waited for the issuer)")
+    print(f"  MMA: loop period (7->7)                     {avg(lambda j: rel[7][j + 1] - rel[7][j]):8.1f}")
+    print(f"  MMA: P_j complete -> QK(j+2) starts         {avg(lambda j: rel[11][j + 2] - rel[8][j]):8.1f}")
+    print(f"  MMA: QK(j+2) issued -> P.V operands ready   {avg(lambda j: rel[9][j] - rel[13][j + 2]):8.1f}")
+    print(f"  MMA: P.V issued -> next loop top            {avg(lambda j: rel[7][j + 1] - rel[10][j]):8.1f}")
     print(f"  P_j complete -> S(j+2) issued               {avg(lambda j: rel[13][j + 2] - rel[8][j]):8.1f}")
 
 
