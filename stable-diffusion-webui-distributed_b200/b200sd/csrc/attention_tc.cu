@@ -11,7 +11,7 @@
 // ([b, s, h*d]) because it feeds the out-projection GEMM as a plain K-major A operand.
 //
 // One CTA = one 128-row Q tile of one (batch, head), kv consumed in tiles of 64.  320 threads:
-//   warp 0    TMA producer (Q once; K ring, V ring — loads issued in the order the MMAs consume them)
+//   warp 0    TMA producer (Q once; K ring of 3, V ring of 2 — or K/V resident and Q tiles streaming, see `resident`)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%2] = Q K_j^T (M128 x N<=64 x K=d),
 //             O_h (+)= P_h V_h for the two 32-row halves h of the kv tile (M128 x N=d_pad x K=32 each, V consumed
 //             MN-major straight from its TMA tile)
@@ -40,7 +40,12 @@
 //              (hence three P buffers), and the rare-path wait for tile j-1 / the final wait can be at most one phase
 //              behind their barrier (the phase before belongs to tile j-4).  P.V of tile j cannot complete before the
 //              waiter's own warp has arrived on p_full.
-//   s_full[2] / p_full[pb] / ring barriers: one waiting side each, strictly alternating with the signalling side.
+//   p_full[pb] 8 warp arrivals; in ring mode + 1 arrival of the producer, whose expect_tx puts the bytes of K_{t+2} and V_t
+//              on the phase of tile t (see the producer): the MMA thread's one wait per tile covers P and its operands.
+//              Waiters: the MMA thread and (ring mode) the producer, neither of which can be lapped — a later phase needs
+//              S of a tile the MMA thread issues after this wait, and the producer's own arrival.
+//   s_full[2] / q_full / q_empty / o_free and resident mode's k_full / v_full: one waiting side, alternating with the
+//              signalling side.
 // All waits carry a suspend hint: a polling loop without it steals issue slots from the warps doing the exponentials
 // (measured: a polling TMA producer cost 25 % of this kernel's time).
 #include <cstddef>
