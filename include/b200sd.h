@@ -123,6 +123,12 @@ int b200sd_cfg_ddim_step(const void* eps, long long pitch_e, float* x, void* xin
 int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float* x, const float* noise, void* xin,
                             long long pitch_x, int B, int HW, float cfg_scale, const float* coef, int* step_counter,
                             int dtype, void* stream);
+/* DPM-Solver++(2M) step on sigma-space latents (k-diffusion sample_dpmpp_2m; sdwui "DPM++ 2M" / "DPM++ 2M Karras"):
+ * old_denoised [B,HW,4] fp32 carries the previous step's x0 prediction (ignored when c2 == 0).
+ * coef[step] = {sigma, sigma_next/sigma, c1, c2, in_scale_next, 0, 0, 0} — 8 floats per row. */
+int b200sd_cfg_dpmpp_2m_step(const void* eps, long long pitch_e, float* x, float* old_denoised, void* xin,
+                             long long pitch_x, int B, int HW, float cfg_scale, const float* coef, int* step_counter,
+                             int dtype, void* stream);
 /* decoded image [B,HW,pitch] (first 3 channels RGB in [-1,1]) -> uint8 [B,HW,3]:
  * trunc(255 * clamp((v+1)/2, 0, 1))  (sdwui process_images_inner) */
 int b200sd_quantize_u8(const void* img, long long pitch, unsigned char* out, int B, int HW, int dtype, void* stream);

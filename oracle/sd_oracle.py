@@ -424,6 +424,42 @@ def sample_euler(unet, x_T, cond, uncond, steps: int, cfg_scale: float):
     return x
 
 
+def sigmas_karras(steps: int):
+    """k-diffusion get_sigmas_karras(n, sigma_min, sigma_max, rho = 7) with sdwui's bounds (the model's own smallest
+    and largest sigma: sd_samplers_kdiffusion.KDiffusionSampler.get_sigmas, use_old_karras_scheduler_sigmas off)."""
+    ac = alphas_cumprod().double()
+    sig = ((1 - ac) / ac) ** 0.5
+    ramp = torch.linspace(0, 1, steps, dtype=torch.float64)
+    min_inv_rho, max_inv_rho = float(sig[0]) ** (1 / 7.0), float(sig[-1]) ** (1 / 7.0)
+    s = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** 7.0
+    return torch.cat([s, s.new_zeros(1)]), sig.log()
+
+
+def sample_dpmpp_2m(unet, x_T, cond, uncond, steps: int, cfg_scale: float, karras: bool = True):
+    """k-diffusion sample_dpmpp_2m (sdwui "DPM++ 2M" / "DPM++ 2M Karras") around the eps-prediction CompVisDenoiser:
+    denoised = x - sigma * eps(x * c_in, t(sigma)); written with t = -log(sigma) exactly as upstream."""
+    sig, log_sig = sigmas_karras(steps) if karras else karras_sigmas_compvis(steps)
+    x = x_T * float(sig[0])
+    old = None
+    for i in range(steps):
+        s, sn = float(sig[i]), float(sig[i + 1])
+        e = cfg_eps(unet, x * (1.0 / math.sqrt(s * s + 1.0)), sigma_to_t(s, log_sig), cond, uncond, cfg_scale)
+        denoised = x - s * e
+        t = -math.log(s)
+        t_next = -math.log(sn) if sn > 0 else math.inf
+        h = t_next - t
+        ratio = sn / s                      # sigma_fn(t_next) / sigma_fn(t)
+        if old is None or sn == 0:
+            x = ratio * x - math.expm1(-h) * denoised
+        else:
+            h_last = t - (-math.log(float(sig[i - 1])))
+            r = h_last / h
+            dd = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old
+            x = ratio * x - math.expm1(-h) * dd
+        old = denoised
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ images / rng
 def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0) -> torch.Tensor:
     """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k."""

@@ -210,6 +210,40 @@ __global__ void cfg_euler_a_step_kernel(const void* eps, long long pitch_e, floa
   }
 }
 
+// DPM-Solver++(2M) (k-diffusion sample_dpmpp_2m) on an eps-prediction model:
+//   denoised = x - sigma * eps;  dd = c1 * denoised - c2 * old_denoised;  x = a * x + (1 - a) * dd;  old = denoised
+// with a = sigma_next / sigma = exp(-h), c1 = 1 + 1/(2r), c2 = 1/(2r), r = h_last / h (c1 = 1, c2 = 0 on the first step and
+// on the step to sigma = 0).  coef row = {sigma, a, c1, c2, in_scale_next, -, -, -}.
+template <bool kBf16>
+__global__ void cfg_dpmpp_2m_step_kernel(const void* eps, long long pitch_e, float4* x, float4* old_denoised, void* xin,
+                                         long long pitch_x, int B, int HW, float cfg, const float* __restrict__ coef,
+                                         int* step_counter) {
+  const int step = *step_counter;
+  const float sigma = coef[step * 8 + 0], a = coef[step * 8 + 1], c1 = coef[step * 8 + 2], c2 = coef[step * 8 + 3],
+              in_next = coef[step * 8 + 4];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * HW) {
+    const int b = i / HW, pix = i % HW;
+    const float4 ec = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b) * HW + pix);
+    const float4 eu = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b + B) * HW + pix);
+    const float4 xv = x[i], ov = old_denoised[i];
+    const float e[4] = {eu.x + cfg * (ec.x - eu.x), eu.y + cfg * (ec.y - eu.y), eu.z + cfg * (ec.z - eu.z),
+                        eu.w + cfg * (ec.w - eu.w)};
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, os[4] = {ov.x, ov.y, ov.z, ov.w};
+    float xn[4], dn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      dn[k] = xs[k] - sigma * e[k];
+      const float dd = c2 != 0.f ? c1 * dn[k] - c2 * os[k] : dn[k];
+      xn[k] = a * xs[k] + (1.0f - a) * dd;
+    }
+    x[i] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    old_denoised[i] = make_float4(dn[0], dn[1], dn[2], dn[3]);
+    write_xin<kBf16>(xin, pitch_x, B, HW, b, pix,
+                     make_float4(xn[0] * in_next, xn[1] * in_next, xn[2] * in_next, xn[3] * in_next));
+  }
+}
+
 __global__ void bump_step_kernel(int* step_counter) { *step_counter += 1; }
 
 template <bool kBf16>
@@ -364,6 +398,21 @@ extern "C" int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float
     cfg_euler_a_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   else
     cfg_euler_a_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_cfg_dpmpp_2m_step(const void* eps, long long pitch_e, float* x, float* old_denoised, void* xin,
+                                        long long pitch_x, int B, int HW, float cfg_scale, const float* coef,
+                                        int* step_counter, int dtype, void* stream) {
+  if (B <= 0) return B200SD_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(old_denoised)) & 15) return B200SD_ERR_INVALID;
+  const int n = B * HW;
+  if (dtype == B200SD_BF16)
+    cfg_dpmpp_2m_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+  else
+    cfg_dpmpp_2m_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
   bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
   RET_LAUNCH();

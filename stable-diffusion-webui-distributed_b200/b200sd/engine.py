@@ -66,28 +66,14 @@ def ddim_img2img_plan(steps: int, denoising_strength: float):
 def euler_a_plan(steps: int):
     """k-diffusion sample_euler_ancestral over CompVisDenoiser sigmas.  Returns (timesteps, coef rows, sigma0):
     row = [sigma, sigma_down, sigma_up, c_in of the NEXT step]."""
-    ac = alphas_cumprod().double()
-    sig_all = ((1 - ac) / ac) ** 0.5
-    log_sig = sig_all.log()
-    tt = torch.linspace(999, 0, steps, dtype=torch.float64)
-    lo, hi = tt.floor().long(), tt.ceil().long()
-    wgt = tt - lo
-    sig = torch.cat([((1 - wgt) * log_sig[lo] + wgt * log_sig[hi]).exp(), tt.new_zeros(1)])
-
-    def sigma_to_t(s: float) -> float:
-        ls = math.log(s)
-        dists = ls - log_sig
-        low = int((dists >= 0).cumsum(0).argmax().clamp(max=len(log_sig) - 2))
-        l0, h0 = float(log_sig[low]), float(log_sig[low + 1])
-        w = min(max((l0 - ls) / (l0 - h0), 0.0), 1.0)
-        return (1 - w) * low + w * (low + 1)
+    sig, log_sig = kdiffusion_sigmas(steps, "uniform")
 
     t_out, rows = [], []
     for i in range(steps):
         s, sn = float(sig[i]), float(sig[i + 1])
         up = min(sn, (sn ** 2 * (s ** 2 - sn ** 2) / s ** 2) ** 0.5)
         down = (sn ** 2 - up ** 2) ** 0.5
-        t_out.append(sigma_to_t(s))
+        t_out.append(sigma_to_t(s, log_sig))
         rows.append([s, down, up, 1.0 / math.sqrt(sn * sn + 1.0)])
     return t_out, rows, float(sig[0])
 
@@ -100,6 +86,74 @@ def euler_plan(steps: int):
         sn = (r[1] ** 2 + r[2] ** 2) ** 0.5   # sigma_next = sqrt(down^2 + up^2)
         rows[i] = [r[0], sn, 0.0, r[3]]
     return t_out, rows, sigma0
+
+
+def kdiffusion_sigmas(steps: int, scheduler: str = "uniform") -> Tuple[torch.Tensor, torch.Tensor]:
+    """sigmas[steps + 1] (last 0) as sdwui's KDiffusionSampler.get_sigmas builds them, and the model's log-sigma table.
+    "uniform": k-diffusion DiscreteSchedule.get_sigmas (timesteps linspace(999, 0, steps), log-sigma interpolation);
+    "karras": get_sigmas_karras(steps, sigma_min = sigmas[0], sigma_max = sigmas[-1], rho = 7)."""
+    ac = alphas_cumprod().double()
+    sig_all = ((1 - ac) / ac) ** 0.5
+    log_sig = sig_all.log()
+    if scheduler == "karras":
+        ramp = torch.linspace(0, 1, steps, dtype=torch.float64)
+        lo, hi = float(sig_all[0]) ** (1 / 7.0), float(sig_all[-1]) ** (1 / 7.0)
+        sig = (hi + ramp * (lo - hi)) ** 7.0
+    elif scheduler == "uniform":
+        tt = torch.linspace(999, 0, steps, dtype=torch.float64)
+        lo, hi = tt.floor().long(), tt.ceil().long()
+        wgt = tt - lo
+        sig = ((1 - wgt) * log_sig[lo] + wgt * log_sig[hi]).exp()
+    else:
+        raise ValueError(f"scheduler {scheduler!r} is not implemented")
+    return torch.cat([sig, sig.new_zeros(1)]), log_sig
+
+
+def sigma_to_t(s: float, log_sig: torch.Tensor) -> float:
+    """k-diffusion DiscreteSchedule.sigma_to_t (quantize = False)"""
+    ls = math.log(s)
+    dists = ls - log_sig
+    low = int((dists >= 0).cumsum(0).argmax().clamp(max=len(log_sig) - 2))
+    l0, h0 = float(log_sig[low]), float(log_sig[low + 1])
+    w = min(max((l0 - ls) / (l0 - h0), 0.0), 1.0)
+    return (1 - w) * low + w * (low + 1)
+
+
+def dpmpp_2m_plan(steps: int, scheduler: str = "karras"):
+    """k-diffusion sample_dpmpp_2m.  Returns (timesteps, coef rows of 8, sigma0);
+    row = [sigma, sigma_next / sigma, c1, c2, c_in of the NEXT step, 0, 0, 0] with denoised_d = c1 * denoised - c2 * old."""
+    sig, log_sig = kdiffusion_sigmas(steps, scheduler)
+    t_out, rows = [], []
+    for i in range(steps):
+        s, sn = float(sig[i]), float(sig[i + 1])
+        c1, c2 = 1.0, 0.0
+        if i > 0 and sn > 0:
+            h = math.log(s / sn)
+            h_last = math.log(float(sig[i - 1]) / s)
+            r = h_last / h
+            c1, c2 = 1.0 + 1.0 / (2.0 * r), 1.0 / (2.0 * r)
+        t_out.append(sigma_to_t(s, log_sig))
+        rows.append([s, sn / s, c1, c2, 1.0 / math.sqrt(sn * sn + 1.0), 0.0, 0.0, 0.0])
+    return t_out, rows, float(sig[0])
+
+
+# sampler names of the sdwui API -> (method, scheduler).  sdwui >= 1.9 sends the scheduler separately ("scheduler" key,
+# "Automatic" = the sampler's default, which is Karras for DPM++ 2M); older versions fold it into the name.
+SAMPLERS = {"DDIM": ("ddim", None), "Euler a": ("euler_a", "uniform"), "Euler": ("euler", "uniform"),
+            "DPM++ 2M": ("dpmpp_2m", "karras"), "DPM++ 2M Karras": ("dpmpp_2m", "karras")}
+
+
+def resolve_sampler(name: str, scheduler: Optional[str] = None):
+    """(method, scheduler) for an API sampler name + optional API scheduler label; ValueError if not implemented."""
+    if name not in SAMPLERS:
+        raise ValueError(f"sampler {name!r} is not implemented on the local executor")
+    method, default = SAMPLERS[name]
+    if method == "dpmpp_2m" and scheduler not in (None, "", "Automatic"):
+        label = scheduler.lower()
+        if label not in ("karras", "uniform"):
+            raise ValueError(f"scheduler {scheduler!r} is not implemented on the local executor")
+        return method, label
+    return method, default
 
 
 def per_image_noise(seed: int, n: int, shape, draws: int = 1) -> torch.Tensor:
@@ -127,6 +181,8 @@ class Plan:
         self.step = torch.zeros((1,), device=dev, dtype=torch.int32)
         self.coef = torch.zeros((MAX_STEPS, 4), device=dev, dtype=torch.float32)
         self.table = torch.zeros((MAX_STEPS, eng.unet_w.emb_total), device=dev, dtype=torch.float32)
+        self.coef8 = torch.zeros((MAX_STEPS, 8), device=dev, dtype=torch.float32)   # DPM++ 2M rows
+        self.old = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)        # its previous x0 prediction
         self.noise = None
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[str, int] = {}
@@ -146,6 +202,11 @@ class Plan:
         ops.select_step(self.table, self.step, self.unet.cur_bias)
         self.unet.run()
         ops.cfg_euler_a_step(self.unet.eps, self.x, None, self.unet.xin, cfg_scale, self.coef, self.step)
+
+    def step_dpmpp_2m(self, cfg_scale: float):
+        ops.select_step(self.table, self.step, self.unet.cur_bias)
+        self.unet.run()
+        ops.cfg_dpmpp_2m_step(self.unet.eps, self.x, self.old, self.unet.xin, cfg_scale, self.coef8, self.step)
 
 
 class SDEngine:
@@ -223,7 +284,8 @@ class SDEngine:
 
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
-               sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None) -> torch.Tensor:
+               sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None,
+               scheduler: Optional[str] = None) -> torch.Tensor:
         """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device): the start latents.
         `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way).
         Returns the final latents fp32 [b, h*w, 4] (NHWC, a view of plan state)."""
@@ -246,13 +308,17 @@ class SDEngine:
                 ts, rows, sigma0 = euler_plan(steps)
                 scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
+            elif sampler in SAMPLERS and SAMPLERS[sampler][0] == "dpmpp_2m":
+                ts, rows, sigma0 = dpmpp_2m_plan(steps, resolve_sampler(sampler, scheduler)[1])
+                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                step_fn = lambda: plan.step_dpmpp_2m(cfg_scale)  # noqa: E731
             else:
                 raise ValueError(f"sampler {sampler!r} is not implemented on the local executor")
             n_evals = len(ts)
             if n_evals > MAX_STEPS:
                 raise ValueError("too many steps")
             plan.table[:n_evals].copy_(self.temb.table(torch.tensor(ts, dtype=torch.float32)))
-            plan.coef[:n_evals].copy_(torch.tensor(rows, dtype=torch.float32))
+            (plan.coef8 if len(rows[0]) == 8 else plan.coef)[:n_evals].copy_(torch.tensor(rows, dtype=torch.float32))
             plan.x.copy_((x_T.to(self.device, torch.float32) * scale0).permute(0, 2, 3, 1).reshape(b, h * w, 4))
             plan.step.zero_()
             ops.pack_unet_input(plan.x, plan.unet.xin, in0)
@@ -343,7 +409,8 @@ class SDEngine:
     @torch.no_grad()
     def txt2img_hires(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20,
                       cfg_scale: float = 7.0, height: int = 512, width: int = 512, hr_scale: float = 2.0,
-                      hr_steps: int = 0, denoising_strength: float = 0.7, sampler: str = "DDIM") -> torch.Tensor:
+                      hr_steps: int = 0, denoising_strength: float = 0.7, sampler: str = "DDIM",
+                      scheduler: Optional[str] = None) -> torch.Tensor:
         """txt2img with sdwui's hires fix and the "Latent" upscaler (StableDiffusionProcessingTxt2Img.sample /
         sample_hr_pass): first pass at (height, width), bilinear resize of the latents to hr_scale x, a fresh per-image
         noise of the large shape from the same seeds, then DDIM img2img from t_enc with `hr_steps` (0 = `steps`)
@@ -355,7 +422,8 @@ class SDEngine:
         uncond = self.encode_prompts(neg_tokens)
         draws = 1 + (steps if sampler == "Euler a" else 0)
         nz = per_image_noise(seed, b, (4, h, w), draws)
-        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None)
+        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
+                          scheduler=scheduler)
         with self._ctx():
             up = torch.empty((b, h2 * w2, 4), device=self.device, dtype=torch.float32)
             ops.resize_latent_bilinear(lat.contiguous(), up, h, w, h2, w2)
@@ -367,7 +435,7 @@ class SDEngine:
 
     @torch.no_grad()
     def txt2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20, cfg_scale: float = 7.0,
-                height: int = 512, width: int = 512, sampler: str = "DDIM") -> torch.Tensor:
+                height: int = 512, width: int = 512, sampler: str = "DDIM", scheduler: Optional[str] = None) -> torch.Tensor:
         """Whole request for this engine's share: returns uint8 [b, H, W, 3] on device."""
         b = tokens.shape[0]
         h, w = height // 8, width // 8
@@ -375,5 +443,6 @@ class SDEngine:
         uncond = self.encode_prompts(neg_tokens)
         draws = 1 + (steps if sampler == "Euler a" else 0)
         nz = per_image_noise(seed, b, (4, h, w), draws)
-        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None)
+        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
+                          scheduler=scheduler)
         return self.decode(lat, h, w)

@@ -272,6 +272,18 @@ def cfg_euler_a_step(eps: torch.Tensor, x: torch.Tensor, noise: Optional[torch.T
     _count(2)
 
 
+def cfg_dpmpp_2m_step(eps: torch.Tensor, x: torch.Tensor, old_denoised: torch.Tensor, xin: torch.Tensor,
+                      cfg_scale: float, coef8: torch.Tensor, step_counter: torch.Tensor):
+    """coef8 [steps, 8] fp32: {sigma, sigma_next/sigma, c1, c2, in_scale_next, 0, 0, 0} per step"""
+    b, hw, _ = x.shape
+    assert coef8.shape[-1] == 8 and old_denoised.shape == x.shape
+    rc = _lib.lib().b200sd_cfg_dpmpp_2m_step(_p(eps), ctypes.c_longlong(eps.stride(1)), _p(x), _p(old_denoised), _p(xin),
+                                             ctypes.c_longlong(xin.stride(1)), b, hw, ctypes.c_float(cfg_scale),
+                                             _p(coef8), _p(step_counter), _dt(xin), _stream())
+    check(rc, "b200sd_cfg_dpmpp_2m_step")
+    _count(2)
+
+
 def image_to_nhwc(img_u8: torch.Tensor, out: torch.Tensor):
     """img_u8 uint8 [B, HW, 3] -> out [B, HW, pitch] channels 0..2 = 2*x/255 - 1"""
     b, hw, _ = img_u8.shape

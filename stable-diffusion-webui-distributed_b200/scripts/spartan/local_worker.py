@@ -23,7 +23,7 @@ from modules.shared import state as master_state
 from .shared import logger
 from .worker import InvalidWorkerResponse, State, Worker
 
-SUPPORTED_SAMPLERS = ("DDIM", "Euler a", "Euler")
+SUPPORTED_SAMPLERS = ("DDIM", "Euler a", "Euler", "DPM++ 2M", "DPM++ 2M Karras")
 
 
 class LocalGPUWorker(Worker):
@@ -145,6 +145,10 @@ class LocalGPUWorker(Worker):
         if sampler not in SUPPORTED_SAMPLERS:
             logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")
             sampler = "Euler a"
+        scheduler = payload.get("scheduler")  # sdwui >= 1.9 sends the noise schedule separately from the sampler
+        if sampler.startswith("DPM++ 2M") and scheduler not in (None, "", "Automatic", "Karras", "Uniform"):
+            logger.warning(f"scheduler '{scheduler}' is not implemented on worker {self.label}: using the sampler's default")
+            scheduler = None
         init_u8 = None
         if payload.get("init_images"):
             if payload.get("image_mask") is not None or payload.get("mask") is not None:
@@ -188,10 +192,11 @@ class LocalGPUWorker(Worker):
                 u8 = eng.txt2img_hires(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
                                        width=width, hr_scale=hr_scale,
                                        hr_steps=int(payload.get("hr_second_pass_steps") or 0),
-                                       denoising_strength=float(payload.get("denoising_strength") or 0.7), sampler=sampler)
+                                       denoising_strength=float(payload.get("denoising_strength") or 0.7), sampler=sampler,
+                                       scheduler=scheduler)
             else:
                 u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
-                                 width=width, sampler=sampler)
+                                 width=width, sampler=sampler, scheduler=scheduler)
             chunks.append(u8)
             if eng.interrupted:
                 break

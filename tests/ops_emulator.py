@@ -167,6 +167,20 @@ def cfg_euler_a_step(eps, x, noise, xin, cfg_scale, coef, step_counter):
     step_counter += 1
 
 
+def cfg_dpmpp_2m_step(eps, x, old_denoised, xin, cfg_scale, coef8, step_counter):
+    b = x.shape[0]
+    s = int(step_counter.item())
+    sigma, a, c1, c2, in_next = (float(c) for c in coef8[s][:5])
+    ec, eu = eps[:b, :, :4].float(), eps[b:, :, :4].float()
+    e = eu + cfg_scale * (ec - eu)
+    dn = x - sigma * e
+    dd = c1 * dn - c2 * old_denoised if c2 != 0 else dn
+    x.copy_(a * x + (1.0 - a) * dd)
+    old_denoised.copy_(dn)
+    pack_unet_input(x, xin, in_next)
+    step_counter += 1
+
+
 def quantize_u8(img, out):
     v = ((img[..., :3].float() + 1.0) * 0.5).clamp(0, 1)
     out.copy_((255.0 * v).to(torch.uint8))
@@ -191,7 +205,7 @@ def resize_latent_bilinear(x, y, h, w, ho, wo):
 
 
 ALL = ["resize_latent_bilinear", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
-       "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step",
+       "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step", "cfg_dpmpp_2m_step",
        "quantize_u8", "image_to_nhwc", "unpack_latent"]
 
 

@@ -237,6 +237,31 @@ def test_euler_parity_tiny(mods):
     assert rel <= 3e-2 and got_u8.shape[0] == b and got_u8.dtype == torch.uint8
 
 
+@pytest.mark.parametrize("name,sched,karras", [("DPM++ 2M", None, True), ("DPM++ 2M Karras", None, True),
+                                               ("DPM++ 2M", "Uniform", False)])
+def test_dpmpp_2m_parity_tiny(mods, name, sched, karras):
+    """sdwui "DPM++ 2M" (k-diffusion sample_dpmpp_2m) with the Karras / uniform noise schedules, through txt2img"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b, hw, steps = 2, 16, 7
+    tok = O.random_prompt_tokens(b, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    x_T = O.per_image_noise(2200, b, (4, hw, hw))
+    cond32 = O.clip_text_encode(dsd, cfgs[2], tok.cuda())
+    unc32 = O.clip_text_encode(dsd, cfgs[2], neg.cuda())
+    with torch.no_grad():
+        ref = O.sample_dpmpp_2m(lambda x, t, c: O.unet_forward(dsd, cfgs[0], x, t, c), x_T.cuda(), cond32, unc32, steps, 7.0,
+                                karras=karras)
+    got_u8 = eng.txt2img(tok, neg, seed=2200, steps=steps, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler=name,
+                         scheduler=sched)
+    torch.cuda.synchronize()
+    assert eng.last_unet_evals == steps
+    z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel = float((z - ref).abs().max() / ref.abs().max())
+    _record(f"dpmpp_2m tiny {name} {sched}", z_rel_max=rel)
+    assert rel <= 3e-2 and got_u8.shape[0] == b and got_u8.dtype == torch.uint8
+
+
 def test_euler_a_parity_tiny(mods):
     C, E, S, O = mods
     cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")

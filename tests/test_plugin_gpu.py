@@ -85,6 +85,26 @@ def test_worker_reply_schema_and_png_lane(env):
     assert wk.loaded_model == "m" and wk.response_time is not None and len(wk.eta_percent_error) <= 1
 
 
+@pytest.mark.parametrize("name,sched,direct_sched", [("DPM++ 2M Karras", None, None), ("DPM++ 2M", "Uniform", "Uniform"),
+                                                     ("DPM++ 2M", "Exponential", None), ("Euler", None, None)])
+def test_worker_sampler_names(env, name, sched, direct_sched):
+    """the API's sampler / scheduler labels reach the executor (an unknown scheduler falls back to the sampler's default)"""
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng)
+    payload = {"prompt": "p q", "negative_prompt": "", "seed": 21, "subseed": 1, "subseed_strength": 0, "batch_size": 2,
+               "n_iter": 1, "steps": 5, "width": 64, "height": 64, "sampler_name": name, "cfg_scale": 6.0}
+    if sched is not None:
+        payload["scheduler"] = sched
+    wk.request(dict(payload), None, False)
+    r = wk.response
+    assert r is not None and r["parameters"]["sampler_name"] == name and wk.state == State.IDLE
+    from b200sd.factory import synthetic_tokens
+    vocab = eng.clip_cfg.vocab
+    direct = eng.txt2img(synthetic_tokens(["p q"] * 2, vocab), synthetic_tokens([""] * 2, vocab), 21, steps=5, cfg_scale=6.0,
+                         height=64, width=64, sampler=name, scheduler=direct_sched).cpu()
+    assert torch.equal(r["tensors"], direct)
+
+
 def test_worker_img2img_request(env):
     """img2img payload as the reference sends it: init_images are PIL images in p.__dict__ (worker.py:365-373)."""
     processing, mscripts, DistributedScript, eng, State, sh = env

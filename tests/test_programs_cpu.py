@@ -120,6 +120,42 @@ def test_sample_matches_oracle_euler(env):
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("sched,karras", [(None, True), ("Karras", True), ("Uniform", False)])
+def test_sample_matches_oracle_dpmpp_2m(env, sched, karras):
+    """sdwui "DPM++ 2M": k-diffusion sample_dpmpp_2m, Karras schedule by default (sdwui >= 1.9) or as the API asks"""
+    C, E, O, cfgs, sd, eng = env
+    b, hw, steps = 2, 8, 6
+    ts, rows, s0 = E.dpmpp_2m_plan(steps, "karras" if karras else "uniform")
+    sig, log_sig = O.sigmas_karras(steps) if karras else O.karras_sigmas_compvis(steps)
+    assert abs(s0 - float(sig[0])) < 1e-12 and len(rows) == steps and rows[0][3] == 0.0 and rows[-1][3] == 0.0
+    assert all(abs(r[0] - float(sig[i])) < 1e-12 and abs(r[1] * r[0] - float(sig[i + 1])) < 1e-12 for i, r in enumerate(rows))
+    assert all(abs(r[2] - r[3] - 1.0) < 1e-12 for r in rows)      # c1 - c2 == 1: a constant x0 prediction is a fixed point
+    assert all(abs(t - O.sigma_to_t(float(sig[i]), log_sig)) < 1e-9 for i, t in enumerate(ts))
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    nz = E.per_image_noise(3100, b, (4, hw, hw), 1)
+    with torch.no_grad():
+        ref = O.sample_dpmpp_2m(lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c), nz[0], cond, unc, steps, 7.0,
+                                karras=karras)
+    lat = eng.sample(cond, unc, nz[0], steps, 7.0, "DPM++ 2M", scheduler=sched)
+    assert eng.last_unet_evals == steps
+    z = lat.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def test_sampler_names_resolve(env):
+    C, E, O, cfgs, sd, eng = env
+    assert E.resolve_sampler("DPM++ 2M") == ("dpmpp_2m", "karras") == E.resolve_sampler("DPM++ 2M Karras")
+    assert E.resolve_sampler("DPM++ 2M", "Automatic") == ("dpmpp_2m", "karras")
+    assert E.resolve_sampler("DPM++ 2M", "Uniform") == ("dpmpp_2m", "uniform")
+    assert E.resolve_sampler("Euler a") == ("euler_a", "uniform") and E.resolve_sampler("DDIM") == ("ddim", None)
+    with pytest.raises(ValueError):
+        E.resolve_sampler("UniPC")
+    with pytest.raises(ValueError):
+        E.resolve_sampler("DPM++ 2M", "Exponential")
+
+
 def test_hires_fix_matches_oracle(env):
     """first pass -> bilinear latent resize -> DDIM img2img from t_enc at the large size -> decode"""
     C, E, O, cfgs, sd, eng = env

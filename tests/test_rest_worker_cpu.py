@@ -37,7 +37,7 @@ class EngineDouble:
             out.append(torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8))
         return torch.stack(out)
 
-    def txt2img(self, tok, neg, seed, steps, cfg_scale, height, width, sampler):
+    def txt2img(self, tok, neg, seed, steps, cfg_scale, height, width, sampler, scheduler=None):
         self.calls.append(("txt2img", int(seed), int(tok.shape[0]), steps, sampler))
         return self._images(seed, tok, tok.shape[0], height, width)
 
