@@ -13,7 +13,9 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../../include/b200sd.h"
+#include "tc_common.cuh"
 
 namespace b200sd {
 
@@ -43,6 +45,51 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     }
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Blackwell packed fp32 (two lanes per instruction: FADD2 / FMUL2 / FFMA2) — these kernels are instruction-issue bound
+// before they are HBM bound when every element costs a scalar convert + add + fma.
+struct F2 { uint64_t v; };
+__device__ __forceinline__ F2 f2_make(float x, float y) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(__float_as_uint(x)), "r"(__float_as_uint(y)));
+  return r;
+}
+__device__ __forceinline__ void f2_get(F2 a, float& x, float& y) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(a.v));
+  x = __uint_as_float(lo);
+  y = __uint_as_float(hi);
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+template <bool kBf16>
+__device__ __forceinline__ void unpack4x2(const uint4& u, F2 (&f)[4]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t;
+    if constexpr (kBf16) t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    else t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[i] = f2_make(t.x, t.y);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(F2 a) {
+  float x, y;
+  f2_get(a, x, y);
+  if constexpr (kBf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(x, y);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
 }
 
 constexpr int kGnUnroll = 4;
@@ -267,6 +314,164 @@ layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restri
   }
 }
 
+// ---- TMA-staged LayerNorm ------------------------------------------------------------------------------------
+// The register version above keeps rows in flight with threads (79 registers -> 24 warps per SM, every warp idle for a
+// DRAM round trip per row: ncu 46 % of the measured HBM bandwidth).  Here every warp is its own pipeline: lane 0 streams
+// the warp's row groups (32 / lpr rows, 2.5 KB for the UNet's widths) through a private ring of shared-memory stages
+// with 1-D bulk copies (cp.async.bulk: the TMA engine without a tensor map), the normalised rows leave through two
+// private output stages by bulk stores, and nothing but __syncwarp and the warp's own mbarriers synchronises — a first
+// version with one producer warp and CTA-wide barriers per 20 KB tile spent 2.3 us per tile in hand-offs (2.6 TB/s with
+// one CTA per SM whatever the ring depth).  The arithmetic is packed fp32 (FADD2 / FFMA2, two accumulators): with a
+// scalar convert + add + fma per element the kernel was instruction-issue bound at 4.3 TB/s.
+constexpr int kLnWarps = 16;
+constexpr int kLnThreads = 32 * kLnWarps;
+constexpr int kLnInDefault = 3, kLnOutDefault = 2;  // input / output stages per warp (B200SD_LN_STAGES="in,out")
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+
+template <bool kBf16, int VPT>
+__global__ void __launch_bounds__(kLnThreads)
+layernorm_staged_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy, int rows,
+                        int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int lpr,
+                        int n_in, int n_out) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int rpw = 32 / lpr;                // rows per warp and tile
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 2u;
+  const uint32_t tile_bytes = static_cast<uint32_t>(rpw) * row_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* gb = reinterpret_cast<float*>(ln_smem);                                  // gamma[C], beta[C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gb + 2 * C);                       // [kLnWarps][8]
+  uint8_t* stages = reinterpret_cast<uint8_t*>(bars + kLnWarps * 8);              // [kLnWarps][n_in + n_out][tile]
+  uint8_t* in_st = stages + static_cast<size_t>(warp) * (n_in + n_out) * tile_bytes;
+  uint8_t* out_st = in_st + static_cast<size_t>(n_in) * tile_bytes;
+  uint64_t* full = bars + warp * 8;
+  if (lane == 0) {
+    for (int s = 0; s < n_in; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    gb[i] = gamma[i];
+    gb[C + i] = beta[i];
+  }
+  __syncthreads();
+  const int num_tiles = (rows + rpw - 1) / rpw;
+  const int tile_step = gridDim.x * kLnWarps;
+  const int tile0 = blockIdx.x * kLnWarps + warp;
+  auto load_tile = [&](int tile, int s) {  // lane 0
+    const int r0 = tile * rpw, nr = min(rpw, rows - r0);
+    mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(nr) * row_bytes);
+    const uint32_t dst = smem_u32(in_st + s * tile_bytes), bar = smem_u32(&full[s]);
+    const uint8_t* src = X + static_cast<long long>(r0) * ldx * 2;
+    if (ldx == C) {
+      bulk_load_1d(dst, src, static_cast<uint32_t>(nr) * row_bytes, bar);
+    } else {
+      for (int r = 0; r < nr; ++r) bulk_load_1d(dst + r * row_bytes, src + static_cast<long long>(r) * ldx * 2, row_bytes, bar);
+    }
+  };
+  if (lane == 0)
+    for (int s = 0; s < n_in; ++s)
+      if (tile0 + s * tile_step < num_tiles) load_tile(tile0 + s * tile_step, s);
+  const int sub = lane & (lpr - 1);   // my position among the lanes of my row
+  const int wrow = lane / lpr;        // which of the warp's rows is mine
+  const int nvec = C / 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  int s = 0, o = 0;
+  uint32_t par = 0;
+  for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    const int r0 = tile * rpw, nr = min(rpw, rows - r0);
+    const bool live = wrow < nr;      // whole-warp shuffles below: dead rows just carry zeros
+    mbar_wait(&full[s], par, 32);
+    const uint8_t* xr = in_st + s * tile_bytes + static_cast<uint32_t>(wrow) * row_bytes;
+    F2 f[VPT][4];                      // my 8 * VPT elements as fp32 pairs
+    F2 acc0 = f2_make(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+    for (int it = 0; it < VPT; ++it) {
+      const int vec = it * lpr + sub;
+      if (live && vec < nvec) {
+        unpack4x2<kBf16>(*reinterpret_cast<const uint4*>(xr + vec * 16), f[it]);
+        acc0 = f2_add(acc0, f2_add(f[it][0], f[it][2]));
+        acc1 = f2_add(acc1, f2_add(f[it][1], f[it][3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[it][i] = f2_make(0.f, 0.f);
+      }
+    }
+    // the inputs are in registers: refill this stage with the tile n_in steps ahead
+    __syncwarp();
+    if (lane == 0 && tile + n_in * tile_step < num_tiles) load_tile(tile + n_in * tile_step, s);
+    float sa, sb;
+    f2_get(f2_add(acc0, acc1), sa, sb);
+    float sum = sa + sb;
+    for (int d = lpr >> 1; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float mean = sum * inv_c;
+    const F2 nmean = f2_make(-mean, -mean);
+    acc0 = f2_make(0.f, 0.f);
+    acc1 = acc0;
+#pragma unroll
+    for (int it = 0; it < VPT; ++it) {
+      if (it * lpr + sub < nvec) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[it][i] = f2_add(f[it][i], nmean);   // keep the centred values
+        acc0 = f2_fma(f[it][0], f[it][0], acc0);
+        acc1 = f2_fma(f[it][1], f[it][1], acc1);
+        acc0 = f2_fma(f[it][2], f[it][2], acc0);
+        acc1 = f2_fma(f[it][3], f[it][3], acc1);
+      }
+    }
+    f2_get(f2_add(acc0, acc1), sa, sb);
+    float var = sa + sb;
+    for (int d = lpr >> 1; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+    const float rstd = rsqrtf(var * inv_c + eps);
+    const F2 rstd2 = f2_make(rstd, rstd);
+    // out_st[o] was the source of the store issued n_out tiles ago: lane 0 has waited for it to be read (below)
+    uint8_t* yr = out_st + o * tile_bytes + static_cast<uint32_t>(wrow) * row_bytes;
+#pragma unroll
+    for (int it = 0; it < VPT; ++it) {
+      const int vec = it * lpr + sub;
+      if (live && vec < nvec) {
+        const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(gb + vec * 8);
+        const ulonglong2 g1 = *reinterpret_cast<const ulonglong2*>(gb + vec * 8 + 4);
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(gb + C + vec * 8);
+        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(gb + C + vec * 8 + 4);
+        const F2 gg[4] = {{g0.x}, {g0.y}, {g1.x}, {g1.y}}, bb[4] = {{b0.x}, {b0.y}, {b1.x}, {b1.y}};
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = pack2<kBf16>(f2_fma(f2_mul(f[it][i], rstd2), gg[i], bb[i]));
+        *reinterpret_cast<uint4*>(yr + vec * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async_smem();  // my generic-proxy writes -> visible to the bulk store
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t src = smem_u32(out_st + o * tile_bytes);
+      uint8_t* dst = Y + static_cast<long long>(r0) * ldy * 2;
+      if (ldy == C) {
+        bulk_store_1d(dst, src, static_cast<uint32_t>(nr) * row_bytes);
+      } else {
+        for (int r = 0; r < nr; ++r) bulk_store_1d(dst + static_cast<long long>(r) * ldy * 2, src + r * row_bytes, row_bytes);
+      }
+      bulk_commit();
+      if (n_out == 2) bulk_wait_read<1>();  // the stage the next tile writes has been read by its store
+      else bulk_wait_read<2>();
+    }
+    __syncwarp();
+    if (++s == n_in) {
+      s = 0;
+      par ^= 1u;
+    }
+    if (++o == n_out) o = 0;
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
 static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_per_cta) {
   if (C % 8 != 0 || C / 8 > 1024) return B200SD_ERR_INVALID;
   const int vx = C / 8;
@@ -284,6 +489,33 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
   pix_per_cta = ppc;
   grid = dim3((HW + ppc - 1) / ppc, NB, 1);
   return B200SD_OK;
+}
+
+template <bool kBf16, int V>
+static void launch_ln_staged_v(int n_in, int n_out, int lpr, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx, uint8_t* Y,
+                               long long ldy, int rows, int C, const float* gamma, const float* beta, float eps) {
+  static bool ready[64] = {};  // per-device opt-in to large dynamic shared memory; first call is outside graph capture
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !ready[dev]) {
+    cudaFuncSetAttribute(layernorm_staged_kernel<kBf16, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    ready[dev] = true;
+  }
+  layernorm_staged_kernel<kBf16, V><<<blocks, kLnThreads, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr, n_in,
+                                                                      n_out);
+}
+
+template <bool kBf16>
+static void launch_ln_staged(int n_in, int n_out, int vpt, int lpr, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx,
+                             uint8_t* Y, long long ldy, int rows, int C, const float* gamma, const float* beta, float eps) {
+  switch (vpt) {
+    case 1: launch_ln_staged_v<kBf16, 1>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 2: launch_ln_staged_v<kBf16, 2>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 3: launch_ln_staged_v<kBf16, 3>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 4: launch_ln_staged_v<kBf16, 4>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    case 5: launch_ln_staged_v<kBf16, 5>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+    default: launch_ln_staged_v<kBf16, 8>(n_in, n_out, lpr, blocks, sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps); break;
+  }
 }
 
 template <bool kBf16>
@@ -367,9 +599,45 @@ extern "C" int b200sd_layernorm(const void* X, long long ldx, void* Y, long long
   if (vpt > 5) vpt = 8;
   const int rows_per_block = 8 * (32 / lpr);
   int blocks = (rows + rows_per_block - 1) / rows_per_block;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int staged = -1;  // B200SD_LN_STAGED=0: the register version
+  if (staged < 0) {
+    const char* e = std::getenv("B200SD_LN_STAGED");
+    staged = e ? std::atoi(e) : 1;
+  }
+  static int n_in = kLnInDefault, n_out = kLnOutDefault, ctas_per_sm = 0;
+  static bool env_read = false;
+  if (!env_read) {
+    if (const char* e = std::getenv("B200SD_LN_STAGES")) {
+      n_in = std::atoi(e);
+      const char* c = e;
+      while (*c && *c != ',') ++c;
+      n_out = *c ? std::atoi(c + 1) : 2;
+      if (n_in < 2 || n_in > 8) n_in = kLnInDefault;
+      if (n_out < 2 || n_out > 3) n_out = kLnOutDefault;
+    }
+    if (const char* e = std::getenv("B200SD_LN_CTAS")) ctas_per_sm = std::atoi(e);
+    env_read = true;
+  }
+  const size_t tile_bytes = static_cast<size_t>(32 / lpr) * C * 2;   // one warp's row group
+  const size_t sh_staged = 2 * static_cast<size_t>(C) * sizeof(float) + kLnWarps * 8 * sizeof(uint64_t) +
+                           static_cast<size_t>(kLnWarps) * (n_in + n_out) * tile_bytes;
+  if (staged && sh_staged <= 227 * 1024 && (ldx * 2) % 16 == 0 && (ldy * 2) % 16 == 0) {
+    // persistent CTAs of 16 autonomous warps
+    blocks = (rows + (32 / lpr) * kLnWarps - 1) / ((32 / lpr) * kLnWarps);
+    int per_sm = sh_staged + 1024 <= 113 * 1024 ? 2 : 1;
+    if (ctas_per_sm > 0) per_sm = ctas_per_sm;
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
+    if (dtype == B200SD_BF16)
+      launch_ln_staged<true>(n_in, n_out, vpt, lpr, blocks, sh_staged, st, static_cast<const uint8_t*>(X), ldx,
+                             static_cast<uint8_t*>(Y), ldy, rows, C, gamma, beta, eps);
+    else
+      launch_ln_staged<false>(n_in, n_out, vpt, lpr, blocks, sh_staged, st, static_cast<const uint8_t*>(X), ldx,
+                              static_cast<uint8_t*>(Y), ldy, rows, C, gamma, beta, eps);
+    return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+  }
   if (blocks > 148 * 8) blocks = 148 * 8;
   const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
     launch_ln<true>(vpt, lpr, blocks, sh, st, static_cast<const uint8_t*>(X), ldx, static_cast<uint8_t*>(Y), ldy, rows, C,
                     gamma, beta, eps);

@@ -297,6 +297,30 @@ def test_groupnorm(ops, nb, hw, c, silu, eps):
     assert_close(f"groupnorm nb{nb} hw{hw} c{c}", out, ref, atol=1e-2, rtol=4e-3)
 
 
+@pytest.mark.parametrize("rows,c,pitch,dt", [(100003, 320, 320, torch.half), (40000, 640, 704, torch.half),
+                                              (20001, 1280, 1280, torch.bfloat16), (5000, 64, 64, torch.half),
+                                              (3, 320, 320, torch.half)])
+def test_layernorm_staged_ring(ops, rows, c, pitch, dt):
+    """many tiles per persistent CTA (the input ring and the output stages wrap), a ragged last tile, rows that are
+    channel slices of a wider buffer (per-row bulk copies), bf16"""
+    g = _gen(rows + c)
+    xw = (_rand((rows, pitch), g, 2.0) + 1.0).to(dt)
+    ow = torch.full((rows, pitch), 7.0, device="cuda", dtype=dt)
+    x, out = xw[:, :c], ow[:, :c]
+    gamma = torch.randn(c, generator=g, device="cuda")
+    beta = torch.randn(c, generator=g, device="cuda")
+    ops.layernorm(x, out, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    tol = dict(atol=1e-2, rtol=4e-3) if dt == torch.half else dict(atol=6e-2, rtol=2e-2)
+    assert_close(f"layernorm staged {rows}x{c}/{pitch}", out, F.layer_norm(x.float(), (c,), gamma, beta, 1e-5), **tol)
+    if pitch > c:
+        assert float((ow[:, c:].float() - 7.0).abs().max()) == 0.0   # nothing written outside the slice
+    out2 = torch.empty_like(ow)[:, :c]
+    ops.layernorm(x, out2, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (77, 1280), (64, 2048)])
 def test_layernorm(ops, rows, c):
     g = _gen(rows + c)

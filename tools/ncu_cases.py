@@ -1,7 +1,7 @@
 """Representative hot-path launches for Nsight Compute (run under `ncu --profile-from-start off ...`).
 
     python tools/ncu_cases.py unet            # one eager SD1.5 UNet evaluation at UNet batch 16 (launch list)
-    python tools/ncu_cases.py conv|geglu|proj|attn|gn   # a single op at its UNet-batch-16 shape (--set full capture)
+    python tools/ncu_cases.py conv|geglu|proj|attn|gn|ln   # a single op at its UNet-batch-16 shape (--set full capture)
 """
 import os
 import sys
@@ -60,6 +60,10 @@ def main():
         st = torch.zeros((ops.groupnorm_stats_floats(nb, 4096, 320, 32),), device="cuda")
         g, b = torch.ones(320, device="cuda"), torch.zeros(320, device="cuda")
         fn = lambda: ops.groupnorm(x, o, st, g, b, 32, 1e-5, True)  # noqa: E731
+    elif case == "ln":
+        x, o = rnd(nb * 4096, 320), torch.empty((nb * 4096, 320), device="cuda", dtype=torch.half)
+        g, b = torch.ones(320, device="cuda"), torch.zeros(320, device="cuda")
+        fn = lambda: ops.layernorm(x, o, g, b)  # noqa: E731
     else:
         raise SystemExit(f"unknown case {case}")
     for _ in range(2):
