@@ -92,6 +92,12 @@ __device__ __forceinline__ uint32_t pack2(F2 a) {
   }
 }
 
+__device__ __forceinline__ float __frcp_rn_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int kGnUnroll = 4;
 
 // block = (C/8, PY): thread (v, py) owns channels [8v, 8v+8) for pixels p0+py, p0+py+PY, ... of its pixel range.
@@ -107,9 +113,9 @@ __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long 
   const int PY = blockDim.y;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  float s[8], q[8];
+  F2 s2[4], q2[4];  // packed fp32 pairs: channel pairs (8v+2i, 8v+2i+1)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (int i = 0; i < 4; ++i) { s2[i] = f2_make(0.f, 0.f); q2[i] = s2[i]; }
   const uint8_t* base = X + (static_cast<long long>(n) * HW) * pitch * 2 + static_cast<long long>(v) * 16;
   const long long rowb = pitch * 2;
   int p = p0 + py;
@@ -119,18 +125,24 @@ __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long 
     for (int k = 0; k < kGnUnroll; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + k * PY) * rowb));
 #pragma unroll
     for (int k = 0; k < kGnUnroll; ++k) {
-      float f[8];
-      unpack8<kBf16>(u[k], f);
+      F2 f[4];
+      unpack4x2<kBf16>(u[k], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      for (int i = 0; i < 4; ++i) { s2[i] = f2_add(s2[i], f[i]); q2[i] = f2_fma(f[i], f[i], q2[i]); }
     }
   }
   for (; p < p1; p += PY) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * rowb));
-    float f[8];
-    unpack8<kBf16>(u, f);
+    F2 f[4];
+    unpack4x2<kBf16>(u, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    for (int i = 0; i < 4; ++i) { s2[i] = f2_add(s2[i], f[i]); q2[i] = f2_fma(f[i], f[i], q2[i]); }
+  }
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f2_get(s2[i], s[2 * i], s[2 * i + 1]);
+    f2_get(q2[i], q[2 * i], q[2 * i + 1]);
   }
   float* mine = sh + static_cast<size_t>(py) * 2 * C;
   *reinterpret_cast<float4*>(mine + v * 8) = make_float4(s[0], s[1], s[2], s[3]);
@@ -219,16 +231,30 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
   const uint8_t* xb = X + (static_cast<long long>(n) * HW) * pitch_x * 2 + static_cast<long long>(v) * 16;
   uint8_t* yb = Y + (static_cast<long long>(n) * HW) * pitch_y * 2 + static_cast<long long>(v) * 16;
   const long long rx = pitch_x * 2, ry = pitch_y * 2;
-  auto emit = [&](const uint4& u, int p) {
-    float f[8];
-    unpack8<kBf16>(u, f);
+  F2 a2[4], b2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i], a[i], b[i]);
-      if (silu) t = __fdividef(t, 1.0f + __expf(-t));
-      f[i] = t;
+  for (int i = 0; i < 4; ++i) {
+    a2[i] = f2_make(a[2 * i], a[2 * i + 1]);
+    b2[i] = f2_make(b[2 * i], b[2 * i + 1]);
+  }
+  const F2 nlog2e = f2_make(-1.4426950408889634f, -1.4426950408889634f), one2 = f2_make(1.0f, 1.0f);
+  auto emit = [&](const uint4& u, int p) {
+    F2 f[4];
+    unpack4x2<kBf16>(u, f);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      F2 t = f2_fma(f[i], a2[i], b2[i]);
+      if (silu) {  // t / (1 + exp(-t)): the two MUFU operations per element stay scalar, the arithmetic around them is packed
+        float ex, ey;
+        f2_get(f2_mul(t, nlog2e), ex, ey);
+        float dx, dy;
+        f2_get(f2_add(f2_make(fast_exp2(ex), fast_exp2(ey)), one2), dx, dy);
+        t = f2_mul(t, f2_make(__frcp_rn_fast(dx), __frcp_rn_fast(dy)));
+      }
+      w[i] = pack2<kBf16>(t);
     }
-    *reinterpret_cast<uint4*>(yb + p * ry) = pack8<kBf16>(f);
+    *reinterpret_cast<uint4*>(yb + p * ry) = make_uint4(w[0], w[1], w[2], w[3]);
   };
   int p = p0 + threadIdx.y;
   for (; p + (kGnUnroll - 1) * PY < p1; p += kGnUnroll * PY) {
