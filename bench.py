@@ -383,6 +383,16 @@ def kernel_rooflines(eng, b, pk):
                  "unit": "TFLOP/s", "frac": at[2] / (at[1] * 1e-3) / 1e12 / peak, "launches": at[0],
                  "note": "QK^T + PV FLOPs; d=40 heads make this kernel exp-throughput (MUFU) bound, see DESIGN.md"}
     breakdown = {k: round(v[1], 3) for k, v in agg.items()}
+    # HBM-bound kernel classes: algorithmic bytes (GroupNorm 2 reads + 1 write of 45.1 M elements per
+    # sample-evaluation, LayerNorm 1 read + 1 write of 34.7 M) over the summed CUDA-event durations, against the measured
+    # copy bandwidth
+    hbm = {}
+    for name, elems, bpe in (("groupnorm", 45.1e6, 6), ("layernorm", 34.7e6, 4)):
+        if name in agg and agg[name][1] > 0:
+            gbs = elems * 2 * b * bpe / (agg[name][1] * 1e-3) / 1e9
+            hbm[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "launches": agg[name][0], "algorithmic_bytes": elems * 2 * b * bpe}
+    roof["hbm_kernels"] = hbm
     return roof, roof_attn, breakdown
 
 

@@ -4,9 +4,9 @@ time go between the softmax warps and the MMA thread?  Needs a trace-enabled lib
 
 events (per kv tile j):
   softmax warp 2, lane 0:  0 loop top   1 S ready (s_full passed)   2 S in registers   3 exp/pack issued
-                           4 P buffer free (o_full passed)   5 P stored   6 proxy fence + syncwarp done (arrive next)
-  MMA thread:              7 waiting for P_j   8 P_j complete (all warps arrived)   9 V_j landed   10 P.V issued + committed
-                           11 before K wait for Q.K^T of tile j   12 K landed   13 Q.K^T issued + committed
+                           5 P stored   6 proxy fence + syncwarp done (arrive next)
+  MMA thread (ring mode):  7 waiting for p_full of tile j (P_j, K_(j+2), V_j)   8 complete   13 Q.K^T of tile j issued
+                           (stamped at index j)   10 P.V of tile j issued + committed
 """
 import ctypes
 import os
@@ -37,37 +37,31 @@ def main():
     t = buf.cpu()
     t0 = int(t[0, 0])
     rel = (t - t0).tolist()
-    print("tile |  softmax: top  Srdy  Sreg  exp  Pfree Pstor fence | MMA: waitP  Pfull  Vrdy  PVdone | QK(j): kwait  krdy  issued")
-    for j in list(range(0, 6)) + list(range(30, 36)) + list(range(60, 64)):
-        r = [rel[e][j] if e != 4 else 0 for e in range(14)]
-        print(f"{j:4d} | " + " ".join(f"{x:7d}" for x in r[:7]) + " | " + " ".join(f"{x:7d}" for x in r[7:11]) + " | " +
-              " ".join(f"{x:7d}" for x in r[11:14]))
-    # steady-state averages over tiles 16..56
+    print("tile |  softmax: top  Srdy  Sreg  exp  Pstor fence | MMA thread: waitP  Pfull  QK(j+2) issued  PV(j) issued")
+    for j in list(range(0, 6)) + list(range(30, 36)) + list(range(58, 62)):
+        r = [rel[e][j] for e in range(14)]
+        print(f"{j:4d} | " + " ".join(f"{r[e]:7d}" for e in (0, 1, 2, 3, 5, 6)) + " | " +
+              f"{r[7]:7d} {r[8]:7d} {rel[13][(j + 2) & 63]:7d} {r[10]:7d}")
     js = range(16, 56)
     def avg(f):
         vals = [f(j) for j in js]
         return sum(vals) / len(vals)
     print("\nsteady state (tiles 16..55), cycles:")
-    print(f"  tile period (softmax loop top to top)      {avg(lambda j: rel[0][j + 1] - rel[0][j]):8.1f}")
-    print(f"  wait for S (0->1)                           {avg(lambda j: rel[1][j] - rel[0][j]):8.1f}")
-    print(f"  TMEM load of 32 columns (1->2)              {avg(lambda j: rel[2][j] - rel[1][j]):8.1f}")
-    print(f"  FFMA2/ex2/pack/max (2->3)                   {avg(lambda j: rel[3][j] - rel[2][j]):8.1f}")
-    print(f"  any_sync + P stores (3->5)                  {avg(lambda j: rel[5][j] - rel[3][j]):8.1f}")
-    print(f"  proxy fence + syncwarp (5->6)               {avg(lambda j: rel[6][j] - rel[5][j]):8.1f}")
-    print(f"  arrive + loop (6->next top)                 {avg(lambda j: rel[0][j + 1] - rel[6][j]):8.1f}")
-    print(f"  MMA: wait for P_j (7->8)                    {avg(lambda j: rel[8][j] - rel[7][j]):8.1f}")
-    print(f"  MMA: this warp's arrive -> P_j complete     {avg(lambda j: rel[8][j] - rel[6][j]):8.1f}")
-    print(f"  MMA: wait V (8->9)                          {avg(lambda j: rel[9][j] - rel[8][j]):8.1f}")
-    print(f"  MMA: issue P.V + commits (9->10)            {avg(lambda j: rel[10][j] - rel[9][j]):8.1f}")
-    print(f"  MMA: QK(j+2) K wait (11->12)                {avg(lambda j: rel[12][j + 2] - rel[11][j + 2]):8.1f}")
-    print(f"  MMA: issue QK(j+2) + commits (12->13)       {avg(lambda j: rel[13][j + 2] - rel[12][j + 2]):8.1f}")
-    print(f"  QK(j+2) issued -> softmax sees S(j+2) ready {avg(lambda j: rel[1][j + 2] - rel[13][j + 2]):8.1f}")
-    print(f"  QK(j+2) issued -> softmax WANTS S(j+2)      {avg(lambda j: rel[0][j + 2] - rel[13][j + 2]):8.1f}  (< 0: the softmax warp waited for the issuer)")
-    print(f"  MMA: loop period (7->7)                     {avg(lambda j: rel[7][j + 1] - rel[7][j]):8.1f}")
-    print(f"  MMA: P_j complete -> QK(j+2) starts         {avg(lambda j: rel[11][j + 2] - rel[8][j]):8.1f}")
-    print(f"  MMA: QK(j+2) issued -> P.V operands ready   {avg(lambda j: rel[9][j] - rel[13][j + 2]):8.1f}")
-    print(f"  MMA: P.V issued -> next loop top            {avg(lambda j: rel[7][j + 1] - rel[10][j]):8.1f}")
-    print(f"  P_j complete -> S(j+2) issued               {avg(lambda j: rel[13][j + 2] - rel[8][j]):8.1f}")
+    print(f"  tile period (softmax loop top to top)        {avg(lambda j: rel[0][j + 1] - rel[0][j]):8.1f}")
+    print(f"  softmax: wait for S (0->1)                   {avg(lambda j: rel[1][j] - rel[0][j]):8.1f}")
+    print(f"  softmax: TMEM load of 32 columns (1->2)      {avg(lambda j: rel[2][j] - rel[1][j]):8.1f}")
+    print(f"  softmax: FFMA2/ex2/pack/max (2->3)           {avg(lambda j: rel[3][j] - rel[2][j]):8.1f}")
+    print(f"  softmax: any_sync + P stores (3->5)          {avg(lambda j: rel[5][j] - rel[3][j]):8.1f}")
+    print(f"  softmax: proxy fence + syncwarp (5->6)       {avg(lambda j: rel[6][j] - rel[5][j]):8.1f}")
+    print(f"  softmax: arrive + loop (6->next top)         {avg(lambda j: rel[0][j + 1] - rel[6][j]):8.1f}")
+    print(f"  MMA: loop period (7->7)                      {avg(lambda j: rel[7][j + 1] - rel[7][j]):8.1f}")
+    print(f"  MMA: wait for P_j + K_(j+2) + V_j (7->8)     {avg(lambda j: rel[8][j] - rel[7][j]):8.1f}")
+    print(f"  MMA: traced warp's arrive -> P_j complete    {avg(lambda j: rel[8][j] - rel[6][j]):8.1f}")
+    print(f"  MMA: issue Q.K(j+2) + commit (8->13)         {avg(lambda j: rel[13][j + 2] - rel[8][j]):8.1f}")
+    print(f"  MMA: issue P.V(j) + commit (13->10)          {avg(lambda j: rel[10][j] - rel[13][j + 2]):8.1f}")
+    print(f"  MMA: P.V issued -> next loop top (10->7)     {avg(lambda j: rel[7][j + 1] - rel[10][j]):8.1f}")
+    print(f"  Q.K(j+2) issued -> softmax sees S(j+2) ready {avg(lambda j: rel[1][j + 2] - rel[13][j + 2]):8.1f}")
+    print(f"  Q.K(j+2) issued -> softmax WANTS S(j+2)      {avg(lambda j: rel[0][j + 2] - rel[13][j + 2]):8.1f}  (< 0: the softmax warp waited for the issuer)")
 
 
 if __name__ == "__main__":
