@@ -498,7 +498,21 @@ layernorm_staged_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* _
   if (lane == 0) bulk_wait<0>();
 }
 
-static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_per_cta) {
+// KB of one image a statistics CTA owns (B200SD_GN_STATS_KB overrides): the per-CTA epilogue (shared-memory reduction,
+// group fold, partial store, fence, ticket) is amortised over this much streaming.  Measured at the bench batch (sum over
+// the UNet's shapes, stats + apply): 48 KB 1.33 ms, 96 KB 1.24, 192 KB 1.20, 384 KB 1.20; 96 keeps a single image
+// (batch 1 x CFG) spread over enough CTAs.
+static int gn_stats_kb() {
+  static int kb = 0;
+  if (kb == 0) {
+    const char* e = std::getenv("B200SD_GN_STATS_KB");
+    kb = e ? std::atoi(e) : 96;
+    if (kb < 16 || kb > 1024) kb = 96;
+  }
+  return kb;
+}
+
+static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_per_cta, int chunk_kb = 48) {
   if (C % 8 != 0 || C / 8 > 1024) return B200SD_ERR_INVALID;
   const int vx = C / 8;
   int py = 512 / vx;
@@ -510,7 +524,7 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
   // are the same whether it is processed alone, in a batch of 32, or on another GPU of a sharded request.
   (void)NB;
   const int quantum = py * kGnUnroll;
-  int ppc = (48 * 1024 / (2 * C) + quantum - 1) / quantum * quantum;
+  int ppc = (chunk_kb * 1024 / (2 * C) + quantum - 1) / quantum * quantum;
   if (ppc < quantum) ppc = quantum;
   pix_per_cta = ppc;
   grid = dim3((HW + ppc - 1) / ppc, NB, 1);
@@ -565,7 +579,7 @@ extern "C" long long b200sd_groupnorm_stats_floats(int NB, int HW, int C, int G)
   if (NB <= 0 || HW <= 0 || G <= 0) return 0;
   dim3 block, grid;
   int ppc;
-  if (gn_geometry(NB, HW, C, block, grid, ppc) != B200SD_OK) return -1;
+  if (gn_geometry(NB, HW, C, block, grid, ppc, gn_stats_kb()) != B200SD_OK) return -1;
   // [NB][G][2] results | NB arrival tickets | [NB][CTAs per image][2G] partial sums
   return static_cast<long long>(NB) * G * 2 + NB + static_cast<long long>(NB) * grid.x * 2 * G;
 }
@@ -576,7 +590,7 @@ extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, in
   if (G <= 0 || C % G != 0 || pitch % 8 != 0 || (reinterpret_cast<uintptr_t>(X) & 15)) return B200SD_ERR_INVALID;
   dim3 block, grid;
   int ppc;
-  int rc = gn_geometry(NB, HW, C, block, grid, ppc);
+  int rc = gn_geometry(NB, HW, C, block, grid, ppc, gn_stats_kb());
   if (rc != B200SD_OK) return rc;
   const size_t sh = static_cast<size_t>(block.y) * 2 * C * sizeof(float);
   if (sh > 48 * 1024) return B200SD_ERR_UNSUPPORTED;
