@@ -247,6 +247,12 @@ class SDEngine:
 
     def plan(self, b: int, h: int, w: int) -> Plan:
         key = (b, h, w)
+        down = 2 ** (len(self.unet_cfg.channel_mult) - 1)
+        if b < 1 or h < down or w < down or h % down or w % down:
+            # the UNet halves the latent len(channel_mult) - 1 times and concatenates skip tensors on the way up: upstream
+            # ldm fails with a size mismatch for other sizes, here it is refused before any buffer is built
+            raise ValueError(f"latent size {h}x{w} (batch {b}) is not a positive multiple of {down}: image sides must be "
+                             f"multiples of {8 * down} pixels")
         if key not in self.plans:
             with self._ctx():
                 self.plans[key] = Plan(self, b, h, w, self.vae_chunk)

@@ -144,6 +144,18 @@ def test_sample_matches_oracle_dpmpp_2m(env, sched, karras):
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
 
 
+def test_sizes_the_unet_cannot_take_are_refused(env):
+    """upstream ldm dies with a tensor size mismatch when the latent is not a multiple of 2^(levels-1); here the request
+    is refused before any buffer exists (the worker turns it into InvalidWorkerResponse, like a remote 500)"""
+    C, E, O, cfgs, sd, eng = env
+    down = 2 ** (len(cfgs[0].channel_mult) - 1)
+    with pytest.raises(ValueError):
+        eng.plan(1, down + 1, down)
+    with pytest.raises(ValueError):
+        eng.plan(0, down, down)
+    assert eng.plan(1, down, 2 * down).b == 1
+
+
 def test_sampler_names_resolve(env):
     C, E, O, cfgs, sd, eng = env
     assert E.resolve_sampler("DPM++ 2M") == ("dpmpp_2m", "karras") == E.resolve_sampler("DPM++ 2M Karras")
