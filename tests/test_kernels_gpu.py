@@ -232,6 +232,23 @@ def test_attention(ops, b, heads, sq, skv, d, ones_col):
     assert_close(f"attention b{b} h{heads} sq{sq} skv{skv} d{d} ones{int(ones_col)}", out, ref, atol=4e-3, rtol=1e-2)
 
 
+@pytest.mark.parametrize("skv", [129, 192, 257, 321, 384, 385, 448, 520, 832])
+def test_attention_ring_lengths(ops, skv):
+    """ring mode (kv longer than two tiles) at every phase of the MMA loop's unroll-by-six and of the K/V/P rings:
+    3 .. 13 kv tiles, full and ragged last tiles — the producer's loads ride on the softmax warps' barrier, so an
+    off-by-one in a slot or parity shows up as a hang (the bounded waits trap) or as garbage"""
+    b, heads, sq, d = 3, 8, 512, 40
+    g = _gen(skv)
+    d_pad = 64
+    q = _padded_heads(b, sq, heads, d, d_pad, g)
+    k = _padded_heads(b, skv, heads, d, d_pad, g)
+    v = _padded_heads(b, skv, heads, d, d_pad, g, True)
+    out = torch.full((b, sq, heads * d), float("nan"), device="cuda", dtype=torch.float16)
+    ops.attention(q, k, v, out, heads, d, d_pad, d ** -0.5, True)
+    torch.cuda.synchronize()
+    assert_close(f"attention ring skv{skv}", out, _attn_ref(q, k, v, heads, d, d_pad, d ** -0.5), atol=4e-3, rtol=1e-2)
+
+
 @pytest.mark.parametrize("ones_col", [False, True])
 def test_attention_growing_logits_forces_rescale(ops, ones_col):
     """Keys ordered so that the row maximum keeps rising tile after tile by far more than 2^8: exercises the lazy-max
