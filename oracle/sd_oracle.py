@@ -10,6 +10,10 @@ arithmetic and ships no tests or golden vectors.  Its call sites into the numeri
 The arithmetic lives in un-vendored third parties (AUTOMATIC1111 sdwui -> CompVis `ldm` openaimodel / model.py /
 attention.py, k-diffusion sampling.py); none is installable offline and the extension pins no version.  This file
 restates their published algorithms with ldm state_dict key names so a real checkpoint loads.
+Partial pins that ARE possible in this image (tests/test_oracle_pins_cpu.py): the CLIP text tower equals
+`transformers.CLIPTextModel` — the class ldm's FrozenCLIPEmbedder wraps — on shared random weights (2e-5), the schedule
+tables equal their closed forms, and the k-diffusion sampler restatements reproduce analytic solutions for synthetic
+denoisers.  The UNet and VAE restatements have no independent counterpart offline and stay unpinned.
 
 Everything here is NCHW fp32 (or whatever dtype/device the caller's tensors have), functional over a dict of
 parameters.  Function docstrings name the upstream symbol they follow.
