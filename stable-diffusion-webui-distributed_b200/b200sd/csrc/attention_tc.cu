@@ -92,8 +92,7 @@ struct AttnParams {
 struct __align__(16) AttnShared {
   uint64_t q_full[2], q_empty[2];
   uint64_t o_free;  // resident mode: the epilogue of a Q tile has read both accumulators
-  uint64_t k_full[kMaxRing], k_empty[kMaxRing];
-  uint64_t v_full[kMaxRing], v_empty[kMaxRing];
+  uint64_t k_full[kMaxRing], v_full[kMaxRing];  // resident mode only (ring mode: the loads land on p_full)
   uint64_t s_full[kSBufs], p_full[kMaxPBufs], o_full[kMaxPBufs];
   uint32_t tmem_base;
   uint32_t pad;
@@ -464,9 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&sh->k_full[s], 1);
-      mbar_init(&sh->k_empty[s], 1);
       mbar_init(&sh->v_full[s], 1);
-      mbar_init(&sh->v_empty[s], 1);
     }
     for (int s = 0; s < kSBufs; ++s) mbar_init(&sh->s_full[s], 1);
     for (int s = 0; s < kMaxPBufs; ++s) {
@@ -488,8 +485,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // operands without a per-instruction broadcast loop.
     const bool leader = elect_one();
     const uint32_t bar0 = warp_uniform(smem_u32(sh));
-    const uint32_t a_k_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_empty));
-    const uint32_t a_v_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_empty));
     const uint32_t a_q_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, q_empty));
     const int k_stages = p.k_stages, v_stages = p.v_stages, chunks = p.chunks;
     if (resident) {
@@ -593,9 +588,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tm_Oa = tm_S + static_cast<uint32_t>(kSBufs * kKv), tm_Ob = tm_Oa + static_cast<uint32_t>(p.dpv);
     const uint32_t bar0 = warp_uniform(smem_u32(sh));
     const uint32_t a_k_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_full));
-    const uint32_t a_k_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, k_empty));
     const uint32_t a_v_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_full));
-    const uint32_t a_v_empty = bar0 + static_cast<uint32_t>(offsetof(AttnShared, v_empty));
     const uint32_t a_s_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, s_full));
     const uint32_t a_p_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, p_full));
     const uint32_t a_o_full = bar0 + static_cast<uint32_t>(offsetof(AttnShared, o_full));
@@ -808,24 +801,6 @@ static long long* g_attn_trace = nullptr;
 static int g_attn_max_smem = 0;
 static bool g_attn_dev_ready[64] = {};
 
-// tuning overrides for experiments: B200SD_ATTN_PBUFS=2|3, B200SD_ATTN_RING="k,v" (ring depths, 1..4 each)
-static void attn_env(int* p_bufs, int* k_st, int* v_st) {
-  static int cached = 0, e_pb = 0, e_k = 0, e_v = 0;
-  if (!cached) {
-    if (const char* s = std::getenv("B200SD_ATTN_PBUFS")) e_pb = std::atoi(s);
-    if (const char* s = std::getenv("B200SD_ATTN_RING")) {
-      e_k = std::atoi(s);
-      const char* c = s;
-      while (*c && *c != ',') ++c;
-      e_v = *c ? std::atoi(c + 1) : e_k;
-    }
-    cached = 1;
-  }
-  *p_bufs = e_pb;
-  *k_st = e_k;
-  *v_st = e_v;
-}
-
 int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
                  long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int v_ones_col,
                  int is_bf16, cudaStream_t stream) {
@@ -866,8 +841,6 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   p.l_col = v_ones_col ? d : -1;
   p.resc_cols = v_ones_col ? ((d + 1 + 15) & ~15) : p.d16;
   p.tmem_cols = (kSBufs * kKv + 2 * p.dpv <= 256) ? 256 : 512;
-  int e_pb, e_k, e_v;
-  attn_env(&e_pb, &e_k, &e_v);
   const int nkv = (Skv + kKv - 1) / kKv;
   p.num_q_tiles = (Sq + kQTile - 1) / kQTile;
   const size_t kvt = static_cast<size_t>(p.chunks) * kKvChunkBytes;
@@ -906,9 +879,6 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     p.q_bufs = 1;
     p.qpc = 1;
     p.p_bufs = 3;
-    (void)e_pb;
-    (void)e_k;
-    (void)e_v;
     const size_t fixed = 1024 + qt + sizeof(AttnShared) + 64 + 3 * kPBytes;
     p.k_stages = 3;  // the producer's slot-reuse argument (see the kernel) is written for exactly this ring: K 3 / V 2 / P 3
     p.v_stages = 2;

@@ -1,9 +1,9 @@
-"""Time the self-attention kernel at its dominant UNet shape (batch 16, 4096 tokens, 8 heads, d = 40) — one process per
-tuning configuration, because the library reads B200SD_ATTN_* once.
+"""Time the self-attention kernel at its dominant UNet shape (batch 16, 4096 tokens, 8 heads, d = 40).
 
-    python tools/attn_sweep.py            # run every configuration in a child process, print one line each
-    python tools/attn_sweep.py --one      # time the configuration given by the current environment
+    python tools/attn_sweep.py            # the default shape plus kv lengths 1024 / 2048 / 8192, one child process each
+    python tools/attn_sweep.py --one      # one timing with the current environment (ATTN_NB, ATTN_SKV)
     ATTN_SKV=8192 python tools/attn_sweep.py --one    # longer kv (per-CTA start-up cost shows as time/kv-tile)
+Build-time experiment knobs go through B200SD_NVCC_EXTRA (e.g. -DB200SD_ATTN_POLY_STRIDE=4, -DB200SD_WAIT_HINT_NS=...).
 """
 import os
 import subprocess
@@ -12,9 +12,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-webui-distributed_b200"))
 
-CONFIGS = [  # (S buffers, P buffers, "k,v" ring depths)
-    ("3", "3", "3,2"), ("3", "2", "2,2"), ("2", "2", "2,2"),
-]
 
 
 def one():
@@ -48,9 +45,7 @@ def one():
     ref = torch.softmax(qq @ kk.T * 40 ** -0.5, dim=-1) @ vv
     err = float((o[0].reshape(sq, 8, 40)[:, 3].float() - ref).abs().max())
     exps = nb * 8 * sq * skv
-    print(f"sbufs={os.environ.get('B200SD_ATTN_SBUFS', '-')} pbufs={os.environ.get('B200SD_ATTN_PBUFS', '-')} "
-          f"ring={os.environ.get('B200SD_ATTN_RING', '-')} nb={nb} skv={skv}: {ms:.4f} ms  ({exps / ms / 1e9:.2f} Texp/s)  "
-          f"max_err={err:.2e}", flush=True)
+    print(f"nb={nb} skv={skv}: {ms:.4f} ms  ({exps / ms / 1e9:.2f} Texp/s)  max_err={err:.2e}", flush=True)
 
 
 def main():
@@ -58,9 +53,6 @@ def main():
         return one()
     base = {k: v for k, v in os.environ.items() if not k.startswith("B200SD_ATTN")}
     me = [sys.executable, os.path.abspath(__file__), "--one"]
-    for sb, pb, ring in CONFIGS:
-        env = dict(base, B200SD_ATTN_SBUFS=sb, B200SD_ATTN_PBUFS=pb, B200SD_ATTN_RING=ring)
-        subprocess.run(me, env=env, check=False, timeout=300)
     for skv in ("1024", "2048", "8192"):
         subprocess.run(me, env=dict(base, ATTN_SKV=skv), check=False, timeout=300)
     subprocess.run(me, env=base, check=False, timeout=300)
