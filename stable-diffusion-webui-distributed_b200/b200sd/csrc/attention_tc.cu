@@ -87,6 +87,8 @@ struct AttnParams {
   int qpc;           // Q tiles per CTA (1 in ring mode)
   int q_bufs;        // Q buffers in shared memory (2 in resident mode: the next Q tile is prefetched)
   int num_q_tiles;
+  int p_tmem;        // P is written back over its own S columns in TMEM (no shared-memory P, no proxy fence)
+  int p_smem;        // P buffers that exist in shared memory: p_bufs, or 0 with p_tmem
 };
 
 struct __align__(16) AttnShared {
@@ -361,10 +363,18 @@ __device__ __forceinline__ void softmax_warps(const AttnParams& p, AttnShared* s
         if (full) softmax32<true, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
         else      softmax32<false, kBf16, kSum>(v, pk, col0, nvalid, scale_log2, m_used, lsum);
       }
-      p_store32(pk, p_row, rx, col0);
+      if (p.p_tmem) {
+        // my 32 P values, packed in pairs, over the first 16 of my own 32 S columns: TMEM lane = query row, column j of
+        // the half = kv rows 2j, 2j+1 — exactly the A-operand layout of the P.V MMA.  Q.K of tile t+2 overwrites the buffer
+        // only after P.V of this tile (same issuing thread, in order).
+        tmem_st_x16(s_row + col0, pk);
+        tmem_st_wait();
+      } else {
+        p_store32(pk, p_row, rx, col0);
+      }
       l += lsum;
       ATTN_TRACE(5, t);
-      fence_proxy_async_smem();
+      if (!p.p_tmem) fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       ATTN_TRACE(6, t);
@@ -439,7 +449,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t kv_bytes = static_cast<uint32_t>(p.chunks) * kKvChunkBytes;
   uint8_t* sQ = smem;                                   // q_bufs x (128 rows x d_pad)
   uint8_t* sP = sQ + static_cast<size_t>(p.q_bufs) * q_bytes;  // p_bufs x 16 KB
-  uint8_t* sK = sP + p.p_bufs * kPBytes;
+  uint8_t* sK = sP + p.p_smem * kPBytes;
   uint8_t* sV = sK + p.k_stages * kv_bytes;
   AttnShared* sh = reinterpret_cast<AttnShared*>(sV + p.v_stages * kv_bytes);
 
@@ -601,8 +611,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t q_lo0 = sdesc_lo(s0, 16);
     const uint32_t q_all = static_cast<uint32_t>(p.q_bufs) * q_bytes;
     const uint32_t p_lo0 = sdesc_lo(s0 + q_all, 16);
-    const uint32_t k_lo0 = sdesc_lo(s0 + q_all + static_cast<uint32_t>(p_bufs) * kPBytes, 16);
-    const uint32_t v_lo0 = sdesc_lo(s0 + q_all + static_cast<uint32_t>(p_bufs) * kPBytes + static_cast<uint32_t>(k_stages) * kv_bytes,
+    const uint32_t p_all = static_cast<uint32_t>(p.p_smem) * kPBytes;
+    const uint32_t k_lo0 = sdesc_lo(s0 + q_all + p_all, 16);
+    const uint32_t v_lo0 = sdesc_lo(s0 + q_all + p_all + static_cast<uint32_t>(k_stages) * kv_bytes,
                                     kKvChunkBytes);  // V is consumed MN-major: LBO = distance between 64-wide chunks
     const uint32_t kv_step = kv_bytes >> 4;
     const uint32_t idesc_qk_full = make_idesc_f16(128, kKv, bf, false, false);
@@ -659,6 +670,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ring of 3, the V ring of 2, the S pair and the p_full parity), so every slot address and barrier parity of a step
       // is a constant: this thread's instruction count per tile bounds the kernel (see the header). ----
       const int nvalid_last = skv - (nkv - 1) * kKv;
+      const bool p_tmem = p.p_tmem != 0;
       const uint32_t idesc_qk_last = make_idesc_f16(128, (nvalid_last + 15) & ~15, bf, false, false);
       auto qk = [&](int tile, uint32_t q_sb, uint32_t kslot) {  // leader only
         const uint32_t idesc = tile == nkv - 1 ? idesc_qk_last : idesc_qk_full;
@@ -692,7 +704,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait_a(a_p_full + static_cast<uint32_t>(u % 3) * 8u, static_cast<uint32_t>(u / 3), 15);  // P_t, K_{t+2}, V_t
           tc_fence_after();
           ATTN_TRACE(8, t);
-          if (leader) {
+          if (leader && p_tmem) {
+            // P lives in S[t & 1]: P.V first, then Q.K of tile t+2 may overwrite the buffer (MMAs execute in issue order)
+            const uint32_t a_p = tm_S + static_cast<uint32_t>(u & 1) * kKv;
+            const uint32_t v_lo = v_lo0 + static_cast<uint32_t>(u & 1) * kv_step;
+            const uint32_t acc = t != 0 ? 1u : 0u;
+            const int ksteps_pv = (t != nkv - 1) ? 4 : ((nvalid_last + 15) & ~15) / 16;
+            umma_f16_ts_lh(tm_Oa, a_p + 0u, v_lo + 0u, hi, idesc_pv, acc);
+            if (ksteps_pv > 2) umma_f16_ts_lh(tm_Ob, a_p + 32u, v_lo + 256u, hi, idesc_pv, acc);
+            if (ksteps_pv > 1) umma_f16_ts_lh(tm_Oa, a_p + 8u, v_lo + 128u, hi, idesc_pv, 1u);
+            if (ksteps_pv > 3) umma_f16_ts_lh(tm_Ob, a_p + 40u, v_lo + 384u, hi, idesc_pv, 1u);
+            umma_commit_a(a_o_full + static_cast<uint32_t>(u % 3) * 8u);
+            if (t + 2 < nkv) qk(t + 2, static_cast<uint32_t>(u & 1), static_cast<uint32_t>((u + 2) % 3));
+            ATTN_TRACE(13, t + 2);
+          } else if (leader) {
             // Q.K of tile t+2 first: S is what the softmax warps wait for next, O is not read until the end
             if (t + 2 < nkv) qk(t + 2, static_cast<uint32_t>(u & 1), static_cast<uint32_t>((u + 2) % 3));
             ATTN_TRACE(13, t + 2);
@@ -739,7 +764,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         ATTN_TRACE(9, t);
         if (leader) {
           const uint32_t acc = pv_j != 0 ? 1u : 0u;  // the first MMA of a Q tile into each accumulator overwrites it
-          if (nvalid == kKv) {
+          if (p.p_tmem) {
+            // P lives in the S buffer of this tile (TMEM): k-step s = columns [8s, 8s+8) of the half's 16 P columns
+            const uint32_t a_p = tm_S + (static_cast<uint32_t>(t) & 1u) * kKv;
+            const int ksteps_pv = ((nvalid + 15) & ~15) / 16;
+            umma_f16_ts_lh(tm_Oa, a_p + 0u, v_lo + 0u, hi, idesc_pv, acc);
+            if (ksteps_pv > 2) umma_f16_ts_lh(tm_Ob, a_p + 32u, v_lo + 256u, hi, idesc_pv, acc);
+            if (ksteps_pv > 1) umma_f16_ts_lh(tm_Oa, a_p + 8u, v_lo + 128u, hi, idesc_pv, 1u);
+            if (ksteps_pv > 3) umma_f16_ts_lh(tm_Ob, a_p + 40u, v_lo + 384u, hi, idesc_pv, 1u);
+          } else if (nvalid == kKv) {
             // k-step s reads P columns [16s, 16s+16) (2 descriptor units apart) and V rows [16s, 16s+16) (128 units apart);
             // the two accumulators alternate so that consecutive MMAs never depend on each other
             umma_f16_ss_lh(tm_Oa, p_lo + 0u, hi, v_lo + 0u, hi, idesc_pv, acc);
@@ -850,8 +883,15 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     const char* e = std::getenv("B200SD_ATTN_RESIDENT");
     e_res = e ? std::atoi(e) : 1;
   }
+  static int e_ptmem = -1;  // B200SD_ATTN_PTMEM=0: P through shared memory (the earlier form) instead of TMEM
+  if (e_ptmem < 0) {
+    const char* e = std::getenv("B200SD_ATTN_PTMEM");
+    e_ptmem = e ? std::atoi(e) : 1;
+  }
+  p.p_tmem = e_ptmem != 0 ? 1 : 0;
+  const size_t p_atom = p.p_tmem ? 0 : kPBytes;   // shared memory per P buffer
   p.resident = (nkv <= 2 && e_res != 0) ? 1 : 0;
-  if (p.resident && 1024 + 2 * qt + 2 * kPBytes + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64 >
+  if (p.resident && 1024 + 2 * qt + 2 * p_atom + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64 >
                         static_cast<size_t>(g_attn_max_smem))
     p.resident = 0;  // d_pad = 192 with two kv tiles: two Q buffers do not fit, use the ring form
   size_t smem;
@@ -872,14 +912,16 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
         break;
       }
     }
-    smem = 1024 + 2 * qt + 2 * kPBytes + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64;
+    p.p_smem = p.p_tmem ? 0 : p.p_bufs;
+    smem = 1024 + 2 * qt + 2 * p_atom + 2 * static_cast<size_t>(nkv) * kvt + sizeof(AttnShared) + 64;
   } else {
     // Ring mode.  shared memory: Q + three P atoms (required by the Q.K-first issue order, see the header) + K ring of 3
     // + V ring of 2: 104 KB for d_pad == 64 (two CTAs per SM), 219 KB for d_pad == 192.
     p.q_bufs = 1;
     p.qpc = 1;
     p.p_bufs = 3;
-    const size_t fixed = 1024 + qt + sizeof(AttnShared) + 64 + 3 * kPBytes;
+    p.p_smem = p.p_tmem ? 0 : p.p_bufs;
+    const size_t fixed = 1024 + qt + sizeof(AttnShared) + 64 + 3 * p_atom;
     p.k_stages = 3;  // the producer's slot-reuse argument (see the kernel) is written for exactly this ring: K 3 / V 2 / P 3
     p.v_stages = 2;
     smem = fixed + static_cast<size_t>(p.k_stages + p.v_stages) * kvt;

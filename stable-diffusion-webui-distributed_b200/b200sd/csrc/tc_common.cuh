@@ -240,6 +240,21 @@ __device__ __forceinline__ void umma_f16_ss_lh(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in TMEM (lane = row, 32-bit column j = K elements 2j, 2j+1): the P.V product of the attention
+// kernel when P is written back over its own S columns
+__device__ __forceinline__ void umma_f16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
