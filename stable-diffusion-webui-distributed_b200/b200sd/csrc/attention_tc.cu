@@ -13,8 +13,8 @@
 // One CTA = one 128-row Q tile of one (batch, head), kv consumed in tiles of 64.  320 threads:
 //   warp 0    TMA producer (Q once; K ring of 3, V ring of 2 — or K/V resident and Q tiles streaming, see `resident`)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer:  S[j%2] = Q K_j^T (M128 x N<=64 x K=d),
-//             O_h (+)= P_h V_h for the two 32-row halves h of the kv tile (M128 x N=d_pad x K=32 each, V consumed
-//             MN-major straight from its TMA tile)
+//             O_h (+)= P_h V_h for the two 32-row halves h of the kv tile (M128 x N=d_pad x K=32 each; A = P straight from
+//             TMEM, where the softmax warps write it over their own S columns; V consumed MN-major from its TMA tile)
 //   warps 2-9 softmax.  Thread pair == query row: TMEM lane = (warp%4)*32 + lane; the two warps of a lane quarter
 //             take the two 32-column halves of the kv tile.
 // The two halves of a row are INDEPENDENT online-softmax streams: each has its own running maximum and its own
@@ -29,17 +29,19 @@
 // element is read from TMEM once (one 32-column load per thread and tile), and with a ones column in V (v_ones_col)
 // the row sums l_a, l_b come out of the P.V MMAs instead of CUDA-core adds.
 //
-// TMEM: S0 @ +0, S1 @ +64 (64 fp32 columns each), O_a @ +128, O_b @ +128 + d_pad.  d_pad == 64: 256 columns and
-// ~100 KB shared memory, two CTAs per SM.
+// TMEM: S0 @ +0, S1 @ +64 (64 fp32 columns each), O_a @ +128, O_b @ +128 + d_pad.  P of tile t replaces S of tile t in
+// place: the warp of (lane quarter, half h) packs its 32 P values into the first 16 of its own 32 S columns (P_a @ +0,
+// P_b @ +32 of the buffer), so nobody overwrites what another warp still has to read, and P.V(t) is issued BEFORE
+// Q.K(t+2) refills the buffer (one thread's MMAs execute in order).  d_pad == 64: 256 columns and ~57 KB shared memory
+// (Q + K ring + V ring), two CTAs per SM.  (B200SD_ATTN_PTMEM=0 keeps the earlier form: P as fp16 in swizzled shared
+// memory, three buffers, Q.K issued first.)
 //
 // mbarrier phase discipline (parity waits alias if a waiter can fall two phases behind):
-//   o_full[pb] P.V of tile j commits to o_full[j%pb].  One thread issues all MMAs in the order ... Q.K(j), P.V(j-2),
-//              Q.K(j+1), P.V(j-1) ... (Q.K first: S is what the softmax warps wait for) and a commit fires when ALL MMAs
-//              issued before it have completed, so "S[j] is ready" (which every softmax thread observes before touching
-//              tile j) already proves that P.V of tiles <= j-3 has completed: P[j%3] is free without a wait of its own
-//              (hence three P buffers), and the rare-path wait for tile j-1 / the final wait can be at most one phase
-//              behind their barrier (the phase before belongs to tile j-4).  P.V of tile j cannot complete before the
-//              waiter's own warp has arrived on p_full.
+//   o_full[pb] P.V of tile j commits to o_full[j%pb].  Waited by the softmax warps before a rescale of O and at the end, and
+//              (ring mode) by the producer for slot reuse; a commit fires when ALL MMAs its thread issued before it have
+//              completed, so it also covers the Q.K products issued earlier.  In the shared-memory-P form the order
+//              Q.K(j), P.V(j-2), Q.K(j+1), ... makes "S[j] ready" prove that P.V of tiles <= j-3 is complete: P[j%3] is
+//              free without a wait of its own (hence three P buffers there).
 //   p_full[pb] 8 warp arrivals; in ring mode + 1 arrival of the producer, whose expect_tx puts the bytes of K_{t+2} and V_t
 //              on the phase of tile t (see the producer): the MMA thread's one wait per tile covers P and its operands.
 //              Waiters: the MMA thread and (ring mode) the producer, neither of which can be lapped — a later phase needs
