@@ -344,6 +344,7 @@ def kernel_rooflines(eng, b, pk):
     ops.select_step(plan.table, plan.step * 0, plan.unet.cur_bias)
     torch.cuda.synchronize()
     recs = []
+    exps = [0.0]   # exponentials of all attention launches (one per S element)
     for fn, a, k in plan.unet.ops:
         name = getattr(fn, "__name__", "op")
         name = "groupnorm" if name == "<lambda>" else name
@@ -357,6 +358,7 @@ def kernel_rooflines(eng, b, pk):
         elif name == "attention":
             bq, sq, skv, heads, d = a[0].shape[0], a[0].shape[1], a[1].shape[1], a[4], a[5]
             flop = 4.0 * bq * heads * sq * skv * d
+            exps[0] += float(bq) * heads * sq * skv
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn(*a, **k)
@@ -381,7 +383,11 @@ def kernel_rooflines(eng, b, pk):
     at = agg.get("attention", [0, 1e-9, 0])
     roof_attn = {"kernel": "attention_tc_kernel", "bound": "tensor", "achieved": at[2] / (at[1] * 1e-3) / 1e12, "peak": peak,
                  "unit": "TFLOP/s", "frac": at[2] / (at[1] * 1e-3) / 1e12 / peak, "launches": at[0],
-                 "note": "QK^T + PV FLOPs; d=40 heads make this kernel exp-throughput (MUFU) bound, see DESIGN.md"}
+                 "note": "QK^T + PV FLOPs; d=40 heads make this kernel exp-throughput (MUFU) bound, see DESIGN.md",
+                 # the pipe that actually bounds it: one MUFU.EX2 per S element, 16 per clock and SM (tools/xu_probe.cu
+                 # measured 4.47 T/s at 1.9 GHz on 148 SMs)
+                 "exp_rate": {"achieved": exps[0] / (at[1] * 1e-3) / 1e12, "peak": 4.47, "unit": "T exp/s",
+                              "frac": exps[0] / (at[1] * 1e-3) / 1e12 / 4.47, "peak_source": "measured (xu_probe, boost clock)"}}
     breakdown = {k: round(v[1], 3) for k, v in agg.items()}
     # HBM-bound kernel classes: algorithmic bytes (GroupNorm 2 reads + 1 write of 45.1 M elements per
     # sample-evaluation, LayerNorm 1 read + 1 write of 34.7 M) over the summed CUDA-event durations, against the measured
