@@ -593,8 +593,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool leader = elect_one();
     ATTN_TRACE_PTR(leader && p.trace && blockIdx.x == 3 && blockIdx.y == 2 && blockIdx.z == 1);
     const bool bf = p.is_bf16 != 0;
-    const bool qk_first = !resident;  // ring mode: Q.K(t+2) before P.V(t) (three P buffers); resident mode: after
-    const int ksteps_qk = p.d16 / 16, k_stages = p.k_stages, v_stages = p.v_stages, p_bufs = p.p_bufs, skv = p.Skv;
+    const int ksteps_qk = p.d16 / 16, k_stages = p.k_stages, p_bufs = p.p_bufs, skv = p.Skv;
     const int T = n_items * nkv;
     const uint32_t tm_S = warp_uniform(tmem_base);
     const uint32_t tm_Oa = tm_S + static_cast<uint32_t>(kSBufs * kKv), tm_Ob = tm_Oa + static_cast<uint32_t>(p.dpv);
@@ -620,18 +619,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t kv_step = kv_bytes >> 4;
     const uint32_t idesc_qk_full = make_idesc_f16(128, kKv, bf, false, false);
     const uint32_t idesc_pv = make_idesc_f16(128, p.dpv, bf, false, true);  // B (= V) is MN-major
-    int qk_t = 0, qk_item = 0, qk_j = 0, q_ks = 0;  // next Q.K: stream index, item, kv tile, K ring slot (ring mode)
-    uint32_t q_kpar = 0, k_lo_ring = k_lo0;
-    auto issue_qk = [&]() {  // S[qk_t & 1] = Q_item K_j^T
+    int qk_t = 0, qk_item = 0, qk_j = 0;  // resident mode, next Q.K: stream index, item (Q tile), kv tile
+    auto issue_qk = [&]() {  // resident mode: S[qk_t & 1] = Q_item K_j^T
       const uint32_t q_sb = static_cast<uint32_t>(qk_t) & 1u;
-      const uint32_t qs = resident ? (static_cast<uint32_t>(qk_item) & 1u) : 0u;
+      const uint32_t qs = static_cast<uint32_t>(qk_item) & 1u;
       const int nvalid = min(kKv, skv - qk_j * kKv);
       ATTN_TRACE(11, qk_t);
-      if (resident ? qk_j == 0 : qk_t == 0)  // ring mode: Q, K_0 and K_1 share q_full[0]
-        mbar_wait_a(a_q_full + qs * 8u, resident ? ((static_cast<uint32_t>(qk_item) >> 1) & 1u) : 0u, 13);
-      const uint32_t kslot = resident ? static_cast<uint32_t>(qk_j) : static_cast<uint32_t>(q_ks);
-      const uint32_t k_lo = resident ? k_lo0 + kslot * kv_step : k_lo_ring;
-      if (resident) mbar_wait_a(a_k_full + kslot * 8u, 0u, 14);  // ring mode: K_t landed on p_full of tile t - 2
+      if (qk_j == 0) mbar_wait_a(a_q_full + qs * 8u, (static_cast<uint32_t>(qk_item) >> 1) & 1u, 13);
+      const uint32_t kslot = static_cast<uint32_t>(qk_j);
+      const uint32_t k_lo = k_lo0 + kslot * kv_step;
+      mbar_wait_a(a_k_full + kslot * 8u, 0u, 14);  // loaded once per CTA
       tc_fence_after();
       ATTN_TRACE(12, qk_t);
       if (leader) {
@@ -649,7 +646,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                            idesc, k != 0 ? 1u : 0u);
           }
         }
-        if (resident && qk_j == nkv - 1) umma_commit_a(a_q_empty + qs * 8u);  // this Q buffer may be refilled
+        if (qk_j == nkv - 1) umma_commit_a(a_q_empty + qs * 8u);  // this Q buffer may be refilled
         umma_commit_a(a_s_full + q_sb * 8u);
       }
       ATTN_TRACE(13, qk_t);
@@ -657,14 +654,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (++qk_j == nkv) {
         qk_j = 0;
         ++qk_item;
-      }
-      if (!resident) {
-        k_lo_ring += kv_step;
-        if (++q_ks == k_stages) {
-          q_ks = 0;
-          q_kpar ^= 1u;
-          k_lo_ring = k_lo0;
-        }
       }
     };
     if (!resident) {
@@ -746,22 +735,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     } else {
       for (int i = 0; i < kSBufs && i < T; ++i) issue_qk();
-      int vs = 0, pb = 0, pv_item = 0, pv_j = 0;
-      uint32_t v_par = 0, p_par = 0, v_lo_ring = v_lo0, p_lo = p_lo0;
+      // ---- resident mode: K / V stay in shared memory, the tiles of all the CTA's Q tiles form one stream ----
+      int pb = 0, pv_item = 0, pv_j = 0;
+      uint32_t p_par = 0, p_lo = p_lo0;
       for (int t = 0; t < T; ++t) {
         const int nvalid = min(kKv, skv - pv_j * kKv);
         ATTN_TRACE(7, t);
         mbar_wait_a(a_p_full + static_cast<uint32_t>(pb) * 8u, p_par, 15);
         ATTN_TRACE(8, t);
-        // softmax t has released its S buffer: refill it two tiles ahead.  In ring mode BEFORE this tile's P.V — S is what
-        // the softmax warps wait for next, O is not read until the end.
-        if (qk_first && qk_t < T) issue_qk();
         // ---- O_a (+)= P[:, 0:32] V[0:32, :],  O_b (+)= P[:, 32:64] V[32:64, :] ----
         if (pv_j == 0 && pv_item > 0)  // the previous Q tile's epilogue has read the accumulators this P.V overwrites
           mbar_wait_a(a_o_free, (static_cast<uint32_t>(pv_item) - 1u) & 1u, 21);
-        const uint32_t vslot = resident ? static_cast<uint32_t>(pv_j) : static_cast<uint32_t>(vs);
-        const uint32_t v_lo = resident ? v_lo0 + vslot * kv_step : v_lo_ring;
-        if (resident) mbar_wait_a(a_v_full + vslot * 8u, 0u, 16);  // ring mode: V_t landed on p_full of tile t
+        const uint32_t vslot = static_cast<uint32_t>(pv_j);
+        const uint32_t v_lo = v_lo0 + vslot * kv_step;
+        mbar_wait_a(a_v_full + vslot * 8u, 0u, 16);  // loaded once per CTA
         tc_fence_after();
         ATTN_TRACE(9, t);
         if (leader) {
@@ -790,14 +777,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_commit_a(a_o_full + static_cast<uint32_t>(pb) * 8u);
         }
         ATTN_TRACE(10, t);
-        if (!resident) {
-          v_lo_ring += kv_step;
-          if (++vs == v_stages) {
-            vs = 0;
-            v_par ^= 1u;
-            v_lo_ring = v_lo0;
-          }
-        }
         p_lo += kPBytes >> 4;
         if (++pb == p_bufs) {
           pb = 0;
@@ -808,7 +787,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pv_j = 0;
           ++pv_item;
         }
-        if (!qk_first && qk_t < T) issue_qk();
+        // softmax t has released its S buffer (and P.V of this tile, which reads P from it, is already in the queue):
+        // refill it two tiles ahead
+        if (qk_t < T) issue_qk();
       }
     }
     __syncwarp();
