@@ -439,6 +439,40 @@ def sigmas_karras(steps: int):
     return torch.cat([s, s.new_zeros(1)]), sig.log()
 
 
+def sigmas_exponential(steps: int):
+    """k-diffusion get_sigmas_exponential(n, sigma_min, sigma_max) with the model's own bounds (sdwui "Exponential";
+    "Polyexponential" is the same schedule at its default rho = 1)."""
+    ac = alphas_cumprod().double()
+    sig = ((1 - ac) / ac) ** 0.5
+    s = torch.linspace(math.log(float(sig[-1])), math.log(float(sig[0])), steps, dtype=torch.float64).exp()
+    return torch.cat([s, s.new_zeros(1)]), sig.log()
+
+
+def sigmas_sgm_uniform(steps: int):
+    """sdwui sd_schedulers.sgm_uniform: sigmas at timesteps linspace(t(sigma_max), t(sigma_min), n + 1)[:-1], then 0."""
+    ac = alphas_cumprod().double()
+    sig = ((1 - ac) / ac) ** 0.5
+    log_sig = sig.log()
+    start, end = sigma_to_t(float(sig[-1]), log_sig), sigma_to_t(float(sig[0]), log_sig)
+    out = []
+    for t in torch.linspace(start, end, steps + 1, dtype=torch.float64)[:-1].tolist():   # DiscreteSchedule.t_to_sigma
+        lo = int(math.floor(t))
+        hi = int(math.ceil(t))
+        w = t - lo
+        out.append(math.exp((1 - w) * float(log_sig[lo]) + w * float(log_sig[hi])))
+    return torch.tensor(out + [0.0], dtype=torch.float64), log_sig
+
+
+def sample_euler_sigmas(unet, x_T, cond, uncond, sig, log_sig, cfg_scale: float):
+    """k-diffusion sample_euler (s_churn 0) over an explicit sigma schedule"""
+    x = x_T * float(sig[0])
+    for i in range(len(sig) - 1):
+        s, sn = float(sig[i]), float(sig[i + 1])
+        e = cfg_eps(unet, x * (1.0 / math.sqrt(s * s + 1.0)), sigma_to_t(s, log_sig), cond, uncond, cfg_scale)
+        x = x + e * (sn - s)
+    return x
+
+
 def sample_dpmpp_2m(unet, x_T, cond, uncond, steps: int, cfg_scale: float, karras: bool = True):
     """k-diffusion sample_dpmpp_2m (sdwui "DPM++ 2M" / "DPM++ 2M Karras") around the eps-prediction CompVisDenoiser:
     denoised = x - sigma * eps(x * c_in, t(sigma)); written with t = -log(sigma) exactly as upstream."""

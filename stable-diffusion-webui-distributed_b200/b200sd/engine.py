@@ -63,10 +63,10 @@ def ddim_img2img_plan(steps: int, denoising_strength: float):
     return math.sqrt(a_start), math.sqrt(1 - a_start), t_out, rows
 
 
-def euler_a_plan(steps: int):
+def euler_a_plan(steps: int, scheduler: str = "uniform"):
     """k-diffusion sample_euler_ancestral over CompVisDenoiser sigmas.  Returns (timesteps, coef rows, sigma0):
     row = [sigma, sigma_down, sigma_up, c_in of the NEXT step]."""
-    sig, log_sig = kdiffusion_sigmas(steps, "uniform")
+    sig, log_sig = kdiffusion_sigmas(steps, scheduler)
 
     t_out, rows = [], []
     for i in range(steps):
@@ -78,10 +78,10 @@ def euler_a_plan(steps: int):
     return t_out, rows, float(sig[0])
 
 
-def euler_plan(steps: int):
+def euler_plan(steps: int, scheduler: str = "uniform"):
     """k-diffusion sample_euler (s_churn = 0) on the same sigmas: the ancestral step with sigma_up = 0, i.e.
     sigma_down = sigma_next and no noise — same coefficient rows, same kernel."""
-    t_out, rows, sigma0 = euler_a_plan(steps)
+    t_out, rows, sigma0 = euler_a_plan(steps, scheduler)
     for i, r in enumerate(rows):
         sn = (r[1] ** 2 + r[2] ** 2) ** 0.5   # sigma_next = sqrt(down^2 + up^2)
         rows[i] = [r[0], sn, 0.0, r[3]]
@@ -91,7 +91,9 @@ def euler_plan(steps: int):
 def kdiffusion_sigmas(steps: int, scheduler: str = "uniform") -> Tuple[torch.Tensor, torch.Tensor]:
     """sigmas[steps + 1] (last 0) as sdwui's KDiffusionSampler.get_sigmas builds them, and the model's log-sigma table.
     "uniform": k-diffusion DiscreteSchedule.get_sigmas (timesteps linspace(999, 0, steps), log-sigma interpolation);
-    "karras": get_sigmas_karras(steps, sigma_min = sigmas[0], sigma_max = sigmas[-1], rho = 7)."""
+    "karras": get_sigmas_karras(steps, sigma_min = sigmas[0], sigma_max = sigmas[-1], rho = 7);
+    "exponential" (= "polyexponential", rho 1): get_sigmas_exponential — log-sigmas equally spaced between the same bounds;
+    "sgm_uniform": sdwui sd_schedulers.sgm_uniform — timesteps linspace(t(sigma_max), t(sigma_min), steps + 1)[:-1]."""
     ac = alphas_cumprod().double()
     sig_all = ((1 - ac) / ac) ** 0.5
     log_sig = sig_all.log()
@@ -99,8 +101,12 @@ def kdiffusion_sigmas(steps: int, scheduler: str = "uniform") -> Tuple[torch.Ten
         ramp = torch.linspace(0, 1, steps, dtype=torch.float64)
         lo, hi = float(sig_all[0]) ** (1 / 7.0), float(sig_all[-1]) ** (1 / 7.0)
         sig = (hi + ramp * (lo - hi)) ** 7.0
-    elif scheduler == "uniform":
-        tt = torch.linspace(999, 0, steps, dtype=torch.float64)
+    elif scheduler in ("exponential", "polyexponential"):
+        sig = torch.linspace(math.log(float(sig_all[-1])), math.log(float(sig_all[0])), steps, dtype=torch.float64).exp()
+    elif scheduler in ("uniform", "sgm_uniform"):
+        # t(sigma_max) = 999 and t(sigma_min) = 0 on the model's own table
+        tt = torch.linspace(999, 0, steps + 1, dtype=torch.float64)[:-1] if scheduler == "sgm_uniform" else \
+            torch.linspace(999, 0, steps, dtype=torch.float64)
         lo, hi = tt.floor().long(), tt.ceil().long()
         wgt = tt - lo
         sig = ((1 - wgt) * log_sig[lo] + wgt * log_sig[hi]).exp()
@@ -143,14 +149,20 @@ SAMPLERS = {"DDIM": ("ddim", None), "Euler a": ("euler_a", "uniform"), "Euler": 
             "DPM++ 2M": ("dpmpp_2m", "karras"), "DPM++ 2M Karras": ("dpmpp_2m", "karras")}
 
 
+# API scheduler labels (sdwui >= 1.9 sd_schedulers.schedulers: label or name) -> kdiffusion_sigmas scheduler
+SCHEDULERS = {"Uniform": "uniform", "uniform": "uniform", "Karras": "karras", "karras": "karras",
+              "Exponential": "exponential", "exponential": "exponential", "Polyexponential": "polyexponential",
+              "polyexponential": "polyexponential", "SGM Uniform": "sgm_uniform", "sgm_uniform": "sgm_uniform"}
+
+
 def resolve_sampler(name: str, scheduler: Optional[str] = None):
     """(method, scheduler) for an API sampler name + optional API scheduler label; ValueError if not implemented."""
     if name not in SAMPLERS:
         raise ValueError(f"sampler {name!r} is not implemented on the local executor")
     method, default = SAMPLERS[name]
-    if method == "dpmpp_2m" and scheduler not in (None, "", "Automatic"):
-        label = scheduler.lower()
-        if label not in ("karras", "uniform"):
+    if default is not None and scheduler not in (None, "", "Automatic"):   # DDIM takes no sigma schedule
+        label = SCHEDULERS.get(scheduler, SCHEDULERS.get(str(scheduler).lower()))
+        if label is None:
             raise ValueError(f"scheduler {scheduler!r} is not implemented on the local executor")
         return method, label
     return method, default
@@ -304,14 +316,14 @@ class SDEngine:
                 scale0, in0 = 1.0, 1.0
                 step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
             elif sampler == "Euler a":
-                ts, rows, sigma0 = euler_a_plan(steps)
+                ts, rows, sigma0 = euler_a_plan(steps, resolve_sampler(sampler, scheduler)[1])
                 scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_euler_a(cfg_scale)  # noqa: E731
                 if noises is None:
                     raise ValueError("Euler a needs the per-image ancestral noises")
                 plan.noise = noises.to(self.device, torch.float32).permute(0, 1, 3, 4, 2).reshape(len(rows), b, h * w, 4).contiguous()
             elif sampler == "Euler":
-                ts, rows, sigma0 = euler_plan(steps)
+                ts, rows, sigma0 = euler_plan(steps, resolve_sampler(sampler, scheduler)[1])
                 scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
             elif sampler in SAMPLERS and SAMPLERS[sampler][0] == "dpmpp_2m":

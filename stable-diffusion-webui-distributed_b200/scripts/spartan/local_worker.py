@@ -146,9 +146,12 @@ class LocalGPUWorker(Worker):
             logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")
             sampler = "Euler a"
         scheduler = payload.get("scheduler")  # sdwui >= 1.9 sends the noise schedule separately from the sampler
-        if sampler.startswith("DPM++ 2M") and scheduler not in (None, "", "Automatic", "Karras", "Uniform"):
-            logger.warning(f"scheduler '{scheduler}' is not implemented on worker {self.label}: using the sampler's default")
-            scheduler = None
+        if scheduler not in (None, "", "Automatic"):
+            from b200sd.engine import SCHEDULERS
+            if sampler == "DDIM" or (scheduler not in SCHEDULERS and str(scheduler).lower() not in SCHEDULERS):
+                if sampler != "DDIM":
+                    logger.warning(f"scheduler '{scheduler}' is not implemented on worker {self.label}: using the sampler's default")
+                scheduler = None
         init_u8 = None
         if payload.get("init_images"):
             if payload.get("image_mask") is not None or payload.get("mask") is not None:

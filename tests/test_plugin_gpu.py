@@ -86,7 +86,8 @@ def test_worker_reply_schema_and_png_lane(env):
 
 
 @pytest.mark.parametrize("name,sched,direct_sched", [("DPM++ 2M Karras", None, None), ("DPM++ 2M", "Uniform", "Uniform"),
-                                                     ("DPM++ 2M", "Exponential", None), ("Euler", None, None)])
+                                                     ("DPM++ 2M", "Align Your Steps", None), ("Euler", None, None),
+                                                     ("Euler a", "Exponential", "Exponential")])
 def test_worker_sampler_names(env, name, sched, direct_sched):
     """the API's sampler / scheduler labels reach the executor (an unknown scheduler falls back to the sampler's default)"""
     processing, mscripts, DistributedScript, eng, State, sh = env

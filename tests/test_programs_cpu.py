@@ -156,6 +156,27 @@ def test_sizes_the_unet_cannot_take_are_refused(env):
     assert eng.plan(1, down, 2 * down).b == 1
 
 
+@pytest.mark.parametrize("label,fn", [("Exponential", "sigmas_exponential"), ("Polyexponential", "sigmas_exponential"),
+                                      ("SGM Uniform", "sigmas_sgm_uniform"), ("Karras", "sigmas_karras")])
+def test_euler_on_the_api_schedulers(env, label, fn):
+    """sdwui >= 1.9 sends the noise schedule separately: the k-diffusion samplers run on any of the implemented ones"""
+    C, E, O, cfgs, sd, eng = env
+    b, hw, steps = 2, 8, 5
+    sig, log_sig = getattr(O, fn)(steps)
+    mine, _ = E.kdiffusion_sigmas(steps, E.SCHEDULERS[label])
+    assert torch.allclose(mine, sig, rtol=1e-12, atol=1e-12)
+    assert all(float(sig[i]) > float(sig[i + 1]) for i in range(steps))
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    nz = E.per_image_noise(3200, b, (4, hw, hw), 1)
+    with torch.no_grad():
+        ref = O.sample_euler_sigmas(lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c), nz[0], cond, unc, sig, log_sig, 7.0)
+    lat = eng.sample(cond, unc, nz[0], steps, 7.0, "Euler", scheduler=label)
+    z = lat.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
 def test_sampler_names_resolve(env):
     C, E, O, cfgs, sd, eng = env
     assert E.resolve_sampler("DPM++ 2M") == ("dpmpp_2m", "karras") == E.resolve_sampler("DPM++ 2M Karras")
@@ -164,8 +185,11 @@ def test_sampler_names_resolve(env):
     assert E.resolve_sampler("Euler a") == ("euler_a", "uniform") and E.resolve_sampler("DDIM") == ("ddim", None)
     with pytest.raises(ValueError):
         E.resolve_sampler("UniPC")
+    assert E.resolve_sampler("DPM++ 2M", "Exponential") == ("dpmpp_2m", "exponential")
+    assert E.resolve_sampler("Euler a", "SGM Uniform") == ("euler_a", "sgm_uniform")
+    assert E.resolve_sampler("DDIM", "Karras") == ("ddim", None)   # the timestep samplers take no sigma schedule
     with pytest.raises(ValueError):
-        E.resolve_sampler("DPM++ 2M", "Exponential")
+        E.resolve_sampler("DPM++ 2M", "Align Your Steps")
 
 
 def test_hires_fix_matches_oracle(env):
