@@ -498,6 +498,43 @@ def sample_dpmpp_2m(unet, x_T, cond, uncond, steps: int, cfg_scale: float, karra
     return x
 
 
+def kdiff_img2img_sigmas(sig: torch.Tensor, steps: int, denoising_strength: float) -> torch.Tensor:
+    """sdwui KDiffusionSampler.sample_img2img: t_enc = int(min(d, 0.999) * steps) (setup_img2img_steps without
+    img2img_fix_steps); sigma_sched = sigmas[steps - t_enc - 1:]; the start is x = init + noise * sigma_sched[0]."""
+    t_enc = int(min(denoising_strength, 0.999) * steps)
+    return sig[steps - t_enc - 1:]
+
+
+def sample_kdiff_img2img(unet, init, noises, cond, uncond, sig_sched, log_sig, cfg_scale: float, method: str):
+    """the tail of a k-diffusion sampler from a noised init latent.  noises[0] noises the start, noises[1:] are the
+    ancestral draws (method "euler_a"); methods: "euler", "euler_a", "dpmpp_2m"."""
+    x = init + noises[0] * float(sig_sched[0])
+    old = None
+    for i in range(len(sig_sched) - 1):
+        s, sn = float(sig_sched[i]), float(sig_sched[i + 1])
+        e = cfg_eps(unet, x * (1.0 / math.sqrt(s * s + 1.0)), sigma_to_t(s, log_sig), cond, uncond, cfg_scale)
+        if method == "euler":
+            x = x + e * (sn - s)
+        elif method == "euler_a":
+            up = min(sn, (sn ** 2 * (s ** 2 - sn ** 2) / s ** 2) ** 0.5)
+            down = (sn ** 2 - up ** 2) ** 0.5
+            x = x + e * (down - s)
+            if up > 0:
+                x = x + noises[1 + i] * up
+        elif method == "dpmpp_2m":
+            denoised = x - s * e
+            if old is None or sn == 0:
+                x = (sn / s) * x + (1 - sn / s) * denoised
+            else:
+                h, h_last = math.log(s / sn), math.log(float(sig_sched[i - 1]) / s)
+                r = h_last / h
+                x = (sn / s) * x + (1 - sn / s) * ((1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old)
+            old = denoised
+        else:
+            raise ValueError(method)
+    return x
+
+
 # ------------------------------------------------------------------------------------------------ images / rng
 def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0) -> torch.Tensor:
     """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k."""

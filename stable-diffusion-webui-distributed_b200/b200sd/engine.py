@@ -63,10 +63,12 @@ def ddim_img2img_plan(steps: int, denoising_strength: float):
     return math.sqrt(a_start), math.sqrt(1 - a_start), t_out, rows
 
 
-def euler_a_plan(steps: int, scheduler: str = "uniform"):
+def euler_a_plan(steps: int, scheduler: str = "uniform", sigmas=None):
     """k-diffusion sample_euler_ancestral over CompVisDenoiser sigmas.  Returns (timesteps, coef rows, sigma0):
-    row = [sigma, sigma_down, sigma_up, c_in of the NEXT step]."""
-    sig, log_sig = kdiffusion_sigmas(steps, scheduler)
+    row = [sigma, sigma_down, sigma_up, c_in of the NEXT step].  `sigmas` = (table ending in 0, log-sigma table of the
+    model) runs an explicit schedule instead (img2img: the tail of the full one)."""
+    sig, log_sig = sigmas if sigmas is not None else kdiffusion_sigmas(steps, scheduler)
+    steps = len(sig) - 1
 
     t_out, rows = [], []
     for i in range(steps):
@@ -78,10 +80,10 @@ def euler_a_plan(steps: int, scheduler: str = "uniform"):
     return t_out, rows, float(sig[0])
 
 
-def euler_plan(steps: int, scheduler: str = "uniform"):
+def euler_plan(steps: int, scheduler: str = "uniform", sigmas=None):
     """k-diffusion sample_euler (s_churn = 0) on the same sigmas: the ancestral step with sigma_up = 0, i.e.
     sigma_down = sigma_next and no noise — same coefficient rows, same kernel."""
-    t_out, rows, sigma0 = euler_a_plan(steps, scheduler)
+    t_out, rows, sigma0 = euler_a_plan(steps, scheduler, sigmas)
     for i, r in enumerate(rows):
         sn = (r[1] ** 2 + r[2] ** 2) ** 0.5   # sigma_next = sqrt(down^2 + up^2)
         rows[i] = [r[0], sn, 0.0, r[3]]
@@ -125,10 +127,19 @@ def sigma_to_t(s: float, log_sig: torch.Tensor) -> float:
     return (1 - w) * low + w * (low + 1)
 
 
-def dpmpp_2m_plan(steps: int, scheduler: str = "karras"):
+def kdiffusion_img2img_sigmas(steps: int, denoising_strength: float, scheduler: str):
+    """sdwui KDiffusionSampler.sample_img2img: t_enc = int(min(d, 0.999) * steps); the sampler runs on
+    sigmas[steps - t_enc - 1:] (t_enc + 1 UNet evaluations) from x = init + noise * sigma_sched[0]."""
+    sig, log_sig = kdiffusion_sigmas(steps, scheduler)
+    t_enc = int(min(denoising_strength, 0.999) * steps)
+    return sig[steps - t_enc - 1:], log_sig
+
+
+def dpmpp_2m_plan(steps: int, scheduler: str = "karras", sigmas=None):
     """k-diffusion sample_dpmpp_2m.  Returns (timesteps, coef rows of 8, sigma0);
     row = [sigma, sigma_next / sigma, c1, c2, c_in of the NEXT step, 0, 0, 0] with denoised_d = c1 * denoised - c2 * old."""
-    sig, log_sig = kdiffusion_sigmas(steps, scheduler)
+    sig, log_sig = sigmas if sigmas is not None else kdiffusion_sigmas(steps, scheduler)
+    steps = len(sig) - 1
     t_out, rows = [], []
     for i in range(steps):
         s, sn = float(sig[i]), float(sig[i + 1])
@@ -303,9 +314,11 @@ class SDEngine:
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
                sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None,
-               scheduler: Optional[str] = None) -> torch.Tensor:
+               scheduler: Optional[str] = None, sigmas=None) -> torch.Tensor:
         """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device): the start latents.
-        `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way).
+        `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way); `sigmas` =
+        (sigma table ending in 0, model log-sigmas) does the same for the k-diffusion samplers, and x_T is then the
+        ALREADY NOISED start (init + noise * sigmas[0]), not unit noise.
         Returns the final latents fp32 [b, h*w, 4] (NHWC, a view of plan state)."""
         b, _, h, w = x_T.shape
         with self._ctx():
@@ -316,19 +329,19 @@ class SDEngine:
                 scale0, in0 = 1.0, 1.0
                 step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
             elif sampler == "Euler a":
-                ts, rows, sigma0 = euler_a_plan(steps, resolve_sampler(sampler, scheduler)[1])
-                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                ts, rows, sigma0 = euler_a_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
+                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_euler_a(cfg_scale)  # noqa: E731
                 if noises is None:
                     raise ValueError("Euler a needs the per-image ancestral noises")
                 plan.noise = noises.to(self.device, torch.float32).permute(0, 1, 3, 4, 2).reshape(len(rows), b, h * w, 4).contiguous()
             elif sampler == "Euler":
-                ts, rows, sigma0 = euler_plan(steps, resolve_sampler(sampler, scheduler)[1])
-                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                ts, rows, sigma0 = euler_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
+                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
             elif sampler in SAMPLERS and SAMPLERS[sampler][0] == "dpmpp_2m":
-                ts, rows, sigma0 = dpmpp_2m_plan(steps, resolve_sampler(sampler, scheduler)[1])
-                scale0, in0 = sigma0, 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
+                ts, rows, sigma0 = dpmpp_2m_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
+                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
                 step_fn = lambda: plan.step_dpmpp_2m(cfg_scale)  # noqa: E731
             else:
                 raise ValueError(f"sampler {sampler!r} is not implemented on the local executor")
@@ -411,18 +424,36 @@ class SDEngine:
 
     @torch.no_grad()
     def img2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, init_u8: torch.Tensor,
-                denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0) -> torch.Tensor:
-        """img2img with DDIM: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining
-        timesteps, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device."""
+                denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, sampler: str = "DDIM",
+                scheduler: Optional[str] = None) -> torch.Tensor:
+        """img2img: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining part of the
+        sampler's schedule, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device."""
         b = tokens.shape[0]
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
         init = self.encode(init_u8)
         _, _, h, w = init.shape
-        noise = per_image_noise(seed, b, (4, h, w))[0].to(self.device)
-        sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
-        lat = self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows))
+        lat = self._sample_from(init, cond, uncond, seed, denoising_strength, steps, cfg_scale, sampler, scheduler)
         return self.decode(lat, h, w)
+
+    def _sample_from(self, init: torch.Tensor, cond, uncond, seed: int, denoising_strength: float, steps: int,
+                     cfg_scale: float, sampler: str, scheduler: Optional[str]) -> torch.Tensor:
+        """the img2img half of a sampler (also the second pass of the hires fix): `init` [b, 4, h, w] latents on the device,
+        fresh per-image noise from `seed`, start at the noise level of t_enc.
+        DDIM: sdwui sd_samplers_timesteps.sample_img2img; k-diffusion samplers: KDiffusionSampler.sample_img2img."""
+        b, _, h, w = init.shape
+        method, sched = resolve_sampler(sampler, scheduler)
+        if method == "ddim":
+            noise = per_image_noise(seed, b, (4, h, w))[0].to(self.device)
+            sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
+            return self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows))
+        sig, log_sig = kdiffusion_img2img_sigmas(steps, denoising_strength, sched)
+        n_evals = len(sig) - 1
+        draws = 1 + (n_evals if method == "euler_a" else 0)
+        nz = per_image_noise(seed, b, (4, h, w), draws)
+        x0 = init + nz[0].to(self.device) * float(sig[0])
+        return self.sample(cond, uncond, x0, n_evals, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
+                           scheduler=scheduler, sigmas=(sig, log_sig))
 
     @torch.no_grad()
     def txt2img_hires(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20,
@@ -431,8 +462,8 @@ class SDEngine:
                       scheduler: Optional[str] = None) -> torch.Tensor:
         """txt2img with sdwui's hires fix and the "Latent" upscaler (StableDiffusionProcessingTxt2Img.sample /
         sample_hr_pass): first pass at (height, width), bilinear resize of the latents to hr_scale x, a fresh per-image
-        noise of the large shape from the same seeds, then DDIM img2img from t_enc with `hr_steps` (0 = `steps`)
-        timesteps, decode at the large size.  Returns uint8 [b, H*hr, W*hr, 3] on device."""
+        noise of the large shape from the same seeds, then the same sampler's img2img half from t_enc with `hr_steps`
+        (0 = `steps`) steps, decode at the large size.  Returns uint8 [b, H*hr, W*hr, 3] on device."""
         b = tokens.shape[0]
         h, w = height // 8, width // 8
         h2, w2 = int(height * hr_scale) // 8, int(width * hr_scale) // 8
@@ -445,10 +476,8 @@ class SDEngine:
         with self._ctx():
             up = torch.empty((b, h2 * w2, 4), device=self.device, dtype=torch.float32)
             ops.resize_latent_bilinear(lat.contiguous(), up, h, w, h2, w2)
-        noise = per_image_noise(seed, b, (4, h2, w2))[0].to(self.device)
-        sa, s1a, ts, rows = ddim_img2img_plan(hr_steps or steps, denoising_strength)
         init = up.reshape(b, h2, w2, 4).permute(0, 3, 1, 2)
-        lat2 = self.sample(cond, uncond, init * sa + noise * s1a, hr_steps or steps, cfg_scale, "DDIM", schedule=(ts, rows))
+        lat2 = self._sample_from(init, cond, uncond, seed, denoising_strength, hr_steps or steps, cfg_scale, sampler, scheduler)
         return self.decode(lat2, h2, w2)
 
     @torch.no_grad()

@@ -157,9 +157,6 @@ class LocalGPUWorker(Worker):
             if payload.get("image_mask") is not None or payload.get("mask") is not None:
                 raise NotImplementedError("inpainting masks are not implemented on the local executor")
             init_u8 = self._init_images_u8(payload["init_images"], batch, width, height)
-            if sampler != "DDIM":
-                logger.warning(f"img2img on worker {self.label} runs DDIM ('{sampler}' start-from-noise-level is not implemented)")
-                sampler = "DDIM"
         denoise = float(payload.get("denoising_strength", 0.75) or 0.75)
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
@@ -183,7 +180,7 @@ class LocalGPUWorker(Worker):
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
             if init_u8 is not None:
                 u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
-                                 cfg_scale=cfg_scale)
+                                 cfg_scale=cfg_scale, sampler=sampler, scheduler=scheduler)
             elif payload.get("enable_hr"):
                 # hires fix (reference eta_hr, worker.py:205): second pass at hr_scale x with the "Latent" upscaler
                 upscaler = payload.get("hr_upscaler") or "Latent"

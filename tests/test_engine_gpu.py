@@ -262,6 +262,34 @@ def test_dpmpp_2m_parity_tiny(mods, name, sched, karras):
     assert rel <= 3e-2 and got_u8.shape[0] == b and got_u8.dtype == torch.uint8
 
 
+def test_img2img_dpmpp_2m_parity_tiny(mods):
+    """img2img on a k-diffusion sampler: the tail of the Karras schedule from init + noise * sigma (t_enc + 1 evaluations)"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b, size, steps, d = 2, 64, 8, 0.6
+    g = torch.Generator().manual_seed(31)
+    init = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    tok = O.random_prompt_tokens(b, vocab_hi=vocab_hi)
+    neg = O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    cond32 = O.clip_text_encode(dsd, cfgs[2], tok.cuda())
+    unc32 = O.clip_text_encode(dsd, cfgs[2], neg.cuda())
+    sig, log_sig = O.sigmas_karras(steps)
+    sched = O.kdiff_img2img_sigmas(sig, steps, d)
+    with torch.no_grad():
+        lat0 = O.vae_encode_mean(dsd, cfgs[1], O.image_to_model_input(init.cuda())) * cfgs[1].scale_factor
+        nz = O.per_image_noise(777, b, tuple(lat0.shape[1:])).cuda()
+        ref = O.sample_kdiff_img2img(lambda x, t, c: O.unet_forward(dsd, cfgs[0], x, t, c), lat0, [nz], cond32, unc32, sched,
+                                     log_sig, 7.0, "dpmpp_2m")
+    got_u8 = eng.img2img(tok, neg, 777, init, d, steps=steps, cfg_scale=7.0, sampler="DPM++ 2M")
+    torch.cuda.synchronize()
+    assert eng.last_unet_evals == len(sched) - 1 == int(d * steps) + 1
+    h, w = lat0.shape[2:]
+    z = eng.plan(b, h, w).x.reshape(b, h, w, 4).permute(0, 3, 1, 2)
+    rel = float((z - ref).abs().max() / ref.abs().max())
+    _record("img2img dpmpp_2m tiny", z_rel_max=rel)
+    assert rel <= 3e-2 and tuple(got_u8.shape) == (b, size, size, 3)
+
+
 def test_euler_a_parity_tiny(mods):
     C, E, S, O = mods
     cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")

@@ -208,6 +208,62 @@ def test_hires_fix_matches_oracle(env):
     assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
 
 
+@pytest.mark.parametrize("sampler,sched,method,sig_fn", [("Euler", None, "euler", "karras_sigmas_compvis"),
+                                                         ("Euler a", None, "euler_a", "karras_sigmas_compvis"),
+                                                         ("DPM++ 2M", None, "dpmpp_2m", "sigmas_karras"),
+                                                         ("DPM++ 2M", "Exponential", "dpmpp_2m", "sigmas_exponential")])
+def test_img2img_on_kdiffusion_samplers(env, sampler, sched, method, sig_fn):
+    """img2img (and the hires second pass) with the k-diffusion samplers: the tail sigmas[steps - t_enc - 1:] of the
+    sampler's schedule from init + noise * sigma (sdwui KDiffusionSampler.sample_img2img)"""
+    C, E, O, cfgs, sd, eng = env
+    b, size, steps, d = 2, 32, 8, 0.6
+    g = torch.Generator().manual_seed(99)
+    init = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    sig, log_sig = getattr(O, sig_fn)(steps)
+    sched_sig = O.kdiff_img2img_sigmas(sig, steps, d)
+    n_evals = len(sched_sig) - 1
+    assert n_evals == int(d * steps) + 1
+    with torch.no_grad():
+        lat0 = O.vae_encode_mean(sd, cfgs[1], O.image_to_model_input(init)) * cfgs[1].scale_factor
+        nz = E.per_image_noise(555, b, tuple(lat0.shape[1:]), 1 + (n_evals if method == "euler_a" else 0))
+        ref = O.sample_kdiff_img2img(lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c), lat0, list(nz), cond, unc,
+                                     sched_sig, log_sig, 7.0, method)
+        ref_u8 = O.to_uint8(O.vae_decode(sd, cfgs[1], ref / cfgs[1].scale_factor))
+    got = eng.img2img(tok, neg, 555, init, d, steps=steps, cfg_scale=7.0, sampler=sampler, scheduler=sched)
+    assert eng.last_unet_evals == n_evals and got.shape == ref_u8.shape
+    h, w = lat0.shape[2:]
+    z = eng.plan(b, h, w).x.reshape(b, h, w, 4).permute(0, 3, 1, 2)
+    assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+    dd = (got.int() - ref_u8.int()).abs()
+    assert float((dd <= 1).float().mean()) == 1.0 and float((dd == 0).float().mean()) > 0.99
+
+
+def test_hires_fix_on_a_kdiffusion_sampler(env):
+    """hires fix with "Euler": first pass sample_euler, bilinear latent resize, then the tail of the same sampler's
+    schedule from the noised upscaled latents (sdwui sample_hr_pass -> sampler.sample_img2img)"""
+    C, E, O, cfgs, sd, eng = env
+    b, steps, hr_steps, d = 2, 5, 6, 0.5
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    cond, unc = O.clip_text_encode(sd, cfgs[2], tok), O.clip_text_encode(sd, cfgs[2], neg)
+    unet = lambda x, t, c: O.unet_forward(sd, cfgs[0], x, t, c)  # noqa: E731
+    with torch.no_grad():
+        x = O.sample_euler(unet, O.per_image_noise(88, b, (4, 8, 8)), cond, unc, steps, 7.0)
+        up = torch.nn.functional.interpolate(x, size=(16, 16), mode="bilinear", antialias=False)
+        sig, log_sig = O.karras_sigmas_compvis(hr_steps)
+        ref = O.sample_kdiff_img2img(unet, up, [O.per_image_noise(88, b, (4, 16, 16))], cond, unc,
+                                     O.kdiff_img2img_sigmas(sig, hr_steps, d), log_sig, 7.0, "euler")
+        ref_u8 = O.to_uint8(O.vae_decode(sd, cfgs[1], ref / cfgs[1].scale_factor))
+    got = eng.txt2img_hires(tok, neg, seed=88, steps=steps, cfg_scale=7.0, height=64, width=64, hr_scale=2.0,
+                            hr_steps=hr_steps, denoising_strength=d, sampler="Euler")
+    assert got.shape == ref_u8.shape and eng.last_unet_evals == int(d * hr_steps) + 1
+    dd = (got.int() - ref_u8.int()).abs()
+    assert float((dd <= 1).float().mean()) == 1.0 and float((dd == 0).float().mean()) > 0.99
+
+
 def test_img2img_matches_oracle(env):
     """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
     C, E, O, cfgs, sd, eng = env
