@@ -536,12 +536,26 @@ def sample_kdiff_img2img(unet, init, noises, cond, uncond, sig_sched, log_sig, c
 
 
 # ------------------------------------------------------------------------------------------------ images / rng
-def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0) -> torch.Tensor:
-    """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k."""
+def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0, subseed: Optional[int] = None,
+                    subseed_strength: float = 0.0) -> torch.Tensor:
+    """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k; with variation
+    seeds (subseed_strength != 0) ImageRNG.first() returns slerp(strength, noise, subnoise(subseed + k))."""
     out = []
     for k in range(n):
         g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
-        out.append(torch.randn(shape, generator=g, dtype=torch.float32))
+        noise = torch.randn(shape, generator=g, dtype=torch.float32)
+        if subseed is not None and subseed_strength != 0:
+            sub = torch.randn(shape, generator=torch.Generator(device="cpu").manual_seed(int(subseed) + k), dtype=torch.float32)
+            # modules/rng.py slerp: unit vectors / angles along dim 1 of the [C, H, W] tensor
+            ln, hn = noise / torch.norm(noise, dim=1, keepdim=True), sub / torch.norm(sub, dim=1, keepdim=True)
+            dot = (ln * hn).sum(1)
+            if float(dot.mean()) > 0.9995:
+                noise = noise * subseed_strength + sub * (1 - subseed_strength)
+            else:
+                om = torch.acos(dot)
+                noise = (torch.sin((1.0 - subseed_strength) * om) / torch.sin(om)).unsqueeze(1) * noise + \
+                        (torch.sin(subseed_strength * om) / torch.sin(om)).unsqueeze(1) * sub
+        out.append(noise)
     return torch.stack(out)
 
 

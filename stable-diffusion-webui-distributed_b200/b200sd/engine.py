@@ -179,14 +179,32 @@ def resolve_sampler(name: str, scheduler: Optional[str] = None):
     return method, default
 
 
-def per_image_noise(seed: int, n: int, shape, draws: int = 1) -> torch.Tensor:
+def slerp(val: float, low: torch.Tensor, high: torch.Tensor) -> torch.Tensor:
+    """sdwui modules/rng.py slerp, applied to one image's [C, H, W] noise (norms and angles along dim 1, as upstream)"""
+    low_norm = low / torch.norm(low, dim=1, keepdim=True)
+    high_norm = high / torch.norm(high, dim=1, keepdim=True)
+    dot = (low_norm * high_norm).sum(1)
+    if float(dot.mean()) > 0.9995:
+        return low * val + high * (1 - val)
+    omega = torch.acos(dot)
+    so = torch.sin(omega)
+    return (torch.sin((1.0 - val) * omega) / so).unsqueeze(1) * low + (torch.sin(val * omega) / so).unsqueeze(1) * high
+
+
+def per_image_noise(seed: int, n: int, shape, draws: int = 1, subseed: Optional[int] = None,
+                    subseed_strength: float = 0.0) -> torch.Tensor:
     """sdwui ImageRNG with randn_source = 'CPU': image k owns torch.Generator('cpu').manual_seed(seed + k);
-    `draws` successive tensors per image (x_T, then ancestral noises).  Returns [draws, n, *shape] fp32 (host)."""
+    `draws` successive tensors per image (x_T, then ancestral noises).  Variation seeds (ImageRNG.first): with a
+    non-zero `subseed_strength` the FIRST draw is slerp(strength, noise(seed + k), noise(subseed + k)).
+    Returns [draws, n, *shape] fp32 (host)."""
     out = torch.empty((draws, n, *shape), dtype=torch.float32)
     for k in range(n):
         g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
         for d in range(draws):
             out[d, k] = torch.randn(shape, generator=g, dtype=torch.float32)
+        if subseed is not None and subseed_strength != 0:
+            sg = torch.Generator(device="cpu").manual_seed(int(subseed) + k)
+            out[0, k] = slerp(float(subseed_strength), out[0, k], torch.randn(shape, generator=sg, dtype=torch.float32))
     return out
 
 
@@ -256,6 +274,7 @@ class SDEngine:
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
         self.encoders: Dict[Tuple[int, int, int], VAEEncoderProgram] = {}
         self.interrupted = False
+        self.variation = (None, 0.0)   # (subseed, subseed_strength) of the request being served: sdwui variation seeds
         self._cap_stream = None
         self.last_unet_evals = 0
         self.graph_replayed_launches = 0   # b200sd kernels launched through graph replays (bench.py gpu_launches)
@@ -444,13 +463,13 @@ class SDEngine:
         b, _, h, w = init.shape
         method, sched = resolve_sampler(sampler, scheduler)
         if method == "ddim":
-            noise = per_image_noise(seed, b, (4, h, w))[0].to(self.device)
+            noise = per_image_noise(seed, b, (4, h, w), 1, *self.variation)[0].to(self.device)
             sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
             return self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows))
         sig, log_sig = kdiffusion_img2img_sigmas(steps, denoising_strength, sched)
         n_evals = len(sig) - 1
         draws = 1 + (n_evals if method == "euler_a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws)
+        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
         x0 = init + nz[0].to(self.device) * float(sig[0])
         return self.sample(cond, uncond, x0, n_evals, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
                            scheduler=scheduler, sigmas=(sig, log_sig))
@@ -470,7 +489,7 @@ class SDEngine:
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
         draws = 1 + (steps if sampler == "Euler a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws)
+        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
         lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
                           scheduler=scheduler)
         with self._ctx():
@@ -489,7 +508,7 @@ class SDEngine:
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
         draws = 1 + (steps if sampler == "Euler a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws)
+        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
         lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
                           scheduler=scheduler)
         return self.decode(lat, h, w)

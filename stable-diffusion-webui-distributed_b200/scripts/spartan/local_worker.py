@@ -169,6 +169,7 @@ class LocalGPUWorker(Worker):
             import random
             subseed = random.randrange(4294967294)
         cfg_scale = float(payload.get("cfg_scale", 7.0))
+        strength = float(payload.get("subseed_strength") or 0.0)
         vocab = eng.clip_cfg.vocab
         if "prompt_tokens" in payload:  # benchmark / tests hand pre-tokenised prompts through
             tok_all = torch.as_tensor(payload["prompt_tokens"]).long().reshape(-1, 77)
@@ -177,6 +178,8 @@ class LocalGPUWorker(Worker):
         neg_all = synthetic_tokens([negative] * batch, vocab)
         chunks = []
         for it in range(n_iter):
+            # variation seeds: image k of iteration `it` blends noise(seed + k) with noise(subseed + k)
+            eng.variation = (subseed + it * batch, strength) if strength != 0 else (None, 0.0)
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
             if init_u8 is not None:
                 u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,

@@ -177,6 +177,28 @@ def test_euler_on_the_api_schedulers(env, label, fn):
     assert float((z - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
 
 
+def test_variation_seeds(env):
+    """subseed / subseed_strength (sdwui ImageRNG.first): strength 0 leaves the noise alone, 1 gives the subseed's noise,
+    in between the spherical interpolation of the oracle; later draws (ancestral noise) are untouched"""
+    C, E, O, cfgs, sd, eng = env
+    shape = (4, 8, 8)
+    base = E.per_image_noise(10, 3, shape, 2)
+    assert torch.equal(E.per_image_noise(10, 3, shape, 2, 500, 0.0), base)
+    full = E.per_image_noise(10, 3, shape, 2, 500, 1.0)
+    assert torch.allclose(full[0], E.per_image_noise(500, 3, shape)[0], atol=1e-5) and torch.equal(full[1], base[1])
+    mid = E.per_image_noise(10, 3, shape, 2, 500, 0.3)
+    assert torch.allclose(mid[0], O.per_image_noise(10, 3, shape, subseed=500, subseed_strength=0.3), atol=1e-6)
+    assert not torch.allclose(mid[0], base[0]) and torch.equal(mid[1], base[1])
+    # through the request path: the engine's variation attribute changes the start noise only when set
+    tok, neg = O.random_prompt_tokens(2, vocab_hi=997), O.empty_prompt_tokens(2, vocab_hi=997)
+    a = eng.txt2img(tok, neg, seed=5, steps=3, cfg_scale=7.0, height=64, width=64, sampler="DDIM").clone()
+    eng.variation = (900, 0.5)
+    b = eng.txt2img(tok, neg, seed=5, steps=3, cfg_scale=7.0, height=64, width=64, sampler="DDIM").clone()
+    eng.variation = (None, 0.0)
+    c = eng.txt2img(tok, neg, seed=5, steps=3, cfg_scale=7.0, height=64, width=64, sampler="DDIM")
+    assert torch.equal(a, c) and not torch.equal(a, b)
+
+
 def test_sampler_names_resolve(env):
     C, E, O, cfgs, sd, eng = env
     assert E.resolve_sampler("DPM++ 2M") == ("dpmpp_2m", "karras") == E.resolve_sampler("DPM++ 2M Karras")
