@@ -196,7 +196,7 @@ def main():
             r = cpu_reference_arm(n_evals, threads, unet_reps=1)
             best = r if best is None or r["value"] > best["value"] else best
         line = {"impl": "reference", "metric": "images/sec SD1.5 512x512 txt2img", "value": best["value"],
-                "unit": "images/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "unit": "images/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": best["sec_per_image"] * 1000.0, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
