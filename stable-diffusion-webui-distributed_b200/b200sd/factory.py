@@ -57,7 +57,38 @@ def default_engine_factory(device: str, size: str = None) -> SDEngine:
     return eng
 
 
+_TOKENIZER = {}
+
+
+def _clip_tokenizer():
+    """transformers.CLIPTokenizer over a LOCAL directory (SD_TOKENIZER=/path with vocab.json + merges.txt — the files of
+    openai/clip-vit-large-patch14, which cannot be fetched offline), or None."""
+    path = os.environ.get("SD_TOKENIZER")
+    if not path:
+        return None
+    if path not in _TOKENIZER:
+        from transformers import CLIPTokenizer
+        _TOKENIZER[path] = CLIPTokenizer(os.path.join(path, "vocab.json"), os.path.join(path, "merges.txt"))
+    return _TOKENIZER[path]
+
+
 def synthetic_tokens(prompts: List[str], vocab: int, ctx: int = 77) -> torch.Tensor:
+    tok = _clip_tokenizer()
+    if tok is not None:
+        # the real BPE ids, padded with the end-of-text token like sdwui's FrozenCLIPEmbedderWithCustomWords (plain
+        # prompts up to 75 tokens; emphasis syntax, BREAK and >75-token chunking are not interpreted)
+        ids = tok(list(prompts), padding="max_length", max_length=ctx, truncation=True, return_tensors="pt").input_ids.long()
+        eos = tok.eos_token_id
+        first_eos = (ids == eos).float().argmax(dim=1)
+        for i in range(ids.shape[0]):
+            ids[i, int(first_eos[i]):] = eos
+        if int(ids.max()) >= vocab:
+            raise ValueError("the tokenizer's ids do not fit the text encoder's vocabulary")
+        return ids
+    return _hashed_tokens(prompts, vocab, ctx)
+
+
+def _hashed_tokens(prompts: List[str], vocab: int, ctx: int = 77) -> torch.Tensor:
     """Deterministic stand-in for the CLIP BPE tokenizer (its vocabulary files are not available offline):
     [BOS] + one id per whitespace-separated word (crc32 mod vocab-3) + [EOS] padding, length 77."""
     bos, eos = vocab - 2, vocab - 1

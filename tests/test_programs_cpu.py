@@ -199,6 +199,25 @@ def test_variation_seeds(env):
     assert torch.equal(a, c) and not torch.equal(a, b)
 
 
+def test_prompts_use_a_local_clip_tokenizer_when_given(env, tmp_path, monkeypatch):
+    """SD_TOKENIZER=<dir with vocab.json + merges.txt> switches the worker from hashed word ids to real BPE ids"""
+    pytest.importorskip("transformers")
+    import json
+    from b200sd import factory
+    vocab = {"<|startoftext|>": 0, "<|endoftext|>": 1}
+    for i, ch in enumerate("abcdefghijklmnopqrstuvwxyz"):
+        vocab[ch], vocab[ch + "</w>"] = 2 + 2 * i, 3 + 2 * i
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n")
+    hashed = factory.synthetic_tokens(["ab c", ""], 997)
+    assert hashed.shape == (2, 77) and int(hashed[0, 0]) == 995 and int(hashed[1, 1]) == 996
+    monkeypatch.setenv("SD_TOKENIZER", str(tmp_path))
+    ids = factory.synthetic_tokens(["ab c", ""], 997)
+    assert ids.shape == (2, 77) and ids[0, :6].tolist() == [0, 2, 5, 7, 1, 1] and ids[1, :3].tolist() == [0, 1, 1]
+    with pytest.raises(ValueError):
+        factory.synthetic_tokens(["z"], 40)
+
+
 def test_sampler_names_resolve(env):
     C, E, O, cfgs, sd, eng = env
     assert E.resolve_sampler("DPM++ 2M") == ("dpmpp_2m", "karras") == E.resolve_sampler("DPM++ 2M Karras")
