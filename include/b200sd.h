@@ -144,6 +144,11 @@ int b200sd_unpack_latent(const void* moments, long long pitch, float* x, int B, 
  * (torch.nn.functional.interpolate(mode="bilinear") in sdwui StableDiffusionProcessingTxt2Img.sample_hr_pass) */
 int b200sd_resize_latent_bilinear(const float* x, float* y, int B, int H, int W, int Ho, int Wo, void* stream);
 
+/* inpainting: x[b,p,:] = x[b,p,:] * latmask[p] + init[b,p,:] * (1 - latmask[p]) on fp32 NHWC latents [B,HW,4]; latmask [HW]
+ * is the request's latent-resolution mask (1 = repaint).  (sdwui CFGDenoiser.apply_blend, before every model call of the
+ * timestep samplers, and once more after sampling) */
+int b200sd_blend_latent(float* x, const float* init, const float* latmask, int B, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

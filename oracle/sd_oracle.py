@@ -670,3 +670,67 @@ def img2img(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, 
         x = c_sap * x0 + c_s1ap * e
     dec = vae_decode(dsd, vae_cfg, x / vae_cfg.scale_factor)
     return to_uint8(dec), x, init
+
+
+# ------------------------------------------------------------------------------------------------ inpainting
+def inpaint_masks(mask_img, width: int, height: int, lat_h: int, lat_w: int, mask_blur: int = 4, invert: bool = False):
+    """sdwui StableDiffusionProcessingImg2Img.init, "whole picture" branch (inpaint_full_res False), mask_round True:
+    binary mask -> optional invert -> cv2.GaussianBlur along x then y (kernel 2*int(2.5*blur+0.5)+1, sigma = blur) ->
+    resize to the image -> overlay mask = clip(2 * mask, 0, 255); latent mask = round(bicubic resize of the mask / 255).
+    Returns (latmask [lat_h, lat_w] float tensor, overlay mask 'L' PIL image)."""
+    import cv2
+    import numpy as np
+    from PIL import Image, ImageOps
+    if mask_img.mode == "RGBA" and mask_img.getextrema()[-1] != (255, 255):
+        m = mask_img.split()[-1].convert("L").point(lambda v: 255 if v > 128 else 0)
+    else:
+        m = mask_img.convert("L")
+    if invert:
+        m = ImageOps.invert(m)
+    if mask_blur > 0:
+        ksize = 2 * int(2.5 * mask_blur + 0.5) + 1
+        a = cv2.GaussianBlur(np.array(m), (ksize, 1), mask_blur)
+        m = Image.fromarray(cv2.GaussianBlur(a, (1, ksize), mask_blur))
+    if m.size != (width, height):
+        m = m.resize((width, height), resample=Image.LANCZOS)
+    overlay = Image.fromarray(np.clip(np.array(m).astype(np.float32) * 2, 0, 255).astype(np.uint8))
+    lat = np.array(m.convert("RGB").resize((lat_w, lat_h)), dtype=np.float32)[..., 0] / 255.0
+    return torch.from_numpy(np.around(lat)), overlay
+
+
+def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, init_u8: torch.Tensor, mask_img,
+                    denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, mask_blur: int = 4,
+                    invert: bool = False):
+    """DDIM inpainting as sdwui runs it (CFGDenoiserTimesteps.mask_before_denoising): before EVERY model call the region
+    to keep is replaced by the clean init latent, x = x * nmask + init * mask; once more after sampling; decode; then
+    apply_overlay pastes the original pixels back through the blurred mask.  Returns (uint8 images, final latents)."""
+    import numpy as np
+    from PIL import Image, ImageOps
+    b, hh, ww = tokens.shape[0], init_u8.shape[1], init_u8.shape[2]
+    cond = clip_text_encode(sd, clip_cfg, tokens)
+    uncond = clip_text_encode(sd, clip_cfg, neg_tokens)
+    init = vae_encode_mean(sd, vae_cfg, image_to_model_input(init_u8)) * vae_cfg.scale_factor
+    latmask, overlay_mask = inpaint_masks(mask_img, ww, hh, init.shape[2], init.shape[3], mask_blur, invert)
+    nmask = latmask[None, None].to(init.dtype)
+    mask = 1.0 - nmask
+    noise = per_image_noise(seed, b, tuple(init.shape[1:]))
+    sa, s1a, rows = ddim_img2img_coefficients(steps, denoising_strength)
+    x = init * sa + noise * s1a
+    for (t, c_sa, c_s1a, c_sap, c_s1ap) in rows:
+        x = x * nmask + init * mask
+        e = cfg_eps(lambda a, tt, c: unet_forward(sd, unet_cfg, a, tt, c), x, t, cond, uncond, cfg_scale)
+        x0 = (x - c_s1a * e) / c_sa
+        x = c_sap * x0 + c_s1ap * e
+    x = x * nmask + init * mask
+    gen = to_uint8(vae_decode(sd, vae_cfg, x / vae_cfg.scale_factor))
+    out = torch.empty_like(gen)
+    inv = ImageOps.invert(overlay_mask.convert("L"))
+    for k in range(b):
+        image = Image.fromarray(init_u8[k].numpy(), "RGB")
+        masked = Image.new("RGBa", (image.width, image.height))
+        masked.paste(image.convert("RGBA").convert("RGBa"), mask=inv)
+        img = Image.fromarray(gen[k].numpy(), "RGB").convert("RGBA")
+        img.alpha_composite(masked.convert("RGBA"))
+        out[k] = torch.from_numpy(np.array(img.convert("RGB")))
+    return out, x
+

@@ -276,6 +276,18 @@ __global__ void unpack_latent_kernel(const void* m, long long pitch, float4* x, 
 
 // bilinear resize of NHWC fp32 latents [B, H*W, 4] -> [B, Ho*Wo, 4], half-pixel centres (align_corners = False), no
 // antialiasing: torch.nn.functional.interpolate(mode="bilinear") as sdwui's "Latent" hires upscaler calls it
+// inpainting: x = x * latmask + init * (1 - latmask), latmask [HW] shared by the channels and the images of the request
+// (sdwui CFGDenoiser.apply_blend: current * nmask + init_latent * mask)
+__global__ void blend_latent_kernel(float4* __restrict__ x, const float4* __restrict__ init, const float* __restrict__ latmask,
+                                    int B, int HW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const float m = latmask[i % HW];
+  const float4 xv = x[i], iv = init[i];
+  x[i] = make_float4(xv.x * m + iv.x * (1.f - m), xv.y * m + iv.y * (1.f - m), xv.z * m + iv.z * (1.f - m),
+                     xv.w * m + iv.w * (1.f - m));
+}
+
 __global__ void resize_latent_bilinear_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H, int W,
                                               int Ho, int Wo) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -449,6 +461,15 @@ extern "C" int b200sd_quantize_u8(const void* img, long long pitch, unsigned cha
   const int blocks = static_cast<int>((n + 255) / 256);
   if (dtype == B200SD_BF16) quantize_u8_kernel<true><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
   else quantize_u8_kernel<false><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_blend_latent(float* x, const float* init, const float* latmask, int B, int HW, void* stream) {
+  if (B <= 0 || HW <= 0) return B200SD_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(init)) & 15) return B200SD_ERR_INVALID;
+  const long long n = static_cast<long long>(B) * HW;
+  blend_latent_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(init), latmask, B, HW);
   RET_LAUNCH();
 }
 

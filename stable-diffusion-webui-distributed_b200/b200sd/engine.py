@@ -224,6 +224,8 @@ class Plan:
         self.table = torch.zeros((MAX_STEPS, eng.unet_w.emb_total), device=dev, dtype=torch.float32)
         self.coef8 = torch.zeros((MAX_STEPS, 8), device=dev, dtype=torch.float32)   # DPM++ 2M rows
         self.old = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)        # its previous x0 prediction
+        self.init = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)     # inpainting: clean init latents
+        self.latmask = torch.ones((h * w,), device=dev, dtype=torch.float32)        # ... and the latent mask (1 = repaint)
         self.noise = None
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[str, int] = {}
@@ -233,6 +235,13 @@ class Plan:
         ops.select_step(self.table, self.step, self.unet.cur_bias)
         self.unet.run()
         ops.cfg_ddim_step(self.unet.eps, self.x, self.unet.xin, cfg_scale, self.coef, self.step)
+
+    def step_ddim_masked(self, cfg_scale: float):
+        """inpainting (sdwui CFGDenoiserTimesteps, mask_before_denoising): the kept region of x is replaced by the clean
+        init latent before every model call"""
+        ops.blend_latent(self.x, self.init, self.latmask)
+        ops.pack_unet_input(self.x, self.unet.xin, 1.0)
+        self.step_ddim(cfg_scale)
 
     def step_euler_a(self, cfg_scale: float):
         ops.select_step(self.table, self.step, self.unet.cur_bias)
@@ -333,7 +342,7 @@ class SDEngine:
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
                sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None,
-               scheduler: Optional[str] = None, sigmas=None) -> torch.Tensor:
+               scheduler: Optional[str] = None, sigmas=None, inpaint=None) -> torch.Tensor:
         """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device): the start latents.
         `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way); `sigmas` =
         (sigma table ending in 0, model log-sigmas) does the same for the k-diffusion samplers, and x_T is then the
@@ -343,10 +352,16 @@ class SDEngine:
         with self._ctx():
             plan = self.plan(b, h, w)
             plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
+            graph_name = f"{sampler}:{cfg_scale}"
             if sampler == "DDIM":
                 ts, rows = schedule if schedule is not None else ddim_plan(steps)
                 scale0, in0 = 1.0, 1.0
                 step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
+                if inpaint is not None:   # (clean init latents [b, 4, h, w], latent mask [h * w])
+                    plan.init.copy_(inpaint[0].to(self.device, torch.float32).permute(0, 2, 3, 1).reshape(b, h * w, 4))
+                    plan.latmask.copy_(inpaint[1].to(self.device, torch.float32).reshape(-1))
+                    step_fn = lambda: plan.step_ddim_masked(cfg_scale)  # noqa: E731
+                    graph_name += ":mask"
             elif sampler == "Euler a":
                 ts, rows, sigma0 = euler_a_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
                 scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
@@ -372,17 +387,21 @@ class SDEngine:
             plan.x.copy_((x_T.to(self.device, torch.float32) * scale0).permute(0, 2, 3, 1).reshape(b, h * w, 4))
             plan.step.zero_()
             ops.pack_unet_input(plan.x, plan.unet.xin, in0)
-            g = self._graph(plan, f"{sampler}:{cfg_scale}", step_fn)
+            if inpaint is not None and sampler != "DDIM":
+                raise ValueError("inpainting masks are implemented for the DDIM sampler only")
+            g = self._graph(plan, graph_name, step_fn)
             self.last_unet_evals = 0
             for _ in range(n_evals):
                 if self.interrupted:
                     break
                 if g is not None:
                     g.replay()
-                    self.graph_replayed_launches += plan.graph_launches[f"{sampler}:{cfg_scale}"]
+                    self.graph_replayed_launches += plan.graph_launches[graph_name]
                 else:
                     step_fn()
                 self.last_unet_evals += 1
+            if inpaint is not None:   # processing.py sample(): samples * nmask + init_latent * mask
+                ops.blend_latent(plan.x, plan.init, plan.latmask)
             return plan.x
 
     @torch.no_grad()
@@ -444,19 +463,22 @@ class SDEngine:
     @torch.no_grad()
     def img2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, init_u8: torch.Tensor,
                 denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, sampler: str = "DDIM",
-                scheduler: Optional[str] = None) -> torch.Tensor:
+                scheduler: Optional[str] = None, latmask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """img2img: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining part of the
-        sampler's schedule, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device."""
+        sampler's schedule, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device.
+        `latmask` fp32 [h * w] (b200sd.inpaint.prepare_mask): inpainting — the region with latmask 0 keeps the init
+        latents at every step (DDIM only); the caller composites the original pixels back (inpaint.apply_overlays)."""
         b = tokens.shape[0]
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
         init = self.encode(init_u8)
         _, _, h, w = init.shape
-        lat = self._sample_from(init, cond, uncond, seed, denoising_strength, steps, cfg_scale, sampler, scheduler)
+        lat = self._sample_from(init, cond, uncond, seed, denoising_strength, steps, cfg_scale, sampler, scheduler,
+                                inpaint=None if latmask is None else (init, latmask))
         return self.decode(lat, h, w)
 
     def _sample_from(self, init: torch.Tensor, cond, uncond, seed: int, denoising_strength: float, steps: int,
-                     cfg_scale: float, sampler: str, scheduler: Optional[str]) -> torch.Tensor:
+                     cfg_scale: float, sampler: str, scheduler: Optional[str], inpaint=None) -> torch.Tensor:
         """the img2img half of a sampler (also the second pass of the hires fix): `init` [b, 4, h, w] latents on the device,
         fresh per-image noise from `seed`, start at the noise level of t_enc.
         DDIM: sdwui sd_samplers_timesteps.sample_img2img; k-diffusion samplers: KDiffusionSampler.sample_img2img."""
@@ -465,7 +487,10 @@ class SDEngine:
         if method == "ddim":
             noise = per_image_noise(seed, b, (4, h, w), 1, *self.variation)[0].to(self.device)
             sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
-            return self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows))
+            return self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows),
+                               inpaint=inpaint)
+        if inpaint is not None:
+            raise ValueError("inpainting masks are implemented for the DDIM sampler only")
         sig, log_sig = kdiffusion_img2img_sigmas(steps, denoising_strength, sched)
         n_evals = len(sig) - 1
         draws = 1 + (n_evals if method == "euler_a" else 0)

@@ -315,6 +315,17 @@ def quantize_u8(img: torch.Tensor, out: torch.Tensor):
     return out
 
 
+def blend_latent(x: torch.Tensor, init: torch.Tensor, latmask: torch.Tensor):
+    """x, init fp32 [B, HW, 4]; latmask fp32 [HW]: x = x * latmask + init * (1 - latmask), in place"""
+    b, hw, _ = x.shape
+    assert x.dtype == init.dtype == latmask.dtype == torch.float32 and x.is_contiguous() and init.is_contiguous()
+    assert init.shape == x.shape and latmask.shape == (hw,) and latmask.is_contiguous()
+    rc = _lib.lib().b200sd_blend_latent(_p(x), _p(init), _p(latmask), b, hw, _stream())
+    check(rc, "b200sd_blend_latent")
+    _count()
+    return x
+
+
 def resize_latent_bilinear(x: torch.Tensor, y: torch.Tensor, h: int, w: int, ho: int, wo: int):
     """x fp32 [B, h*w, 4] -> y fp32 [B, ho*wo, 4] (F.interpolate bilinear, align_corners=False, no antialias)"""
     b = x.shape[0]

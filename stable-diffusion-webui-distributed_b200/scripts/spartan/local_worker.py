@@ -153,10 +153,31 @@ class LocalGPUWorker(Worker):
                     logger.warning(f"scheduler '{scheduler}' is not implemented on worker {self.label}: using the sampler's default")
                 scheduler = None
         init_u8 = None
+        inpaint = None
         if payload.get("init_images"):
-            if payload.get("image_mask") is not None or payload.get("mask") is not None:
-                raise NotImplementedError("inpainting masks are not implemented on the local executor")
             init_u8 = self._init_images_u8(payload["init_images"], batch, width, height)
+            mask_img = payload.get("image_mask") if payload.get("image_mask") is not None else payload.get("mask")
+            if mask_img is not None:
+                # inpainting (reference worker.py:365-373 sends `image_mask` as the API's `mask`): whole-picture mode with
+                # the original content under the mask; the other modes fall back to it with a warning
+                from b200sd import inpaint as inp
+                from PIL import Image
+                if isinstance(mask_img, str):
+                    data = mask_img.split(",", 1)[1] if mask_img.startswith("data:") else mask_img
+                    mask_img = Image.open(io.BytesIO(base64.b64decode(data)))
+                if int(payload.get("inpainting_fill", 1) or 0) != 1:
+                    logger.warning(f"inpainting_fill={payload.get('inpainting_fill')} is not implemented on worker {self.label}: using 'original'")
+                if payload.get("inpaint_full_res") not in (None, False, 0):
+                    logger.warning(f"'only masked' inpainting is not implemented on worker {self.label}: inpainting the whole picture")
+                if sampler != "DDIM":
+                    logger.warning(f"inpainting on worker {self.label} runs DDIM ('{sampler}' with a mask is not implemented)")
+                    sampler = "DDIM"
+                down = 2 ** (len(eng.vae_cfg.ch_mult) - 1)   # 8 for the kl-f8 autoencoder
+                blur = payload.get("mask_blur")
+                inpaint = inp.prepare_mask(mask_img, width, height, height // down, width // down,
+                                           mask_blur=4 if blur is None else int(blur),
+                                           invert=bool(payload.get("inpainting_mask_invert") or 0))
+                inpaint_overlays = inp.overlays_for(init_u8, inpaint)
         denoise = float(payload.get("denoising_strength", 0.75) or 0.75)
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
@@ -182,8 +203,9 @@ class LocalGPUWorker(Worker):
             eng.variation = (subseed + it * batch, strength) if strength != 0 else (None, 0.0)
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
             if init_u8 is not None:
+                kw = {} if inpaint is None else {"latmask": inpaint.latmask}
                 u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
-                                 cfg_scale=cfg_scale, sampler=sampler, scheduler=scheduler)
+                                 cfg_scale=cfg_scale, sampler=sampler, scheduler=scheduler, **kw)
             elif payload.get("enable_hr"):
                 # hires fix (reference eta_hr, worker.py:205): second pass at hr_scale x with the "Latent" upscaler
                 upscaler = payload.get("hr_upscaler") or "Latent"
@@ -211,6 +233,9 @@ class LocalGPUWorker(Worker):
                 torch.cuda.current_stream().synchronize()
         else:  # an engine double in the host-logic tests; the real engine refuses non-CUDA devices
             host = images.to(torch.uint8).contiguous()
+        if inpaint is not None:   # sdwui apply_overlay: the original pixels come back through the blurred mask
+            from b200sd import inpaint as inp
+            host = inp.apply_overlays(host, inpaint_overlays)
         n = host.shape[0]
         seeds = [seed + i for i in range(n)]
         subseeds = [subseed + i for i in range(n)]

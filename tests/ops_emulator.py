@@ -197,6 +197,12 @@ def unpack_latent(moments, x, scale):
     return x
 
 
+def blend_latent(x, init, latmask):
+    m = latmask[None, :, None]
+    x.copy_(x * m + init * (1.0 - m))
+    return x
+
+
 def resize_latent_bilinear(x, y, h, w, ho, wo):
     b = x.shape[0]
     t = F.interpolate(x.reshape(b, h, w, 4).permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", antialias=False)
@@ -204,7 +210,7 @@ def resize_latent_bilinear(x, y, h, w, ho, wo):
     return y
 
 
-ALL = ["resize_latent_bilinear", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
+ALL = ["resize_latent_bilinear", "blend_latent", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
        "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step", "cfg_dpmpp_2m_step",
        "quantize_u8", "image_to_nhwc", "unpack_latent"]
 

@@ -457,6 +457,22 @@ def test_quantize_u8(ops):
 
 
 
+def test_blend_latent(ops):
+    """inpainting blend: x = x * latmask + init * (1 - latmask), mask shared by channels and images, in place"""
+    g = _gen(5)
+    b, hw = 3, 1000
+    x = torch.randn((b, hw, 4), generator=g, device="cuda")
+    init = torch.randn((b, hw, 4), generator=g, device="cuda")
+    m = (torch.rand((hw,), generator=g, device="cuda") > 0.5).float()
+    m[::7] = 0.25
+    ref = x * m[None, :, None] + init * (1 - m[None, :, None])
+    ops.blend_latent(x, init, m)
+    torch.cuda.synchronize()
+    assert torch.allclose(x, ref, rtol=0, atol=1e-6)
+    keep = (m == 0)[None, :, None].expand_as(x)
+    assert torch.equal(x[keep], init[keep])
+
+
 def test_resize_latent_bilinear(ops):
     """F.interpolate(mode="bilinear", antialias=False) on NHWC fp32 latents, integer and fractional scales"""
     g = _gen(77)

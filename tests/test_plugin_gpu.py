@@ -127,6 +127,40 @@ def test_worker_img2img_request(env):
     assert torch.equal(r["tensors"], direct)  # two runs of the same request are bit-identical (deterministic kernels)
 
 
+def test_worker_inpainting_request(env):
+    """img2img with a mask as the reference forwards it (`image_mask` in p.__dict__ -> API field `mask`,
+    worker.py:365-373, 406-410): mask pipeline + per-step latent blend + overlay; equals the direct engine call"""
+    processing, mscripts, DistributedScript, eng, State, sh = env
+    w, wk = _fresh_world(DistributedScript, lambda d: eng)
+    from PIL import Image, ImageDraw
+    from b200sd import inpaint as inp
+    from b200sd.factory import synthetic_tokens
+    g = torch.Generator().manual_seed(6)
+    arr = torch.randint(0, 256, (64, 64, 3), generator=g, dtype=torch.uint8)
+    mask = Image.new("L", (64, 64), 0)
+    ImageDraw.Draw(mask).rectangle((16, 20, 47, 50), fill=255)
+    payload = {"prompt": "a b", "negative_prompt": "", "seed": 12, "subseed": 1, "subseed_strength": 0, "batch_size": 2,
+               "n_iter": 1, "steps": 8, "width": 64, "height": 64, "sampler_name": "DDIM", "cfg_scale": 7.0,
+               "denoising_strength": 0.75, "init_images": [Image.fromarray(arr.numpy())], "image_mask": mask, "mask_blur": 2,
+               "inpainting_fill": 1, "inpaint_full_res": False, "inpainting_mask_invert": 0}
+    wk.request(dict(payload), None, False)
+    r = wk.response
+    assert r is not None and tuple(r["tensors"].shape) == (2, 64, 64, 3) and wk.state == State.IDLE
+    vocab = eng.clip_cfg.vocab
+    init = arr[None].expand(2, -1, -1, -1).contiguous()
+    down = 2 ** (len(eng.vae_cfg.ch_mult) - 1)
+    m = inp.prepare_mask(mask, 64, 64, 64 // down, 64 // down, mask_blur=2)
+    direct = eng.img2img(synthetic_tokens(["a b"] * 2, vocab), synthetic_tokens([""] * 2, vocab), 12, init, 0.75, steps=8,
+                         cfg_scale=7.0, latmask=m.latmask).cpu()
+    direct = inp.apply_overlays(direct, inp.overlays_for(init, m))
+    assert torch.equal(r["tensors"], direct)
+    # outside the (blurred) mask the request returns the init image
+    assert torch.equal(r["tensors"][:, :4], init[:, :4])
+    plain = eng.img2img(synthetic_tokens(["a b"] * 2, vocab), synthetic_tokens([""] * 2, vocab), 12, init, 0.75, steps=8,
+                        cfg_scale=7.0).cpu()
+    assert not torch.equal(plain[:, :4], init[:, :4])
+
+
 def test_rest_worker_serves_the_executor(env):
     """SURVEY §8 f1 on a GPU: POST /sdapi/v1/txt2img -> LocalGPUWorker -> SDEngine; the PNGs decode to exactly the images
     a direct engine call produces (PNG is lossless, the kernels are deterministic)."""

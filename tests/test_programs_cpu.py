@@ -305,6 +305,42 @@ def test_hires_fix_on_a_kdiffusion_sampler(env):
     assert float((dd <= 1).float().mean()) == 1.0 and float((dd == 0).float().mean()) > 0.99
 
 
+@pytest.mark.parametrize("blur,invert", [(4, False), (0, True)])
+def test_inpainting_matches_oracle(env, blur, invert):
+    """img2img with a mask: mask pipeline on the host, the kept region forced back to the init latents
+    before every DDIM evaluation and after the last one, original pixels composited back through the blurred mask"""
+    from PIL import Image, ImageDraw
+    from b200sd import inpaint as inp
+    C, E, O, cfgs, sd, eng = env
+    b, size, steps = 2, 32, 8
+    g = torch.Generator().manual_seed(77)
+    init = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    mask_img = Image.new("L", (size, size), 0)
+    ImageDraw.Draw(mask_img).ellipse((6, 8, 24, 26), fill=255)
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    with torch.no_grad():
+        ref_u8, ref_x = O.img2img_inpaint(sd, *cfgs, tok, neg, 4242, init, mask_img, 0.75, steps=steps, mask_blur=blur,
+                                          invert=invert)
+    down = 2 ** (len(cfgs[1].ch_mult) - 1)
+    m = inp.prepare_mask(mask_img, size, size, size // down, size // down, mask_blur=blur, invert=invert)
+    assert m.latmask.shape == ((size // down) ** 2,) and 0 < float(m.latmask.mean()) < 1
+    assert set(m.latmask.unique().tolist()) <= {0.0, 1.0}
+    got = eng.img2img(tok, neg, 4242, init, 0.75, steps=steps, cfg_scale=7.0, latmask=m.latmask)
+    h = size // down
+    z = eng.plan(b, h, h).x.reshape(b, h, h, 4).permute(0, 3, 1, 2)
+    assert float((z - ref_x).abs().max()) <= 1e-3 * float(ref_x.abs().max())
+    # the kept region carries the init latents exactly
+    lat0 = eng.encode(init)
+    keep = (m.latmask.reshape(h, h) == 0)[None, None].expand_as(z)
+    assert torch.equal(z[keep], lat0[keep])
+    final = inp.apply_overlays(got.cpu(), inp.overlays_for(init, m))
+    d = (final.int() - ref_u8.int()).abs()
+    assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
+    with pytest.raises(ValueError):
+        eng.img2img(tok, neg, 1, init, 0.75, steps=steps, cfg_scale=7.0, sampler="Euler", latmask=m.latmask)
+
+
 def test_img2img_matches_oracle(env):
     """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
     C, E, O, cfgs, sd, eng = env
