@@ -700,7 +700,7 @@ def inpaint_masks(mask_img, width: int, height: int, lat_h: int, lat_w: int, mas
 
 def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, init_u8: torch.Tensor, mask_img,
                     denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, mask_blur: int = 4,
-                    invert: bool = False):
+                    invert: bool = False, inpainting_fill: int = 1):
     """DDIM inpainting as sdwui runs it (CFGDenoiserTimesteps.mask_before_denoising): before EVERY model call the region
     to keep is replaced by the clean init latent, x = x * nmask + init * mask; once more after sampling; decode; then
     apply_overlay pastes the original pixels back through the blurred mask.  Returns (uint8 images, final latents)."""
@@ -709,11 +709,38 @@ def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, see
     b, hh, ww = tokens.shape[0], init_u8.shape[1], init_u8.shape[2]
     cond = clip_text_encode(sd, clip_cfg, tokens)
     uncond = clip_text_encode(sd, clip_cfg, neg_tokens)
-    init = vae_encode_mean(sd, vae_cfg, image_to_model_input(init_u8)) * vae_cfg.scale_factor
+    enc_in = init_u8
+    if inpainting_fill == 0:   # modules/masking.py fill(): cascade of blurs of the surroundings, with the BLURRED mask
+        from PIL import ImageFilter
+        import cv2
+        m = mask_img.convert("L") if not (mask_img.mode == "RGBA" and mask_img.getextrema()[-1] != (255, 255)) else \
+            mask_img.split()[-1].convert("L").point(lambda v: 255 if v > 128 else 0)
+        if invert:
+            m = ImageOps.invert(m)
+        if mask_blur > 0:
+            ksize = 2 * int(2.5 * mask_blur + 0.5) + 1
+            m = Image.fromarray(cv2.GaussianBlur(cv2.GaussianBlur(np.array(m), (ksize, 1), mask_blur), (1, ksize), mask_blur))
+        filled = []
+        for k in range(b):
+            image = Image.fromarray(init_u8[k].numpy(), "RGB")
+            mod = Image.new("RGBA", image.size)
+            masked = Image.new("RGBa", image.size)
+            masked.paste(image.convert("RGBA").convert("RGBa"), mask=ImageOps.invert(m))
+            for radius, repeats in [(256, 1), (64, 1), (16, 2), (4, 4), (2, 2), (0, 1)]:
+                blurred = masked.filter(ImageFilter.GaussianBlur(radius)).convert("RGBA")
+                for _ in range(repeats):
+                    mod.alpha_composite(blurred)
+            filled.append(torch.from_numpy(np.array(mod.convert("RGB"))))
+        enc_in = torch.stack(filled)
+    init = vae_encode_mean(sd, vae_cfg, image_to_model_input(enc_in)) * vae_cfg.scale_factor
     latmask, overlay_mask = inpaint_masks(mask_img, ww, hh, init.shape[2], init.shape[3], mask_blur, invert)
     nmask = latmask[None, None].to(init.dtype)
     mask = 1.0 - nmask
     noise = per_image_noise(seed, b, tuple(init.shape[1:]))
+    if inpainting_fill == 2:     # "latent noise"
+        init = init * mask + noise * nmask
+    elif inpainting_fill == 3:   # "latent nothing"
+        init = init * mask
     sa, s1a, rows = ddim_img2img_coefficients(steps, denoising_strength)
     x = init * sa + noise * s1a
     for (t, c_sa, c_s1a, c_sap, c_s1ap) in rows:

@@ -463,16 +463,25 @@ class SDEngine:
     @torch.no_grad()
     def img2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, init_u8: torch.Tensor,
                 denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, sampler: str = "DDIM",
-                scheduler: Optional[str] = None, latmask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                scheduler: Optional[str] = None, latmask: Optional[torch.Tensor] = None,
+                inpainting_fill: int = 1) -> torch.Tensor:
         """img2img: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining part of the
         sampler's schedule, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device.
         `latmask` fp32 [h * w] (b200sd.inpaint.prepare_mask): inpainting — the region with latmask 0 keeps the init
-        latents at every step (DDIM only); the caller composites the original pixels back (inpaint.apply_overlays)."""
+        latents at every step (DDIM only); the caller composites the original pixels back (inpaint.apply_overlays).
+        `inpainting_fill` 2 ("latent noise") / 3 ("latent nothing") replace the repainted region of the init latents by
+        the request's start noise / by zeros first (sdwui Img2Img.init); 0 ("fill") is image-space work the caller does
+        before the call (inpaint.fill_masked), 1 keeps the original content."""
         b = tokens.shape[0]
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
         init = self.encode(init_u8)
         _, _, h, w = init.shape
+        if latmask is not None and inpainting_fill in (2, 3):
+            nm = latmask.to(self.device, torch.float32).reshape(1, 1, h, w)
+            init = init * (1.0 - nm)
+            if inpainting_fill == 2:   # create_random_tensors(shape, seeds): the same first draw the sampler starts from
+                init = init + per_image_noise(seed, b, (4, h, w), 1, *self.variation)[0].to(self.device) * nm
         lat = self._sample_from(init, cond, uncond, seed, denoising_strength, steps, cfg_scale, sampler, scheduler,
                                 inpaint=None if latmask is None else (init, latmask))
         return self.decode(lat, h, w)

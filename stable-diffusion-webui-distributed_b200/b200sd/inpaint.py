@@ -11,7 +11,7 @@ from typing import List, Optional
 
 import numpy as np
 import torch
-from PIL import Image, ImageOps
+from PIL import Image, ImageFilter, ImageOps
 
 
 @dataclass
@@ -20,6 +20,7 @@ class InpaintMask:
     overlay_mask: Image.Image      # 'L', image resolution: where the ORIGINAL pixels are pasted back (inverted alpha)
     width: int
     height: int
+    fill_mask: Optional[Image.Image] = None   # 'L', image resolution: the blurred mask itself (inpainting_fill 0)
 
 
 def create_binary_mask(image: Image.Image, round_mask: bool = True) -> Image.Image:
@@ -48,7 +49,26 @@ def prepare_mask(mask: Image.Image, width: int, height: int, lat_h: int, lat_w: 
     latmask = np.moveaxis(np.array(lat, dtype=np.float32), 2, 0)[0] / 255.0
     if round_mask:
         latmask = np.around(latmask)
-    return InpaintMask(torch.from_numpy(np.ascontiguousarray(latmask, dtype=np.float32)).reshape(-1), overlay, width, height)
+    return InpaintMask(torch.from_numpy(np.ascontiguousarray(latmask, dtype=np.float32)).reshape(-1), overlay, width, height, m)
+
+
+def fill_masked(init_images_u8: torch.Tensor, mask: InpaintMask) -> torch.Tensor:
+    """inpainting_fill = 0 ("fill", sdwui modules/masking.py fill): the masked region of every init image is replaced by a
+    cascade of blurs of its surroundings before the image is encoded.  uint8 [b, H, W, 3] -> same."""
+    m = mask.fill_mask
+    out = torch.empty_like(init_images_u8)
+    for k in range(init_images_u8.shape[0]):
+        image = Image.fromarray(init_images_u8[k].cpu().numpy(), "RGB")
+        image_mod = Image.new("RGBA", (image.width, image.height))
+        image_masked = Image.new("RGBa", (image.width, image.height))
+        image_masked.paste(image.convert("RGBA").convert("RGBa"), mask=ImageOps.invert(m.convert("L")))
+        image_masked = image_masked.convert("RGBa")
+        for radius, repeats in [(256, 1), (64, 1), (16, 2), (4, 4), (2, 2), (0, 1)]:
+            blurred = image_masked.filter(ImageFilter.GaussianBlur(radius)).convert("RGBA")
+            for _ in range(repeats):
+                image_mod.alpha_composite(blurred)
+        out[k] = torch.from_numpy(np.array(image_mod.convert("RGB")))
+    return out
 
 
 def overlays_for(init_images_u8: torch.Tensor, mask: InpaintMask) -> List[Image.Image]:

@@ -165,8 +165,6 @@ class LocalGPUWorker(Worker):
                 if isinstance(mask_img, str):
                     data = mask_img.split(",", 1)[1] if mask_img.startswith("data:") else mask_img
                     mask_img = Image.open(io.BytesIO(base64.b64decode(data)))
-                if int(payload.get("inpainting_fill", 1) or 0) != 1:
-                    logger.warning(f"inpainting_fill={payload.get('inpainting_fill')} is not implemented on worker {self.label}: using 'original'")
                 if payload.get("inpaint_full_res") not in (None, False, 0):
                     logger.warning(f"'only masked' inpainting is not implemented on worker {self.label}: inpainting the whole picture")
                 if sampler != "DDIM":
@@ -178,6 +176,10 @@ class LocalGPUWorker(Worker):
                                            mask_blur=4 if blur is None else int(blur),
                                            invert=bool(payload.get("inpainting_mask_invert") or 0))
                 inpaint_overlays = inp.overlays_for(init_u8, inpaint)
+                fill = payload.get("inpainting_fill")
+                inpaint_fill = 1 if fill is None else int(fill)
+                if inpaint_fill == 0:   # "fill": blur the surroundings into the masked region before encoding
+                    init_u8 = inp.fill_masked(init_u8, inpaint)
         denoise = float(payload.get("denoising_strength", 0.75) or 0.75)
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
@@ -203,7 +205,7 @@ class LocalGPUWorker(Worker):
             eng.variation = (subseed + it * batch, strength) if strength != 0 else (None, 0.0)
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
             if init_u8 is not None:
-                kw = {} if inpaint is None else {"latmask": inpaint.latmask}
+                kw = {} if inpaint is None else {"latmask": inpaint.latmask, "inpainting_fill": inpaint_fill}
                 u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
                                  cfg_scale=cfg_scale, sampler=sampler, scheduler=scheduler, **kw)
             elif payload.get("enable_hr"):

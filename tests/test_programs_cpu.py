@@ -341,6 +341,36 @@ def test_inpainting_matches_oracle(env, blur, invert):
         eng.img2img(tok, neg, 1, init, 0.75, steps=steps, cfg_scale=7.0, sampler="Euler", latmask=m.latmask)
 
 
+@pytest.mark.parametrize("fill", [0, 2, 3])
+def test_inpainting_fill_modes(env, fill):
+    """inpainting_fill 0 ("fill": image-space blur cascade before encoding), 2 ("latent noise"), 3 ("latent nothing")"""
+    from PIL import Image, ImageDraw
+    from b200sd import inpaint as inp
+    C, E, O, cfgs, sd, eng = env
+    b, size, steps = 2, 32, 6
+    g = torch.Generator().manual_seed(78)
+    init = torch.randint(0, 256, (b, size, size, 3), generator=g, dtype=torch.uint8)
+    mask_img = Image.new("L", (size, size), 0)
+    ImageDraw.Draw(mask_img).rectangle((8, 8, 23, 25), fill=255)
+    tok = O.random_prompt_tokens(b, vocab_hi=997)
+    neg = O.empty_prompt_tokens(b, vocab_hi=997)
+    with torch.no_grad():
+        ref_u8, ref_x = O.img2img_inpaint(sd, *cfgs, tok, neg, 99, init, mask_img, 0.75, steps=steps, mask_blur=2,
+                                          inpainting_fill=fill)
+    down = 2 ** (len(cfgs[1].ch_mult) - 1)
+    m = inp.prepare_mask(mask_img, size, size, size // down, size // down, mask_blur=2)
+    enc_in = inp.fill_masked(init, m) if fill == 0 else init
+    if fill == 0:
+        assert not torch.equal(enc_in, init)
+    got = eng.img2img(tok, neg, 99, enc_in, 0.75, steps=steps, cfg_scale=7.0, latmask=m.latmask, inpainting_fill=fill)
+    h = size // down
+    z = eng.plan(b, h, h).x.reshape(b, h, h, 4).permute(0, 3, 1, 2)
+    assert float((z - ref_x).abs().max()) <= 1e-3 * float(ref_x.abs().max())
+    final = inp.apply_overlays(got.cpu(), inp.overlays_for(init, m))
+    d = (final.int() - ref_u8.int()).abs()
+    assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
+
+
 def test_img2img_matches_oracle(env):
     """VAE encoder program (asymmetric stride-2 padding) + DDIM started at t_enc + decode."""
     C, E, O, cfgs, sd, eng = env

@@ -41,7 +41,7 @@ class EngineDouble:
         self.calls.append(("txt2img", int(seed), int(tok.shape[0]), steps, sampler))
         return self._images(seed, tok, tok.shape[0], height, width)
 
-    def img2img(self, tok, neg, seed, init_u8, denoising_strength, steps, cfg_scale, sampler="DDIM", scheduler=None, latmask=None):
+    def img2img(self, tok, neg, seed, init_u8, denoising_strength, steps, cfg_scale, sampler="DDIM", scheduler=None, latmask=None, inpainting_fill=1):
         self.calls.append(("img2img", int(seed), int(tok.shape[0]), steps, float(denoising_strength)))
         b, h, w, _ = init_u8.shape
         return self._images(seed, tok, b, h, w, extra=int(init_u8.sum()) % 997)
