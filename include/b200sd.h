@@ -129,6 +129,21 @@ int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float* x, const 
 int b200sd_cfg_dpmpp_2m_step(const void* eps, long long pitch_e, float* x, float* old_denoised, void* xin,
                              long long pitch_x, int B, int HW, float cfg_scale, const float* coef, int* step_counter,
                              int dtype, void* stream);
+/* ---- generic sampler building blocks: every sampler of the reference's ETA table (scripts/spartan/worker.py:75-94)
+ * beyond the four fused ones above is, per model evaluation, one b200sd_cfg_eps plus a few b200sd_latent_lincomb on
+ * fp32 NHWC latents [B,HW,4], with coefficient rows selected on the device by *step_counter (graph replay safe). */
+/* e = eps_uncond + cfg_scale * (eps_cond - eps_uncond), fp32 [B,HW,4].  (sdwui CFGDenoiser; equals k-diffusion
+ * to_d(x, sigma, denoised) for the eps-prediction CompVisDenoiser) */
+int b200sd_cfg_eps(const void* eps, long long pitch_e, float* e, int B, int HW, float cfg_scale, int dtype, void* stream);
+/* dst = sum_{k<n_src} c[k] * srcs[k], c = coef + (*step_counter) * ld + col0.  srcs / idx_strides are HOST arrays of
+ * n_src (<= 8) device pointers / element strides: a source with idx_strides[k] != 0 is a stack of tensors and tensor
+ * (int)coef[(*step_counter) * ld + idx_col] of it is read (per-step noise draws).  xin != NULL: dst * c[n_src] is also
+ * packed as the next UNet input [2B,HW,pitch_x].  dst may alias a source. */
+int b200sd_latent_lincomb(float* dst, const float* const* srcs, const long long* idx_strides, int n_src,
+                          const float* coef, int ld, int col0, int idx_col, const int* step_counter, void* xin,
+                          long long pitch_x, int B, int HW, int dtype, void* stream);
+/* *step_counter += 1 on the device. */
+int b200sd_bump_step(int* step_counter, void* stream);
 /* decoded image [B,HW,pitch] (first 3 channels RGB in [-1,1]) -> uint8 [B,HW,3]:
  * trunc(255 * clamp((v+1)/2, 0, 1))  (sdwui process_images_inner) */
 int b200sd_quantize_u8(const void* img, long long pitch, unsigned char* out, int B, int HW, int dtype, void* stream);

@@ -535,14 +535,450 @@ def sample_kdiff_img2img(unet, init, noises, cond, uncond, sig_sched, log_sig, c
     return x
 
 
+# ------------------------------------------------------------------------------------------------ k-diffusion, the rest
+# Restated in k-diffusion's own shape: a `model(x, sigma) -> denoised` callable (CompVisDenoiser around the CFG'd eps
+# network) and samplers over a sigma table.  (k-diffusion sampling.py / external.py; sdwui sd_samplers_cfg_denoiser.py)
+def kdiff_model(unet, cond, uncond, cfg_scale: float, log_sig: torch.Tensor, mask=None):
+    """CompVisDenoiser.forward inside sdwui's CFGDenoiser: denoised = x + eps(x * c_in, t(sigma)) * c_out with
+    c_in = 1 / sqrt(sigma^2 + 1), c_out = -sigma.  `mask` = (init_latent, nmask): CFGDenoiser's last lines for the
+    k-diffusion samplers (mask_before_denoising False): denoised = init_latent * mask + nmask * denoised."""
+    def model(x, sigma: float):
+        e = cfg_eps(unet, x * (1.0 / math.sqrt(sigma * sigma + 1.0)), sigma_to_t(sigma, log_sig), cond, uncond, cfg_scale)
+        den = x - sigma * e
+        if mask is not None:
+            init, nmask = mask
+            den = init * (1.0 - nmask) + nmask * den
+        return den
+    return model
+
+
+def to_d(x, sigma: float, denoised):
+    """k-diffusion to_d"""
+    return (x - denoised) / sigma
+
+
+def get_ancestral_step(sigma_from: float, sigma_to: float, eta: float = 1.0):
+    """k-diffusion get_ancestral_step"""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+def k_sample_euler(model, x, sigmas):
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        d = to_d(x, s, model(x, s))
+        x = x + d * (sn - s)
+    return x
+
+
+def k_sample_euler_ancestral(model, x, sigmas, noises):
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        denoised = model(x, s)
+        down, up = get_ancestral_step(s, sn)
+        x = x + to_d(x, s, denoised) * (down - s)
+        if sn > 0:
+            x = x + noises[i] * up
+    return x
+
+
+def k_sample_heun(model, x, sigmas):
+    """sample_heun with s_churn = 0"""
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        d = to_d(x, s, model(x, s))
+        dt = sn - s
+        if sn == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            d_2 = to_d(x_2, sn, model(x_2, sn))
+            x = x + (d + d_2) / 2 * dt
+    return x
+
+
+def k_sample_dpm_2(model, x, sigmas):
+    """sample_dpm_2 with s_churn = 0"""
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        d = to_d(x, s, model(x, s))
+        if sn == 0:
+            x = x + d * (sn - s)
+        else:
+            sigma_mid = math.exp(0.5 * math.log(s) + 0.5 * math.log(sn))     # sigma.log().lerp(sigma_next.log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - s)
+            d_2 = to_d(x_2, sigma_mid, model(x_2, sigma_mid))
+            x = x + d_2 * (sn - s)
+    return x
+
+
+def k_sample_dpm_2_ancestral(model, x, sigmas, noises):
+    """sample_dpm_2_ancestral, eta = s_noise = 1; noises[k] = k-th noise_sampler call"""
+    k = 0
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        denoised = model(x, s)
+        down, up = get_ancestral_step(s, sn)
+        d = to_d(x, s, denoised)
+        if down == 0:
+            x = x + d * (down - s)
+        else:
+            sigma_mid = math.exp(0.5 * math.log(s) + 0.5 * math.log(down))
+            x_2 = x + d * (sigma_mid - s)
+            d_2 = to_d(x_2, sigma_mid, model(x_2, sigma_mid))
+            x = x + d_2 * (down - s)
+            x = x + noises[k] * up
+            k += 1
+    return x
+
+
+def k_sample_dpmpp_2s_ancestral(model, x, sigmas, noises):
+    """sample_dpmpp_2s_ancestral, eta = s_noise = 1"""
+    sigma_fn = lambda t: math.exp(-t)  # noqa: E731
+    t_fn = lambda sigma: -math.log(sigma)  # noqa: E731
+    k = 0
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        denoised = model(x, s)
+        down, up = get_ancestral_step(s, sn)
+        if down == 0:
+            x = x + to_d(x, s, denoised) * (down - s)
+        else:
+            t, t_next = t_fn(s), t_fn(down)
+            r = 1 / 2
+            h = t_next - t
+            sm = t + r * h
+            x_2 = (sigma_fn(sm) / sigma_fn(t)) * x - math.expm1(-h * r) * denoised
+            denoised_2 = model(x_2, sigma_fn(sm))
+            x = (sigma_fn(t_next) / sigma_fn(t)) * x - math.expm1(-h) * denoised_2
+        if sn > 0:
+            x = x + noises[k] * up
+            k += 1
+    return x
+
+
+def k_sample_dpmpp_2m(model, x, sigmas):
+    t_fn = lambda sigma: -math.log(sigma)  # noqa: E731
+    old = None
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        denoised = model(x, s)
+        if old is None or sn == 0:
+            x = (sn / s) * x + (1 - sn / s) * denoised if sn > 0 else denoised
+        else:
+            t, t_next = t_fn(s), t_fn(sn)
+            h = t_next - t
+            h_last = t - t_fn(float(sigmas[i - 1]))
+            r = h_last / h
+            denoised_d = (1 + 1 / (2 * r)) * denoised - (1 / (2 * r)) * old
+            x = (sn / s) * x - math.expm1(-h) * denoised_d
+        old = denoised
+    return x
+
+
+def linear_multistep_coeff(order: int, t, i: int, j: int) -> float:
+    """k-diffusion linear_multistep_coeff"""
+    from scipy import integrate
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def k_sample_lms(model, x, sigmas, order: int = 4):
+    """sample_lms"""
+    sig = [float(v) for v in sigmas]
+    ds = []
+    for i in range(len(sig) - 1):
+        d = to_d(x, sig[i], model(x, sig[i]))
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sig, i, j) for j in range(cur_order)]
+        x = x + sum(coeff * dd for coeff, dd in zip(coeffs, reversed(ds)))
+    return x
+
+
+def brownian_pair(z1, z2, s: float, ss: float, sn: float):
+    """The two noise_sampler calls of one DPM++ SDE step, (sigma -> sigma_s) and (sigma -> sigma_next).  Upstream:
+    BrownianTreeNoiseSampler, (W(t1) - W(t0)) / sqrt|t1 - t0| of ONE Brownian motion on the sigma axis (torchsde, absent
+    offline), so the second value contains the first interval's increment.  Restated from two independent N(0,1) draws:
+    z1 drives [sigma_s, sigma], z2 drives [sigma_next, sigma_s]."""
+    n1 = z1
+    n2 = (math.sqrt(s - ss) * z1 + math.sqrt(ss - sn) * z2) / math.sqrt(s - sn)
+    return n1, n2
+
+
+def k_sample_dpmpp_sde(model, x, sigmas, draws, eta: float = 1.0, s_noise: float = 1.0, r: float = 1 / 2):
+    """sample_dpmpp_sde; draws[2k], draws[2k + 1] feed the k-th step that is not the final Euler step (brownian_pair)"""
+    sigma_fn = lambda t: math.exp(-t)  # noqa: E731
+    t_fn = lambda sigma: -math.log(sigma)  # noqa: E731
+    k = 0
+    for i in range(len(sigmas) - 1):
+        s, sn = float(sigmas[i]), float(sigmas[i + 1])
+        denoised = model(x, s)
+        if sn == 0:
+            x = x + to_d(x, s, denoised) * (sn - s)
+        else:
+            t, t_next = t_fn(s), t_fn(sn)
+            h = t_next - t
+            sm = t + h * r
+            fac = 1 / (2 * r)
+            n1, n2 = brownian_pair(draws[2 * k], draws[2 * k + 1], s, sigma_fn(sm), sn)
+            k += 1
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(sm), eta)
+            s_ = t_fn(sd)
+            x_2 = (sigma_fn(s_) / sigma_fn(t)) * x - math.expm1(t - s_) * denoised
+            x_2 = x_2 + n1 * s_noise * su
+            denoised_2 = model(x_2, sigma_fn(sm))
+            sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
+            t_next_ = t_fn(sd)
+            denoised_d = (1 - fac) * denoised + fac * denoised_2
+            x = (sigma_fn(t_next_) / sigma_fn(t)) * x - math.expm1(t - t_next_) * denoised_d
+            x = x + n2 * s_noise * su
+    return x
+
+
+class DPMSolver:
+    """k-diffusion DPMSolver (eta = 0 paths): t = -log sigma, eps = (x - model(x, sigma)) / sigma"""
+
+    def __init__(self, model):
+        self.model = model
+        self.nfe = 0
+
+    @staticmethod
+    def sigma(t):
+        return math.exp(-t)
+
+    def eps(self, cache, key, x, t):
+        if key in cache:
+            return cache[key], cache
+        self.nfe += 1
+        e = (x - self.model(x, self.sigma(t))) / self.sigma(t)
+        return e, {key: e, **cache}
+
+    def dpm_solver_1_step(self, x, t, t_next, cache=None):
+        cache = {} if cache is None else cache
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        return x - self.sigma(t_next) * math.expm1(h) * eps, cache
+
+    def dpm_solver_2_step(self, x, t, t_next, r1=1 / 2, cache=None):
+        cache = {} if cache is None else cache
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        s1 = t + r1 * h
+        u1 = x - self.sigma(s1) * math.expm1(r1 * h) * eps
+        eps_r1, cache = self.eps(cache, "eps_r1", u1, s1)
+        x_2 = x - self.sigma(t_next) * math.expm1(h) * eps - self.sigma(t_next) / (2 * r1) * math.expm1(h) * (eps_r1 - eps)
+        return x_2, cache
+
+    def dpm_solver_3_step(self, x, t, t_next, r1=1 / 3, r2=2 / 3, cache=None):
+        cache = {} if cache is None else cache
+        h = t_next - t
+        eps, cache = self.eps(cache, "eps", x, t)
+        s1 = t + r1 * h
+        s2 = t + r2 * h
+        u1 = x - self.sigma(s1) * math.expm1(r1 * h) * eps
+        eps_r1, cache = self.eps(cache, "eps_r1", u1, s1)
+        u2 = x - self.sigma(s2) * math.expm1(r2 * h) * eps - \
+            self.sigma(s2) * (r2 / r1) * (math.expm1(r2 * h) / (r2 * h) - 1) * (eps_r1 - eps)
+        eps_r2, cache = self.eps(cache, "eps_r2", u2, s2)
+        x_3 = x - self.sigma(t_next) * math.expm1(h) * eps - self.sigma(t_next) / r2 * (math.expm1(h) / h - 1) * (eps_r2 - eps)
+        return x_3, cache
+
+    def dpm_solver_fast(self, x, t_start, t_end, nfe):
+        m = math.floor(nfe / 3) + 1
+        ts = torch.linspace(t_start, t_end, m + 1, dtype=torch.float64).tolist()
+        orders = [3] * (m - 2) + [2, 1] if nfe % 3 == 0 else [3] * (m - 1) + [nfe % 3]
+        for i in range(len(orders)):
+            t, t_next = ts[i], ts[i + 1]
+            if orders[i] == 1:
+                x, _ = self.dpm_solver_1_step(x, t, t_next)
+            elif orders[i] == 2:
+                x, _ = self.dpm_solver_2_step(x, t, t_next)
+            else:
+                x, _ = self.dpm_solver_3_step(x, t, t_next)
+        return x
+
+    def dpm_solver_adaptive(self, x, t_start, t_end, order=3, rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0, icoeff=1.0,
+                            dcoeff=0.0, accept_safety=0.81):
+        """forward in t, eta = 0; returns (x, info)"""
+        b1, b2, b3 = (pcoeff + icoeff + dcoeff) / order, -(pcoeff + 2 * dcoeff) / order, dcoeff / order
+        errs, h = [], h_init
+        s = t_start
+        x_prev = x
+        info = dict(steps=0, nfe=0, n_accept=0, n_reject=0)
+        while s < t_end - 1e-5:
+            cache = {}
+            t = min(t_end, s + h)
+            eps, cache = self.eps(cache, "eps", x, s)
+            x_low, cache = self.dpm_solver_2_step(x, s, t, r1=1 / 3, cache=cache)
+            x_high, cache = self.dpm_solver_3_step(x, s, t, cache=cache)
+            delta = torch.maximum(torch.full_like(x_low, atol), rtol * torch.maximum(x_low.abs(), x_prev.abs()))
+            error = float(torch.linalg.norm((x_low - x_high) / delta) / x.numel() ** 0.5)
+            inv_error = 1 / (error + 1e-8)                     # PIDStepSizeController.propose_step
+            if not errs:
+                errs = [inv_error, inv_error, inv_error]
+            errs[0] = inv_error
+            factor = errs[0] ** b1 * errs[1] ** b2 * errs[2] ** b3
+            factor = 1 + math.atan(factor - 1)
+            accept = factor >= accept_safety
+            if accept:
+                errs[2] = errs[1]
+                errs[1] = errs[0]
+            h *= factor
+            if accept:
+                x_prev = x_low
+                x = x_high
+                s = t
+                info["n_accept"] += 1
+            else:
+                info["n_reject"] += 1
+            info["nfe"] += order
+            info["steps"] += 1
+        return x, info
+
+
+def k_sample_dpm_fast(model, x, sigma_min: float, sigma_max: float, n: int):
+    """sample_dpm_fast"""
+    return DPMSolver(model).dpm_solver_fast(x, -math.log(sigma_max), -math.log(sigma_min), n)
+
+
+def k_sample_dpm_adaptive(model, x, sigma_min: float, sigma_max: float):
+    """sample_dpm_adaptive (defaults)"""
+    return DPMSolver(model).dpm_solver_adaptive(x, -math.log(sigma_max), -math.log(sigma_min))
+
+
+def sample_plms(unet, x, cond, uncond, timesteps, cfg_scale: float, mask=None):
+    """sdwui sd_samplers_timesteps_impl.plms over ascending `timesteps` (the model there is the CFG'd eps network;
+    `mask` = (init_latent, nmask): CFGDenoiser with mask_before_denoising — the input is blended before every call)."""
+    ac = alphas_cumprod().double()
+    ts = [int(t) for t in timesteps]
+    alphas = [float(ac[t]) for t in ts]
+    alphas_prev = [float(ac[0])] + [float(ac[t]) for t in ts[:-1]]
+
+    def model(xx, t):
+        if mask is not None:
+            init, nmask = mask
+            xx = init * (1.0 - nmask) + nmask * xx
+        return cfg_eps(unet, xx, t, cond, uncond, cfg_scale)
+
+    old_eps = []
+    for i in range(len(ts) - 1):
+        index = len(ts) - 1 - i
+        t_here, t_next = ts[index], ts[max(index - 1, 0)]
+        a_t, a_prev = alphas[index], alphas_prev[index]
+
+        def get_x_prev(e_t):
+            pred_x0 = (x - math.sqrt(1 - a_t) * e_t) / math.sqrt(a_t)
+            return math.sqrt(a_prev) * pred_x0 + math.sqrt(1.0 - a_prev) * e_t
+
+        e_t = model(x, t_here)
+        if len(old_eps) == 0:
+            e_t_next = model(get_x_prev(e_t), t_next)
+            e_t_prime = (e_t + e_t_next) / 2
+        elif len(old_eps) == 1:
+            e_t_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_t_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_t_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        x_prev = get_x_prev(e_t_prime)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+        x = x_prev
+    return x
+
+
+def model_sigmas():
+    """CompVisDenoiser.sigmas / log_sigmas of the SD schedule"""
+    ac = alphas_cumprod().double()
+    sig = ((1 - ac) / ac) ** 0.5
+    return sig, sig.log()
+
+
+def run_sampler(name: str, unet, cond, uncond, cfg_scale: float, steps: int, noise0, draws=None, init=None,
+                denoising_strength: Optional[float] = None, mask=None):
+    """One sampling run as sdwui dispatches it by sampler NAME (sd_samplers_kdiffusion.samplers_k_diffusion /
+    sd_samplers_timesteps): txt2img from noise0 (x = noise0 * sigmas[0]), or — with `init` and `denoising_strength` — the
+    img2img half (KDiffusionSampler.sample_img2img: sigma_sched = sigmas[steps - t_enc - 1:], x = init + noise0 * sigma_sched[0];
+    timestep samplers: timesteps[:t_enc], x = init sqrt(a) + noise0 sqrt(1 - a)).  draws: per-image N(0,1) tensors consumed
+    by the stochastic samplers in call order.  mask = (init_latent, nmask) for inpainting.  Returns the final latents
+    (before the caller's final mask blend)."""
+    karras = name.endswith(" Karras") or name == "DPM++ 2M"
+    base = name[:-len(" Karras")] if name.endswith(" Karras") else name
+    if base in ("DDIM", "PLMS"):
+        ts = ddim_timesteps(steps)
+        if init is not None:
+            ac = alphas_cumprod().double()
+            t_enc = max(1, min(int(min(denoising_strength, 0.999) * steps), len(ts) - 1))
+            a = float(ac[ts[t_enc]])
+            x = init * math.sqrt(a) + noise0 * math.sqrt(1 - a)
+            ts = ts[:t_enc]
+        else:
+            x = noise0
+        if base == "PLMS":
+            return sample_plms(unet, x, cond, uncond, ts, cfg_scale, mask)
+        raise ValueError("DDIM: use sample_ddim / img2img")
+    sig, log_sig = sigmas_karras(steps) if karras else karras_sigmas_compvis(steps)
+    if init is not None:
+        sig = kdiff_img2img_sigmas(sig, steps, denoising_strength)
+        x = init + noise0 * float(sig[0])
+    else:
+        x = noise0 * float(sig[0])
+    model = kdiff_model(unet, cond, uncond, cfg_scale, log_sig, mask)
+    if base == "Euler":
+        return k_sample_euler(model, x, sig)
+    if base == "Euler a":
+        return k_sample_euler_ancestral(model, x, sig, draws)
+    if base == "Heun":
+        return k_sample_heun(model, x, sig)
+    if base == "DPM2":
+        return k_sample_dpm_2(model, x, sig)
+    if base == "DPM2 a":
+        return k_sample_dpm_2_ancestral(model, x, sig, draws)
+    if base == "DPM++ 2S a":
+        return k_sample_dpmpp_2s_ancestral(model, x, sig, draws)
+    if base == "DPM++ 2M":
+        return k_sample_dpmpp_2m(model, x, sig)
+    if base == "DPM++ SDE":
+        return k_sample_dpmpp_sde(model, x, sig, draws)
+    if base == "LMS":
+        return k_sample_lms(model, x, sig)
+    if base in ("DPM fast", "DPM adaptive"):
+        all_sig, _ = model_sigmas()
+        lo, hi = (float(all_sig[0]), float(all_sig[-1])) if init is None else (float(sig[-2]), float(sig[0]))
+        if base == "DPM fast":
+            return k_sample_dpm_fast(model, x, lo, hi, len(sig) - 1)
+        return k_sample_dpm_adaptive(model, x, lo, hi)[0]
+    raise ValueError(name)
+
+
 # ------------------------------------------------------------------------------------------------ images / rng
 def per_image_noise(seed: int, n: int, shape, subseed_offset: int = 0, subseed: Optional[int] = None,
                     subseed_strength: float = 0.0) -> torch.Tensor:
-    """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded seed + k; with variation
-    seeds (subseed_strength != 0) ImageRNG.first() returns slerp(strength, noise, subnoise(subseed + k))."""
+    """sdwui rng.ImageRNG with randn_source='CPU': image k is drawn from its own generator seeded all_seeds[k]; with
+    variation seeds (subseed_strength != 0) ImageRNG.first() returns slerp(strength, noise, subnoise(subseed + k)).
+    processing.py: all_seeds[k] = seed + (k if subseed_strength == 0 else 0), all_subseeds[k] = subseed + k — with
+    variation seeds every image shares the base seed and only the subseed advances."""
     out = []
+    variation = subseed is not None and subseed_strength != 0
     for k in range(n):
-        g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + (0 if variation else k))
         noise = torch.randn(shape, generator=g, dtype=torch.float32)
         if subseed is not None and subseed_strength != 0:
             sub = torch.randn(shape, generator=torch.Generator(device="cpu").manual_seed(int(subseed) + k), dtype=torch.float32)

@@ -246,6 +246,58 @@ __global__ void cfg_dpmpp_2m_step_kernel(const void* eps, long long pitch_e, flo
 
 __global__ void bump_step_kernel(int* step_counter) { *step_counter += 1; }
 
+// ---- generic sampler building blocks (every k-diffusion / timestep sampler beyond the four fused ones above is a short
+// list of these per model evaluation; b200sd/samplers.py holds the coefficient algebra) ----
+// e[b, pix, :] (fp32) = eu + cfg * (ec - eu): sdwui CFGDenoiser's combine.  For an eps-prediction model wrapped by
+// k-diffusion's CompVisDenoiser, to_d(x, sigma, denoised) = (x - denoised) / sigma is exactly this e.
+template <bool kBf16>
+__global__ void cfg_eps_kernel(const void* eps, long long pitch_e, float4* __restrict__ e, int B, int HW, float cfg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int b = i / HW, pix = i % HW;
+  const float4 ec = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b) * HW + pix);
+  const float4 eu = read_eps4<kBf16>(eps, pitch_e, static_cast<long long>(b + B) * HW + pix);
+  e[i] = make_float4(eu.x + cfg * (ec.x - eu.x), eu.y + cfg * (ec.y - eu.y), eu.z + cfg * (ec.z - eu.z),
+                     eu.w + cfg * (ec.w - eu.w));
+}
+
+constexpr int kMaxLincomb = 8;
+struct LincombParams {
+  const float4* src[kMaxLincomb];
+  long long idx_stride[kMaxLincomb];  // in float4 elements; != 0: the source is a stack of tensors indexed by `idx`
+  int n;
+};
+// dst = sum_k c[k] * src_k with c = coef[row * ld + col0 ...], row = *step_counter; sources with an index stride read
+// tensor (int)coef[row * ld + idx_col] of their stack (the per-step noise draws).  With xin != null the result times
+// c[n] is also written as the next UNet input (both CFG halves).  dst may alias a source (same element, same thread).
+template <bool kBf16>
+__global__ void latent_lincomb_kernel(float4* dst, const LincombParams p, const float* __restrict__ coef, int ld,
+                                      int col0, int idx_col, const int* __restrict__ step_counter, void* xin,
+                                      long long pitch_x, int B, int HW) {
+  const int row = *step_counter;
+  const float* c = coef + static_cast<long long>(row) * ld + col0;
+  const long long idx = idx_col >= 0 ? static_cast<long long>(coef[static_cast<long long>(row) * ld + idx_col]) : 0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < kMaxLincomb; ++k) {
+    if (k < p.n) {
+      const float w = c[k];
+      if (w != 0.f) {  // a zero weight must not propagate a stale buffer's NaN / Inf
+        const float4 v = p.src[k][idx * p.idx_stride[k] + i];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+    }
+  }
+  dst[i] = acc;
+  if (xin != nullptr) {
+    const float s = c[p.n];
+    write_xin<kBf16>(xin, pitch_x, B, HW, i / HW, i % HW, make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s));
+  }
+}
+
+
 template <bool kBf16>
 __global__ void quantize_u8_kernel(const void* img, long long pitch, unsigned char* out, long long npix) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -426,6 +478,46 @@ extern "C" int b200sd_cfg_dpmpp_2m_step(const void* eps, long long pitch_e, floa
   else
     cfg_dpmpp_2m_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
+  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  RET_LAUNCH();
+}
+
+
+extern "C" int b200sd_cfg_eps(const void* eps, long long pitch_e, float* e, int B, int HW, float cfg_scale, int dtype,
+                              void* stream) {
+  if (B <= 0 || HW <= 0) return B200SD_OK;
+  if (pitch_e % 4 || (reinterpret_cast<uintptr_t>(e) & 15)) return B200SD_ERR_INVALID;
+  const int n = B * HW;
+  if (dtype == B200SD_BF16) cfg_eps_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
+  else cfg_eps_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_latent_lincomb(float* dst, const float* const* srcs, const long long* idx_strides, int n_src,
+                                     const float* coef, int ld, int col0, int idx_col, const int* step_counter,
+                                     void* xin, long long pitch_x, int B, int HW, int dtype, void* stream) {
+  if (B <= 0 || HW <= 0) return B200SD_OK;
+  if (n_src < 1 || n_src > kMaxLincomb || ld <= 0 || col0 < 0 || col0 + n_src + (xin != nullptr ? 1 : 0) > ld ||
+      idx_col >= ld || (reinterpret_cast<uintptr_t>(dst) & 15) || (xin != nullptr && pitch_x % 4))
+    return B200SD_ERR_INVALID;
+  LincombParams p{};
+  p.n = n_src;
+  for (int k = 0; k < n_src; ++k) {
+    if (srcs[k] == nullptr || (reinterpret_cast<uintptr_t>(srcs[k]) & 15) || (idx_strides != nullptr && idx_strides[k] % 4))
+      return B200SD_ERR_INVALID;
+    p.src[k] = reinterpret_cast<const float4*>(srcs[k]);
+    p.idx_stride[k] = idx_strides != nullptr ? idx_strides[k] / 4 : 0;
+    if (p.idx_stride[k] != 0 && idx_col < 0) return B200SD_ERR_INVALID;
+  }
+  const int n = B * HW;
+  if (dtype == B200SD_BF16)
+    latent_lincomb_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
+  else
+    latent_lincomb_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
+  RET_LAUNCH();
+}
+
+extern "C" int b200sd_bump_step(int* step_counter, void* stream) {
   bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
   RET_LAUNCH();
 }

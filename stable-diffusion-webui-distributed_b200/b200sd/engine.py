@@ -8,17 +8,20 @@ exchange; results meet once, at the end (bench: one NCCL all-gather; plugin path
 import contextlib
 import math
 import threading
+from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import ops
+from . import samplers as S
 from .clip_text import ClipText
 from .config import CLIPConfig, UNetConfig, VAEConfig
 from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
 from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
 
 MAX_STEPS = 256
+NOISE_SAMPLERS = ("Euler a", "stage")   # graph-name prefixes of the step graphs that may read Plan.noise
 _CAPTURE_LOCK = threading.Lock()  # CUDA graph captures are serialised across the per-device worker threads
 
 
@@ -157,7 +160,7 @@ def dpmpp_2m_plan(steps: int, scheduler: str = "karras", sigmas=None):
 # sampler names of the sdwui API -> (method, scheduler).  sdwui >= 1.9 sends the scheduler separately ("scheduler" key,
 # "Automatic" = the sampler's default, which is Karras for DPM++ 2M); older versions fold it into the name.
 SAMPLERS = {"DDIM": ("ddim", None), "Euler a": ("euler_a", "uniform"), "Euler": ("euler", "uniform"),
-            "DPM++ 2M": ("dpmpp_2m", "karras"), "DPM++ 2M Karras": ("dpmpp_2m", "karras")}
+            "DPM++ 2M": ("dpmpp_2m", "karras"), "DPM++ 2M Karras": ("dpmpp_2m", "karras"), **S.GENERIC}
 
 
 # API scheduler labels (sdwui >= 1.9 sd_schedulers.schedulers: label or name) -> kdiffusion_sigmas scheduler
@@ -193,19 +196,47 @@ def slerp(val: float, low: torch.Tensor, high: torch.Tensor) -> torch.Tensor:
 
 def per_image_noise(seed: int, n: int, shape, draws: int = 1, subseed: Optional[int] = None,
                     subseed_strength: float = 0.0) -> torch.Tensor:
-    """sdwui ImageRNG with randn_source = 'CPU': image k owns torch.Generator('cpu').manual_seed(seed + k);
-    `draws` successive tensors per image (x_T, then ancestral noises).  Variation seeds (ImageRNG.first): with a
-    non-zero `subseed_strength` the FIRST draw is slerp(strength, noise(seed + k), noise(subseed + k)).
+    """sdwui ImageRNG with randn_source = 'CPU': image k owns torch.Generator('cpu').manual_seed(all_seeds[k]);
+    `draws` successive tensors per image (x_T, then ancestral noises).  processing.py: all_seeds[k] = seed + k when
+    subseed_strength == 0, but seed for EVERY image when variation seeds are on (only all_subseeds[k] = subseed + k
+    varies; the reference dispatcher mirrors this by not offsetting `seed`, scripts/distributed.py:297-305).
+    Variation seeds (ImageRNG.first): the FIRST draw is slerp(strength, noise(seed), noise(subseed + k)).
     Returns [draws, n, *shape] fp32 (host)."""
     out = torch.empty((draws, n, *shape), dtype=torch.float32)
+    variation = subseed is not None and subseed_strength != 0
     for k in range(n):
-        g = torch.Generator(device="cpu").manual_seed(int(seed) + k)
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + (0 if variation else k))
         for d in range(draws):
             out[d, k] = torch.randn(shape, generator=g, dtype=torch.float32)
-        if subseed is not None and subseed_strength != 0:
+        if variation:
             sg = torch.Generator(device="cpu").manual_seed(int(subseed) + k)
             out[0, k] = slerp(float(subseed_strength), out[0, k], torch.randn(shape, generator=sg, dtype=torch.float32))
     return out
+
+
+@dataclass
+class Program:
+    """what one sampling run executes (SDEngine.program)"""
+    sampler: str
+    method: str
+    fused: Optional[str] = None          # "ddim" | "euler_a" | "euler" | "dpmpp_2m": the fused per-step kernels
+    ts: List[float] = field(default_factory=list)      # fused: timestep per evaluation
+    rows: List[List[float]] = field(default_factory=list)   # fused: coefficient row per evaluation
+    sp: Optional[S.SamplerPlan] = None   # generic stage list
+    adaptive: Optional[tuple] = None     # DPM adaptive: (sigma_min, sigma_max, sigma -> timestep)
+    draws: int = 0                       # N(0,1) draws per image after the start noise
+    init_scale: float = 0.0              # start latents = init * init_scale + noise * noise_scale
+    noise_scale: float = 1.0
+    in0: float = 1.0                     # scale of the first UNet input
+    timestep_sampler: bool = False
+
+    def start(self, noise0: torch.Tensor, init: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = noise0 * self.noise_scale
+        return x if init is None else x + init * self.init_scale
+
+    @property
+    def n_evals(self) -> Optional[int]:
+        return len(self.ts) if self.fused else (len(self.sp.stages) if self.sp is not None else None)
 
 
 # ------------------------------------------------------------------------------------------------ plans
@@ -226,9 +257,27 @@ class Plan:
         self.old = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)        # its previous x0 prediction
         self.init = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)     # inpainting: clean init latents
         self.latmask = torch.ones((h * w,), device=dev, dtype=torch.float32)        # ... and the latent mask (1 = repaint)
-        self.noise = None
+        # generic stage machine (b200sd/samplers.py): named fp32 latents, coefficient rows selected by `step`
+        self.lat = {"x": self.x}
+        for name in ("e", "u", "h1", "h2", "h3", "d"):
+            self.lat[name] = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)
+        self.coefL = torch.zeros((MAX_STEPS, S.COEF_LD), device=dev, dtype=torch.float32)
+        self.noise = None            # [rows, b, h*w, 4] fp32, persistent: captured graphs bake its address
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[str, int] = {}
+
+    def noise_rows(self, rows: int) -> torch.Tensor:
+        """the request's per-step noises live in ONE buffer per plan (the step graphs hold its raw address); it grows in
+        powers of two, and growing drops the graphs that captured the old address"""
+        if self.noise is None or self.noise.shape[0] < rows:
+            cap = 32
+            while cap < rows:
+                cap *= 2
+            self.noise = torch.zeros((cap, self.b, self.h * self.w, 4), device=self.x.device, dtype=torch.float32)
+            for name in [n for n in self.graphs if n.split(":")[0] in NOISE_SAMPLERS]:  # incl. every "stage" graph
+                del self.graphs[name]
+                self.graph_launches.pop(name, None)
+        return self.noise
 
     # one sampler step = select this step's biases, UNet on [cond | uncond], CFG + update + repack
     def step_ddim(self, cfg_scale: float):
@@ -252,6 +301,28 @@ class Plan:
         ops.select_step(self.table, self.step, self.unet.cur_bias)
         self.unet.run()
         ops.cfg_euler_a_step(self.unet.eps, self.x, None, self.unet.xin, cfg_scale, self.coef, self.step)
+
+    def stage(self, lcs, ev: str, cfg_scale: float, masked: bool, timestep_sampler: bool):
+        """one model evaluation of a generic sampler program + its linear combinations (samplers.Stage.lcs)"""
+        lat = self.lat
+        if masked and timestep_sampler:   # sdwui CFGDenoiser, mask_before_denoising: the evaluated tensor is blended first
+            ops.blend_latent(lat[ev], self.init, self.latmask)
+            ops.pack_unet_input(lat[ev], self.unet.xin, 1.0)
+        ops.select_step(self.table, self.step, self.unet.cur_bias)
+        self.unet.run()
+        ops.cfg_eps(self.unet.eps, lat["e"], cfg_scale)
+        if masked and not timestep_sampler:
+            # k-diffusion samplers: denoised = denoised * nmask + init_latent * mask (CFGDenoiser.forward's last lines);
+            # re-expressed on e = (ev - denoised) / sigma
+            ops.latent_lincomb(lat["d"], [lat[ev], lat["e"]], self.coefL, S.MASK_COL, self.step)
+            ops.blend_latent(lat["d"], self.init, self.latmask)
+            ops.latent_lincomb(lat["e"], [lat[ev], lat["d"]], self.coefL, S.MASK_COL + 2, self.step)
+        col = 0
+        for dst, srcs, pack in lcs:
+            ops.latent_lincomb(lat[dst], [self.noise if n == "n" else lat[n] for n in srcs], self.coefL, col, self.step,
+                               self.unet.xin if pack else None, S.IDX_COL if "n" in srcs else -1)
+            col += len(srcs) + int(pack)
+        ops.bump_step(self.step)
 
     def step_dpmpp_2m(self, cfg_scale: float):
         ops.select_step(self.table, self.step, self.unet.cur_bias)
@@ -339,70 +410,224 @@ class SDEngine:
             plan.x.copy_(saved[0]); plan.step.copy_(saved[1]); plan.unet.xin.copy_(saved[2])
         return plan.graphs[name]
 
+    # ------------------------------------------------------------------------------------------ sampler programs
+    def program(self, sampler: str, scheduler: Optional[str], steps: int, denoise: Optional[float] = None,
+                masked: bool = False) -> "Program":
+        """(sampler name, API scheduler, steps[, img2img denoising strength]) -> what to run: the fused per-step kernels
+        for DDIM / Euler a / Euler / DPM++ 2M, a stage list (b200sd/samplers.py) for every other sampler of the
+        reference's table.  With `denoise` the program is the img2img half: the sampler's schedule from t_enc on
+        (sdwui sd_samplers_timesteps.sample_img2img / KDiffusionSampler.sample_img2img)."""
+        method, sched = resolve_sampler(sampler, scheduler)
+        pr = Program(sampler, method)
+        if method in ("ddim", "plms"):
+            ac = alphas_cumprod().double()
+            ts_all = torch.clamp(torch.arange(0, 1000, 1000 // steps) + 1, 0, 999)
+            if denoise is None:
+                sub = ts_all
+            else:
+                t_enc = max(1, min(int(min(denoise, 0.999) * steps), len(ts_all) - 1))
+                a_start = float(ac[ts_all[t_enc]])
+                pr.init_scale, pr.noise_scale = math.sqrt(a_start), math.sqrt(1 - a_start)
+                sub = ts_all[:t_enc]
+            if method == "ddim":
+                pr.fused = "ddim"
+                a = ac[sub]
+                a_prev = ac[torch.cat([sub.new_zeros(1), sub[:-1]])]
+                for i in range(len(sub) - 1, 0, -1):
+                    at, ap = float(a[i]), float(a_prev[i])
+                    pr.ts.append(float(sub[i]))
+                    pr.rows.append([math.sqrt(at), math.sqrt(1 - at), math.sqrt(ap), math.sqrt(1 - ap)])
+            else:
+                pr.sp = S.plms([int(t) for t in sub], [float(v) for v in ac])
+            pr.timestep_sampler = True
+            return pr
+        sig, log_sig = kdiffusion_sigmas(steps, sched)
+        if denoise is not None:
+            t_enc = int(min(denoise, 0.999) * steps)
+            sig = sig[steps - t_enc - 1:]
+            pr.init_scale, pr.noise_scale = 1.0, float(sig[0])
+        else:
+            pr.noise_scale = float(sig[0])
+        pr.in0 = S.c_in(float(sig[0]))
+        if method in ("euler_a", "euler", "dpmpp_2m") and not masked:   # with a mask: the same sampler as stages
+            pr.fused = method
+            fn = {"euler_a": euler_a_plan, "euler": euler_plan, "dpmpp_2m": dpmpp_2m_plan}[method]
+            pr.ts, pr.rows, _ = fn(len(sig) - 1, sched, (sig, log_sig))
+            pr.draws = len(pr.rows) if method == "euler_a" else 0
+            return pr
+        sg = [float(v) for v in sig]
+        t_of = lambda v: sigma_to_t(v, log_sig)  # noqa: E731
+        if method in ("dpm_fast", "dpm_adaptive"):
+            # sdwui passes sigma_min / sigma_max instead of a schedule: the model's own extremes for txt2img, the ends
+            # of the (positive part of the) tail for img2img; DPM fast spends n = steps evaluations
+            sig_all = log_sig.exp()
+            lo, hi = (float(sig_all[0]), float(sig_all[-1])) if denoise is None else (sg[-2], sg[0])
+            if method == "dpm_fast":
+                pr.sp = S.dpm_fast(lo, hi, len(sg) - 1, t_of)
+            else:
+                pr.adaptive = (lo, hi, t_of)
+            return pr
+        pr.sp = S.BUILDERS[method](sg, t_of)
+        pr.draws = pr.sp.draws
+        return pr
+
+    def _stage_graph(self, plan: Plan, st, cfg_scale: float, masked: bool, ts_sampler: bool):
+        name = f"stage:{hash((st.lcs, st.ev))}:{cfg_scale}:{int(masked)}{int(ts_sampler)}"
+        fn = lambda: plan.stage(st.lcs, st.ev, cfg_scale, masked, ts_sampler)  # noqa: E731
+        return name, fn, self._graph(plan, name, fn)
+
+    @torch.no_grad()
+    def run_program(self, cond: torch.Tensor, uncond: torch.Tensor, x_start: torch.Tensor, pr: "Program", cfg_scale: float,
+                    noises: Optional[torch.Tensor] = None, inpaint=None) -> torch.Tensor:
+        """cond/uncond [b, 77, ctx] on device; x_start [b, 4, h, w] fp32 (host or device) = Program.start(...): the start
+        latents in the sampler's own space; noises [pr.draws, b, 4, h, w]: the per-image N(0,1) draws after the first;
+        inpaint = (clean init latents [b, 4, h, w], latent mask [h * w]).  Returns the final latents fp32 [b, h*w, 4]
+        (NHWC, a view of plan state)."""
+        b, _, h, w = x_start.shape
+        if pr.draws and (noises is None or noises.shape[0] < pr.draws):
+            raise ValueError(f"{pr.sampler} needs {pr.draws} per-image noise draws")
+        if inpaint is not None and pr.fused not in (None, "ddim"):
+            # the fused Euler / Euler a / DPM++ 2M kernels do not carry the mask: same sampler, generic stages
+            raise ValueError("masked sampling of a fused sampler must be requested through a generic program")
+        with self._ctx():
+            plan = self.plan(b, h, w)
+            plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
+            masked = inpaint is not None
+            if masked:   # (clean init latents [b, 4, h, w], latent mask [h * w])
+                plan.init.copy_(inpaint[0].to(self.device, torch.float32).permute(0, 2, 3, 1).reshape(b, h * w, 4))
+                plan.latmask.copy_(inpaint[1].to(self.device, torch.float32).reshape(-1))
+            plan.x.copy_(x_start.to(self.device, torch.float32).permute(0, 2, 3, 1).reshape(b, h * w, 4))
+            plan.step.zero_()
+            ops.pack_unet_input(plan.x, plan.unet.xin, pr.in0)
+            self.last_unet_evals = 0
+            if pr.adaptive is not None:
+                self._run_dpm_adaptive(plan, pr, cfg_scale, masked)
+            elif pr.fused is not None:
+                self._run_fused(plan, pr, cfg_scale, noises, masked)
+            else:
+                self._run_stages(plan, pr.sp, cfg_scale, noises, masked)
+            if masked:   # processing.py sample(): samples * nmask + init_latent * mask
+                ops.blend_latent(plan.x, plan.init, plan.latmask)
+            return plan.x
+
+    def _upload_noises(self, plan: Plan, noises: torch.Tensor, mix=None):
+        """draws [D, b, 4, h, w] (host) -> rows of the plan's persistent noise stack, mixed as the program says"""
+        d = noises.to(torch.float32)
+        if mix is not None:
+            d = torch.stack([sum(w * d[i] for i, w in row) for row in mix]) if mix else d[:0]
+        n = d.shape[0]
+        if n:
+            plan.noise_rows(n)[:n].copy_(d.to(self.device).permute(0, 1, 3, 4, 2).reshape(n, plan.b, plan.h * plan.w, 4))
+        elif plan.noise is None:
+            plan.noise_rows(1)
+
+    def _run_fused(self, plan: Plan, pr: "Program", cfg_scale: float, noises, masked: bool):
+        n_evals = len(pr.ts)
+        if n_evals > MAX_STEPS:
+            raise ValueError("too many steps")
+        if n_evals == 0:   # img2img at a very low denoising strength runs zero evaluations: the noised init comes back
+            return
+        name = f"{pr.sampler if pr.fused != 'ddim' else 'DDIM'}:{cfg_scale}"
+        if pr.fused == "ddim":
+            step_fn = (lambda: plan.step_ddim_masked(cfg_scale)) if masked else (lambda: plan.step_ddim(cfg_scale))
+            name += ":mask" if masked else ""
+        elif pr.fused == "euler_a":
+            self._upload_noises(plan, noises[:n_evals])
+            name = f"Euler a:{cfg_scale}"
+            step_fn = lambda: plan.step_euler_a(cfg_scale)  # noqa: E731
+        elif pr.fused == "euler":
+            step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
+        else:
+            step_fn = lambda: plan.step_dpmpp_2m(cfg_scale)  # noqa: E731
+        plan.table[:n_evals].copy_(self.temb.table(torch.tensor(pr.ts, dtype=torch.float32)))
+        (plan.coef8 if len(pr.rows[0]) == 8 else plan.coef)[:n_evals].copy_(torch.tensor(pr.rows, dtype=torch.float32))
+        g = self._graph(plan, name, step_fn)
+        for _ in range(n_evals):
+            if self.interrupted:
+                break
+            if g is not None:
+                g.replay()
+                self.graph_replayed_launches += plan.graph_launches[name]
+            else:
+                step_fn()
+            self.last_unet_evals += 1
+
+    def _run_stages(self, plan: Plan, sp, cfg_scale: float, noises, masked: bool):
+        stages = sp.stages
+        if len(stages) > MAX_STEPS:
+            raise ValueError("too many model evaluations")
+        if not stages:
+            return
+        self._upload_noises(plan, noises if noises is not None else torch.zeros((0, plan.b, 4, plan.h, plan.w)), sp.mix)
+        plan.table[:len(stages)].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32)))
+        plan.coefL[:len(stages)].copy_(torch.tensor([st.row() for st in stages], dtype=torch.float32))
+        for st in stages:
+            if self.interrupted:
+                break
+            name, fn, g = self._stage_graph(plan, st, cfg_scale, masked, sp.timestep_sampler)
+            if g is not None:
+                g.replay()
+                self.graph_replayed_launches += plan.graph_launches[name]
+            else:
+                fn()
+            self.last_unet_evals += 1
+
+    def _run_dpm_adaptive(self, plan: Plan, pr: "Program", cfg_scale: float, masked: bool):
+        """k-diffusion sample_dpm_adaptive -> DPMSolver.dpm_solver_adaptive(order 3, rtol 0.05, atol 0.0078, h_init 0.05,
+        PI controller icoeff 1, accept_safety 0.81, eta 0): the step size depends on an error norm over the WHOLE batch, so
+        the host reads one scalar per attempted step (3 evaluations) and rewrites three coefficient / time-embedding rows.
+        (Being batch-coupled upstream, this sampler is the one whose images depend on how the request was sharded.)"""
+        sigma_min, sigma_max, t_of = pr.adaptive
+        t_start, t_end = -math.log(sigma_max), -math.log(sigma_min)
+        rtol, atol, order = 0.05, 0.0078, 3
+        pid = S.PIDStepSizeController(0.05, 0.0, 1.0, 0.0, order, 0.81)
+        s = t_start
+        x_prev = plan.x.clone()
+        if plan.noise is None:
+            plan.noise_rows(1)
+        while s < t_end - 1e-5:
+            if self.interrupted:
+                break
+            t = min(t_end, s + pid.h)
+            stages = S.dpm_adaptive_attempt(s, t, t_of)
+            plan.table[:3].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32)))
+            plan.coefL[:3].copy_(torch.tensor([st.row() for st in stages], dtype=torch.float32))
+            plan.step.zero_()
+            ops.pack_unet_input(plan.x, plan.unet.xin, S.c_in(math.exp(-s)))
+            for st in stages:
+                name, fn, g = self._stage_graph(plan, st, cfg_scale, masked, False)
+                if g is not None:
+                    g.replay()
+                    self.graph_replayed_launches += plan.graph_launches[name]
+                else:
+                    fn()
+                self.last_unet_evals += 1
+            x_low, x_high = plan.lat["h3"], plan.lat["u"]
+            delta = torch.maximum(torch.full_like(x_low, atol), rtol * torch.maximum(x_low.abs(), x_prev.abs()))
+            error = float(torch.linalg.norm((x_low - x_high) / delta) / x_low.numel() ** 0.5)
+            if pid.propose_step(error):
+                x_prev.copy_(x_low)
+                plan.x.copy_(x_high)
+                s = t
+
     @torch.no_grad()
     def sample(self, cond: torch.Tensor, uncond: torch.Tensor, x_T: torch.Tensor, steps: int, cfg_scale: float,
                sampler: str = "DDIM", noises: Optional[torch.Tensor] = None, schedule=None,
                scheduler: Optional[str] = None, sigmas=None, inpaint=None) -> torch.Tensor:
-        """cond/uncond [b, 77, ctx] fp16 on device, x_T [b, 4, h, w] fp32 (host or device): the start latents.
-        `schedule` = (timesteps, coef rows) overrides the full DDIM schedule (img2img starts part-way); `sigmas` =
-        (sigma table ending in 0, model log-sigmas) does the same for the k-diffusion samplers, and x_T is then the
-        ALREADY NOISED start (init + noise * sigmas[0]), not unit noise.
-        Returns the final latents fp32 [b, h*w, 4] (NHWC, a view of plan state)."""
-        b, _, h, w = x_T.shape
-        with self._ctx():
-            plan = self.plan(b, h, w)
-            plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
-            graph_name = f"{sampler}:{cfg_scale}"
-            if sampler == "DDIM":
-                ts, rows = schedule if schedule is not None else ddim_plan(steps)
-                scale0, in0 = 1.0, 1.0
-                step_fn = lambda: plan.step_ddim(cfg_scale)  # noqa: E731
-                if inpaint is not None:   # (clean init latents [b, 4, h, w], latent mask [h * w])
-                    plan.init.copy_(inpaint[0].to(self.device, torch.float32).permute(0, 2, 3, 1).reshape(b, h * w, 4))
-                    plan.latmask.copy_(inpaint[1].to(self.device, torch.float32).reshape(-1))
-                    step_fn = lambda: plan.step_ddim_masked(cfg_scale)  # noqa: E731
-                    graph_name += ":mask"
-            elif sampler == "Euler a":
-                ts, rows, sigma0 = euler_a_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
-                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
-                step_fn = lambda: plan.step_euler_a(cfg_scale)  # noqa: E731
-                if noises is None:
-                    raise ValueError("Euler a needs the per-image ancestral noises")
-                plan.noise = noises.to(self.device, torch.float32).permute(0, 1, 3, 4, 2).reshape(len(rows), b, h * w, 4).contiguous()
-            elif sampler == "Euler":
-                ts, rows, sigma0 = euler_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
-                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
-                step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
-            elif sampler in SAMPLERS and SAMPLERS[sampler][0] == "dpmpp_2m":
-                ts, rows, sigma0 = dpmpp_2m_plan(steps, resolve_sampler(sampler, scheduler)[1], sigmas)
-                scale0, in0 = (sigma0 if sigmas is None else 1.0), 1.0 / math.sqrt(sigma0 * sigma0 + 1.0)
-                step_fn = lambda: plan.step_dpmpp_2m(cfg_scale)  # noqa: E731
-            else:
-                raise ValueError(f"sampler {sampler!r} is not implemented on the local executor")
-            n_evals = len(ts)
-            if n_evals > MAX_STEPS:
-                raise ValueError("too many steps")
-            plan.table[:n_evals].copy_(self.temb.table(torch.tensor(ts, dtype=torch.float32)))
-            (plan.coef8 if len(rows[0]) == 8 else plan.coef)[:n_evals].copy_(torch.tensor(rows, dtype=torch.float32))
-            plan.x.copy_((x_T.to(self.device, torch.float32) * scale0).permute(0, 2, 3, 1).reshape(b, h * w, 4))
-            plan.step.zero_()
-            ops.pack_unet_input(plan.x, plan.unet.xin, in0)
-            if inpaint is not None and sampler != "DDIM":
-                raise ValueError("inpainting masks are implemented for the DDIM sampler only")
-            g = self._graph(plan, graph_name, step_fn)
-            self.last_unet_evals = 0
-            for _ in range(n_evals):
-                if self.interrupted:
-                    break
-                if g is not None:
-                    g.replay()
-                    self.graph_replayed_launches += plan.graph_launches[graph_name]
-                else:
-                    step_fn()
-                self.last_unet_evals += 1
-            if inpaint is not None:   # processing.py sample(): samples * nmask + init_latent * mask
-                ops.blend_latent(plan.x, plan.init, plan.latmask)
-            return plan.x
+        """txt2img sampling from unit noise x_T [b, 4, h, w] (the historical entry point; tests drive it directly).
+        `schedule` = (timesteps, coef rows) overrides the DDIM schedule and `sigmas` = (sigma table ending in 0, model
+        log-sigmas) the k-diffusion one — x_T is then the ALREADY NOISED start.  Requests go through program() /
+        run_program()."""
+        pr = self.program(sampler, scheduler, steps)
+        if schedule is not None:
+            pr.ts, pr.rows = list(schedule[0]), list(schedule[1])
+            pr.noise_scale = 1.0
+        if sigmas is not None:
+            fn = {"euler_a": euler_a_plan, "euler": euler_plan, "dpmpp_2m": dpmpp_2m_plan}[pr.fused]
+            pr.ts, pr.rows, sigma0 = fn(len(sigmas[0]) - 1, None, sigmas)
+            pr.noise_scale, pr.in0 = 1.0, S.c_in(sigma0)
+            pr.draws = len(pr.rows) if pr.fused == "euler_a" else 0
+        return self.run_program(cond, uncond, x_T.to(torch.float32) * pr.noise_scale, pr, cfg_scale, noises, inpaint)
 
     @torch.no_grad()
     def decode(self, latents: torch.Tensor, h: int, w: int) -> torch.Tensor:
@@ -467,8 +692,10 @@ class SDEngine:
                 inpainting_fill: int = 1) -> torch.Tensor:
         """img2img: VAE-encode the init images (posterior mean), noise them to t_enc, run the remaining part of the
         sampler's schedule, decode.  init_u8 uint8 [b, H, W, 3].  Returns uint8 [b, H, W, 3] on device.
-        `latmask` fp32 [h * w] (b200sd.inpaint.prepare_mask): inpainting — the region with latmask 0 keeps the init
-        latents at every step (DDIM only); the caller composites the original pixels back (inpaint.apply_overlays).
+        `latmask` fp32 [h * w] (b200sd.inpaint.prepare_mask): inpainting — the region with latmask 0 is held to the init
+        latents (timestep samplers: blended into x before every model call; k-diffusion samplers: blended into the
+        denoised prediction, as sdwui's CFGDenoiser does); the caller composites the original pixels back
+        (inpaint.apply_overlays).
         `inpainting_fill` 2 ("latent noise") / 3 ("latent nothing") replace the repainted region of the init latents by
         the request's start noise / by zeros first (sdwui Img2Img.init); 0 ("fill") is image-space work the caller does
         before the call (inpaint.fill_masked), 1 keeps the original content."""
@@ -490,23 +717,12 @@ class SDEngine:
                      cfg_scale: float, sampler: str, scheduler: Optional[str], inpaint=None) -> torch.Tensor:
         """the img2img half of a sampler (also the second pass of the hires fix): `init` [b, 4, h, w] latents on the device,
         fresh per-image noise from `seed`, start at the noise level of t_enc.
-        DDIM: sdwui sd_samplers_timesteps.sample_img2img; k-diffusion samplers: KDiffusionSampler.sample_img2img."""
+        DDIM / PLMS: sdwui sd_samplers_timesteps.sample_img2img; k-diffusion samplers: KDiffusionSampler.sample_img2img."""
         b, _, h, w = init.shape
-        method, sched = resolve_sampler(sampler, scheduler)
-        if method == "ddim":
-            noise = per_image_noise(seed, b, (4, h, w), 1, *self.variation)[0].to(self.device)
-            sa, s1a, ts, rows = ddim_img2img_plan(steps, denoising_strength)
-            return self.sample(cond, uncond, init * sa + noise * s1a, steps, cfg_scale, "DDIM", schedule=(ts, rows),
-                               inpaint=inpaint)
-        if inpaint is not None:
-            raise ValueError("inpainting masks are implemented for the DDIM sampler only")
-        sig, log_sig = kdiffusion_img2img_sigmas(steps, denoising_strength, sched)
-        n_evals = len(sig) - 1
-        draws = 1 + (n_evals if method == "euler_a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
-        x0 = init + nz[0].to(self.device) * float(sig[0])
-        return self.sample(cond, uncond, x0, n_evals, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
-                           scheduler=scheduler, sigmas=(sig, log_sig))
+        pr = self.program(sampler, scheduler, steps, denoise=denoising_strength, masked=inpaint is not None)
+        nz = per_image_noise(seed, b, (4, h, w), 1 + pr.draws, *self.variation)
+        return self.run_program(cond, uncond, pr.start(nz[0].to(self.device), init), pr, cfg_scale,
+                                noises=nz[1:] if pr.draws else None, inpaint=inpaint)
 
     @torch.no_grad()
     def txt2img_hires(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20,
@@ -522,16 +738,19 @@ class SDEngine:
         h2, w2 = int(height * hr_scale) // 8, int(width * hr_scale) // 8
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
-        draws = 1 + (steps if sampler == "Euler a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
-        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
-                          scheduler=scheduler)
+        lat = self._sample_txt(cond, uncond, seed, b, h, w, steps, cfg_scale, sampler, scheduler)
         with self._ctx():
             up = torch.empty((b, h2 * w2, 4), device=self.device, dtype=torch.float32)
             ops.resize_latent_bilinear(lat.contiguous(), up, h, w, h2, w2)
         init = up.reshape(b, h2, w2, 4).permute(0, 3, 1, 2)
         lat2 = self._sample_from(init, cond, uncond, seed, denoising_strength, hr_steps or steps, cfg_scale, sampler, scheduler)
         return self.decode(lat2, h2, w2)
+
+    def _sample_txt(self, cond, uncond, seed: int, b: int, h: int, w: int, steps: int, cfg_scale: float, sampler: str,
+                    scheduler: Optional[str]) -> torch.Tensor:
+        pr = self.program(sampler, scheduler, steps)
+        nz = per_image_noise(seed, b, (4, h, w), 1 + pr.draws, *self.variation)
+        return self.run_program(cond, uncond, pr.start(nz[0]), pr, cfg_scale, noises=nz[1:] if pr.draws else None)
 
     @torch.no_grad()
     def txt2img(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, seed: int, steps: int = 20, cfg_scale: float = 7.0,
@@ -541,8 +760,5 @@ class SDEngine:
         h, w = height // 8, width // 8
         cond = self.encode_prompts(tokens)
         uncond = self.encode_prompts(neg_tokens)
-        draws = 1 + (steps if sampler == "Euler a" else 0)
-        nz = per_image_noise(seed, b, (4, h, w), draws, *self.variation)
-        lat = self.sample(cond, uncond, nz[0], steps, cfg_scale, sampler, noises=nz[1:] if draws > 1 else None,
-                          scheduler=scheduler)
+        lat = self._sample_txt(cond, uncond, seed, b, h, w, steps, cfg_scale, sampler, scheduler)
         return self.decode(lat, h, w)

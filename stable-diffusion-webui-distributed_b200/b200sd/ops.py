@@ -335,3 +335,40 @@ def resize_latent_bilinear(x: torch.Tensor, y: torch.Tensor, h: int, w: int, ho:
     check(rc, "b200sd_resize_latent_bilinear")
     _count()
     return y
+
+
+def cfg_eps(eps: torch.Tensor, e: torch.Tensor, cfg_scale: float):
+    """eps [2B, HW, pitch] (cond | uncond) -> e fp32 [B, HW, 4] = eu + cfg * (ec - eu)"""
+    b, hw, _ = e.shape
+    assert e.dtype == torch.float32 and e.is_contiguous()
+    rc = _lib.lib().b200sd_cfg_eps(_p(eps), ctypes.c_longlong(eps.stride(1)), _p(e), b, hw, ctypes.c_float(cfg_scale),
+                                   _dt(eps), _stream())
+    check(rc, "b200sd_cfg_eps")
+    _count()
+    return e
+
+
+def latent_lincomb(dst: torch.Tensor, srcs, coef: torch.Tensor, col0: int, step_counter: torch.Tensor,
+                   xin: Optional[torch.Tensor] = None, idx_col: int = -1):
+    """dst fp32 [B, HW, 4] = sum_k coef[*step, col0 + k] * srcs[k]; a source of shape [R, B, HW, 4] is a stack indexed by
+    (int)coef[*step, idx_col]; with `xin` the result * coef[*step, col0 + len(srcs)] is packed as the next UNet input."""
+    b, hw, _ = dst.shape
+    n = len(srcs)
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and coef.dtype == torch.float32 and coef.is_contiguous()
+    ptrs = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    strides = (ctypes.c_longlong * n)(*[(s.stride(0) if s.dim() == 4 else 0) for s in srcs])
+    for s in srcs:
+        assert s.dtype == torch.float32 and s.is_contiguous() and s.shape[-3:] == dst.shape
+    rc = _lib.lib().b200sd_latent_lincomb(_p(dst), ptrs, strides, n, _p(coef), coef.shape[1], col0, idx_col,
+                                          _p(step_counter), _p(xin),
+                                          ctypes.c_longlong(0 if xin is None else xin.stride(1)), b, hw,
+                                          F16 if xin is None else _dt(xin), _stream())
+    check(rc, "b200sd_latent_lincomb")
+    _count()
+    return dst
+
+
+def bump_step(step_counter: torch.Tensor):
+    rc = _lib.lib().b200sd_bump_step(_p(step_counter), _stream())
+    check(rc, "b200sd_bump_step")
+    _count()

@@ -210,7 +210,32 @@ def resize_latent_bilinear(x, y, h, w, ho, wo):
     return y
 
 
-ALL = ["resize_latent_bilinear", "blend_latent", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
+def cfg_eps(eps, e, cfg_scale):
+    b = e.shape[0]
+    ec, eu = eps[:b, :, :4].float(), eps[b:, :, :4].float()
+    e.copy_(eu + cfg_scale * (ec - eu))
+    return e
+
+
+def latent_lincomb(dst, srcs, coef, col0, step_counter, xin=None, idx_col=-1):
+    row = int(step_counter.item())
+    idx = int(coef[row, idx_col]) if idx_col >= 0 else 0
+    acc = torch.zeros_like(dst)
+    for k, s in enumerate(srcs):
+        w = float(coef[row, col0 + k])
+        if w != 0.0:
+            acc = acc + w * (s[idx] if s.dim() == 4 else s)
+    dst.copy_(acc)
+    if xin is not None:
+        pack_unet_input(dst, xin, float(coef[row, col0 + len(srcs)]))
+    return dst
+
+
+def bump_step(step_counter):
+    step_counter += 1
+
+
+ALL = ["cfg_eps", "latent_lincomb", "bump_step", "resize_latent_bilinear", "blend_latent", "linear", "pick_block_n", "conv2d", "attention", "groupnorm", "groupnorm_stats_floats", "layernorm", "upsample2x", "softmax_rows_", "silu",
        "timestep_embedding", "fold_bias", "select_step", "pack_unet_input", "cfg_ddim_step", "cfg_euler_a_step", "cfg_dpmpp_2m_step",
        "quantize_u8", "image_to_nhwc", "unpack_latent"]
 

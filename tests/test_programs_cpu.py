@@ -185,10 +185,16 @@ def test_variation_seeds(env):
     base = E.per_image_noise(10, 3, shape, 2)
     assert torch.equal(E.per_image_noise(10, 3, shape, 2, 500, 0.0), base)
     full = E.per_image_noise(10, 3, shape, 2, 500, 1.0)
-    assert torch.allclose(full[0], E.per_image_noise(500, 3, shape)[0], atol=1e-5) and torch.equal(full[1], base[1])
+    # sdwui processing.py: with variation seeds EVERY image uses the base seed (all_seeds[k] = seed) and only the subseed
+    # advances (all_subseeds[k] = subseed + k): the later draws of all images are image 0's
+    assert torch.allclose(full[0], E.per_image_noise(500, 3, shape)[0], atol=1e-5)
+    assert all(torch.equal(full[1, k], base[1, 0]) for k in range(3))
     mid = E.per_image_noise(10, 3, shape, 2, 500, 0.3)
     assert torch.allclose(mid[0], O.per_image_noise(10, 3, shape, subseed=500, subseed_strength=0.3), atol=1e-6)
-    assert not torch.allclose(mid[0], base[0]) and torch.equal(mid[1], base[1])
+    assert not torch.allclose(mid[0], base[0]) and all(torch.equal(mid[1, k], base[1, 0]) for k in range(3))
+    import math
+    s0 = E.slerp(0.3, base[0, 0], E.per_image_noise(501, 1, shape)[0, 0])   # image 1: noise(seed) with subnoise(subseed + 1)
+    assert torch.allclose(mid[0, 1], s0, atol=1e-6)
     # through the request path: the engine's variation attribute changes the start noise only when set
     tok, neg = O.random_prompt_tokens(2, vocab_hi=997), O.empty_prompt_tokens(2, vocab_hi=997)
     a = eng.txt2img(tok, neg, seed=5, steps=3, cfg_scale=7.0, height=64, width=64, sampler="DDIM").clone()
@@ -337,8 +343,10 @@ def test_inpainting_matches_oracle(env, blur, invert):
     final = inp.apply_overlays(got.cpu(), inp.overlays_for(init, m))
     d = (final.int() - ref_u8.int()).abs()
     assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
-    with pytest.raises(ValueError):
-        eng.img2img(tok, neg, 1, init, 0.75, steps=steps, cfg_scale=7.0, sampler="Euler", latmask=m.latmask)
+    # the k-diffusion samplers take masks too (tests/test_samplers_cpu.py compares them with the oracle): kept region intact
+    got_e = eng.img2img(tok, neg, 1, init, 0.75, steps=steps, cfg_scale=7.0, sampler="Euler", latmask=m.latmask)
+    z_e = eng.plan(b, h, h).x.reshape(b, h, h, 4).permute(0, 3, 1, 2)
+    assert got_e.shape == got.shape and torch.equal(z_e[keep], lat0[keep])
 
 
 @pytest.mark.parametrize("fill", [0, 2, 3])
