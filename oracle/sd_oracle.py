@@ -1197,3 +1197,150 @@ def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, see
         out[k] = torch.from_numpy(np.array(img.convert("RGB")))
     return out, x
 
+
+
+# ------------------------------------------------------------------------------------------------ "only masked" inpainting
+def get_crop_region(mask, pad: int = 0):
+    """sdwui modules/masking.py get_crop_region (numpy mask [h, w]): columns / rows that are entirely zero are trimmed"""
+    h, w = mask.shape
+    crop_left = 0
+    for i in range(w):
+        if not (mask[:, i] == 0).all():
+            break
+        crop_left += 1
+    crop_right = 0
+    for i in reversed(range(w)):
+        if not (mask[:, i] == 0).all():
+            break
+        crop_right += 1
+    crop_top = 0
+    for i in range(h):
+        if not (mask[i] == 0).all():
+            break
+        crop_top += 1
+    crop_bottom = 0
+    for i in reversed(range(h)):
+        if not (mask[i] == 0).all():
+            break
+        crop_bottom += 1
+    return (int(max(crop_left - pad, 0)), int(max(crop_top - pad, 0)), int(min(w - crop_right + pad, w)),
+            int(min(h - crop_bottom + pad, h)))
+
+
+def expand_crop_region(crop_region, processing_width, processing_height, image_width, image_height):
+    """sdwui modules/masking.py expand_crop_region"""
+    x1, y1, x2, y2 = crop_region
+    ratio_crop_region = (x2 - x1) / (y2 - y1)
+    ratio_processing = processing_width / processing_height
+    if ratio_crop_region > ratio_processing:
+        desired_height = (x2 - x1) / ratio_processing
+        desired_height_diff = int(desired_height - (y2 - y1))
+        y1 -= desired_height_diff // 2
+        y2 += desired_height_diff - desired_height_diff // 2
+        if y2 >= image_height:
+            diff = y2 - image_height
+            y2 -= diff
+            y1 -= diff
+        if y1 < 0:
+            y2 -= y1
+            y1 -= y1
+        if y2 >= image_height:
+            y2 = image_height
+    else:
+        desired_width = (y2 - y1) * ratio_processing
+        desired_width_diff = int(desired_width - (x2 - x1))
+        x1 -= desired_width_diff // 2
+        x2 += desired_width_diff - desired_width_diff // 2
+        if x2 >= image_width:
+            diff = x2 - image_width
+            x2 -= diff
+            x1 -= diff
+        if x1 < 0:
+            x2 -= x1
+            x1 -= x1
+        if x2 >= image_width:
+            x2 = image_width
+    return x1, y1, x2, y2
+
+
+def resize_image(resize_mode: int, im, width: int, height: int):
+    """sdwui modules/images.py resize_image without an upscaler: 0 just resize, 1 crop and resize, 2 resize and fill"""
+    from PIL import Image
+    if resize_mode == 0:
+        return im.resize((width, height), resample=Image.LANCZOS)
+    ratio = width / height
+    src_ratio = im.width / im.height
+    if resize_mode == 1:
+        src_w = width if ratio > src_ratio else im.width * height // im.height
+        src_h = height if ratio <= src_ratio else im.height * width // im.width
+        resized = im.resize((src_w, src_h), resample=Image.LANCZOS)
+        res = Image.new("RGB", (width, height))
+        res.paste(resized, box=(width // 2 - src_w // 2, height // 2 - src_h // 2))
+        return res
+    src_w = width if ratio < src_ratio else im.width * height // im.height
+    src_h = height if ratio >= src_ratio else im.height * width // im.width
+    resized = im.resize((src_w, src_h), resample=Image.LANCZOS)
+    res = Image.new("RGB", (width, height))
+    res.paste(resized, box=(width // 2 - src_w // 2, height // 2 - src_h // 2))
+    if ratio < src_ratio:
+        fill_height = height // 2 - src_h // 2
+        if fill_height > 0:
+            res.paste(resized.resize((width, fill_height), box=(0, 0, width, 0)), box=(0, 0))
+            res.paste(resized.resize((width, fill_height), box=(0, resized.height, width, resized.height)),
+                      box=(0, fill_height + src_h))
+    elif ratio > src_ratio:
+        fill_width = width // 2 - src_w // 2
+        if fill_width > 0:
+            res.paste(resized.resize((fill_width, height), box=(0, 0, 0, height)), box=(0, 0))
+            res.paste(resized.resize((fill_width, height), box=(resized.width, 0, resized.width, height)),
+                      box=(fill_width + src_w, 0))
+    return res
+
+
+def only_masked_setup(init_image, mask_img, width: int, height: int, lat_h: int, lat_w: int, mask_blur: int = 4,
+                      invert: bool = False, padding: int = 32):
+    """sdwui StableDiffusionProcessingImg2Img.init with inpaint_full_res ("Only masked"): returns
+    (crop_region, paste_to, processing-size init image (PIL RGB), latent mask tensor [lat_h, lat_w], overlay image RGBA)."""
+    import cv2
+    import numpy as np
+    from PIL import Image, ImageOps
+    if mask_img.mode == "RGBA" and mask_img.getextrema()[-1] != (255, 255):
+        image_mask = mask_img.split()[-1].convert("L").point(lambda v: 255 if v > 128 else 0)
+    else:
+        image_mask = mask_img.convert("L")
+    if invert:
+        image_mask = ImageOps.invert(image_mask)
+    if mask_blur > 0:
+        ks = 2 * int(2.5 * mask_blur + 0.5) + 1
+        image_mask = Image.fromarray(cv2.GaussianBlur(np.array(image_mask), (ks, 1), mask_blur))
+        image_mask = Image.fromarray(cv2.GaussianBlur(np.array(image_mask), (1, ks), mask_blur))
+    mask_for_overlay = image_mask
+    mask = image_mask.convert("L")
+    crop_region = get_crop_region(np.array(mask), padding)
+    crop_region = expand_crop_region(crop_region, width, height, mask.width, mask.height)
+    x1, y1, x2, y2 = crop_region
+    image_mask = resize_image(2, mask.crop(crop_region), width, height)
+    paste_to = (x1, y1, x2 - x1, y2 - y1)
+    image = init_image.convert("RGB")
+    image_masked = Image.new("RGBa", (image.width, image.height))
+    image_masked.paste(image.convert("RGBA").convert("RGBa"), mask=ImageOps.invert(mask_for_overlay.convert("L")))
+    overlay = image_masked.convert("RGBA")
+    image = resize_image(2, image.crop(crop_region), width, height)
+    latmask = image_mask.convert("RGB").resize((lat_w, lat_h))
+    latmask = np.moveaxis(np.array(latmask, dtype=np.float32), 2, 0) / 255
+    latmask = np.around(latmask[0])
+    return crop_region, paste_to, image, torch.from_numpy(latmask), overlay
+
+
+def apply_overlay(image, paste_loc, overlay):
+    """sdwui processing.py apply_overlay"""
+    from PIL import Image
+    if paste_loc is not None:
+        x, y, w, h = paste_loc
+        base_image = Image.new("RGBA", (overlay.width, overlay.height))
+        image = resize_image(1, image, w, h)
+        base_image.paste(image, (x, y))
+        image = base_image
+    image = image.convert("RGBA")
+    image.alpha_composite(overlay)
+    return image.convert("RGB")

@@ -21,6 +21,7 @@ from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
 from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
 
 MAX_STEPS = 256
+MAX_PLANS = 6        # distinct (batch, latent h, w) kept per engine; the least recently used one is dropped beyond that
 NOISE_SAMPLERS = ("Euler a", "stage")   # graph-name prefixes of the step graphs that may read Plan.noise
 _CAPTURE_LOCK = threading.Lock()  # CUDA graph captures are serialised across the per-device worker threads
 
@@ -376,9 +377,24 @@ class SDEngine:
             raise ValueError(f"latent size {h}x{w} (batch {b}) is not a positive multiple of {down}: image sides must be "
                              f"multiples of {8 * down} pixels")
         if key not in self.plans:
+            while len(self.plans) >= MAX_PLANS:   # LRU: a client varying sizes must not walk the device out of memory
+                old = self.plans.pop(next(iter(self.plans)))
+                old.graphs.clear()
             with self._ctx():
                 self.plans[key] = Plan(self, b, h, w, self.vae_chunk)
+        else:
+            self.plans[key] = self.plans.pop(key)   # most recently used last
         return self.plans[key]
+
+    def release(self):
+        """drop every plan, graph and encoder program (factory.evict / LocalGPUWorker.restart)"""
+        for p in self.plans.values():
+            p.graphs.clear()
+        self.plans.clear()
+        self.encoders.clear()
+        if self.device.type == "cuda":
+            with self._ctx():
+                torch.cuda.empty_cache()
 
     @torch.no_grad()
     def encode_prompts(self, tokens: torch.Tensor) -> torch.Tensor:
@@ -671,6 +687,8 @@ class SDEngine:
             c = min(self.vae_chunk, b)
             key = (c, hh, ww)
             if key not in self.encoders:
+                while len(self.encoders) >= MAX_PLANS:
+                    self.encoders.pop(next(iter(self.encoders)))
                 self.encoders[key] = VAEEncoderProgram(self.vae_enc_w, c, hh, ww)
             enc = self.encoders[key]
             imgs = images_u8.to(self.device).reshape(b, hh * ww, 3)

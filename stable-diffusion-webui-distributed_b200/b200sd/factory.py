@@ -3,6 +3,7 @@
 Weights: `SD_CKPT=/path/model.safetensors` (ldm key names) when present, otherwise the seeded synthetic SD1.5
 weights of synth.py (no checkpoint exists offline — every benchmark / parity number in this repo uses those).
 """
+import logging
 import os
 import threading
 import zlib
@@ -14,6 +15,7 @@ from . import config as C
 from .engine import SDEngine
 from .synth import make_state_dict
 
+log = logging.getLogger("distributed")
 _LOCK = threading.Lock()
 _ENGINES: Dict[str, SDEngine] = {}
 _STATE: Dict[str, Dict[str, torch.Tensor]] = {}
@@ -51,10 +53,32 @@ def default_engine_factory(device: str, size: str = None) -> SDEngine:
     with _LOCK:
         eng = _ENGINES.get(key)
     if eng is None:
+        if size != "tiny" and not os.environ.get("SD_CKPT"):
+            log.warning("b200sd: SD_CKPT is not set — serving SEEDED SYNTHETIC %s weights (images are noise); "
+                        "set SD_CKPT=/path/model.safetensors for a real checkpoint", size)
+        if size != "tiny" and not os.environ.get("SD_TOKENIZER"):
+            log.warning("b200sd: SD_TOKENIZER is not set — prompts are hashed to token ids, not BPE-tokenised")
         eng = SDEngine(state_dict(size), *configs(size), device=device)
         with _LOCK:
             _ENGINES[key] = eng
     return eng
+
+
+def evict(device: str) -> int:
+    """forget the cached engines of `device` (LocalGPUWorker.restart): their weights, plans and graphs are freed once the
+    last reference goes"""
+    with _LOCK:
+        keys = [k for k in _ENGINES if k.startswith(f"{device}:")]
+        for k in keys:
+            _ENGINES.pop(k).release()
+    return len(keys)
+
+
+def model_identity(size: str = None) -> str:
+    """what /sd-models and /options report as the loaded checkpoint"""
+    size = size or os.environ.get("B200SD_MODEL", "sd15")
+    ckpt = os.environ.get("SD_CKPT")
+    return os.path.basename(ckpt) if ckpt and size == "sd15" else f"synthetic-{size}-seed0"
 
 
 _TOKENIZER = {}

@@ -17,13 +17,17 @@ import json
 import time
 from threading import Thread
 
+import numpy as np
 import torch
 from modules.shared import state as master_state
 
 from .shared import logger
 from .worker import InvalidWorkerResponse, State, Worker
 
-SUPPORTED_SAMPLERS = ("DDIM", "Euler a", "Euler", "DPM++ 2M", "DPM++ 2M Karras")
+def supported_samplers():
+    """every sampler name of the reference's ETA table (worker.py:75-94) plus Euler a — b200sd.engine.SAMPLERS"""
+    from b200sd.engine import SAMPLERS
+    return tuple(SAMPLERS)
 
 
 class LocalGPUWorker(Worker):
@@ -80,6 +84,10 @@ class LocalGPUWorker(Worker):
         return []
 
     def restart(self) -> bool:
+        """reference Worker.restart posts /server-restart; here: drop the engine (weights, plans, graphs) — the next
+        request rebuilds it"""
+        from b200sd import factory
+        factory.evict(self.device)
         self._engine = None
         return True
 
@@ -142,7 +150,7 @@ class LocalGPUWorker(Worker):
         steps = int(payload["steps"])
         width, height = int(payload["width"]), int(payload["height"])
         sampler = payload.get("sampler_name") or payload.get("sampler_index") or "Euler a"
-        if sampler not in SUPPORTED_SAMPLERS:
+        if sampler not in supported_samplers():
             logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")
             sampler = "Euler a"
         scheduler = payload.get("scheduler")  # sdwui >= 1.9 sends the noise schedule separately from the sampler
@@ -155,32 +163,41 @@ class LocalGPUWorker(Worker):
         init_u8 = None
         inpaint = None
         if payload.get("init_images"):
-            init_u8 = self._init_images_u8(payload["init_images"], batch, width, height)
+            init_pil = self._init_images_pil(payload["init_images"])
             mask_img = payload.get("image_mask") if payload.get("image_mask") is not None else payload.get("mask")
             if mask_img is not None:
-                # inpainting (reference worker.py:365-373 sends `image_mask` as the API's `mask`): whole-picture mode with
-                # the original content under the mask; the other modes fall back to it with a warning
+                # inpainting (reference worker.py:365-373 sends `image_mask` as the API's `mask`, :406-410 the other fields)
                 from b200sd import inpaint as inp
                 from PIL import Image
                 if isinstance(mask_img, str):
                     data = mask_img.split(",", 1)[1] if mask_img.startswith("data:") else mask_img
                     mask_img = Image.open(io.BytesIO(base64.b64decode(data)))
-                if payload.get("inpaint_full_res") not in (None, False, 0):
-                    logger.warning(f"'only masked' inpainting is not implemented on worker {self.label}: inpainting the whole picture")
-                if sampler != "DDIM":
-                    logger.warning(f"inpainting on worker {self.label} runs DDIM ('{sampler}' with a mask is not implemented)")
-                    sampler = "DDIM"
                 down = 2 ** (len(eng.vae_cfg.ch_mult) - 1)   # 8 for the kl-f8 autoencoder
                 blur = payload.get("mask_blur")
-                inpaint = inp.prepare_mask(mask_img, width, height, height // down, width // down,
-                                           mask_blur=4 if blur is None else int(blur),
-                                           invert=bool(payload.get("inpainting_mask_invert") or 0))
-                inpaint_overlays = inp.overlays_for(init_u8, inpaint)
-                fill = payload.get("inpainting_fill")
-                inpaint_fill = 1 if fill is None else int(fill)
-                if inpaint_fill == 0:   # "fill": blur the surroundings into the masked region before encoding
-                    init_u8 = inp.fill_masked(init_u8, inpaint)
-        denoise = float(payload.get("denoising_strength", 0.75) or 0.75)
+                kw = dict(mask_blur=4 if blur is None else int(blur), invert=bool(payload.get("inpainting_mask_invert") or 0))
+                if payload.get("inpaint_full_res") not in (None, False, 0):   # "Only masked"
+                    pad = payload.get("inpaint_full_res_padding")
+                    inpaint = inp.prepare_mask_only_masked(mask_img, width, height, height // down, width // down,
+                                                           padding=32 if pad is None else int(pad), **kw)
+                    if inpaint is not None:
+                        full = torch.stack([torch.from_numpy(np.array(im.convert("RGB"))) for im in
+                                            (init_pil[i % len(init_pil)] for i in range(batch))])
+                        inpaint_overlays = inp.overlays_for(full, inpaint)
+                        init_u8 = inp.crop_init_images([init_pil[i % len(init_pil)] for i in range(batch)], inpaint)
+                if inpaint is None and init_u8 is None:
+                    init_u8 = self._init_images_u8(init_pil, batch, width, height)
+                    if payload.get("inpaint_full_res") in (None, False, 0):
+                        inpaint = inp.prepare_mask(mask_img, width, height, height // down, width // down, **kw)
+                        inpaint_overlays = inp.overlays_for(init_u8, inpaint)
+                if inpaint is not None:
+                    fill = payload.get("inpainting_fill")
+                    inpaint_fill = 1 if fill is None else int(fill)
+                    if inpaint_fill == 0:   # "fill": blur the surroundings into the masked region before encoding
+                        init_u8 = inp.fill_masked(init_u8, inpaint)
+            else:
+                init_u8 = self._init_images_u8(init_pil, batch, width, height)
+        ds = payload.get("denoising_strength")
+        denoise = 0.75 if ds is None else float(ds)   # an explicit 0 stays 0 (the noised init comes back untouched)
         prompt = payload.get("prompt", "") or ""
         negative = payload.get("negative_prompt", "") or ""
         seed = int(payload.get("seed", -1))
@@ -202,11 +219,13 @@ class LocalGPUWorker(Worker):
         chunks = []
         for it in range(n_iter):
             # variation seeds: image k of iteration `it` blends noise(seed + k) with noise(subseed + k)
+            # sdwui processing.py: all_seeds[k] = seed + (k if subseed_strength == 0 else 0), all_subseeds[k] = subseed + k
             eng.variation = (subseed + it * batch, strength) if strength != 0 else (None, 0.0)
+            seed_it = seed if strength != 0 else seed + it * batch
             tok = tok_all[:batch] if tok_all.shape[0] >= batch else tok_all[:1].expand(batch, -1)
             if init_u8 is not None:
                 kw = {} if inpaint is None else {"latmask": inpaint.latmask, "inpainting_fill": inpaint_fill}
-                u8 = eng.img2img(tok, neg_all, seed + it * batch, init_u8, denoising_strength=denoise, steps=steps,
+                u8 = eng.img2img(tok, neg_all, seed_it, init_u8, denoising_strength=denoise, steps=steps,
                                  cfg_scale=cfg_scale, sampler=sampler, scheduler=scheduler, **kw)
             elif payload.get("enable_hr"):
                 # hires fix (reference eta_hr, worker.py:205): second pass at hr_scale x with the "Latent" upscaler
@@ -216,13 +235,13 @@ class LocalGPUWorker(Worker):
                 hr_scale = float(payload.get("hr_scale") or 2.0)
                 if payload.get("hr_resize_x") and payload.get("hr_resize_y"):
                     hr_scale = float(payload["hr_resize_x"]) / width
-                u8 = eng.txt2img_hires(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
+                u8 = eng.txt2img_hires(tok, neg_all, seed_it, steps=steps, cfg_scale=cfg_scale, height=height,
                                        width=width, hr_scale=hr_scale,
                                        hr_steps=int(payload.get("hr_second_pass_steps") or 0),
-                                       denoising_strength=float(payload.get("denoising_strength") or 0.7), sampler=sampler,
+                                       denoising_strength=0.7 if ds is None else float(ds), sampler=sampler,
                                        scheduler=scheduler)
             else:
-                u8 = eng.txt2img(tok, neg_all, seed + it * batch, steps=steps, cfg_scale=cfg_scale, height=height,
+                u8 = eng.txt2img(tok, neg_all, seed_it, steps=steps, cfg_scale=cfg_scale, height=height,
                                  width=width, sampler=sampler, scheduler=scheduler)
             chunks.append(u8)
             if eng.interrupted:
@@ -237,9 +256,9 @@ class LocalGPUWorker(Worker):
             host = images.to(torch.uint8).contiguous()
         if inpaint is not None:   # sdwui apply_overlay: the original pixels come back through the blurred mask
             from b200sd import inpaint as inp
-            host = inp.apply_overlays(host, inpaint_overlays)
+            host = inp.apply_overlays(host, inpaint_overlays, inpaint.paste_to)
         n = host.shape[0]
-        seeds = [seed + i for i in range(n)]
+        seeds = [seed + (i if strength == 0 else 0) for i in range(n)]
         subseeds = [subseed + i for i in range(n)]
         infotexts = [f"{prompt}\nNegative prompt: {negative}\nSteps: {steps}, Sampler: {sampler}, CFG scale: {cfg_scale}, "
                      f"Seed: {s}, Size: {width}x{height}" for s in seeds]
@@ -253,10 +272,9 @@ class LocalGPUWorker(Worker):
                 "info": json.dumps(info)}
 
     @staticmethod
-    def _init_images_u8(init_images, batch: int, width: int, height: int) -> torch.Tensor:
-        """payload['init_images'] (PIL images, as sdwui holds them, or the API's base64 PNG strings) -> uint8
-        [batch, H, W, 3]; image i of the job uses init_images[i % len] (sdwui repeats a single init image per batch)."""
-        import numpy as np
+    def _init_images_pil(init_images):
+        """payload['init_images'] (PIL images, as sdwui holds them, the API's base64 PNG strings, or uint8 HWC tensors)
+        -> RGB PIL images at their own size"""
         from PIL import Image
         out = []
         for item in init_images:
@@ -264,13 +282,20 @@ class LocalGPUWorker(Worker):
                 data = item.split(",", 1)[1] if item.startswith("data:") else item
                 item = Image.open(io.BytesIO(base64.b64decode(data)))
             if isinstance(item, torch.Tensor):
-                arr = item.to(torch.uint8).cpu().numpy()
-            else:
-                img = item.convert("RGB")
-                if img.size != (width, height):
-                    img = img.resize((width, height), Image.LANCZOS)
-                arr = np.asarray(img)
-            out.append(torch.from_numpy(np.ascontiguousarray(arr)))
+                item = Image.fromarray(item.to(torch.uint8).cpu().numpy())
+            out.append(item.convert("RGB"))
+        return out
+
+    @staticmethod
+    def _init_images_u8(init_images, batch: int, width: int, height: int) -> torch.Tensor:
+        """RGB PIL images -> uint8 [batch, H, W, 3] at the processing size (resize_mode 0, LANCZOS); image i of the job uses
+        init_images[i % len] (sdwui repeats a single init image per batch)."""
+        from PIL import Image
+        out = []
+        for img in init_images:
+            if img.size != (width, height):
+                img = img.resize((width, height), Image.LANCZOS)
+            out.append(torch.from_numpy(np.ascontiguousarray(np.asarray(img))))
         return torch.stack([out[i % len(out)] for i in range(batch)])
 
     @staticmethod

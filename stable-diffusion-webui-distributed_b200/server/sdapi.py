@@ -65,6 +65,10 @@ class DevicePool:
                 w._engine.interrupted = True
 
 
+MAX_BATCH = 64      # images per call and device
+MAX_SIDE = 2048     # pixels
+
+
 def _jsonable_reply(rep: dict) -> dict:
     """the API reply: images / parameters / info only (the host-tensor fast lane stays in-process)"""
     return {"images": rep["images"], "parameters": rep["parameters"], "info": rep["info"]}
@@ -96,6 +100,16 @@ def create_app(engine_factory: Callable, devices: Optional[List[int]] = None, ap
         payload.setdefault("steps", 20)
         payload.setdefault("width", 512)
         payload.setdefault("height", 512)
+        # bound what one request may allocate: every distinct (batch, size) builds activation buffers and graphs
+        try:
+            bs, ni = int(payload["batch_size"]), int(payload["n_iter"])
+            wd, ht, st = int(payload["width"]), int(payload["height"]), int(payload["steps"])
+        except (TypeError, ValueError):
+            raise HTTPException(status_code=422, detail="batch_size, n_iter, steps, width, height must be integers")
+        if not (1 <= bs <= MAX_BATCH and 1 <= ni <= 64 and 1 <= st <= 150 and 64 <= wd <= MAX_SIDE and 64 <= ht <= MAX_SIDE
+                and wd % 64 == 0 and ht % 64 == 0):
+            raise HTTPException(status_code=422, detail=f"out of range: batch_size 1..{MAX_BATCH}, n_iter 1..64, steps 1..150, "
+                                                         f"width/height multiples of 64 in 64..{MAX_SIDE}")
         if img2img and not payload.get("init_images"):
             raise HTTPException(status_code=404, detail="Init image not found")
         if not img2img:

@@ -399,3 +399,34 @@ def test_img2img_matches_oracle(env):
     assert got.shape == ref_u8.shape
     d = (got.int() - ref_u8.int()).abs()
     assert float((d <= 1).float().mean()) == 1.0 and float((d == 0).float().mean()) > 0.99
+
+
+@pytest.mark.parametrize("size,box,proc", [((96, 64), (20, 10, 50, 30), (64, 64)), ((64, 96), (2, 60, 30, 94), (64, 32)),
+                                            ((80, 80), (0, 0, 80, 12), (32, 64))])
+def test_only_masked_inpainting_geometry(size, box, proc):
+    """inpaint_full_res ("Only masked", reference worker.py:406-410 forwards the field): crop region, processing-size init,
+    latent mask, overlay and the final paste-back equal the oracle's restatement of sdwui's Img2Img.init / apply_overlay"""
+    import numpy as np
+    from PIL import Image, ImageDraw
+    from b200sd import inpaint as inp
+    from oracle import sd_oracle as O
+    g = torch.Generator().manual_seed(3)
+    w, h = size
+    init = Image.fromarray(torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8).numpy(), "RGB")
+    mask = Image.new("L", size, 0)
+    ImageDraw.Draw(mask).ellipse(box, fill=255)
+    pw, ph = proc
+    crop, paste_to, proc_init, latmask, overlay = O.only_masked_setup(init, mask, pw, ph, ph // 8, pw // 8, mask_blur=2, padding=6)
+    m = inp.prepare_mask_only_masked(mask, pw, ph, ph // 8, pw // 8, mask_blur=2, padding=6)
+    assert m.crop == tuple(crop) and m.paste_to == tuple(paste_to)
+    assert torch.equal(m.latmask.reshape(ph // 8, pw // 8), latmask)
+    mine = inp.crop_init_images([init], m)
+    assert torch.equal(mine[0], torch.from_numpy(np.array(proc_init)))
+    full = torch.from_numpy(np.asarray(init))[None]
+    ov = inp.overlays_for(full, m)
+    assert np.array_equal(np.array(ov[0]), np.array(overlay))
+    gen = torch.randint(0, 256, (1, ph, pw, 3), generator=g, dtype=torch.uint8)
+    ref = O.apply_overlay(Image.fromarray(gen[0].numpy(), "RGB"), paste_to, overlay)
+    out = inp.apply_overlays(gen, ov, m.paste_to)
+    assert out.shape == (1, h, w, 3) and torch.equal(out[0], torch.from_numpy(np.array(ref)))
+    assert inp.prepare_mask_only_masked(Image.new("L", size, 0), pw, ph, ph // 8, pw // 8, mask_blur=0) is None
