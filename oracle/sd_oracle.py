@@ -27,6 +27,9 @@ import torch
 import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
+# bench.py's stock-PyTorch comparator flips this: attention through F.scaled_dot_product_attention (the fused library
+# kernel a stock fp16 pipeline would use) instead of the explicit softmax(q k^T) v the parity checks run
+USE_SDPA = False
 
 
 # ------------------------------------------------------------------------------------------------ configs
@@ -146,8 +149,11 @@ def cross_attention(sd: SD, p: str, x, context, heads: int):
     b, n, c = q.shape
     d = c // heads
     q, k, v = (t.reshape(b, -1, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
-    sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
-    out = torch.matmul(torch.softmax(sim.float(), dim=-1).to(v.dtype), v)
+    if USE_SDPA:
+        out = F.scaled_dot_product_attention(q, k, v)
+    else:
+        sim = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
+        out = torch.matmul(torch.softmax(sim.float(), dim=-1).to(v.dtype), v)
     out = out.permute(0, 2, 1, 3).reshape(b, n, c)
     return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
 
@@ -248,6 +254,10 @@ def _vae_attn(sd, p, x):
     k = F.conv2d(h, sd[p + ".k.weight"], sd[p + ".k.bias"])
     v = F.conv2d(h, sd[p + ".v.weight"], sd[p + ".v.bias"])
     b, c, hh, ww = q.shape
+    if USE_SDPA:
+        qs, ks, vs = (t.reshape(b, 1, c, hh * ww).transpose(-1, -2) for t in (q, k, v))
+        h = F.scaled_dot_product_attention(qs, ks, vs).transpose(-1, -2).reshape(b, c, hh, ww)
+        return x + F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
     k = k.reshape(b, c, hh * ww)
     w_ = torch.softmax((torch.bmm(q, k) * (c ** -0.5)).float(), dim=2).to(q.dtype)
@@ -1136,15 +1146,16 @@ def inpaint_masks(mask_img, width: int, height: int, lat_h: int, lat_w: int, mas
 
 def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, seed: int, init_u8: torch.Tensor, mask_img,
                     denoising_strength: float = 0.75, steps: int = 20, cfg_scale: float = 7.0, mask_blur: int = 4,
-                    invert: bool = False, inpainting_fill: int = 1):
+                    invert: bool = False, inpainting_fill: int = 1, device="cpu"):
     """DDIM inpainting as sdwui runs it (CFGDenoiserTimesteps.mask_before_denoising): before EVERY model call the region
     to keep is replaced by the clean init latent, x = x * nmask + init * mask; once more after sampling; decode; then
     apply_overlay pastes the original pixels back through the blurred mask.  Returns (uint8 images, final latents)."""
     import numpy as np
     from PIL import Image, ImageOps
     b, hh, ww = tokens.shape[0], init_u8.shape[1], init_u8.shape[2]
-    cond = clip_text_encode(sd, clip_cfg, tokens)
-    uncond = clip_text_encode(sd, clip_cfg, neg_tokens)
+    sd = {k: v.to(device) for k, v in sd.items()}
+    cond = clip_text_encode(sd, clip_cfg, tokens.to(device))
+    uncond = clip_text_encode(sd, clip_cfg, neg_tokens.to(device))
     enc_in = init_u8
     if inpainting_fill == 0:   # modules/masking.py fill(): cascade of blurs of the surroundings, with the BLURRED mask
         from PIL import ImageFilter
@@ -1168,11 +1179,11 @@ def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, see
                     mod.alpha_composite(blurred)
             filled.append(torch.from_numpy(np.array(mod.convert("RGB"))))
         enc_in = torch.stack(filled)
-    init = vae_encode_mean(sd, vae_cfg, image_to_model_input(enc_in)) * vae_cfg.scale_factor
+    init = vae_encode_mean(sd, vae_cfg, image_to_model_input(enc_in.to(device))) * vae_cfg.scale_factor
     latmask, overlay_mask = inpaint_masks(mask_img, ww, hh, init.shape[2], init.shape[3], mask_blur, invert)
-    nmask = latmask[None, None].to(init.dtype)
+    nmask = latmask[None, None].to(init.dtype).to(device)
     mask = 1.0 - nmask
-    noise = per_image_noise(seed, b, tuple(init.shape[1:]))
+    noise = per_image_noise(seed, b, tuple(init.shape[1:])).to(device)
     if inpainting_fill == 2:     # "latent noise"
         init = init * mask + noise * nmask
     elif inpainting_fill == 3:   # "latent nothing"
@@ -1185,7 +1196,7 @@ def img2img_inpaint(sd: SD, unet_cfg, vae_cfg, clip_cfg, tokens, neg_tokens, see
         x0 = (x - c_s1a * e) / c_sa
         x = c_sap * x0 + c_s1ap * e
     x = x * nmask + init * mask
-    gen = to_uint8(vae_decode(sd, vae_cfg, x / vae_cfg.scale_factor))
+    gen = to_uint8(vae_decode(sd, vae_cfg, x / vae_cfg.scale_factor)).cpu()
     out = torch.empty_like(gen)
     inv = ImageOps.invert(overlay_mask.convert("L"))
     for k in range(b):

@@ -406,8 +406,10 @@ class SDEngine:
         if not self.use_graphs or self.device.type != "cuda":
             return None
         if name not in plan.graphs:
-            # eager warm-up on scratch state: save what the step mutates
-            saved = (plan.x.clone(), plan.step.clone(), plan.unet.xin.clone())
+            # eager warm-up on scratch state: save what a step mutates (x, counter, UNet input, and the generic stage
+            # machine's latents — a multistep stage SHIFTS its history, which must not happen twice)
+            state = [plan.x, plan.step, plan.unet.xin, plan.old] + [v for k, v in plan.lat.items() if k != "x"]
+            saved = [t.clone() for t in state]
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
@@ -423,7 +425,8 @@ class SDEngine:
                     fn()
                 plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
             plan.graphs[name] = g
-            plan.x.copy_(saved[0]); plan.step.copy_(saved[1]); plan.unet.xin.copy_(saved[2])
+            for t, v in zip(state, saved):
+                t.copy_(v)
         return plan.graphs[name]
 
     # ------------------------------------------------------------------------------------------ sampler programs

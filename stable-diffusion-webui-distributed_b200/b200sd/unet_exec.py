@@ -195,6 +195,7 @@ class UNetProgram:
         self.gn_need = 0
         self.ctx_kv: Dict[str, torch.Tensor] = {}
         self.ops: List = []
+        self.op_flops: List = []
         self._build()
         # one statistics buffer serves every GroupNorm (they run back to back on one stream); zeroed once, here
         self.stats_all = torch.zeros((max(1, self.gn_need),), device=self.dev, dtype=torch.float32)
@@ -211,8 +212,11 @@ class UNetProgram:
             ops.linear(ctx2, self.w.t[key + ".attn2.kv.w"], buf.reshape(n * l, -1), bias=self.w.t[key + ".attn2.kv.b"])
 
     # ---------------------------------------------------------------- program construction
-    def _emit(self, fn, *a, **k):
+    def _emit(self, fn, *a, algo_flops=None, **k):
+        """algo_flops: the launch's ALGORITHMIC FLOPs when they differ from 2*M*N*K of the packed operands (zero-padded
+        head columns / latent channels are layout, not work) — read by bench.py's roofline, never by the kernels"""
         self.ops.append((fn, a, k))
+        self.op_flops.append(algo_flops)
 
     def _gn(self, x, out, name, eps, silu):
         holder = [None]
@@ -258,7 +262,8 @@ class UNetProgram:
             # --- self attention
             self._emit(ops.layernorm, hcur, a, t[tb + ".norm1.g"], t[tb + ".norm1.beta"], 1e-5)
             qkv = self.pool.get(n, hw, 3 * heads * dp)
-            self._emit(ops.linear, a, t[tb + ".attn1.qkv.w"], qkv, bias=t[tb + ".attn1.qkv.b"])
+            self._emit(ops.linear, a, t[tb + ".attn1.qkv.w"], qkv, bias=t[tb + ".attn1.qkv.b"],
+                       algo_flops=2.0 * n * hw * 3 * c * c)
             q, k, v = (qkv[..., j * heads * dp:(j + 1) * heads * dp] for j in range(3))
             o = self.pool.get(n, hw, c)
             self._emit(ops.attention, q, k, v, o, heads, d, dp, scale, dp > d)
@@ -269,7 +274,7 @@ class UNetProgram:
             # --- cross attention (K/V of the context are precomputed per request)
             self._emit(ops.layernorm, h1, a, t[tb + ".norm2.g"], t[tb + ".norm2.beta"], 1e-5)
             q2 = self.pool.get(n, hw, heads * dp)
-            self._emit(ops.linear, a, t[tb + ".attn2.q.w"], q2)
+            self._emit(ops.linear, a, t[tb + ".attn2.q.w"], q2, algo_flops=2.0 * n * hw * c * c)
             kv = torch.zeros((n, self.ctx_len, 2 * heads * dp), device=self.dev, dtype=self.dt)
             self.ctx_kv[tb] = kv
             self._emit(ops.attention, q2, kv[..., :heads * dp], kv[..., heads * dp:], o, heads, d, dp, scale, dp > d)
@@ -329,7 +334,8 @@ class UNetProgram:
                 tmp = None
                 if kind == "conv_in":
                     dest = final_dest
-                    self._emit(ops.conv2d, self.xin.unflatten(1, (h, wd)), t[key + ".w"], dest, ksize=3, bias=t[key + ".b"])
+                    self._emit(ops.conv2d, self.xin.unflatten(1, (h, wd)), t[key + ".w"], dest, ksize=3, bias=t[key + ".b"],
+                               algo_flops=2.0 * n * h * wd * 9 * cfg.in_channels * layer[2])
                 elif kind == "res":
                     dest = final_dest if last else self.pool.get(n, h * wd, layer[2])
                     tmp = None if last else dest
@@ -378,7 +384,7 @@ class UNetProgram:
         a = self.pool.get(n, self.h * self.wd, cfg.model_channels)
         self._gn(final, a, "out.gn", 1e-5, True)
         self._emit(ops.conv2d, a.unflatten(1, (self.h, self.wd)), t["out.conv.w"], self.eps.reshape(-1, 32), ksize=3,
-                   bias=t["out.conv.b"])
+                   bias=t["out.conv.b"], algo_flops=2.0 * n * self.h * self.wd * 9 * cfg.model_channels * cfg.out_channels)
         self.pool.put(a)
 
     # ---------------------------------------------------------------- execution

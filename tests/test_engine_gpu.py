@@ -308,3 +308,220 @@ def test_euler_a_parity_tiny(mods):
     rel = float((z - ref).abs().max() / ref.abs().max())
     _record("euler_a tiny", z_rel_max=rel)
     assert rel <= 3e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# round 2: what is measured is what is asserted.  Round-1 measurements of the uint8 images of full sampler runs: max 1 LSB,
+# mean 0.09-0.15 LSB, 85-91 % of pixels identical (gpurun_out/engine_parity.jsonl); one SD1.5 UNet evaluation rel-rms 1.4e-3.
+U8_MAX, U8_MEAN, U8_EXACT = 2, 0.3, 0.80
+UNET_REL_RMS = 3e-3
+
+
+def _u8_check(name, got, ref_u8, u8_max=U8_MAX, **extra):
+    du8 = (got.int().cpu() - ref_u8.int().cpu()).abs().float()
+    rec = dict(u8_mean=float(du8.mean()), u8_max=float(du8.max()), u8_exact=float((du8 == 0).float().mean()), **extra)
+    _record(name, **rec)
+    assert got.shape == ref_u8.shape
+    assert rec["u8_max"] <= u8_max and rec["u8_mean"] <= U8_MEAN and rec["u8_exact"] >= U8_EXACT, rec
+    return rec
+
+
+def test_tight_unet_and_image_tolerances_sd15(mods):
+    """the round-1 tests above keep their loose historical bounds; this one asserts what is actually measured"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b, hw = 2, 64
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    cond32, unc32 = O.clip_text_encode(dsd, cfgs[2], tok.cuda()), O.clip_text_encode(dsd, cfgs[2], neg.cuda())
+    x = O.per_image_noise(1000, b, (4, hw, hw)).cuda()
+    with torch.no_grad():
+        ref = O.unet_forward(dsd, cfgs[0], torch.cat([x, x]), torch.full((2 * b,), 651.0, device="cuda"), torch.cat([cond32, unc32]))
+    from b200sd import ops
+    plan = eng.plan(b, hw, hw)
+    plan.unet.set_context(torch.cat([cond32, unc32]).half().contiguous())
+    plan.table[:1].copy_(eng.temb.table(torch.tensor([651.0])))
+    plan.step.zero_()
+    plan.x.copy_(x.permute(0, 2, 3, 1).reshape(b, hw * hw, 4))
+    ops.pack_unet_input(plan.x, plan.unet.xin, 1.0)
+    ops.select_step(plan.table, plan.step, plan.unet.cur_bias)
+    plan.unet.run()
+    got = plan.unet.eps[..., :4].float().reshape(2 * b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel_rms = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    _record("unet_eval tight sd15", rel_rms=rel_rms)
+    assert rel_rms <= UNET_REL_RMS
+    with torch.no_grad():
+        ref_u8, _, _ = O.txt2img(dsd, *cfgs, tok, neg, seed=1000, steps=20, cfg_scale=7.0, height=512, width=512, device="cuda")
+    eng.use_graphs = True
+    got_u8 = eng.txt2img(tok, neg, seed=1000, steps=20, cfg_scale=7.0, height=512, width=512, sampler="DDIM")
+    eng.use_graphs = False
+    _u8_check("txt2img tight sd15 ddim", got_u8, ref_u8)
+
+
+def _oracle_run(O, dsd, cfgs, name, tok, neg, seed, steps, hw, draws_n, init=None, denoise=None, mask=None):
+    from b200sd import engine as E
+    b = tok.shape[0]
+    cond32, unc32 = O.clip_text_encode(dsd, cfgs[2], tok.cuda()), O.clip_text_encode(dsd, cfgs[2], neg.cuda())
+    nz = E.per_image_noise(seed, b, (4, hw, hw), 1 + draws_n).cuda()
+    unet = lambda x, t, c: O.unet_forward(dsd, cfgs[0], x, t, c)  # noqa: E731
+    with torch.no_grad():
+        z = O.run_sampler(name, unet, cond32, unc32, 7.0, steps, nz[0], list(nz[1:]), init=init, denoising_strength=denoise,
+                          mask=mask)
+    return z
+
+
+@pytest.mark.parametrize("name", ["Euler a", "DPM++ 2M Karras", "Heun", "DPM++ SDE Karras", "PLMS", "LMS"])
+def test_sd15_sampler_parity(mods, name):
+    """SD1.5-size, 512x512, 20 steps, CUDA graphs on: the samplers beyond DDIM against the oracle's k-diffusion / sdwui
+    restatement — latents and decoded uint8 images"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b, hw, steps = 2, 64, 20
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    pr = eng.program(name, None, steps)
+    ref_z = _oracle_run(O, dsd, cfgs, name, tok, neg, 5100, steps, hw, pr.draws)
+    with torch.no_grad():
+        ref_u8 = O.to_uint8(O.vae_decode(dsd, cfgs[1], ref_z / cfgs[1].scale_factor))
+    eng.use_graphs = True
+    got = eng.txt2img(tok, neg, seed=5100, steps=steps, cfg_scale=7.0, height=512, width=512, sampler=name)
+    eng.use_graphs = False
+    z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel_rms = float((z - ref_z).pow(2).mean().sqrt() / ref_z.pow(2).mean().sqrt())
+    _u8_check(f"sd15 sampler {name}", got, ref_u8, z_rel_rms=rel_rms, evals=eng.last_unet_evals)
+    assert rel_rms <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["Euler", "LMS", "Heun", "DPM2", "DPM2 a", "DPM++ 2S a", "DPM++ SDE", "DPM fast", "DPM adaptive",
+                                  "LMS Karras", "DPM2 Karras", "DPM2 a Karras", "DPM++ 2S a Karras", "DPM++ SDE Karras", "PLMS"])
+def test_every_reference_sampler_on_gpu_tiny(mods, name):
+    """reference scripts/spartan/worker.py:75-94: no name of the table falls back; each runs as stage graphs of
+    b200sd_cfg_eps + b200sd_latent_lincomb and matches the oracle"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b, hw, steps = 2, 16, 7
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    pr = eng.program(name, None, steps)
+    ref_z = _oracle_run(O, dsd, cfgs, name, tok, neg, 5200, steps, hw, pr.draws)
+    eng.use_graphs = True
+    eng.txt2img(tok, neg, seed=5200, steps=steps, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler=name)
+    eng.use_graphs = False
+    z = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel = float((z - ref_z).abs().max() / ref_z.abs().max())
+    _record(f"tiny sampler {name}", z_rel_max=rel, evals=eng.last_unet_evals)
+    assert rel <= 3e-2, rel
+
+
+def test_euler_a_graph_reads_this_requests_noise(mods):
+    """the Euler a step graph used to bake the FIRST request's noise tensor address.  Two requests with
+    different seeds and step counts on one engine, graphs on, must equal the eager runs."""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    b, hw = 2, 16
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    reqs = [(11, 5), (9999, 9), (12345, 40), (7, 5)]     # 40 steps outgrows the 32-row noise stack: graphs are rebuilt
+    eng.use_graphs = True
+    with_graphs = [eng.txt2img(tok, neg, seed=s, steps=n, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler="Euler a").clone()
+                   for s, n in reqs]
+    eng.use_graphs = False
+    eager = [eng.txt2img(tok, neg, seed=s, steps=n, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler="Euler a").clone()
+             for s, n in reqs]
+    for a, c in zip(with_graphs, eager):
+        assert torch.equal(a, c)
+    assert not torch.equal(with_graphs[0], with_graphs[3])
+
+
+def test_sd15_hires_fix_parity(mods):
+    """hires fix at SD1.5 size: 256x256 first pass, Latent upscale x2, Euler a second pass from t_enc at 512x512"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b, steps, hr_steps, d = 2, 12, 10, 0.6
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    pr1, pr2 = eng.program("Euler a", None, steps), eng.program("Euler a", None, hr_steps, denoise=d)
+    z1 = _oracle_run(O, dsd, cfgs, "Euler a", tok, neg, 5300, steps, 32, pr1.draws)
+    up = torch.nn.functional.interpolate(z1, size=(64, 64), mode="bilinear", antialias=False)
+    z2 = _oracle_run(O, dsd, cfgs, "Euler a", tok, neg, 5300, hr_steps, 64, pr2.draws, init=up, denoise=d)
+    with torch.no_grad():
+        ref_u8 = O.to_uint8(O.vae_decode(dsd, cfgs[1], z2 / cfgs[1].scale_factor))
+    eng.use_graphs = True
+    got = eng.txt2img_hires(tok, neg, seed=5300, steps=steps, cfg_scale=7.0, height=256, width=256, hr_scale=2.0,
+                            hr_steps=hr_steps, denoising_strength=d, sampler="Euler a")
+    eng.use_graphs = False
+    _u8_check("sd15 hires euler_a", got, ref_u8)
+
+
+def test_sd15_img2img_kdiffusion_parity(mods):
+    """img2img at 512x512 on a k-diffusion sampler (DPM++ 2M Karras): encode, noise to sigma_sched[0], the schedule's tail"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b, steps, d = 2, 20, 0.75
+    g = torch.Generator().manual_seed(4322)
+    init = torch.randint(0, 256, (b, 512, 512, 3), generator=g, dtype=torch.uint8)
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    with torch.no_grad():
+        lat0 = O.vae_encode_mean(dsd, cfgs[1], O.image_to_model_input(init.cuda())) * cfgs[1].scale_factor
+    z = _oracle_run(O, dsd, cfgs, "DPM++ 2M Karras", tok, neg, 5400, steps, 64, 0, init=lat0, denoise=d)
+    with torch.no_grad():
+        ref_u8 = O.to_uint8(O.vae_decode(dsd, cfgs[1], z / cfgs[1].scale_factor))
+    eng.use_graphs = True
+    got = eng.img2img(tok, neg, 5400, init, d, steps=steps, cfg_scale=7.0, sampler="DPM++ 2M Karras")
+    eng.use_graphs = False
+    assert eng.last_unet_evals == int(d * steps) + 1
+    _u8_check("sd15 img2img dpmpp_2m_karras", got, ref_u8)
+
+
+@pytest.mark.parametrize("sampler", ["DDIM", "Euler a"])
+def test_sd15_inpainting_parity(mods, sampler):
+    """inpainting at SD1.5 size against the ORACLE (round 1 compared the engine with itself): mask pipeline, per-step blend
+    (DDIM: model input; Euler a: denoised prediction), final blend, overlay composite"""
+    from PIL import Image, ImageDraw
+    from b200sd import inpaint as inp
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b, steps, d = 2, 20, 0.75
+    g = torch.Generator().manual_seed(4323)
+    init = torch.randint(0, 256, (b, 512, 512, 3), generator=g, dtype=torch.uint8)
+    mask_img = Image.new("L", (512, 512), 0)
+    ImageDraw.Draw(mask_img).ellipse((120, 150, 400, 380), fill=255)
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    m = inp.prepare_mask(mask_img, 512, 512, 64, 64, mask_blur=4)
+    if sampler == "DDIM":
+        with torch.no_grad():
+            ref_u8, _ = O.img2img_inpaint(sd, *cfgs, tok, neg, 5500, init, mask_img, d, steps=steps, mask_blur=4, device="cuda")
+    else:
+        with torch.no_grad():
+            lat0 = O.vae_encode_mean(dsd, cfgs[1], O.image_to_model_input(init.cuda())) * cfgs[1].scale_factor
+        latmask, overlay_mask = O.inpaint_masks(mask_img, 512, 512, 64, 64, 4, False)
+        nmask = latmask[None, None].cuda()
+        pr = eng.program(sampler, None, steps, denoise=d, masked=True)
+        z = _oracle_run(O, dsd, cfgs, sampler, tok, neg, 5500, steps, 64, pr.draws, init=lat0, denoise=d, mask=(lat0, nmask))
+        z = z * nmask + lat0 * (1 - nmask)
+        with torch.no_grad():
+            gen = O.to_uint8(O.vae_decode(dsd, cfgs[1], z / cfgs[1].scale_factor)).cpu()
+        ref_u8 = torch.stack([torch.from_numpy(__import__("numpy").array(O.apply_overlay(
+            Image.fromarray(gen[k].numpy(), "RGB"), None, inp.overlays_for(init[k:k + 1], m)[0]))) for k in range(b)])
+    eng.use_graphs = True
+    got = eng.img2img(tok, neg, 5500, init, d, steps=steps, cfg_scale=7.0, sampler=sampler, latmask=m.latmask).cpu()
+    eng.use_graphs = False
+    final = inp.apply_overlays(got, inp.overlays_for(init, m))
+    # the latent mask is a hard 0/1 edge: a few pixels next to it decode 3 LSB apart (measured: max 2 DDIM, 3 Euler a;
+    # mean 0.05 LSB, 95 % identical) — the mean / exact bounds stay the tight ones
+    _u8_check(f"sd15 inpainting {sampler}", final, ref_u8, u8_max=4)
+    assert torch.equal(final[:, :60], init[:, :60])     # far outside the blurred mask: the original pixels
+
+
+def test_bench_batch_spot_check_against_oracle(mods):
+    """the benchmark's configuration itself — batch 32, 20 DDIM timesteps, graphs on — with images 0, 13 and 31 checked
+    against the oracle run on each of them alone (image k depends on seed + k only)"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "sd15")
+    b = 32
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    eng.use_graphs = True
+    got = eng.txt2img(tok, neg, seed=1000, steps=20, cfg_scale=7.0, height=512, width=512, sampler="DDIM").cpu()
+    eng.use_graphs = False
+    for k in (0, 13, 31):
+        with torch.no_grad():
+            ref_u8, _, _ = O.txt2img(dsd, *cfgs, tok[k:k + 1], neg[k:k + 1], seed=1000 + k, steps=20, cfg_scale=7.0, height=512,
+                                     width=512, device="cuda")
+        _u8_check(f"bench batch32 image {k}", got[k:k + 1], ref_u8)
+    eng.plans.pop((32, 64, 64), None)
+    torch.cuda.empty_cache()

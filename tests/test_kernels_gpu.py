@@ -482,3 +482,34 @@ def test_resize_latent_bilinear(ops):
         ops.resize_latent_bilinear(x, y, h, w, ho, wo)
         ref = F.interpolate(x.reshape(b, h, w, 4).permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", antialias=False)
         assert torch.allclose(y.reshape(b, ho, wo, 4).permute(0, 3, 1, 2), ref, atol=1e-5, rtol=1e-5)
+
+
+def test_cfg_eps_and_latent_lincomb(ops):
+    """the two generic sampler kernels (b200sd_cfg_eps, b200sd_latent_lincomb): CFG combine, a device-selected coefficient
+    row, an indexed noise stack, in-place destination, zero weights that must not read a NaN buffer, the packed UNet input"""
+    g = _gen(91)
+    b, hw, pitch = 3, 257, 32
+    eps = _rand((2 * b, hw, pitch), g)
+    e = torch.empty((b, hw, 4), device="cuda")
+    ops.cfg_eps(eps, e, 6.5)
+    ec, eu = eps[:b, :, :4].float(), eps[b:, :, :4].float()
+    assert torch.allclose(e, eu + 6.5 * (ec - eu), atol=1e-6, rtol=1e-6)
+    x = torch.randn((b, hw, 4), generator=g, device="cuda")
+    h = torch.full((b, hw, 4), float("nan"), device="cuda")
+    noise = torch.randn((5, b, hw, 4), generator=g, device="cuda")
+    coef = torch.zeros((4, 32), device="cuda")
+    coef[2, 3:8] = torch.tensor([0.5, -1.25, 0.0, 2.0, 0.75])    # x, e, h (weight 0), noise, pack scale
+    coef[2, 31] = 3.0                                              # noise row
+    step = torch.tensor([2], device="cuda", dtype=torch.int32)
+    xin = torch.zeros((2 * b, hw, 64), device="cuda", dtype=torch.float16)
+    want = 0.5 * x - 1.25 * e + 2.0 * noise[3]
+    ops.latent_lincomb(x, [x, e, h, noise], coef, 3, step, xin, idx_col=31)
+    assert torch.allclose(x, want, atol=1e-6, rtol=1e-6) and not torch.isnan(x).any()
+    assert torch.equal(xin[:b, :, :4], (want * 0.75).half()) and torch.equal(xin[b:, :, :4], (want * 0.75).half())
+    assert float(xin[..., 4:].abs().max()) == 0.0
+    ops.bump_step(step)
+    assert int(step.item()) == 3
+    u = torch.empty_like(x)
+    coef[3, 0:2] = torch.tensor([1.0, 1.0])
+    ops.latent_lincomb(u, [x, e], coef, 0, step)
+    assert torch.allclose(u, x + e, atol=1e-6, rtol=1e-6)

@@ -130,3 +130,12 @@ def test_sde_noise_pair_has_the_brownian_covariance():
     n1, n2 = O.brownian_pair(z1, z2, s, ss, sn)
     assert abs(float(n1.var()) - 1) < 0.02 and abs(float(n2.var()) - 1) < 0.02
     assert abs(float((n1 * n2).mean()) - math.sqrt((s - ss) / (s - sn))) < 0.02
+
+
+def test_graph_warmup_must_not_shift_history():
+    """engine._graph runs a stage eagerly once before capturing it: the state it saves and restores must include the
+    multistep history (found on the GPU: PLMS's first multistep stage was shifted twice)"""
+    import inspect
+    from b200sd import engine as E
+    src = inspect.getsource(E.SDEngine._graph)
+    assert "plan.lat.items()" in src and "plan.old" in src
