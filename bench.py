@@ -646,18 +646,23 @@ def world_level(args, world, b, tokens, seed0, init_pil, eng0, local0):
         imgs = None if init_pil is None else [init_pil[i % len(init_pil)] for i in range(gb)]
         for _ in range(2):
             out = plugin_request(script, gb, toks, seed0, args.workload, imgs)
-        assert len(out.images) == gb, (len(out.images), gb)
+        # the warm-up requests built plans and captured graphs on the devices this process had not used yet: their ETA
+        # errors say nothing about steady state, and the scheduler would read them as lag (complementary jobs, bonus images)
+        for wk in w.get_workers():
+            wk.eta_percent_error = []
         for d in devs:
             torch.cuda.synchronize(d)
         reps = max(2, min(args.steps, 5))
+        n_img = 0
         t0 = time.perf_counter()
         for _ in range(reps):
-            plugin_request(script, gb, toks, seed0, args.workload, imgs)
+            out = plugin_request(script, gb, toks, seed0, args.workload, imgs)
+            n_img += len(out.images)
         for d in devs:
             torch.cuda.synchronize(d)
         dt = (time.perf_counter() - t0) / reps
-        res.append({"value": gb / dt, "unit": "images/s", "global_batch": gb, "per_gpu_batch": gb // world, "n_gpus": world,
-                    "ms_per_request": dt * 1000.0, "requests_timed": reps,
+        res.append({"value": n_img / reps / dt, "unit": "images/s", "global_batch": gb, "per_gpu_batch": gb // world, "n_gpus": world,
+                    "images_returned_per_request": n_img / reps, "ms_per_request": dt * 1000.0, "requests_timed": reps,
                     "jobs": [j.batch_size for j in w.jobs if j.batch_size > 0],
                     "path": "ONE process: process_images -> DistributedScript.before_process -> World.optimize_jobs -> one "
                             "thread per LocalGPUWorker job -> collector (tensors lane) -> postprocess; wall clock, host "

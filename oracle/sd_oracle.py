@@ -45,10 +45,25 @@ class UNetConfig:
     num_heads: int = 8
     context_dim: int = 768
     transformer_depth: int = 1
+    # sgm/modules/diffusionmodules/openaimodel.py::UNetModel (sd_xl_base.yaml): transformer_depth per level,
+    # num_head_channels, use_linear_in_transformer, adm_in_channels (label_emb)
+    transformer_depths: Optional[Tuple[int, ...]] = None
+    middle_depth: Optional[int] = None
+    num_head_channels: int = 0
+    linear_proj: bool = False
+    adm_in_channels: int = 0
 
     @property
     def time_embed_dim(self):
         return 4 * self.model_channels
+
+    def depth(self, level):
+        if self.transformer_depths is not None:
+            return self.transformer_depths[level]
+        return self.transformer_depth if level in self.attention_levels else 0
+
+    def heads(self, channels):
+        return channels // self.num_head_channels if self.num_head_channels else self.num_heads
 
 
 @dataclass
@@ -69,6 +84,11 @@ class CLIPConfig:
     layers: int = 12
     heads: int = 12
     ctx: int = 77
+    xl_width: int = 0      # SDXL: second text tower (OpenCLIP ViT-bigG), see sdxl_conditioner
+    xl_layers: int = 0
+    xl_heads: int = 0
+    xl_proj: int = 0
+    size_embed_dim: int = 256
 
 
 SD15_UNET = UNetConfig()
@@ -78,12 +98,21 @@ SD15_CLIP = CLIPConfig()
 TINY_UNET = UNetConfig(model_channels=64, num_heads=2, context_dim=64)
 TINY_VAE = VAEConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1)
 TINY_CLIP = CLIPConfig(vocab=1000, width=64, layers=2, heads=2)
+SDXL_UNET = UNetConfig(channel_mult=(1, 2, 4), transformer_depths=(0, 2, 10), middle_depth=10, num_head_channels=64,
+                       context_dim=2048, linear_proj=True, adm_in_channels=2816)
+SDXL_VAE = VAEConfig(scale_factor=0.13025)
+SDXL_CLIP = CLIPConfig(xl_width=1280, xl_layers=32, xl_heads=20, xl_proj=1280)
+TINYXL_UNET = UNetConfig(model_channels=64, channel_mult=(1, 2, 4), transformer_depths=(0, 1, 2), middle_depth=2,
+                         num_head_channels=64, context_dim=128, linear_proj=True, adm_in_channels=64 + 6 * 16)
+TINYXL_VAE = VAEConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1, scale_factor=0.13025)
+TINYXL_CLIP = CLIPConfig(vocab=1000, width=64, layers=3, heads=2, xl_width=64, xl_layers=3, xl_heads=2, xl_proj=64,
+                         size_embed_dim=16)
 
 
 # ------------------------------------------------------------------------------------------------ UNet topology
 def unet_layout(cfg: UNetConfig):
     """Block list of UNetModel.__init__: returns (input_blocks, middle, output_blocks); each block is a list of
-    ('conv_in', cin, cout) | ('res', cin, cout) | ('attn', c) | ('down', c) | ('up', c)."""
+    ('conv_in', cin, cout) | ('res', cin, cout) | ('attn', c, depth) | ('down', c) | ('up', c)."""
     mc = cfg.model_channels
     inputs = [[("conv_in", cfg.in_channels, mc)]]
     chans = [mc]
@@ -92,22 +121,23 @@ def unet_layout(cfg: UNetConfig):
         for _ in range(cfg.num_res_blocks):
             blk = [("res", ch, mult * mc)]
             ch = mult * mc
-            if level in cfg.attention_levels:
-                blk.append(("attn", ch))
+            if cfg.depth(level):
+                blk.append(("attn", ch, cfg.depth(level)))
             inputs.append(blk)
             chans.append(ch)
         if level != len(cfg.channel_mult) - 1:
             inputs.append([("down", ch)])
             chans.append(ch)
-    middle = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    middle = [("res", ch, ch), ("attn", ch, cfg.middle_depth if cfg.middle_depth is not None else cfg.transformer_depth),
+              ("res", ch, ch)]
     outputs = []
     for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
         for i in range(cfg.num_res_blocks + 1):
             ich = chans.pop()
             blk = [("res", ch + ich, mult * mc)]
             ch = mult * mc
-            if level in cfg.attention_levels:
-                blk.append(("attn", ch))
+            if cfg.depth(level):
+                blk.append(("attn", ch, cfg.depth(level)))
             if level and i == cfg.num_res_blocks:
                 blk.append(("up", ch))
             outputs.append(blk)
@@ -172,17 +202,24 @@ def transformer_block(sd: SD, p: str, x, context, heads: int):
     return F.linear(h, sd[p + ".ff.net.2.weight"], sd[p + ".ff.net.2.bias"]) + x
 
 
-def spatial_transformer(sd: SD, p: str, x, context, heads: int, depth: int = 1):
-    """attention.py::SpatialTransformer.forward (conv proj_in/out, SD1.x)."""
+def spatial_transformer(sd: SD, p: str, x, context, heads: int, depth: int = 1, use_linear: bool = False):
+    """attention.py::SpatialTransformer.forward: conv proj_in/out (SD1.x) or, with use_linear (SD2 / SDXL), Linear
+    layers applied after / before the (b c h w <-> b (h w) c) rearrange."""
     b, c, h, w = x.shape
     x_in = x
     x = _gn(x, sd, p + ".norm", 1e-6)
-    x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    if not use_linear:
+        x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+    if use_linear:
+        x = F.linear(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     for i in range(depth):
         x = transformer_block(sd, f"{p}.transformer_blocks.{i}", x, context, heads)
+    if use_linear:
+        x = F.linear(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     x = x.reshape(b, h, w, c).permute(0, 3, 1, 2)
-    x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+    if not use_linear:
+        x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     return x + x_in
 
 
@@ -195,7 +232,7 @@ def _run_block(sd, cfg, prefix, blk, h, emb, context):
         elif kind == "res":
             h = res_block(sd, p, h, emb)
         elif kind == "attn":
-            h = spatial_transformer(sd, p, h, context, cfg.num_heads, cfg.transformer_depth)
+            h = spatial_transformer(sd, p, h, context, cfg.heads(layer[1]), layer[2], cfg.linear_proj)
         elif kind == "down":
             h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
         elif kind == "up":
@@ -204,13 +241,17 @@ def _run_block(sd, cfg, prefix, blk, h, emb, context):
     return h
 
 
-def unet_forward(sd: SD, cfg: UNetConfig, x, t, context, prefix: str = "model.diffusion_model."):
-    """openaimodel.UNetModel.forward(x, timesteps, context) -> eps."""
+def unet_forward(sd: SD, cfg: UNetConfig, x, t, context, prefix: str = "model.diffusion_model.", y=None):
+    """openaimodel.UNetModel.forward(x, timesteps, context, y) -> eps.  y [N, adm_in_channels]: SDXL's vector conditioning,
+    emb = time_embed(t_emb) + label_emb(y)."""
     sdp = _Prefixed(sd, prefix)
     inputs, middle, outputs = unet_layout(cfg)
     emb = timestep_embedding(t, cfg.model_channels).to(x.dtype)
     emb = F.linear(emb, sdp["time_embed.0.weight"], sdp["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sdp["time_embed.2.weight"], sdp["time_embed.2.bias"])
+    if cfg.adm_in_channels:
+        le = F.linear(y.to(x.dtype), sdp["label_emb.0.0.weight"], sdp["label_emb.0.0.bias"])
+        emb = emb + F.linear(F.silu(le), sdp["label_emb.0.2.weight"], sdp["label_emb.0.2.bias"])
     hs = []
     h = x
     for i, blk in enumerate(inputs):
@@ -330,6 +371,77 @@ def clip_text_encode(sd: SD, cfg: CLIPConfig, tokens, prefix: str = "cond_stage_
         h = h * torch.sigmoid(1.702 * h)
         x = x + F.linear(h, s[p + ".mlp.fc2.weight"], s[p + ".mlp.fc2.bias"])
     return F.layer_norm(x, (cfg.width,), s["final_layer_norm.weight"], s["final_layer_norm.bias"], 1e-5)
+
+
+def clip_text_hidden(sd: SD, cfg: CLIPConfig, tokens, layer_idx: int, prefix: str):
+    """transformers CLIPTextModel(output_hidden_states=True).hidden_states[layer_idx]: the residual stream after
+    `layer_idx` encoder layers, no final LayerNorm (sgm FrozenCLIPEmbedder layer="hidden", layer_idx=11 for SDXL)."""
+    s = _Prefixed(sd, prefix)
+    x = s["embeddings.token_embedding.weight"][tokens] + s["embeddings.position_embedding.weight"][None, :tokens.shape[1]]
+    n = tokens.shape[1]
+    mask = torch.full((n, n), float("-inf"), device=x.device, dtype=x.dtype).triu(1)
+    d = cfg.width // cfg.heads
+    for i in range(layer_idx):
+        p = f"encoder.layers.{i}"
+        h = F.layer_norm(x, (cfg.width,), s[p + ".layer_norm1.weight"], s[p + ".layer_norm1.bias"], 1e-5)
+        q = F.linear(h, s[p + ".self_attn.q_proj.weight"], s[p + ".self_attn.q_proj.bias"])
+        k = F.linear(h, s[p + ".self_attn.k_proj.weight"], s[p + ".self_attn.k_proj.bias"])
+        v = F.linear(h, s[p + ".self_attn.v_proj.weight"], s[p + ".self_attn.v_proj.bias"])
+        b = x.shape[0]
+        q, k, v = (t.reshape(b, n, cfg.heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+        att = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5 + mask, dim=-1) @ v
+        x = x + F.linear(att.permute(0, 2, 1, 3).reshape(b, n, cfg.width), s[p + ".self_attn.out_proj.weight"],
+                         s[p + ".self_attn.out_proj.bias"])
+        h = F.layer_norm(x, (cfg.width,), s[p + ".layer_norm2.weight"], s[p + ".layer_norm2.bias"], 1e-5)
+        h = F.linear(h, s[p + ".mlp.fc1.weight"], s[p + ".mlp.fc1.bias"])
+        x = x + F.linear(h * torch.sigmoid(1.702 * h), s[p + ".mlp.fc2.weight"], s[p + ".mlp.fc2.bias"])
+    return x
+
+
+def open_clip_text(sd: SD, cfg: CLIPConfig, tokens, prefix: str):
+    """sgm FrozenOpenCLIPEmbedder2 (arch ViT-bigG-14, layer="penultimate", legacy=False, always_return_pooled):
+    open_clip text transformer (pre-LN resblocks, packed in_proj, GELU MLP, causal mask).  Returns
+    (penultimate residual stream [B, 77, W] — no ln_final —, pooled [B, proj] = ln_final(last)[EOS] @ text_projection,
+    EOS = argmax of the token ids)."""
+    s = _Prefixed(sd, prefix)
+    w, heads, n = cfg.xl_width, cfg.xl_heads, tokens.shape[1]
+    x = s["token_embedding.weight"][tokens] + s["positional_embedding"][None, :n]
+    mask = torch.full((n, n), float("-inf"), device=x.device, dtype=x.dtype).triu(1)
+    d = w // heads
+    b = x.shape[0]
+    penultimate = None
+    for i in range(cfg.xl_layers):
+        p = f"transformer.resblocks.{i}"
+        if i == cfg.xl_layers - 1:
+            penultimate = x
+        h = F.layer_norm(x, (w,), s[p + ".ln_1.weight"], s[p + ".ln_1.bias"], 1e-5)
+        q, k, v = F.linear(h, s[p + ".attn.in_proj_weight"], s[p + ".attn.in_proj_bias"]).chunk(3, dim=-1)
+        q, k, v = (t.reshape(b, n, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+        att = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5 + mask, dim=-1) @ v
+        x = x + F.linear(att.permute(0, 2, 1, 3).reshape(b, n, w), s[p + ".attn.out_proj.weight"], s[p + ".attn.out_proj.bias"])
+        h = F.layer_norm(x, (w,), s[p + ".ln_2.weight"], s[p + ".ln_2.bias"], 1e-5)
+        x = x + F.linear(F.gelu(F.linear(h, s[p + ".mlp.c_fc.weight"], s[p + ".mlp.c_fc.bias"])), s[p + ".mlp.c_proj.weight"],
+                         s[p + ".mlp.c_proj.bias"])
+    last = F.layer_norm(x, (w,), s["ln_final.weight"], s["ln_final.bias"], 1e-5)
+    pooled = last[torch.arange(b, device=x.device), tokens.argmax(dim=-1)] @ s["text_projection"]
+    return penultimate, pooled
+
+
+def sdxl_conditioner(sd: SD, cfg: CLIPConfig, tokens, width: int, height: int, zero_txt: bool = False,
+                     crop=(0, 0)):
+    """sgm GeneralConditioner as sdwui feeds it (sd_models_xl.get_learned_conditioning): crossattn = cat(CLIP-L hidden
+    layer 11, bigG penultimate) [B, 77, 2048]; vector = cat(bigG pooled, Fourier(original_size h, w), Fourier(crop top,
+    left), Fourier(target_size h, w)) [B, 2816], each scalar through timestep_embedding(., 256).  zero_txt: sdwui's
+    force_zero_embeddings=['txt'] for an all-empty negative prompt — both text outputs are zeros, the size part stays."""
+    b = tokens.shape[0]
+    h0 = clip_text_hidden(sd, cfg, tokens, cfg.layers - 1, "conditioner.embedders.0.transformer.text_model.")
+    h1, pooled = open_clip_text(sd, cfg, tokens, "conditioner.embedders.1.model.")
+    ctx = torch.cat([h0, h1], dim=-1)
+    if zero_txt:
+        ctx, pooled = torch.zeros_like(ctx), torch.zeros_like(pooled)
+    scal = torch.tensor([height, width, crop[0], crop[1], height, width], dtype=torch.float32, device=ctx.device)
+    emb = timestep_embedding(scal, cfg.size_embed_dim).reshape(1, -1).expand(b, -1).to(ctx.dtype)
+    return ctx, torch.cat([pooled, emb], dim=-1)
 
 
 # ------------------------------------------------------------------------------------------------ schedule / samplers

@@ -1,42 +1,136 @@
-"""CLIP ViT-L/14 text tower in plain torch (fp16 on the GPU).
+"""Text conditioning in plain torch (fp16 / bf16 on the GPU).
 
 Runs once per request (cond + uncond prompts), 0.04 % of an image's FLOPs — SURVEY.md §8 a-ext x13 keeps it out of
-kernel scope ("run in torch").  Same math as transformers' CLIPTextModel: causal mask, quick-gelu MLP, final LN,
-last hidden state (sdwui CLIP_stop_at_last_layers = 1).
+kernel scope ("run in torch").
+  * SD1.x: CLIP ViT-L/14 text tower, same math as transformers' CLIPTextModel — causal mask, quick-gelu MLP, final LN,
+    last hidden state (sdwui CLIP_stop_at_last_layers = 1).
+  * SDXL (sgm GeneralConditioner, sd_xl_base.yaml): the CLIP-L tower read at hidden layer 11 (no final LN) next to an
+    OpenCLIP ViT-bigG tower (penultimate layer; pooled = ln_final(last)[EOS] @ text_projection), and the vector
+    conditioning cat(pooled, Fourier features of original size, crop, target size) that feeds the UNet's label_emb.
 """
-from typing import Dict
+import math
+from typing import Dict, NamedTuple, Optional
 
 import torch
 import torch.nn.functional as F
 
-from .config import CLIP_PREFIX, CLIPConfig
+from .config import CLIP_PREFIX, XL_PREFIX0, XL_PREFIX1, CLIPConfig
+
+
+class Cond(NamedTuple):
+    ctx: torch.Tensor                 # [B, 77, context_dim] cross-attention context
+    y: Optional[torch.Tensor] = None  # [B, adm_in_channels] vector conditioning (SDXL), or None
+
+
+def _attend(q, k, v, mask):
+    d = q.shape[-1]
+    return torch.softmax((q @ k.transpose(-1, -2)).float() * d ** -0.5 + mask, dim=-1).to(q.dtype) @ v
 
 
 class ClipText:
-    def __init__(self, sd: Dict[str, torch.Tensor], cfg: CLIPConfig, device, dtype=torch.float16):
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: CLIPConfig, device, dtype=torch.float16, prefix: str = CLIP_PREFIX):
         self.cfg, self.device, self.dtype = cfg, device, dtype
-        n = len(CLIP_PREFIX)
-        self.w = {k[n:]: v.to(device=device, dtype=dtype) for k, v in sd.items() if k.startswith(CLIP_PREFIX)}
+        n = len(prefix)
+        self.w = {k[n:]: v.to(device=device, dtype=dtype) for k, v in sd.items() if k.startswith(prefix)}
 
     @torch.no_grad()
-    def __call__(self, tokens: torch.Tensor) -> torch.Tensor:
-        """tokens int64 [B, 77] -> [B, 77, width]"""
+    def hidden(self, tokens: torch.Tensor, layers: int) -> torch.Tensor:
+        """residual stream after `layers` encoder layers (transformers hidden_states[layers]), no final LayerNorm"""
         w, cfg = self.w, self.cfg
         tokens = tokens.to(self.device)
         b, n = tokens.shape
         x = w["embeddings.token_embedding.weight"][tokens] + w["embeddings.position_embedding.weight"][None, :n]
         mask = torch.full((n, n), float("-inf"), device=self.device, dtype=torch.float32).triu(1)
         d = cfg.width // cfg.heads
-        for i in range(cfg.layers):
+        for i in range(layers):
             p = f"encoder.layers.{i}"
             h = F.layer_norm(x, (cfg.width,), w[p + ".layer_norm1.weight"], w[p + ".layer_norm1.bias"], 1e-5)
             q, k, v = (F.linear(h, w[f"{p}.self_attn.{m}_proj.weight"], w[f"{p}.self_attn.{m}_proj.bias"])
                        .reshape(b, n, cfg.heads, d).permute(0, 2, 1, 3) for m in "qkv")
-            att = torch.softmax((q @ k.transpose(-1, -2)).float() * d ** -0.5 + mask, dim=-1).to(x.dtype) @ v
-            att = att.permute(0, 2, 1, 3).reshape(b, n, cfg.width)
+            att = _attend(q, k, v, mask).permute(0, 2, 1, 3).reshape(b, n, cfg.width)
             x = x + F.linear(att, w[p + ".self_attn.out_proj.weight"], w[p + ".self_attn.out_proj.bias"])
             h = F.layer_norm(x, (cfg.width,), w[p + ".layer_norm2.weight"], w[p + ".layer_norm2.bias"], 1e-5)
             h = F.linear(h, w[p + ".mlp.fc1.weight"], w[p + ".mlp.fc1.bias"])
             h = h * torch.sigmoid(1.702 * h)
             x = x + F.linear(h, w[p + ".mlp.fc2.weight"], w[p + ".mlp.fc2.bias"])
-        return F.layer_norm(x, (cfg.width,), w["final_layer_norm.weight"], w["final_layer_norm.bias"], 1e-5)
+        return x
+
+    @torch.no_grad()
+    def __call__(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens int64 [B, 77] -> [B, 77, width]: last hidden state after the final LayerNorm"""
+        w, cfg = self.w, self.cfg
+        return F.layer_norm(self.hidden(tokens, cfg.layers), (cfg.width,), w["final_layer_norm.weight"],
+                            w["final_layer_norm.bias"], 1e-5)
+
+
+class OpenClipText:
+    """OpenCLIP text transformer (ViT-bigG-14 for SDXL): pre-LN resblocks with a packed in_proj, GELU MLP, causal mask"""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: CLIPConfig, device, dtype, prefix: str = XL_PREFIX1):
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        n = len(prefix)
+        self.w = {k[n:]: v.to(device=device, dtype=dtype) for k, v in sd.items() if k.startswith(prefix)}
+
+    @torch.no_grad()
+    def __call__(self, tokens: torch.Tensor):
+        """-> (penultimate residual stream [B, 77, W], pooled [B, proj])"""
+        w, cfg = self.w, self.cfg
+        tokens = tokens.to(self.device)
+        b, n = tokens.shape
+        wd, heads = cfg.xl_width, cfg.xl_heads
+        d = wd // heads
+        x = w["token_embedding.weight"][tokens] + w["positional_embedding"][None, :n]
+        mask = torch.full((n, n), float("-inf"), device=self.device, dtype=torch.float32).triu(1)
+        penultimate = None
+        for i in range(cfg.xl_layers):
+            p = f"transformer.resblocks.{i}"
+            if i == cfg.xl_layers - 1:
+                penultimate = x
+            h = F.layer_norm(x, (wd,), w[p + ".ln_1.weight"], w[p + ".ln_1.bias"], 1e-5)
+            q, k, v = (t.reshape(b, n, heads, d).permute(0, 2, 1, 3)
+                       for t in F.linear(h, w[p + ".attn.in_proj_weight"], w[p + ".attn.in_proj_bias"]).chunk(3, dim=-1))
+            att = _attend(q, k, v, mask).permute(0, 2, 1, 3).reshape(b, n, wd)
+            x = x + F.linear(att, w[p + ".attn.out_proj.weight"], w[p + ".attn.out_proj.bias"])
+            h = F.layer_norm(x, (wd,), w[p + ".ln_2.weight"], w[p + ".ln_2.bias"], 1e-5)
+            x = x + F.linear(F.gelu(F.linear(h, w[p + ".mlp.c_fc.weight"], w[p + ".mlp.c_fc.bias"])),
+                             w[p + ".mlp.c_proj.weight"], w[p + ".mlp.c_proj.bias"])
+        last = F.layer_norm(x, (wd,), w["ln_final.weight"], w["ln_final.bias"], 1e-5)
+        pooled = last[torch.arange(b, device=self.device), tokens.argmax(dim=-1)] @ w["text_projection"]
+        return penultimate, pooled
+
+
+def fourier(scalars: torch.Tensor, dim: int) -> torch.Tensor:
+    """sgm ConcatTimestepEmbedderND's timestep_embedding(x, dim): cat(cos, sin)(x * 10000^(-k / (dim / 2)))"""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=scalars.device) / half)
+    args = scalars[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+class Conditioner:
+    """tokens -> Cond for either model family"""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: CLIPConfig, device, dtype):
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        self.xl = cfg.xl_width > 0
+        if self.xl:
+            self.t0 = ClipText(sd, cfg, device, dtype, XL_PREFIX0)
+            self.t1 = OpenClipText(sd, cfg, device, dtype, XL_PREFIX1)
+        else:
+            self.t0 = ClipText(sd, cfg, device, dtype)
+
+    @torch.no_grad()
+    def __call__(self, tokens: torch.Tensor, width: int = 512, height: int = 512, zero_txt: bool = False) -> Cond:
+        """zero_txt (SDXL): sdwui's force_zero_embeddings=['txt'] for an all-empty negative prompt"""
+        if not self.xl:
+            return Cond(self.t0(tokens))
+        cfg = self.cfg
+        b = tokens.shape[0]
+        h0 = self.t0.hidden(tokens, cfg.layers - 1)
+        h1, pooled = self.t1(tokens)
+        ctx = torch.cat([h0, h1], dim=-1)
+        if zero_txt:
+            ctx, pooled = torch.zeros_like(ctx), torch.zeros_like(pooled)
+        scal = torch.tensor([height, width, 0, 0, height, width], dtype=torch.float32, device=self.device)
+        size = fourier(scal, cfg.size_embed_dim).reshape(1, -1).expand(b, -1).to(ctx.dtype)
+        return Cond(ctx, torch.cat([pooled, size], dim=-1))

@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from . import samplers as S
-from .clip_text import ClipText
+from .clip_text import Cond, Conditioner
 from .config import CLIPConfig, UNetConfig, VAEConfig
 from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
 from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
@@ -253,7 +253,7 @@ class Plan:
         self.x = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)
         self.step = torch.zeros((1,), device=dev, dtype=torch.int32)
         self.coef = torch.zeros((MAX_STEPS, 4), device=dev, dtype=torch.float32)
-        self.table = torch.zeros((MAX_STEPS, eng.unet_w.emb_total), device=dev, dtype=torch.float32)
+        self.table = torch.zeros((MAX_STEPS, self.unet.cur_bias.numel()), device=dev, dtype=torch.float32)
         self.coef8 = torch.zeros((MAX_STEPS, 8), device=dev, dtype=torch.float32)   # DPM++ 2M rows
         self.old = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)        # its previous x0 prediction
         self.init = torch.zeros((b, h * w, 4), device=dev, dtype=torch.float32)     # inpainting: clean init latents
@@ -350,12 +350,13 @@ class SDEngine:
             self.unet_w = UNetWeights(sd, unet_cfg, self.device, dtype)
             self.vae_w = VAEDecoderWeights(sd, vae_cfg, self.device, dtype)
             self.vae_enc_w = VAEEncoderWeights(sd, vae_cfg, self.device, dtype)
-            self.clip = ClipText(sd, clip_cfg, self.device, dtype)
+            self.clip = Conditioner(sd, clip_cfg, self.device, dtype)
             self.temb = TimeEmbedding(self.unet_w)
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
         self.encoders: Dict[Tuple[int, int, int], VAEEncoderProgram] = {}
         self.interrupted = False
         self.variation = (None, 0.0)   # (subseed, subseed_strength) of the request being served: sdwui variation seeds
+        self._y = None                 # SDXL vector conditioning of the run in progress
         self._cap_stream = None
         self.last_unet_evals = 0
         self.graph_replayed_launches = 0   # b200sd kernels launched through graph replays (bench.py gpu_launches)
@@ -397,9 +398,17 @@ class SDEngine:
                 torch.cuda.empty_cache()
 
     @torch.no_grad()
-    def encode_prompts(self, tokens: torch.Tensor) -> torch.Tensor:
+    def encode_prompts(self, tokens: torch.Tensor, width: int = 512, height: int = 512, zero_txt: bool = False):
+        """tokens [b, 77] -> cross-attention context [b, 77, ctx] (SD1.x), or Cond(ctx, vector conditioning) for SDXL"""
         with self._ctx():
-            return self.clip(tokens)
+            c = self.clip(tokens, width, height, zero_txt)
+            return c if c.y is not None else c.ctx
+
+    def _conds(self, tokens: torch.Tensor, neg_tokens: torch.Tensor, width: int, height: int):
+        """(cond, uncond) of a request.  SDXL: an all-empty negative prompt ([BOS] + EOS padding in every row) gets zero
+        text embeddings, as sdwui's sd_models_xl.get_learned_conditioning does (force_zero_embeddings=['txt'])."""
+        empty_neg = self.clip.xl and bool((neg_tokens[:, 1:] == neg_tokens[:, -1:]).all())
+        return (self.encode_prompts(tokens, width, height), self.encode_prompts(neg_tokens, width, height, zero_txt=empty_neg))
 
     def _graph(self, plan: Plan, name: str, fn):
         """Run fn eagerly once (per-device kernel attribute setup must not happen under capture), then capture."""
@@ -508,9 +517,13 @@ class SDEngine:
         if inpaint is not None and pr.fused not in (None, "ddim"):
             # the fused Euler / Euler a / DPM++ 2M kernels do not carry the mask: same sampler, generic stages
             raise ValueError("masked sampling of a fused sampler must be requested through a generic program")
+        cond = cond if isinstance(cond, Cond) else Cond(cond)
+        uncond = uncond if isinstance(uncond, Cond) else Cond(uncond)
         with self._ctx():
             plan = self.plan(b, h, w)
-            plan.unet.set_context(torch.cat([cond, uncond]).to(self.dtype).contiguous())
+            plan.unet.set_context(torch.cat([cond.ctx, uncond.ctx]).to(self.dtype).contiguous())
+            # SDXL: the vector conditioning of [cond | uncond] enters through the time-embedding table (per-sample rows)
+            self._y = None if cond.y is None else torch.cat([cond.y, uncond.y]).to(self.device)
             masked = inpaint is not None
             if masked:   # (clean init latents [b, 4, h, w], latent mask [h * w])
                 plan.init.copy_(inpaint[0].to(self.device, torch.float32).permute(0, 2, 3, 1).reshape(b, h * w, 4))
@@ -558,7 +571,7 @@ class SDEngine:
             step_fn = lambda: plan.step_euler(cfg_scale)  # noqa: E731
         else:
             step_fn = lambda: plan.step_dpmpp_2m(cfg_scale)  # noqa: E731
-        plan.table[:n_evals].copy_(self.temb.table(torch.tensor(pr.ts, dtype=torch.float32)))
+        plan.table[:n_evals].copy_(self.temb.table(torch.tensor(pr.ts, dtype=torch.float32), self._y))
         (plan.coef8 if len(pr.rows[0]) == 8 else plan.coef)[:n_evals].copy_(torch.tensor(pr.rows, dtype=torch.float32))
         g = self._graph(plan, name, step_fn)
         for _ in range(n_evals):
@@ -578,7 +591,7 @@ class SDEngine:
         if not stages:
             return
         self._upload_noises(plan, noises if noises is not None else torch.zeros((0, plan.b, 4, plan.h, plan.w)), sp.mix)
-        plan.table[:len(stages)].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32)))
+        plan.table[:len(stages)].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32), self._y))
         plan.coefL[:len(stages)].copy_(torch.tensor([st.row() for st in stages], dtype=torch.float32))
         for st in stages:
             if self.interrupted:
@@ -609,7 +622,7 @@ class SDEngine:
                 break
             t = min(t_end, s + pid.h)
             stages = S.dpm_adaptive_attempt(s, t, t_of)
-            plan.table[:3].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32)))
+            plan.table[:3].copy_(self.temb.table(torch.tensor([st.t for st in stages], dtype=torch.float32), self._y))
             plan.coefL[:3].copy_(torch.tensor([st.row() for st in stages], dtype=torch.float32))
             plan.step.zero_()
             ops.pack_unet_input(plan.x, plan.unet.xin, S.c_in(math.exp(-s)))
@@ -721,8 +734,7 @@ class SDEngine:
         the request's start noise / by zeros first (sdwui Img2Img.init); 0 ("fill") is image-space work the caller does
         before the call (inpaint.fill_masked), 1 keeps the original content."""
         b = tokens.shape[0]
-        cond = self.encode_prompts(tokens)
-        uncond = self.encode_prompts(neg_tokens)
+        cond, uncond = self._conds(tokens, neg_tokens, init_u8.shape[2], init_u8.shape[1])
         init = self.encode(init_u8)
         _, _, h, w = init.shape
         if latmask is not None and inpainting_fill in (2, 3):
@@ -757,13 +769,14 @@ class SDEngine:
         b = tokens.shape[0]
         h, w = height // 8, width // 8
         h2, w2 = int(height * hr_scale) // 8, int(width * hr_scale) // 8
-        cond = self.encode_prompts(tokens)
-        uncond = self.encode_prompts(neg_tokens)
+        cond, uncond = self._conds(tokens, neg_tokens, width, height)
         lat = self._sample_txt(cond, uncond, seed, b, h, w, steps, cfg_scale, sampler, scheduler)
         with self._ctx():
             up = torch.empty((b, h2 * w2, 4), device=self.device, dtype=torch.float32)
             ops.resize_latent_bilinear(lat.contiguous(), up, h, w, h2, w2)
         init = up.reshape(b, h2, w2, 4).permute(0, 3, 1, 2)
+        if self.clip.xl:   # SDXL's vector conditioning carries the target size: the second pass gets its own (sdwui hr_c / hr_uc)
+            cond, uncond = self._conds(tokens, neg_tokens, w2 * 8, h2 * 8)
         lat2 = self._sample_from(init, cond, uncond, seed, denoising_strength, hr_steps or steps, cfg_scale, sampler, scheduler)
         return self.decode(lat2, h2, w2)
 
@@ -779,7 +792,6 @@ class SDEngine:
         """Whole request for this engine's share: returns uint8 [b, H, W, 3] on device."""
         b = tokens.shape[0]
         h, w = height // 8, width // 8
-        cond = self.encode_prompts(tokens)
-        uncond = self.encode_prompts(neg_tokens)
+        cond, uncond = self._conds(tokens, neg_tokens, width, height)
         lat = self._sample_txt(cond, uncond, seed, b, h, w, steps, cfg_scale, sampler, scheduler)
         return self.decode(lat, h, w)

@@ -44,6 +44,10 @@ def configs(size: str = "sd15"):
         return C.SD15_UNET, C.SD15_VAE, C.SD15_CLIP
     if size == "tiny":
         return C.TINY_UNET, C.TINY_VAE, C.TINY_CLIP
+    if size == "sdxl":
+        return C.SDXL_UNET, C.SDXL_VAE, C.SDXL_CLIP
+    if size == "tinyxl":
+        return C.TINYXL_UNET, C.TINYXL_VAE, C.TINYXL_CLIP
     raise ValueError(size)
 
 
@@ -58,7 +62,9 @@ def default_engine_factory(device: str, size: str = None) -> SDEngine:
                         "set SD_CKPT=/path/model.safetensors for a real checkpoint", size)
         if size != "tiny" and not os.environ.get("SD_TOKENIZER"):
             log.warning("b200sd: SD_TOKENIZER is not set — prompts are hashed to token ids, not BPE-tokenised")
-        eng = SDEngine(state_dict(size), *configs(size), device=device)
+        # SDXL runs in bf16 (BASELINE config 4; its VAE overflows fp16 — sdwui upcasts it)
+        dtype = torch.bfloat16 if size in ("sdxl", "tinyxl") else torch.float16
+        eng = SDEngine(state_dict(size), *configs(size), device=device, dtype=dtype)
         with _LOCK:
             _ENGINES[key] = eng
     return eng

@@ -9,7 +9,8 @@ from typing import Dict
 
 import torch
 
-from .config import CLIP_PREFIX, UNET_PREFIX, VAE_PREFIX, CLIPConfig, UNetConfig, VAEConfig, unet_layout
+from .config import (CLIP_PREFIX, UNET_PREFIX, VAE_PREFIX, XL_PREFIX0, XL_PREFIX1, CLIPConfig, UNetConfig, VAEConfig,
+                     unet_layout)
 
 
 class _Init:
@@ -45,6 +46,9 @@ def _unet(i: _Init, cfg: UNetConfig):
     ted = cfg.time_embed_dim
     i.lin(p + "time_embed.0", ted, cfg.model_channels)
     i.lin(p + "time_embed.2", ted, ted)
+    if cfg.adm_in_channels:
+        i.lin(p + "label_emb.0.0", ted, cfg.adm_in_channels)
+        i.lin(p + "label_emb.0.2", ted, ted)
 
     def res(key, cin, cout):
         i.norm(key + ".in_layers.0", cin)
@@ -55,10 +59,13 @@ def _unet(i: _Init, cfg: UNetConfig):
         if cin != cout:
             i.conv(key + ".skip_connection", cout, cin, 1)
 
-    def attn(key, c):
+    def attn(key, c, depth):
         i.norm(key + ".norm", c)
-        i.conv(key + ".proj_in", c, c, 1)
-        for d in range(cfg.transformer_depth):
+        if cfg.linear_proj:
+            i.lin(key + ".proj_in", c, c)
+        else:
+            i.conv(key + ".proj_in", c, c, 1)
+        for d in range(depth):
             t = f"{key}.transformer_blocks.{d}"
             for n in ("norm1", "norm2", "norm3"):
                 i.norm(f"{t}.{n}", c)
@@ -69,7 +76,10 @@ def _unet(i: _Init, cfg: UNetConfig):
                 i.lin(f"{t}.{a}.to_out.0", c, c)
             i.lin(f"{t}.ff.net.0.proj", 8 * c, c)
             i.lin(f"{t}.ff.net.2", c, 4 * c)
-        i.conv(key + ".proj_out", c, c, 1)
+        if cfg.linear_proj:
+            i.lin(key + ".proj_out", c, c)
+        else:
+            i.conv(key + ".proj_out", c, c, 1)
 
     def block(prefix, layers):
         for j, layer in enumerate(layers):
@@ -79,7 +89,7 @@ def _unet(i: _Init, cfg: UNetConfig):
             elif layer[0] == "res":
                 res(key, layer[1], layer[2])
             elif layer[0] == "attn":
-                attn(key, layer[1])
+                attn(key, layer[1], layer[2])
             elif layer[0] == "down":
                 i.conv(key + ".op", layer[1], layer[1], 3)
             elif layer[0] == "up":
@@ -146,8 +156,25 @@ def _vae(i: _Init, cfg: VAEConfig):
     i.conv(p + "decoder.conv_out", cfg.out_ch, cin, 3, gain=0.7)  # keeps most pixels inside (-1, 1)
 
 
-def _clip(i: _Init, cfg: CLIPConfig):
-    p = CLIP_PREFIX
+def _open_clip(i: _Init, cfg: CLIPConfig, p: str):
+    """OpenCLIP text tower key names (sgm FrozenOpenCLIPEmbedder2.model)"""
+    w = cfg.xl_width
+    i.sd[p + "token_embedding.weight"] = 0.02 * torch.randn((cfg.vocab, w), generator=i.g)
+    i.sd[p + "positional_embedding"] = 0.01 * torch.randn((cfg.ctx, w), generator=i.g)
+    for l in range(cfg.xl_layers):
+        k = f"{p}transformer.resblocks.{l}"
+        i.norm(k + ".ln_1", w)
+        i.w(k + ".attn.in_proj_weight", (3 * w, w))
+        i.b(k + ".attn.in_proj_bias", 3 * w)
+        i.lin(k + ".attn.out_proj", w, w)
+        i.norm(k + ".ln_2", w)
+        i.lin(k + ".mlp.c_fc", 4 * w, w)
+        i.lin(k + ".mlp.c_proj", w, 4 * w)
+    i.norm(p + "ln_final", w)
+    i.sd[p + "text_projection"] = torch.randn((w, cfg.xl_proj), generator=i.g) / math.sqrt(w)
+
+
+def _clip(i: _Init, cfg: CLIPConfig, p: str = CLIP_PREFIX):
     i.sd[p + "embeddings.token_embedding.weight"] = 0.02 * torch.randn((cfg.vocab, cfg.width), generator=i.g)
     i.sd[p + "embeddings.position_embedding.weight"] = 0.01 * torch.randn((cfg.ctx, cfg.width), generator=i.g)
     for l in range(cfg.layers):
@@ -166,5 +193,9 @@ def make_state_dict(unet: UNetConfig, vae: VAEConfig, clip: CLIPConfig, seed: in
     i = _Init(seed)
     _unet(i, unet)
     _vae(i, vae)
-    _clip(i, clip)
+    if clip.xl_width:      # SDXL: sgm conditioner key names, two towers
+        _clip(i, clip, XL_PREFIX0)
+        _open_clip(i, clip, XL_PREFIX1)
+    else:
+        _clip(i, clip)
     return i.sd

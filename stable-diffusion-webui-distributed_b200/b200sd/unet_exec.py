@@ -93,9 +93,11 @@ class UNetWeights:
 
     def _pack(self):
         cfg = self.cfg
-        heads = cfg.num_heads
         self._lin("time_embed.0", "time_embed.0")
         self._lin("time_embed.2", "time_embed.2")
+        if cfg.adm_in_channels:   # SDXL vector conditioning
+            self._lin("label_emb.0", "label_emb.0.0")
+            self._lin("label_emb.2", "label_emb.0.2")
         inputs, middle, outputs = self.layout
         emb_w, emb_b, conv1_b = [], [], []
         off = 0
@@ -115,13 +117,14 @@ class UNetWeights:
             self.res_off[key] = off
             off += cout
 
-        def attn(key, c):
+        def attn(key, c, depth):
+            heads = cfg.heads(c)
             d = c // heads
             dp = _pad64(d)
             self._norm(key + ".norm", key + ".norm")
-            self._lin(key + ".proj_in", key + ".proj_in")
+            self._lin(key + ".proj_in", key + ".proj_in")    # conv 1x1 (SD1.x) and Linear (SDXL) are the same GEMM in NHWC
             self._lin(key + ".proj_out", key + ".proj_out")
-            for i in range(cfg.transformer_depth):
+            for i in range(depth):
                 t = f"{key}.transformer_blocks.{i}"
                 for n in ("norm1", "norm2", "norm3"):
                     self._norm(f"{t}.{n}", f"{t}.{n}")
@@ -156,7 +159,7 @@ class UNetWeights:
                 elif layer[0] == "res":
                     res(key, layer[1], layer[2])
                 elif layer[0] == "attn":
-                    attn(key, layer[1])
+                    attn(key, layer[1], layer[2])
                 elif layer[0] == "down":
                     self._conv(key, key + ".op")
                 elif layer[0] == "up":
@@ -186,11 +189,13 @@ class UNetProgram:
         self.pool = Pool(self.dev, self.dt)
         self.ctx_len = ctx_len
         cfg = self.cfg
-        self.heads = cfg.num_heads
         # persistent I/O
         self.xin = torch.zeros((n, h * wd, 64), device=self.dev, dtype=self.dt)    # latent channels 0..3, rest zero
         self.eps = torch.zeros((n, h * wd, 32), device=self.dev, dtype=self.dt)    # eps channels 0..3
-        self.cur_bias = torch.zeros((w.emb_total,), device=self.dev, dtype=torch.float32)
+        # this step's conv1 biases (time embedding folded in): one row of Cout floats per ResBlock — or, with a vector
+        # conditioning (SDXL: the embedding differs per sample), n rows per ResBlock, block r at offset n * res_off[r]
+        self.per_sample = cfg.adm_in_channels > 0
+        self.cur_bias = torch.zeros((w.emb_total * (n if self.per_sample else 1),), device=self.dev, dtype=torch.float32)
         self.gn_stats: List[torch.Tensor] = []
         self.gn_need = 0
         self.ctx_kv: Dict[str, torch.Tensor] = {}
@@ -229,9 +234,15 @@ class UNetProgram:
         n, hw, t = self.n, h * wd, self.w.t
         a = self.pool.get(n, hw, cin)
         self._gn(x, a, key + ".gn1", 1e-5, True)
-        bsl = self.cur_bias[self.w.res_off[key]: self.w.res_off[key] + cout]
+        off = self.w.res_off[key]
         b = self.pool.get(n, hw, cout)
-        self._emit(ops.conv2d, a.unflatten(1, (h, wd)), t[key + ".conv1.w"], b.reshape(n * hw, cout), ksize=3, bias=bsl)
+        if self.per_sample:   # a bias row per image: rows [i * hw, (i + 1) * hw) of the GEMM take row i
+            bsl = self.cur_bias[n * off: n * (off + cout)]
+            self._emit(ops.conv2d, a.unflatten(1, (h, wd)), t[key + ".conv1.w"], b.reshape(n * hw, cout), ksize=3, bias=bsl,
+                       bias_group_rows=hw)
+        else:
+            bsl = self.cur_bias[off: off + cout]
+            self._emit(ops.conv2d, a.unflatten(1, (h, wd)), t[key + ".conv1.w"], b.reshape(n * hw, cout), ksize=3, bias=bsl)
         self.pool.put(a)
         c = self.pool.get(n, hw, cout)
         self._gn(b, c, key + ".gn2", 1e-5, True)
@@ -248,8 +259,8 @@ class UNetProgram:
         if s is not None:
             self.pool.put(s)
 
-    def _attn(self, key, x, c, h, wd, dest):
-        n, hw, t, heads = self.n, h * wd, self.w.t, self.heads
+    def _attn(self, key, x, c, depth, h, wd, dest):
+        n, hw, t, heads = self.n, h * wd, self.w.t, self.cfg.heads(c)
         d = c // heads
         dp = _pad64(d)
         scale = d ** -0.5
@@ -257,7 +268,7 @@ class UNetProgram:
         self._gn(x, a, key + ".norm", 1e-6, False)
         hcur = self.pool.get(n, hw, c)
         self._emit(ops.linear, a, t[key + ".proj_in.w"], hcur, bias=t[key + ".proj_in.b"])
-        for i in range(self.cfg.transformer_depth):
+        for i in range(depth):
             tb = f"{key}.transformer_blocks.{i}"
             # --- self attention
             self._emit(ops.layernorm, hcur, a, t[tb + ".norm1.g"], t[tb + ".norm1.beta"], 1e-5)
@@ -343,7 +354,7 @@ class UNetProgram:
                 elif kind == "attn":
                     dest = final_dest if last else self.pool.get(n, h * wd, layer[1])
                     tmp = None if last else dest
-                    self._attn(key, x, layer[1], h, wd, dest)
+                    self._attn(key, x, layer[1], layer[2], h, wd, dest)
                 elif kind == "down":
                     dest = final_dest
                     self._emit(ops.conv2d, x.unflatten(1, (h, wd)), t[key + ".w"], dest, ksize=3, stride=2, bias=t[key + ".b"])
@@ -395,24 +406,48 @@ class UNetProgram:
 
 class TimeEmbedding:
     """time_embed MLP + all ResBlock emb_layers for every sampler timestep at once -> fp32 bias table
-    table[step] = conv1_bias_all + Linear(SiLU(time_embed(t_step)))  (ldm ResBlock: h + emb_out[..., None, None])."""
+    table[step] = conv1_bias_all + Linear(SiLU(time_embed(t_step)))  (ldm ResBlock: h + emb_out[..., None, None]).
+    With a vector conditioning y [n, adm] (SDXL: emb = time_embed(t) + label_emb(y), sgm UNetModel.forward) the embedding
+    differs per sample: table[step] holds, per ResBlock, n rows of Cout floats (UNetProgram.per_sample)."""
 
     def __init__(self, w: UNetWeights):
         self.w = w
 
-    def table(self, timesteps: torch.Tensor) -> torch.Tensor:
+    def table(self, timesteps: torch.Tensor, y: torch.Tensor = None) -> torch.Tensor:
         w, t = self.w, self.w.t
         dev, dt = w.device, w.dtype
-        n = timesteps.numel()
+        steps = timesteps.numel()
         mc, ted = w.cfg.model_channels, w.cfg.time_embed_dim
+        ns = 1 if y is None else y.shape[0]
+        n = steps * ns
+        ts = timesteps.to(device=dev, dtype=torch.float32)
+        if y is not None:
+            ts = ts.repeat_interleave(ns)          # row = step * ns + sample
         sin = torch.empty((n, mc), device=dev, dtype=dt)
-        ops.timestep_embedding(timesteps.to(device=dev, dtype=torch.float32).contiguous(), sin)
+        ops.timestep_embedding(ts.contiguous(), sin)
         h1 = torch.empty((n, ted), device=dev, dtype=dt)
         ops.linear(sin, t["time_embed.0.w"], h1, bias=t["time_embed.0.b"], flags=ops.EPI_SILU)
         h2 = torch.empty((n, ted), device=dev, dtype=dt)
-        ops.linear(h1, t["time_embed.2.w"], h2, bias=t["time_embed.2.b"], flags=ops.EPI_SILU)  # SiLU of emb_layers.0
+        if y is None:
+            ops.linear(h1, t["time_embed.2.w"], h2, bias=t["time_embed.2.b"], flags=ops.EPI_SILU)  # SiLU of emb_layers.0
+        else:
+            l1 = torch.empty((ns, ted), device=dev, dtype=dt)
+            ops.linear(y.to(device=dev, dtype=dt).contiguous(), t["label_emb.0.w"], l1, bias=t["label_emb.0.b"], flags=ops.EPI_SILU)
+            le = torch.empty((ns, ted), device=dev, dtype=dt)
+            ops.linear(l1, t["label_emb.2.w"], le, bias=t["label_emb.2.b"])
+            # emb = time_embed(t) + label_emb(y), then emb_layers' SiLU: the label part rides in as the GEMM's residual
+            ops.linear(h1, t["time_embed.2.w"], h2, bias=t["time_embed.2.b"], residual=le.repeat(steps, 1).contiguous(),
+                       flags=ops.EPI_SILU)
         emb = torch.empty((n, w.emb_total), device=dev, dtype=dt)
         ops.linear(h2, t["emb_all.w"], emb, bias=t["emb_all.b"])
         table = torch.empty((n, w.emb_total), device=dev, dtype=torch.float32)
         ops.fold_bias(emb, t["conv1_bias_all"], table)
-        return table
+        if y is None:
+            return table
+        # [steps, ns, sum Cout] -> per step, ResBlock after ResBlock, ns rows of its Cout floats
+        tv = table.reshape(steps, ns, w.emb_total)
+        parts = []
+        offs = sorted(w.res_off.values()) + [w.emb_total]
+        for a, b in zip(offs[:-1], offs[1:]):
+            parts.append(tv[:, :, a:b].reshape(steps, ns * (b - a)))
+        return torch.cat(parts, dim=1).contiguous()
