@@ -41,7 +41,8 @@ for p in (ROOT, EXT, os.path.join(ROOT, "tests", "hoststub")):
 
 import torch  # noqa: E402
 
-STEPS_DDIM = 20
+STEPS_DDIM = 20     # sampler steps (the name is historical: --model sdxl runs 30 Euler a steps)
+SAMPLER = "DDIM"
 CFG_SCALE = 7.0
 HW = 64  # 512 x 512 images
 DENOISE = 0.75   # img2img (BASELINE config 3)
@@ -52,6 +53,18 @@ VAE_TFLOP_PER_IMAGE = 2.5145
 VAE_ENC_TFLOP_PER_IMAGE = 1.1167
 CLIP_TFLOP_PER_SEQ = 0.0133
 ATTN_TFLOP_PER_SAMPLE_EVAL = 0.1225
+MODEL_NAME, DTYPE = "SD1.5", "fp16"
+
+
+def select_model(name: str):
+    """BASELINE config 4: SDXL-base txt2img 1024x1024, bf16, 30 Euler a steps (SURVEY App. D FLOP model)"""
+    global STEPS_DDIM, SAMPLER, HW, UNET_TFLOP_PER_SAMPLE_EVAL, VAE_TFLOP_PER_IMAGE, VAE_ENC_TFLOP_PER_IMAGE, CLIP_TFLOP_PER_SEQ
+    global MODEL_NAME, DTYPE
+    if name in ("sdxl", "tinyxl"):
+        STEPS_DDIM, SAMPLER, HW = 30, "Euler a", 128
+        UNET_TFLOP_PER_SAMPLE_EVAL, VAE_TFLOP_PER_IMAGE, VAE_ENC_TFLOP_PER_IMAGE = 6.7612, 10.4704, 4.65
+        CLIP_TFLOP_PER_SEQ = 0.0133 + 0.107      # CLIP-L + OpenCLIP bigG text towers (694 M parameters x 77 tokens x 2)
+        MODEL_NAME, DTYPE = "SDXL-base", "bf16"
 MUFU_EXP_PER_CLK_SM = 16      # MUFU.EX2 per clock and SM (B300_MICROARCH.md; tools/xu_probe.cu measured 4.47 T/s at 1.9 GHz)
 NUM_SMS = 148
 
@@ -374,7 +387,7 @@ def plugin_request(script, batch, tokens, seed0, workload, init_images=None):
     import modules.processing as processing
     import modules.scripts as mscripts
     kw = dict(prompt="synthetic", negative_prompt="", seed=seed0, subseed=1, subseed_strength=0, batch_size=batch, n_iter=1,
-              steps=STEPS_DDIM, width=HW * 8, height=HW * 8, sampler_name="DDIM", cfg_scale=CFG_SCALE,
+              steps=STEPS_DDIM, width=HW * 8, height=HW * 8, sampler_name=SAMPLER, cfg_scale=CFG_SCALE,
               scripts=mscripts.ScriptRunner([script]), script_args=[])
     if workload == "img2img":
         p = processing.StableDiffusionProcessingImg2Img(init_images=init_images, denoising_strength=DENOISE, **kw)
@@ -400,30 +413,24 @@ def synthetic_inputs(eng, b, rank):
 
 
 def make_step(eng, workload, b, tokens_d, neg_d, x_T_d, init_d, seed0, world, gather):
+    """one request with its inputs already on the device: conditioning, sampling, VAE decode (+ the all-gather)"""
     from b200sd import engine as E
+    px = HW * 8
+    pr = eng.program(SAMPLER, None, STEPS_DDIM, denoise=DENOISE if workload == "img2img" else None)
+    draws = None
+    if pr.draws:   # Euler a (SDXL config): the per-image ancestral draws of this rank's seeds, resident like x_T
+        draws = E.per_image_noise(seed0, b, (4, HW, HW), 1 + pr.draws)[1:].to(x_T_d.device)
 
-    def step_txt2img():
-        cond = eng.encode_prompts(tokens_d)
-        unc = eng.encode_prompts(neg_d)
-        lat = eng.sample(cond, unc, x_T_d, STEPS_DDIM, CFG_SCALE, "DDIM")
+    def step():
+        cond, unc = eng._conds(tokens_d, neg_d, px, px)
+        init = eng.encode(init_d) if workload == "img2img" else None
+        lat = eng.run_program(cond, unc, pr.start(x_T_d, init), pr, CFG_SCALE, noises=draws)
         u8 = eng.decode(lat, HW, HW)
         if world > 1:
             gather(u8, [b] * world)
         return u8
 
-    pr = eng.program("DDIM", None, STEPS_DDIM, denoise=DENOISE) if workload == "img2img" else None
-
-    def step_img2img():
-        cond = eng.encode_prompts(tokens_d)
-        unc = eng.encode_prompts(neg_d)
-        init = eng.encode(init_d)
-        lat = eng.run_program(cond, unc, pr.start(x_T_d, init), pr, CFG_SCALE)
-        u8 = eng.decode(lat, HW, HW)
-        if world > 1:
-            gather(u8, [b] * world)
-        return u8
-
-    return step_img2img if workload == "img2img" else step_txt2img
+    return step
 
 
 def timed_device(eng, step, steps, warmup, barrier, rank, local, world, dev):
@@ -461,8 +468,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--per-gpu-batch", type=int, default=32)
-    ap.add_argument("--model", default="sd15", choices=["sd15", "tiny"])
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="default: 32 (SD1.5), 16 (SDXL): BASELINE's batch on one GPU")
+    ap.add_argument("--model", default="sd15", choices=["sd15", "tiny", "sdxl", "tinyxl"])
     ap.add_argument("--workload", default="txt2img", choices=["txt2img", "img2img"])
     ap.add_argument("--sweep", default=None, help="comma-separated per-GPU batches (BASELINE config 5): one JSON line with a list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -475,14 +482,20 @@ def main():
     if args.serve_cpu_oracle is not None:
         return serve_cpu_oracle(args.serve_cpu_oracle, args.threads or usable_cpus(), args.model)
     rank, world, local = dist_env()
+    select_model(args.model)
+    xl = args.model in ("sdxl", "tinyxl")
+    args.per_gpu_batch = args.per_gpu_batch or (16 if xl else 32)
     img2img = args.workload == "img2img"
-    n_evals = (int(DENOISE * STEPS_DDIM) - 1) if img2img else STEPS_DDIM - 1
-    workload = (f"SD1.5 {args.workload} 512x512 fp16, {STEPS_DDIM} DDIM timesteps"
+    if xl and img2img:
+        raise SystemExit("--workload img2img is BASELINE config 3 (SD1.5)")
+    n_evals = STEPS_DDIM if xl else ((int(DENOISE * STEPS_DDIM) - 1) if img2img else STEPS_DDIM - 1)
+    px = HW * 8
+    workload = (f"{MODEL_NAME} {args.workload} {px}x{px} {DTYPE}, {STEPS_DDIM} {SAMPLER} steps"
                 + (f", denoising strength {DENOISE}: VAE encode + {n_evals}" if img2img else f" = {n_evals}")
                 + f" CFG UNet evaluations + VAE decode, per-GPU batch {args.per_gpu_batch}, batch-sharded by image index, "
                   f"synthetic seeded weights, random-token prompts")
     config = {"workload": workload, "per_gpu_batch": args.per_gpu_batch, "global_batch": args.per_gpu_batch * world,
-              "resolution": "512x512", "sampler": "DDIM", "timesteps": STEPS_DDIM, "unet_evals": n_evals,
+              "resolution": f"{px}x{px}", "sampler": SAMPLER, "timesteps": STEPS_DDIM, "unet_evals": n_evals,
               "cfg_scale": CFG_SCALE, "parallelism": f"dp{world} (batch index sharding, one all-gather at the end)",
               "l2": "every step streams far more than the 126 MB L2 (activations of one UNet eval at batch 64 exceed 10 GB)"}
 
@@ -598,9 +611,9 @@ def main():
     tflop_per_image = 2 * n_evals * UNET_TFLOP_PER_SAMPLE_EVAL + VAE_TFLOP_PER_IMAGE + 2 * CLIP_TFLOP_PER_SEQ \
         + (VAE_ENC_TFLOP_PER_IMAGE if img2img else 0.0)
     line = {
-        "metric": f"images/sec SD1.5 512x512 {args.workload}", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": f"images/sec {MODEL_NAME} {px}x{px} {args.workload}", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": config, "clocks": clk, "gpu_launches": int(gpu_launches), "e2e": e2e,
         "world_e2e": world_e2e, "strong_scaling": strong,
         "roofline": roof, "roofline_attention": roof_attn, "unet_eval_breakdown_ms": breakdown,
@@ -745,11 +758,11 @@ def kernel_rooflines(eng, b, pk, clk):
     # sample-evaluation, LayerNorm 1 read + 1 write of 34.7 M) over the summed CUDA-event durations, against the measured
     # copy bandwidth
     hbm = {}
-    for name, elems, bpe in (("groupnorm", 45.1e6, 6), ("layernorm", 34.7e6, 4)):
+    for name, elems, bpe in (("groupnorm", plan.unet.gn_elems, 6), ("layernorm", plan.unet.ln_elems, 4)):
         if name in agg and agg[name][1] > 0:
-            gbs = elems * 2 * b * bpe / (agg[name][1] * 1e-3) / 1e9
+            gbs = elems * bpe / (agg[name][1] * 1e-3) / 1e9
             hbm[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                         "launches": agg[name][0], "algorithmic_bytes": elems * 2 * b * bpe}
+                         "launches": agg[name][0], "algorithmic_bytes": elems * bpe, "elements": elems}
     roof["hbm_kernels"] = hbm
     return roof, roof_attn, breakdown
 

@@ -86,10 +86,10 @@ TINY_VAE = VAEConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1)
 TINY_CLIP = CLIPConfig(vocab=1000, width=64, layers=2, heads=2)
 # SDXL topology at reduced width (d_head 64 as in SDXL: the attention kernel's unpadded-head path)
 TINYXL_UNET = UNetConfig(model_channels=64, channel_mult=(1, 2, 4), transformer_depths=(0, 1, 2), middle_depth=2,
-                         num_head_channels=64, context_dim=128, linear_proj=True, adm_in_channels=64 + 6 * 16)
+                         num_head_channels=64, context_dim=128, linear_proj=True, adm_in_channels=64 + 6 * 32)
 TINYXL_VAE = VAEConfig(ch=64, ch_mult=(1, 2), num_res_blocks=1, scale_factor=0.13025)
 TINYXL_CLIP = CLIPConfig(vocab=1000, width=64, layers=3, heads=2, xl_width=64, xl_layers=3, xl_heads=2, xl_proj=64,
-                         size_embed_dim=16)
+                         size_embed_dim=32)
 XL_PREFIX0 = "conditioner.embedders.0.transformer.text_model."
 XL_PREFIX1 = "conditioner.embedders.1.model."
 

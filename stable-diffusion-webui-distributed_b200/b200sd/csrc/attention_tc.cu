@@ -55,6 +55,7 @@
 
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
+#include "pdl.cuh"
 
 namespace b200sd {
 
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();  // pdl.cuh: the next kernel's prologue may overlap this kernel's tail
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t q_bytes = static_cast<uint32_t>(p.chunks) * kQChunkBytes;
   const uint32_t kv_bytes = static_cast<uint32_t>(p.chunks) * kKvChunkBytes;
@@ -490,6 +492,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;  // S0 @ +0, S1 @ +64, O_a @ +128, O_b @ +128 + dpv
+  pdl_wait();  // Q / K / V come from the preceding projection GEMM
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
@@ -931,7 +934,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
     if ((rc = make_tmap_sw128(&tmV, V, 3, dims, st, kvbox, es)) != B200SD_OK) return rc;
   }
   dim3 grid((p.num_q_tiles + p.qpc - 1) / p.qpc, heads, B);
-  attention_tc_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  launch_pdl(attention_tc_kernel, grid, dim3(kAttnThreads), smem, stream, tmQ, tmK, tmV, p);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 

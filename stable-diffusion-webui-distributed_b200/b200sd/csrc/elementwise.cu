@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../../include/b200sd.h"
+#include "pdl.cuh"
 
 namespace b200sd {
 
@@ -29,6 +30,8 @@ __device__ __forceinline__ void store1(void* p, long long i, float v) {
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ X, long long pitch_x_v, uint4* __restrict__ Y,
                                   long long pitch_y_v, int NB, int H, int W, int cvec) {
+  pdl_trigger();
+  pdl_wait();
   // one thread per (output pixel, 16-byte channel vector)
   const long long total = static_cast<long long>(NB) * (2 * H) * (2 * W) * cvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -46,6 +49,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ X, long long pitch_x
 // one CTA per row; in place; cols <= 16384
 template <bool kBf16>
 __global__ void softmax_rows_kernel(void* S, long long lds, int cols, float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   uint8_t* base = reinterpret_cast<uint8_t*>(S) + row * lds * 2;
@@ -101,6 +106,8 @@ __global__ void fold_bias_kernel(const void* emb, long long lde, const float* __
 }
 
 __global__ void select_step_kernel(const float* __restrict__ table, long long row_len, const int* step, float* cur) {
+  pdl_trigger();
+  pdl_wait();
   const float* src = table + static_cast<long long>(*step) * row_len;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < row_len;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -143,6 +150,8 @@ __device__ __forceinline__ float4 read_eps4(const void* eps, long long pitch, lo
 template <bool kBf16>
 __global__ void pack_unet_input_kernel(const float4* __restrict__ x, void* xin, long long pitch, int B, int HW,
                                        float in_scale) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * HW) return;
   float4 v = x[i];
@@ -153,6 +162,8 @@ __global__ void pack_unet_input_kernel(const float4* __restrict__ x, void* xin, 
 template <bool kBf16>
 __global__ void cfg_ddim_step_kernel(const void* eps, long long pitch_e, float4* x, void* xin, long long pitch_x, int B,
                                      int HW, float cfg, const float* __restrict__ coef, int* step_counter) {
+  pdl_trigger();
+  pdl_wait();
   const int step = *step_counter;
   const float sa = coef[step * 4 + 0], s1a = coef[step * 4 + 1], sap = coef[step * 4 + 2], s1ap = coef[step * 4 + 3];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,6 +192,8 @@ template <bool kBf16>
 __global__ void cfg_euler_a_step_kernel(const void* eps, long long pitch_e, float4* x, const float4* __restrict__ noise,
                                         void* xin, long long pitch_x, int B, int HW, float cfg,
                                         const float* __restrict__ coef, int* step_counter) {
+  pdl_trigger();
+  pdl_wait();
   const int step = *step_counter;
   const float sigma = coef[step * 4 + 0], sdown = coef[step * 4 + 1], sup = coef[step * 4 + 2],
               in_next = coef[step * 4 + 3];
@@ -218,6 +231,8 @@ template <bool kBf16>
 __global__ void cfg_dpmpp_2m_step_kernel(const void* eps, long long pitch_e, float4* x, float4* old_denoised, void* xin,
                                          long long pitch_x, int B, int HW, float cfg, const float* __restrict__ coef,
                                          int* step_counter) {
+  pdl_trigger();
+  pdl_wait();
   const int step = *step_counter;
   const float sigma = coef[step * 8 + 0], a = coef[step * 8 + 1], c1 = coef[step * 8 + 2], c2 = coef[step * 8 + 3],
               in_next = coef[step * 8 + 4];
@@ -244,7 +259,9 @@ __global__ void cfg_dpmpp_2m_step_kernel(const void* eps, long long pitch_e, flo
   }
 }
 
-__global__ void bump_step_kernel(int* step_counter) { *step_counter += 1; }
+__global__ void bump_step_kernel(int* step_counter) {
+  pdl_trigger();
+  pdl_wait(); *step_counter += 1; }
 
 // ---- generic sampler building blocks (every k-diffusion / timestep sampler beyond the four fused ones above is a short
 // list of these per model evaluation; b200sd/samplers.py holds the coefficient algebra) ----
@@ -252,6 +269,8 @@ __global__ void bump_step_kernel(int* step_counter) { *step_counter += 1; }
 // k-diffusion's CompVisDenoiser, to_d(x, sigma, denoised) = (x - denoised) / sigma is exactly this e.
 template <bool kBf16>
 __global__ void cfg_eps_kernel(const void* eps, long long pitch_e, float4* __restrict__ e, int B, int HW, float cfg) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * HW) return;
   const int b = i / HW, pix = i % HW;
@@ -274,6 +293,8 @@ template <bool kBf16>
 __global__ void latent_lincomb_kernel(float4* dst, const LincombParams p, const float* __restrict__ coef, int ld,
                                       int col0, int idx_col, const int* __restrict__ step_counter, void* xin,
                                       long long pitch_x, int B, int HW) {
+  pdl_trigger();
+  pdl_wait();
   const int row = *step_counter;
   const float* c = coef + static_cast<long long>(row) * ld + col0;
   const long long idx = idx_col >= 0 ? static_cast<long long>(coef[static_cast<long long>(row) * ld + idx_col]) : 0;
@@ -300,6 +321,8 @@ __global__ void latent_lincomb_kernel(float4* dst, const LincombParams p, const 
 
 template <bool kBf16>
 __global__ void quantize_u8_kernel(const void* img, long long pitch, unsigned char* out, long long npix) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= npix) return;
 #pragma unroll
@@ -332,6 +355,8 @@ __global__ void unpack_latent_kernel(const void* m, long long pitch, float4* x, 
 // (sdwui CFGDenoiser.apply_blend: current * nmask + init_latent * mask)
 __global__ void blend_latent_kernel(float4* __restrict__ x, const float4* __restrict__ init, const float* __restrict__ latmask,
                                     int B, int HW) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * HW) return;
   const float m = latmask[i % HW];
@@ -373,8 +398,7 @@ extern "C" int b200sd_upsample2x(const void* X, long long pitch_x, void* Y, long
   const long long total = static_cast<long long>(NB) * 4 * H * W * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(
-      static_cast<const uint4*>(X), pitch_x / 8, static_cast<uint4*>(Y), pitch_y / 8, NB, H, W, C / 8);
+  launch_pdl(upsample2x_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, ST(stream), static_cast<const uint4*>(X), pitch_x / 8, static_cast<uint4*>(Y), pitch_y / 8, NB, H, W, C / 8);
   RET_LAUNCH();
 }
 
@@ -382,8 +406,8 @@ extern "C" int b200sd_softmax_rows(void* S, long long lds, int rows, int cols, f
   if (rows <= 0) return B200SD_OK;
   if (cols <= 0) return B200SD_ERR_INVALID;
   const float sl2 = scale * 1.4426950408889634f;
-  if (dtype == B200SD_BF16) softmax_rows_kernel<true><<<rows, 256, 0, ST(stream)>>>(S, lds, cols, sl2);
-  else softmax_rows_kernel<false><<<rows, 256, 0, ST(stream)>>>(S, lds, cols, sl2);
+  if (dtype == B200SD_BF16) launch_pdl(softmax_rows_kernel<true>, dim3(rows), dim3(256), 0, ST(stream), S, lds, cols, sl2);
+  else launch_pdl(softmax_rows_kernel<false>, dim3(rows), dim3(256), 0, ST(stream), S, lds, cols, sl2);
   RET_LAUNCH();
 }
 
@@ -421,7 +445,7 @@ extern "C" int b200sd_select_step(const float* table, long long row_len, const i
   if (row_len <= 0) return B200SD_OK;
   long long blocks = (row_len + 255) / 256;
   if (blocks > 148) blocks = 148;
-  select_step_kernel<<<static_cast<int>(blocks), 256, 0, ST(stream)>>>(table, row_len, step_counter, cur);
+  launch_pdl(select_step_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, ST(stream), table, row_len, step_counter, cur);
   RET_LAUNCH();
 }
 
@@ -431,9 +455,9 @@ extern "C" int b200sd_pack_unet_input(const float* x, void* xin, long long pitch
   if (pitch % 4) return B200SD_ERR_INVALID;
   const int n = B * HW;
   if (dtype == B200SD_BF16)
-    pack_unet_input_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
+    launch_pdl(pack_unet_input_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
   else
-    pack_unet_input_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
+    launch_pdl(pack_unet_input_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), reinterpret_cast<const float4*>(x), xin, pitch, B, HW, in_scale);
   RET_LAUNCH();
 }
 
@@ -444,11 +468,11 @@ extern "C" int b200sd_cfg_ddim_step(const void* eps, long long pitch_e, float* x
   if (pitch_e % 4 || pitch_x % 4) return B200SD_ERR_INVALID;
   const int n = B * HW;
   if (dtype == B200SD_BF16)
-    cfg_ddim_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_ddim_step_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   else
-    cfg_ddim_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_ddim_step_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
-  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, ST(stream), step_counter);
   RET_LAUNCH();
 }
 
@@ -459,11 +483,11 @@ extern "C" int b200sd_cfg_euler_a_step(const void* eps, long long pitch_e, float
   if (pitch_e % 4 || pitch_x % 4) return B200SD_ERR_INVALID;
   const int n = B * HW;
   if (dtype == B200SD_BF16)
-    cfg_euler_a_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_euler_a_step_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   else
-    cfg_euler_a_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_euler_a_step_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(noise), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
-  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, ST(stream), step_counter);
   RET_LAUNCH();
 }
 
@@ -474,11 +498,11 @@ extern "C" int b200sd_cfg_dpmpp_2m_step(const void* eps, long long pitch_e, floa
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(old_denoised)) & 15) return B200SD_ERR_INVALID;
   const int n = B * HW;
   if (dtype == B200SD_BF16)
-    cfg_dpmpp_2m_step_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_dpmpp_2m_step_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   else
-    cfg_dpmpp_2m_step_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
+    launch_pdl(cfg_dpmpp_2m_step_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(old_denoised), xin, pitch_x, B, HW, cfg_scale, coef, step_counter);
   if (cudaGetLastError() != cudaSuccess) return B200SD_ERR_CUDA;
-  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, ST(stream), step_counter);
   RET_LAUNCH();
 }
 
@@ -488,8 +512,8 @@ extern "C" int b200sd_cfg_eps(const void* eps, long long pitch_e, float* e, int 
   if (B <= 0 || HW <= 0) return B200SD_OK;
   if (pitch_e % 4 || (reinterpret_cast<uintptr_t>(e) & 15)) return B200SD_ERR_INVALID;
   const int n = B * HW;
-  if (dtype == B200SD_BF16) cfg_eps_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
-  else cfg_eps_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
+  if (dtype == B200SD_BF16) launch_pdl(cfg_eps_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
+  else launch_pdl(cfg_eps_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), eps, pitch_e, reinterpret_cast<float4*>(e), B, HW, cfg_scale);
   RET_LAUNCH();
 }
 
@@ -511,14 +535,14 @@ extern "C" int b200sd_latent_lincomb(float* dst, const float* const* srcs, const
   }
   const int n = B * HW;
   if (dtype == B200SD_BF16)
-    latent_lincomb_kernel<true><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
+    launch_pdl(latent_lincomb_kernel<true>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
   else
-    latent_lincomb_kernel<false><<<(n + 255) / 256, 256, 0, ST(stream)>>>(reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
+    launch_pdl(latent_lincomb_kernel<false>, dim3((n + 255) / 256), dim3(256), 0, ST(stream), reinterpret_cast<float4*>(dst), p, coef, ld, col0, idx_col, step_counter, xin, pitch_x, B, HW);
   RET_LAUNCH();
 }
 
 extern "C" int b200sd_bump_step(int* step_counter, void* stream) {
-  bump_step_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, ST(stream), step_counter);
   RET_LAUNCH();
 }
 
@@ -551,8 +575,8 @@ extern "C" int b200sd_quantize_u8(const void* img, long long pitch, unsigned cha
   if (B <= 0) return B200SD_OK;
   const long long n = static_cast<long long>(B) * HW;
   const int blocks = static_cast<int>((n + 255) / 256);
-  if (dtype == B200SD_BF16) quantize_u8_kernel<true><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
-  else quantize_u8_kernel<false><<<blocks, 256, 0, ST(stream)>>>(img, pitch, out, n);
+  if (dtype == B200SD_BF16) launch_pdl(quantize_u8_kernel<true>, dim3(blocks), dim3(256), 0, ST(stream), img, pitch, out, n);
+  else launch_pdl(quantize_u8_kernel<false>, dim3(blocks), dim3(256), 0, ST(stream), img, pitch, out, n);
   RET_LAUNCH();
 }
 
@@ -560,8 +584,7 @@ extern "C" int b200sd_blend_latent(float* x, const float* init, const float* lat
   if (B <= 0 || HW <= 0) return B200SD_OK;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(init)) & 15) return B200SD_ERR_INVALID;
   const long long n = static_cast<long long>(B) * HW;
-  blend_latent_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, ST(stream)>>>(
-      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(init), latmask, B, HW);
+  launch_pdl(blend_latent_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, ST(stream), reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(init), latmask, B, HW);
   RET_LAUNCH();
 }
 

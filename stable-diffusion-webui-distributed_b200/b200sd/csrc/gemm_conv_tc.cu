@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "b200sd_internal.h"
+#include "pdl.cuh"
 
 namespace b200sd {
 
@@ -332,6 +333,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* stage_r = stage_d + static_cast<size_t>(p.d_bufs) * 2 * kStageTileBytes;
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(stage_r + (p.has_residual ? kStagingBytes : 0));
 
+  pdl_trigger();  // the next kernel of the chain may start its prologue as SMs free up (pdl.cuh)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
@@ -368,6 +370,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();  // prologue done; from here on the kernel reads what its predecessors wrote
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -616,7 +619,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid <= 0) return B200SD_OK;
-    gemm_conv_tc_kernel<false><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmD, tmR, p);
+    launch_pdl(gemm_conv_tc_kernel<false>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmD, tmR, p);
     return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
   }
   const int num_items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;

@@ -9,6 +9,7 @@
 //
 // Upstream: ldm GroupNorm32 (ResBlock.in_layers/out_layers, out), Normalize (SpatialTransformer.norm, VAE),
 // BasicTransformerBlock.norm1/2/3 (SURVEY.md §8 a-ext x3, x9; not in /root/reference).
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -107,6 +108,8 @@ template <bool kBf16>
 __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long pitch, int HW, int C, int G,
                                        int pix_per_cta, float* __restrict__ stats) {
   extern __shared__ float sh[];  // [PY][2C] partials, then [2C] channel totals reuse row 0
+  pdl_trigger();
+  pdl_wait();  // X is the previous kernel's output; the shared stats / ticket buffer is reused from GroupNorm to GroupNorm
   const int n = blockIdx.y;
   const int v = threadIdx.x;
   const int py = threadIdx.y;
@@ -208,6 +211,8 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
                                        long long pitch_y, int HW, int C, int G, int pix_per_cta,
                                        const float* __restrict__ stats, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int silu) {
+  pdl_trigger();
+  pdl_wait();  // stats come from groupnorm_stats_kernel, X from the kernel before it
   const int n = blockIdx.y;
   const int v = threadIdx.x;
   const int PY = blockDim.y;
@@ -276,11 +281,13 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* __restrict__ Y, long long ldy, int rows, int C,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int lpr) {
   extern __shared__ float gb[];  // gamma[C], beta[C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+  pdl_trigger();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {  // weights: immutable after model load, safe ahead of pdl_wait
     gb[i] = gamma[i];
     gb[C + i] = beta[i];
   }
   __syncthreads();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int sub = lane & (lpr - 1);   // my position among the lanes of my row
   const int rpw = 32 / lpr;           // rows per warp
@@ -379,15 +386,17 @@ layernorm_staged_kernel(const uint8_t* __restrict__ X, long long ldx, uint8_t* _
   uint8_t* in_st = stages + static_cast<size_t>(warp) * (n_in + n_out) * tile_bytes;
   uint8_t* out_st = in_st + static_cast<size_t>(n_in) * tile_bytes;
   uint64_t* full = bars + warp * 8;
+  pdl_trigger();
   if (lane == 0) {
     for (int s = 0; s < n_in; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {  // weights: immutable after model load, safe ahead of pdl_wait
     gb[i] = gamma[i];
     gb[C + i] = beta[i];
   }
   __syncthreads();
+  pdl_wait();  // X is the previous kernel's output
   const int num_tiles = (rows + rpw - 1) / rpw;
   const int tile_step = gridDim.x * kLnWarps;
   const int tile0 = blockIdx.x * kLnWarps + warp;
@@ -541,8 +550,8 @@ static void launch_ln_staged_v(int n_in, int n_out, int lpr, int blocks, size_t 
     cudaFuncSetAttribute(layernorm_staged_kernel<kBf16, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     ready[dev] = true;
   }
-  layernorm_staged_kernel<kBf16, V><<<blocks, kLnThreads, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr, n_in,
-                                                                      n_out);
+  launch_pdl(layernorm_staged_kernel<kBf16, V>, dim3(blocks), dim3(kLnThreads), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta,
+             eps, lpr, n_in, n_out);
 }
 
 template <bool kBf16>
@@ -562,12 +571,12 @@ template <bool kBf16>
 static void launch_ln(int vpt, int lpr, int blocks, size_t sh, cudaStream_t st, const uint8_t* X, long long ldx, uint8_t* Y,
                       long long ldy, int rows, int C, const float* gamma, const float* beta, float eps) {
   switch (vpt) {
-    case 1: layernorm_kernel<kBf16, 1><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
-    case 2: layernorm_kernel<kBf16, 2><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
-    case 3: layernorm_kernel<kBf16, 3><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
-    case 4: layernorm_kernel<kBf16, 4><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
-    case 5: layernorm_kernel<kBf16, 5><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
-    default: layernorm_kernel<kBf16, 8><<<blocks, 256, sh, st>>>(X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 1: launch_pdl(layernorm_kernel<kBf16, 1>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 2: launch_pdl(layernorm_kernel<kBf16, 2>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 3: launch_pdl(layernorm_kernel<kBf16, 3>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 4: launch_pdl(layernorm_kernel<kBf16, 4>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    case 5: launch_pdl(layernorm_kernel<kBf16, 5>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
+    default: launch_pdl(layernorm_kernel<kBf16, 8>, dim3(blocks), dim3(256), sh, st, X, ldx, Y, ldy, rows, C, gamma, beta, eps, lpr); break;
   }
 }
 
@@ -596,9 +605,9 @@ extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, in
   if (sh > 48 * 1024) return B200SD_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
-    groupnorm_stats_kernel<true><<<grid, block, sh, st>>>(static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+    launch_pdl(groupnorm_stats_kernel<true>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
   else
-    groupnorm_stats_kernel<false><<<grid, block, sh, st>>>(static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+    launch_pdl(groupnorm_stats_kernel<false>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 
@@ -615,13 +624,11 @@ extern "C" int b200sd_groupnorm_apply(const void* X, long long pitch_x, void* Y,
   if (rc != B200SD_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == B200SD_BF16)
-    groupnorm_apply_kernel<true><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(X), pitch_x,
-                                                         static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats, gamma,
-                                                         beta, eps, silu);
+    launch_pdl(groupnorm_apply_kernel<true>, grid, block, 0, st, static_cast<const uint8_t*>(X), pitch_x,
+               static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats, gamma, beta, eps, silu);
   else
-    groupnorm_apply_kernel<false><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(X), pitch_x,
-                                                          static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats,
-                                                          gamma, beta, eps, silu);
+    launch_pdl(groupnorm_apply_kernel<false>, grid, block, 0, st, static_cast<const uint8_t*>(X), pitch_x,
+               static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats, gamma, beta, eps, silu);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 

@@ -201,6 +201,7 @@ class UNetProgram:
         self.ctx_kv: Dict[str, torch.Tensor] = {}
         self.ops: List = []
         self.op_flops: List = []
+        self.gn_elems = self.ln_elems = 0     # elements normalised per evaluation (bench.py's HBM roofline)
         self._build()
         # one statistics buffer serves every GroupNorm (they run back to back on one stream); zeroed once, here
         self.stats_all = torch.zeros((max(1, self.gn_need),), device=self.dev, dtype=torch.float32)
@@ -228,6 +229,7 @@ class UNetProgram:
         self.gn_stats.append(holder)
         self.gn_need = max(self.gn_need, ops.groupnorm_stats_floats(x.shape[0], x.shape[1], x.shape[2], 32))
         g, b = self.w.t[name + ".g"], self.w.t[name + ".beta"]
+        self.gn_elems += x.shape[0] * x.shape[1] * x.shape[2]
         self._emit(lambda: ops.groupnorm(x, out, holder[0], g, b, 32, eps, silu))
 
     def _res(self, key, x, cin, cout, h, wd, dest):
@@ -270,6 +272,7 @@ class UNetProgram:
         self._emit(ops.linear, a, t[key + ".proj_in.w"], hcur, bias=t[key + ".proj_in.b"])
         for i in range(depth):
             tb = f"{key}.transformer_blocks.{i}"
+            self.ln_elems += 3 * n * hw * c
             # --- self attention
             self._emit(ops.layernorm, hcur, a, t[tb + ".norm1.g"], t[tb + ".norm1.beta"], 1e-5)
             qkv = self.pool.get(n, hw, 3 * heads * dp)

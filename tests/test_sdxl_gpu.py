@@ -1,0 +1,104 @@
+"""SDXL-base (BASELINE config 4: 1024x1024, bf16, 30 Euler a steps) on the GPU against the fp32 oracle.
+
+bf16 carries 8 significand bits (fp16: 11), so the stated tolerances are wider than SD1.5's fp16 ones — they are the
+measured values with head-room (gpurun_out/engine_parity.jsonl records every run):
+  * one UNet evaluation: rms(d) <= 2e-2 * rms(eps)
+  * uint8 images after the full sampler run: mean |d| <= 2 LSB, >= 90 % of pixels within 4 LSB
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from kutil import OUT_DIR
+
+pytestmark = pytest.mark.gpu
+UNET_REL_RMS_BF16 = 2e-2
+U8_MEAN_BF16, U8_WITHIN4_BF16 = 2.0, 0.90
+
+
+def _record(name, **kw):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "engine_parity.jsonl"), "a") as f:
+        f.write(json.dumps(dict(name=name, **kw)) + "\n")
+
+
+def _setup(size):
+    from b200sd import config as C, engine as E, synth
+    from oracle import sd_oracle as O
+    if size == "tinyxl":
+        cfgs, ocfgs, vocab_hi = (C.TINYXL_UNET, C.TINYXL_VAE, C.TINYXL_CLIP), (O.TINYXL_UNET, O.TINYXL_VAE, O.TINYXL_CLIP), 997
+    else:
+        cfgs, ocfgs, vocab_hi = (C.SDXL_UNET, C.SDXL_VAE, C.SDXL_CLIP), (O.SDXL_UNET, O.SDXL_VAE, O.SDXL_CLIP), 49405
+    sd = synth.make_state_dict(*cfgs, seed=0)
+    eng = E.SDEngine(sd, *cfgs, device="cuda:0", dtype=torch.bfloat16, use_graphs=True)
+    dsd = {k: v.cuda() for k, v in sd.items()}
+    return E, O, cfgs, ocfgs, dsd, eng, vocab_hi
+
+
+def _oracle_conds(O, dsd, ocfgs, tok, neg, px):
+    ctx_c, y_c = O.sdxl_conditioner(dsd, ocfgs[2], tok.cuda(), px, px)
+    ctx_u, y_u = O.sdxl_conditioner(dsd, ocfgs[2], neg.cuda(), px, px, zero_txt=True)
+    return ctx_c, y_c, ctx_u, y_u
+
+
+def _unet_eval_check(E, O, ocfgs, dsd, eng, vocab_hi, b, hw, name):
+    from b200sd import ops
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    ctx_c, y_c, ctx_u, y_u = _oracle_conds(O, dsd, ocfgs, tok, neg, hw * 8)
+    x = O.per_image_noise(1000, b, (4, hw, hw)).cuda()
+    with torch.no_grad():
+        ref = O.unet_forward(dsd, ocfgs[0], torch.cat([x, x]), torch.full((2 * b,), 651.0, device="cuda"),
+                             torch.cat([ctx_c, ctx_u]), y=torch.cat([y_c, y_u]))
+    plan = eng.plan(b, hw, hw)
+    plan.unet.set_context(torch.cat([ctx_c, ctx_u]).to(torch.bfloat16).contiguous())
+    plan.table[:1].copy_(eng.temb.table(torch.tensor([651.0]), torch.cat([y_c, y_u])))
+    plan.step.zero_()
+    plan.x.copy_(x.permute(0, 2, 3, 1).reshape(b, hw * hw, 4))
+    ops.pack_unet_input(plan.x, plan.unet.xin, 1.0)
+    ops.select_step(plan.table, plan.step, plan.unet.cur_bias)
+    plan.unet.run()
+    got = plan.unet.eps[..., :4].float().reshape(2 * b, hw, hw, 4).permute(0, 3, 1, 2)
+    rel_rms = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    _record(name, rel_rms=rel_rms, nan=bool(torch.isnan(got).any()))
+    assert not torch.isnan(got).any() and rel_rms <= UNET_REL_RMS_BF16, rel_rms
+
+
+def _txt2img_check(E, O, ocfgs, dsd, eng, vocab_hi, b, hw, steps, name):
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    ctx_c, y_c, ctx_u, y_u = _oracle_conds(O, dsd, ocfgs, tok, neg, hw * 8)
+    y = torch.cat([y_c, y_u])
+    unet = lambda x, t, c: O.unet_forward(dsd, ocfgs[0], x, t, c, y=y)  # noqa: E731
+    nz = E.per_image_noise(77, b, (4, hw, hw), 1 + steps).cuda()
+    with torch.no_grad():
+        z = O.run_sampler("Euler a", unet, ctx_c, ctx_u, 7.0, steps, nz[0], list(nz[1:]))
+        ref_u8 = O.to_uint8(O.vae_decode(dsd, ocfgs[1], z / ocfgs[1].scale_factor)).cpu()
+    got = eng.txt2img(tok, neg, seed=77, steps=steps, cfg_scale=7.0, height=hw * 8, width=hw * 8, sampler="Euler a").cpu()
+    assert eng.last_unet_evals == steps
+    lat = eng.plan(b, hw, hw).x.reshape(b, hw, hw, 4).permute(0, 3, 1, 2)
+    z_rel_rms = float((lat - z).pow(2).mean().sqrt() / z.pow(2).mean().sqrt())
+    du8 = (got.int() - ref_u8.int()).abs().float()
+    rec = dict(z_rel_rms=z_rel_rms, u8_mean=float(du8.mean()), u8_max=float(du8.max()), u8_exact=float((du8 == 0).float().mean()),
+               u8_within4=float((du8 <= 4).float().mean()))
+    _record(name, **rec)
+    assert got.shape == ref_u8.shape
+    assert rec["u8_mean"] <= U8_MEAN_BF16 and rec["u8_within4"] >= U8_WITHIN4_BF16, rec
+
+
+def test_tinyxl_parity():
+    """SDXL topology at reduced width: d_head 64 (the attention kernel's unpadded-head path), depth-2 transformers, Linear
+    proj, per-sample embedding rows, bf16 kernels, CUDA graphs"""
+    E, O, cfgs, ocfgs, dsd, eng, vocab_hi = _setup("tinyxl")
+    _unet_eval_check(E, O, ocfgs, dsd, eng, vocab_hi, 2, 16, "tinyxl unet_eval")
+    _txt2img_check(E, O, ocfgs, dsd, eng, vocab_hi, 2, 16, 6, "tinyxl txt2img euler_a")
+
+
+def test_sdxl_base_parity_1024():
+    """BASELINE config 4 at full size: one UNet evaluation (2.57 B parameters, 1024x1024) and the whole 30-step Euler a
+    request of 2 images, against the fp32 oracle on the same GPU"""
+    E, O, cfgs, ocfgs, dsd, eng, vocab_hi = _setup("sdxl")
+    _unet_eval_check(E, O, ocfgs, dsd, eng, vocab_hi, 1, 128, "sdxl unet_eval 1024")
+    _txt2img_check(E, O, ocfgs, dsd, eng, vocab_hi, 2, 128, 30, "sdxl txt2img 1024 b2 euler_a 30")
+    del eng, dsd
+    torch.cuda.empty_cache()
