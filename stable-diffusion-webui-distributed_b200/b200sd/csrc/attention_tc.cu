@@ -824,7 +824,10 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
                  long long ldo, int B, int heads, int Sq, int Skv, int d, int d_pad, float scale, int v_ones_col,
                  int is_bf16, cudaStream_t stream) {
   if (B <= 0 || heads <= 0 || Sq <= 0) return B200SD_OK;
-  if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 64 != 0 || d_pad < d) return B200SD_ERR_INVALID;
+  // d_pad: the head pitch in Q / K / V.  A multiple of 16 (the P.V MMA's N); the shared-memory tiles stay whole 64-column
+  // chunks — a box that runs past its head reads the next head's first columns (never multiplied: Q.K^T stops at d16, P.V
+  // at d_pad) or, for the last head, the tensor map's zero fill.
+  if (Skv <= 0 || d <= 0 || d % 8 != 0 || d_pad % 16 != 0 || d_pad < d) return B200SD_ERR_INVALID;
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8) return B200SD_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
        reinterpret_cast<uintptr_t>(O)) & 15)
@@ -849,7 +852,7 @@ int attention_tc(const void* Q, long long ldq, const void* K, long long ldk, con
   AttnParams p{};
   p.B = B; p.heads = heads; p.Sq = Sq; p.Skv = Skv; p.d = d; p.d_pad = d_pad;
   p.d16 = (d + 15) & ~15;
-  p.chunks = d_pad / 64;
+  p.chunks = (d_pad + 63) / 64;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.O = O; p.ldo = ldo; p.is_bf16 = is_bf16;
   p.trace = g_attn_trace;

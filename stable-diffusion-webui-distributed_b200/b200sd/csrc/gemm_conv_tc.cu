@@ -62,15 +62,18 @@ struct GemmKernelParams {
                                    // reading its buffer while the next chunk is staged)
 };
 
-struct __align__(8) GemmBarriers {
+struct __align__(16) GemmBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full[2][2];  // [group][buffer]: residual staging tile landed
   uint32_t tmem_base;
-  uint32_t pad;
+  uint32_t pad[3];          // bias_s starts 16-byte aligned (float4 reads)
+  float bias_s[2][2][128];  // [group][value | GEGLU gate][chunk ordinal * 32 + column]: this tile's bias, staged per group
 };
+
+static_assert(offsetof(GemmBarriers, bias_s) % 16 == 0, "bias_s must be 16-byte aligned");
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below the fp16
 // output rounding): two MUFU ops (rcp, ex2) + a degree-5 Horner chain instead of erff()'s branchy ~30 instructions.
@@ -227,20 +230,44 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
     if (group < nchunks) load_residual(base & 1u, group);
     if (group + 2 < nchunks) load_residual((base + 1u) & 1u, group + 2);
   }
+  // One bias row for the whole tile (everything but the per-image conv1 biases): the group's 128 threads fetch the <= 128
+  // floats its chunks need with ONE coalesced load each while the tile's MMAs are still running, and the chunk loop reads
+  // them back as shared-memory broadcasts.  (ncu, round 1: the per-chunk __ldg of the bias was the epilogue's largest
+  // long-scoreboard stall, 6-10 % of the kernel's samples.)  The previous tile's reads are behind the group barrier that
+  // ended its last chunk.
+  const bool bias_staged = p.bias != nullptr && p.bias_group_rows <= 0;
+  float* bs_v = bars->bias_s[group][0];
+  float* bs_g = bars->bias_s[group][1];
+  if (bias_staged) {
+    const int k = r >> 5, j = r & 31, c = group + 2 * k;
+    if (c < nchunks) {
+      const int col = n_tile * p.block_n + c * kChunkCols + j;
+      bs_v[r] = __ldg(p.bias + col);
+      if (geglu) bs_g[r] = __ldg(p.bias + col + out_bn);
+    }
+    group_bar_sync(group);
+  }
   mbar_wait(tmem_full_bar, full_parity, 4);
   tc_fence_after();
 
   uint32_t ci = 0;
   for (int c = group; c < nchunks; c += 2, ++ci) {
     const int buf = static_cast<int>((base + ci) & 1u);
-    uint32_t v[32];
+    uint32_t v[32], g[32];
     tmem_ld_x32(taddr_row + c * kChunkCols, v);
+    if (geglu) tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);  // both loads in flight, one wait
     tmem_ld_wait();
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
     const int col_in = n_tile * p.block_n + c * kChunkCols;  // column in the [N] space of the GEMM (bias index)
-    if (bias_row) {
+    if (bias_staged) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bs_v + ci * 32 + j);
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+      }
+    } else if (bias_row) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + col_in + j));
@@ -248,14 +275,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       }
     }
     if (geglu) {
-      uint32_t g[32];
-      tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);
-      tmem_ld_wait();
       const int gcol = col_in + out_bn;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + j));
+        if (bias_staged) b = *reinterpret_cast<const float4*>(bs_g + ci * 32 + j);
+        else if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + j));
         const F2 y01 = f2_mul(f2(f[j], f[j + 1]),
                               gelu_erf2(f2_add(f2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), f2(b.x, b.y))));
         const F2 y23 = f2_mul(f2(f[j + 2], f[j + 3]),

@@ -12,6 +12,12 @@
 //   * nothing before pdl_wait() touches global memory (shared memory, TMEM, barriers, descriptor prefetch only).
 // Kernels launched the ordinary way are unaffected (griddepcontrol.* are no-ops for them), and B200SD_PDL=0 turns the
 // launch attribute off at run time.
+//
+// Measured (round 2, one B200, whole txt2img requests, PDL on every launch vs none): per-GPU batch 1: 8.35 -> 8.75 images/s
+// (+4.8 %); batch 4: 18.5 -> 18.5; batch 32: 22.4 -> 21.6 (-3.3 %: with every SM busy there is no tail to hide a prologue
+// in, and the early-resident dependents cost more than the launch gap they save).  Hence the rule in launch_pdl(): the
+// attribute is set only on grids that do not fill the machine (fewer CTAs than SMs) — the latency-bound regime of small
+// batches, where boundaries are a visible share of the time.  B200SD_PDL=2 forces it on every launch.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -21,12 +27,14 @@ namespace b200sd {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  static const bool on = [] {
+constexpr unsigned kPdlMaxCtas = 148;  // grids below one CTA per SM
+
+inline int pdl_mode() {  // 0 off, 1 small grids only (default), 2 every launch
+  static const int mode = [] {
     const char* e = getenv("B200SD_PDL");
-    return e == nullptr || e[0] != '0';
+    return e == nullptr ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
   }();
-  return on;
+  return mode;
 }
 
 template <typename... KArgs, typename... Args>
@@ -41,7 +49,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int mode = pdl_mode();
+  cfg.numAttrs = (mode == 2 || (mode == 1 && grid.x * grid.y * grid.z < kPdlMaxCtas)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -23,7 +23,10 @@ from .weights import pack_conv, pack_geglu, pad_heads
 
 
 def _pad64(d: int) -> int:
-    return (d + 63) // 64 * 64
+    """head pitch of q / k / v: d itself when it is a multiple of 64 (SDXL), otherwise d + 1 (room for V's ones column)
+    rounded up to the P.V MMA's N granularity of 16 — 40 -> 48, 80 -> 96, 160 -> 176 (round 1 padded to 64 / 128 / 192:
+    a quarter more q/k/v projection FLOPs and bytes for d = 40)"""
+    return d if d % 64 == 0 else (d + 1 + 15) // 16 * 16
 
 
 class Pool:

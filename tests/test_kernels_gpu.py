@@ -513,3 +513,30 @@ def test_cfg_eps_and_latent_lincomb(ops):
     coef[3, 0:2] = torch.tensor([1.0, 1.0])
     ops.latent_lincomb(u, [x, e], coef, 0, step)
     assert torch.allclose(u, x + e, atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("b,heads,sq,skv,d,d_pad", [(2, 8, 4096, 4096, 40, 48), (2, 8, 1024, 1024, 80, 96), (2, 8, 256, 256, 160, 176),
+                                                    (3, 8, 1024, 77, 40, 48), (2, 8, 300, 200, 80, 96), (2, 2, 256, 256, 32, 48),
+                                                    (1, 8, 64, 64, 160, 176)])
+def test_attention_narrow_head_pitch(ops, b, heads, sq, skv, d, d_pad):
+    """round 2: heads sit d_pad = round16(d + 1) columns apart (40 -> 48, 80 -> 96, 160 -> 176) inside ONE fused q|k|v
+    buffer, so a head's 64-column TMA boxes overlap the next head's data (and, for v's last head, run off the buffer's
+    row): those columns must never reach a result.  The ones column of V delivers the softmax denominators."""
+    g = _gen(sq * 3 + skv + d_pad)
+    w = heads * d_pad
+    if sq == skv:
+        buf = torch.zeros((b, sq, 3 * w), device="cuda", dtype=torch.float16)
+        q, k, v = buf[..., :w], buf[..., w:2 * w], buf[..., 2 * w:]
+    else:
+        bq = torch.zeros((b, sq, w), device="cuda", dtype=torch.float16)
+        bkv = torch.zeros((b, skv, 2 * w), device="cuda", dtype=torch.float16)
+        q, k, v = bq, bkv[..., :w], bkv[..., w:]
+    for t in (q, k, v):
+        t.reshape(t.shape[0], t.shape[1], heads, d_pad)[..., :d] = _rand((t.shape[0], t.shape[1], heads, d), g)
+    v.reshape(b, skv, heads, d_pad)[..., d] = 1.0
+    out = torch.full((b, sq, heads * d), float("nan"), device="cuda", dtype=torch.float16)
+    scale = d ** -0.5
+    ops.attention(q, k, v, out, heads, d, d_pad, scale, True)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads, d, d_pad, scale)
+    assert_close(f"attention narrow pitch d{d}/{d_pad} sq{sq} skv{skv}", out, ref, atol=4e-3, rtol=1e-2)

@@ -2,8 +2,9 @@
 
 bf16 carries 8 significand bits (fp16: 11), so the stated tolerances are wider than SD1.5's fp16 ones — they are the
 measured values with head-room (gpurun_out/engine_parity.jsonl records every run):
-  * one UNet evaluation: rms(d) <= 2e-2 * rms(eps)
-  * uint8 images after the full sampler run: mean |d| <= 2 LSB, >= 90 % of pixels within 4 LSB
+  * one UNet evaluation: rms(d) <= 3e-2 * rms(eps)   (measured 1.2e-2 at reduced width, 1.8e-2 at SDXL size)
+  * uint8 images after the full sampler run: mean |d| <= 2 LSB, >= 95 % of pixels within 4 LSB
+    (measured at 1024x1024, 30 Euler a steps: mean 0.69 LSB, max 6, 99.996 % within 4; reduced width: 1.18 / 11 / 98.7 %)
 """
 import json
 import os
@@ -14,8 +15,8 @@ import torch
 from kutil import OUT_DIR
 
 pytestmark = pytest.mark.gpu
-UNET_REL_RMS_BF16 = 2e-2
-U8_MEAN_BF16, U8_WITHIN4_BF16 = 2.0, 0.90
+UNET_REL_RMS_BF16 = 3e-2
+U8_MEAN_BF16, U8_WITHIN4_BF16 = 2.0, 0.95
 
 
 def _record(name, **kw):
