@@ -50,6 +50,8 @@ const char* b200sd_version(void);
 /* debug: a device buffer of 16 x 64 int64 that one CTA of every later b200sd_attention launch fills with clock64()
  * stamps of its per-tile pipeline events (tools/attn_trace.py); NULL switches it off (default). */
 int b200sd_debug_attention_trace(void* device_buffer);
+/* debug only: clock64 timeline of CTA 0 of the GEMM / conv kernel (tools/gemm_trace.py; trace-enabled builds). */
+int b200sd_debug_gemm_trace(void* device_buffer);
 
 /* ---- tensor-core ops (tcgen05 + TMA) ----------------------------------------------------------- */
 

@@ -60,7 +60,20 @@ struct GemmKernelParams {
   int pair;                        // 1: launched as CTA pairs (tcgen05 cta_group::2, 256-row tiles)
   int d_bufs;                      // output staging buffers per epilogue group (2, or 3 so a TMA store may still be
                                    // reading its buffer while the next chunk is staged)
+  long long* trace;                // debug: clock64 timeline of CTA 0 ([32 events][64 tiles]), or null
 };
+
+// debug timeline (b200sd_debug_gemm_trace; build with -DB200SD_GEMM_TRACE_ENABLE=1, tools/gemm_trace.py): CTA 0 stamps, per
+// tile it processes, events of the producer lane, the MMA lane and thread 0 of each epilogue group.  Compiled out by default.
+#ifndef B200SD_GEMM_TRACE_ENABLE
+#define B200SD_GEMM_TRACE_ENABLE 0
+#endif
+#if B200SD_GEMM_TRACE_ENABLE
+#define GEMM_TRACE(cond, ev, j) \
+  do { if ((cond) && p.trace != nullptr && blockIdx.x == 0) p.trace[(ev) * 64 + ((j) & 63)] = clock64(); } while (0)
+#else
+#define GEMM_TRACE(cond, ev, j) do { } while (0)
+#endif
 
 struct __align__(16) GemmBarriers {
   uint64_t full[kMaxStages];
@@ -193,7 +206,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
                                               GemmBarriers* bars, uint8_t* stage_d, uint8_t* stage_r,
                                               uint64_t* tmem_full_bar, uint32_t full_parity, uint32_t tmem_acc,
                                               int m_tile, int n_tile, int quarter, int group, int lane,
-                                              uint32_t (&uses)[2], uint32_t& chunk_count, uint32_t& d_slot) {
+                                              uint32_t (&uses)[2], uint32_t& chunk_count, uint32_t& d_slot, int tile_it) {
   const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
   const bool leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
   const TileCoord tc = tile_coord(p, m_tile);
@@ -247,8 +260,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
     }
     group_bar_sync(group);
   }
+  const bool tracer = leader;                     // one thread per epilogue group; events 8.. (group 0), 20.. (group 1)
+  const int ev0 = 8 + 12 * group;
+  GEMM_TRACE(tracer, ev0 + 0, tile_it);           // epilogue: waiting for the accumulator
   mbar_wait(tmem_full_bar, full_parity, 4);
   tc_fence_after();
+  GEMM_TRACE(tracer, ev0 + 1, tile_it);           // epilogue: accumulator complete
 
   uint32_t ci = 0;
   for (int c = group; c < nchunks; c += 2, ++ci) {
@@ -257,6 +274,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
     tmem_ld_x32(taddr_row + c * kChunkCols, v);
     if (geglu) tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);  // both loads in flight, one wait
     tmem_ld_wait();
+    GEMM_TRACE(tracer && ci < 4, ev0 + 2 + 2 * ci, tile_it);   // chunk ci: accumulator columns in registers
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -327,6 +345,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       else bulk_wait_read<0>();
     }
     group_bar_sync(group);
+    GEMM_TRACE(tracer && ci < 4, ev0 + 3 + 2 * ci, tile_it);   // chunk ci: staged, group barrier passed
     if (leader) {
       const int col = n_tile * out_bn + c * kChunkCols;
       if (p.mode == 0) tma_store_2d(tmD, dt, col, tc.c1);
@@ -411,9 +430,11 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tx_bytes = (kPair ? 2u : 1u) * (p.a_bytes + p.b_bytes);
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = first_item; item < num_items; item += item_step) {
+      int pit = 0;
+      for (int item = first_item; item < num_items; item += item_step, ++pit) {
         const int n_tile = item % p.num_n_tiles;
         const int m_tile = kPair ? 2 * (item / p.num_n_tiles) + rank : item / p.num_n_tiles;
+        GEMM_TRACE(leader, 0, pit);   // producer: tile start
         int cx = 0, cy = 0, cn = 0;
         if (conv) {
           const int tx = m_tile % p.tiles_x;
@@ -451,6 +472,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
+        GEMM_TRACE(leader, 1, pit);   // producer: last k-block's loads issued
       }
       __syncwarp();
     }
@@ -478,12 +500,15 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int it = 0;
       for (int item = first_item; item < num_items; item += item_step, ++it) {
         const uint32_t acc = static_cast<uint32_t>(it) & 1u;
+        GEMM_TRACE(leader, 2, it);    // MMA: wants the accumulator
         mbar_wait_a(a_tempty + acc * 8u, ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u, 2);
         tc_fence_after();
+        GEMM_TRACE(leader, 3, it);    // MMA: accumulator free
         const uint32_t tmem_acc = tmem0 + acc * kAccStride;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait_a(a_full + static_cast<uint32_t>(stage) * 8u, phase, 3);
           tc_fence_after();
+          GEMM_TRACE(leader && kb == 0, 4, it);   // MMA: first operands landed
           if (leader) {
             if constexpr (kPair) {
 #pragma unroll
@@ -508,6 +533,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (kPair) umma_commit_pair(&bars->tmem_full[acc]);
           else umma_commit_a(a_tfull + acc * 8u);
         }
+        GEMM_TRACE(leader, 5, it);    // MMA: last MMA issued + committed
       }
       __syncwarp();
     }
@@ -526,10 +552,10 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tmem_acc = tmem_base + acc * kAccStride;
       if (p.is_bf16)
         epilogue_tile<true>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                            n_tile, quarter, group, lane, uses, chunk_count, d_slot);
+                            n_tile, quarter, group, lane, uses, chunk_count, d_slot, it);
       else
         epilogue_tile<false>(p, &tmD, &tmR, bars, stage_d, stage_r, &bars->tmem_full[acc], acc_phase, tmem_acc, m_tile,
-                             n_tile, quarter, group, lane, uses, chunk_count, d_slot);
+                             n_tile, quarter, group, lane, uses, chunk_count, d_slot, it);
       tc_fence_before();
       // the MMA issuer (leader CTA) may overwrite this accumulator once BOTH CTAs have drained theirs
       // one (possibly remote) arrival per warp: 256 remote arrivals per tile cost more than a short tile's MMAs
@@ -538,6 +564,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
         else mbar_arrive(&bars->tmem_empty[acc]);
       }
+      GEMM_TRACE(lane == 0 && quarter == ((2 + 4 * group) & 3), 8 + 12 * group + 10, it);   // epilogue: accumulator released
     }
     bulk_wait<0>();  // the issuing threads' TMA stores must have completed before the CTA (and its smem) goes away
   }
@@ -555,6 +582,7 @@ gemm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static long long* g_gemm_trace = nullptr;
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 static bool g_dev_ready[64] = {};
@@ -623,6 +651,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     dbufs_env = e ? atoi(e) : 0;
   }
   p.d_bufs = dbufs_env == 3 ? 3 : 2;
+  p.trace = g_gemm_trace;
   const int staging = p.d_bufs * 2 * static_cast<int>(kStageTileBytes) + (p.has_residual ? static_cast<int>(kStagingBytes) : 0);
   const int budget = g_max_smem - 1024 /*align*/ - staging - static_cast<int>(sizeof(GemmBarriers)) - 64;
   int stages = budget / static_cast<int>(stage_bytes);
@@ -832,3 +861,10 @@ int conv_tc(const void* X, long long pitch_c, int NB, int Hin, int Win, int C, c
 }
 
 }  // namespace b200sd
+
+// debug hook: device buffer of 32 * 64 int64 that CTA 0 of later GEMM / conv launches fills with clock64 stamps (only in
+// builds with -DB200SD_GEMM_TRACE_ENABLE=1; tools/gemm_trace.py)
+extern "C" int b200sd_debug_gemm_trace(void* device_buffer) {
+  b200sd::g_gemm_trace = static_cast<long long*>(device_buffer);
+  return B200SD_OK;
+}
