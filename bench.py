@@ -472,6 +472,8 @@ def main():
     ap.add_argument("--model", default="sd15", choices=["sd15", "tiny", "sdxl", "tinyxl"])
     ap.add_argument("--workload", default="txt2img", choices=["txt2img", "img2img"])
     ap.add_argument("--sweep", default=None, help="comma-separated per-GPU batches (BASELINE config 5): one JSON line with a list")
+    ap.add_argument("--sweep-out", default=None, help="also run the sweep of --sweep-batches after the main measurement -> JSON file")
+    ap.add_argument("--sweep-batches", default="1,2,4,8,16,64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-world", action="store_true")
@@ -524,8 +526,10 @@ def main():
     from b200sd.sharding import all_gather_images
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if world > 1:
@@ -535,24 +539,29 @@ def main():
     eng = factory.default_engine_factory(dev, args.model)
 
     # ---------------- BASELINE config 5: per-GPU batch sweep (device-timed whole requests, weak scaling per batch)
-    if args.sweep:
+    def run_sweep(batches):
         rows = []
-        for b in [int(v) for v in args.sweep.split(",")]:
-            tokens, neg, seed0, x_T, init_u8 = synthetic_inputs(eng, b, rank)
-            step = make_step(eng, args.workload, b, tokens.to(dev), neg.to(dev), x_T.to(dev), init_u8.to(dev), seed0, world,
+        for bb in batches:
+            tk, ng, sd0, xt, iu8 = synthetic_inputs(eng, bb, rank)
+            step = make_step(eng, args.workload, bb, tk.to(dev), ng.to(dev), xt.to(dev), iu8.to(dev), sd0, world,
                              all_gather_images)
-            ms, clk, _ = timed_device(eng, step, args.steps, args.warmup, barrier, rank, local, world, dev)
-            rows.append({"per_gpu_batch": b, "global_batch": b * world, "value": world * b * args.steps / (ms / 1000.0),
-                         "ms_per_step": ms / args.steps, "clocks": clk})
-            eng.plans.clear()
+            ms, ck, _ = timed_device(eng, step, args.steps, args.warmup, barrier, rank, local, world, dev)
+            rows.append({"per_gpu_batch": bb, "global_batch": bb * world, "value": world * bb * args.steps / (ms / 1000.0),
+                         "ms_per_step": ms / args.steps, "clocks": ck})
+            eng.plans.pop((bb, HW, HW), None)
             torch.cuda.empty_cache()
+        tfl = 2 * n_evals * UNET_TFLOP_PER_SAMPLE_EVAL + VAE_TFLOP_PER_IMAGE + 2 * CLIP_TFLOP_PER_SEQ
+        for r in rows:
+            r["step_roofline_frac"] = r["value"] * tfl / world / peaks()["tflops_sustained"]
+        return {"metric": f"images/sec {MODEL_NAME} {px}x{px} {args.workload}", "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "scaling": "weak per batch (per-GPU batch fixed, N ranks)",
+                "dtype": DTYPE, "workload": args.workload, "pdl": os.environ.get("B200SD_PDL", "default (small grids only)"),
+                "sweep": rows}
+
+    if args.sweep:
+        res = run_sweep([int(v) for v in args.sweep.split(",")])
         if rank == 0:
-            tfl = 2 * n_evals * UNET_TFLOP_PER_SAMPLE_EVAL + VAE_TFLOP_PER_IMAGE + 2 * CLIP_TFLOP_PER_SEQ
-            for r in rows:
-                r["step_roofline_frac"] = r["value"] * tfl / world / peaks()["tflops_sustained"]
-            print(json.dumps({"metric": "images/sec SD1.5 512x512 txt2img", "unit": "images/s", "n_gpus": world,
-                              "steps": args.steps, "warmup": max(3, args.warmup), "scaling": "weak", "dtype": "fp16",
-                              "workload": args.workload, "sweep": rows}))
+            print(json.dumps(res))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -592,12 +601,24 @@ def main():
                "path": "hoststub process_images -> DistributedScript.before_process -> LocalGPUWorker.request -> "
                        "postprocess_batch_list -> postprocess (thin-client world, 1 local GPU per rank)"}
 
+    if args.sweep_out:
+        res = run_sweep([int(v) for v in args.sweep_batches.split(",")])
+        res["sweep"].append({"per_gpu_batch": b, "global_batch": b * world, "value": value, "ms_per_step": elapsed_ms / args.steps,
+                             "clocks": clk, "note": "the main measurement of this run"})
+        if rank == 0:
+            with open(args.sweep_out, "w") as f:
+                json.dump(res, f)
+
     # ---------------- one process, ONE World over all N GPUs (rank 0 drives; the other ranks idle at the barrier)
     world_e2e = strong = None
     if not args.no_world and not args.no_e2e:
+        # the other ranks wait on a HOST barrier (gloo): an NCCL barrier would park a spinning kernel on their GPUs, which
+        # rank 0 is about to drive from this process
         barrier()
         if rank == 0:
             world_e2e, strong = world_level(args, world, b, tokens, seed0, init_pil, eng, local)
+        if world > 1:
+            dist.barrier(group=cpu_group)
         barrier()
 
     # ---------------- roofline of the dominant kernel: per-launch CUDA-event timing of one eager UNet evaluation
