@@ -133,28 +133,78 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// gelu on two values.  erf by Abramowitz-Stegun 7.1.28: erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 for z >= 0, |error| < 3e-7
+// (gelu: 9e-7 absolute over [-12, 12]): ONE MUFU op per element (the reciprocal; the 16th power is four packed squarings)
+// where 7.1.26 above needs two (rcp and ex2).  tools/gemm_trace.py, round 2: a GEGLU tile's epilogue took 6000 clocks against
+// 2400 for its MMAs at K = 320 — 32768 MUFU lane-operations per tile are 2048 clocks of the SM's 16-lane MUFU pipe on their
+// own, and the two-MUFU dependency chain kept the eight epilogue warps latency-bound on top.  An overflow of the 16th power
+// (z > ~15) gives rcp(inf) = 0, i.e. erf = 1, which is the right limit.
 __device__ __forceinline__ F2 gelu_erf2(F2 x) {
   float x0, x1;
   f2_get(x, x0, x1);
   const F2 z = f2_mul(f2(fabsf(x0), fabsf(x1)), f2(0.70710678118654752440f, 0.70710678118654752440f));
-  const F2 d = f2_fma(f2(0.3275911f, 0.3275911f), z, f2(1.0f, 1.0f));
-  float d0, d1;
-  f2_get(d, d0, d1);
-  const F2 t = f2(rcp_approx(d0), rcp_approx(d1));
-  // -(a1 t + a2 t^2 + ... + a5 t^5): coefficients negated so that erf_abs = 1 + (-poly t) e is a single FFMA2
-  F2 poly = f2_fma(f2(-1.061405429f, -1.061405429f), t, f2(1.453152027f, 1.453152027f));
-  poly = f2_fma(poly, t, f2(-1.421413741f, -1.421413741f));
-  poly = f2_fma(poly, t, f2(0.284496736f, 0.284496736f));
-  poly = f2_fma(poly, t, f2(-0.254829592f, -0.254829592f));
-  const F2 npt = f2_mul(poly, t);
-  const F2 arg = f2_mul(f2_mul(z, z), f2(-1.4426950408889634f, -1.4426950408889634f));  // exp(-z^2) = 2^(-z^2 log2 e)
-  float a0, a1;
-  f2_get(arg, a0, a1);
-  const F2 erf_abs = f2_fma(npt, f2(fast_exp2(a0), fast_exp2(a1)), f2(1.0f, 1.0f));
-  float e0, e1;
-  f2_get(erf_abs, e0, e1);
+  F2 q = f2_fma(f2(0.0000430638f, 0.0000430638f), z, f2(0.0002765672f, 0.0002765672f));
+  q = f2_fma(q, z, f2(0.0001520143f, 0.0001520143f));
+  q = f2_fma(q, z, f2(0.0092705272f, 0.0092705272f));
+  q = f2_fma(q, z, f2(0.0422820123f, 0.0422820123f));
+  q = f2_fma(q, z, f2(0.0705230784f, 0.0705230784f));
+  q = f2_fma(q, z, f2(1.0f, 1.0f));
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);
+  q = f2_mul(q, q);
+  float q0, q1;
+  f2_get(q, q0, q1);
+  const float e0 = 1.0f - rcp_approx(q0), e1 = 1.0f - rcp_approx(q1);   // erf(|x| / sqrt 2)
   const F2 h = f2_fma(f2(0.5f, 0.5f), f2(copysignf(e0, x0), copysignf(e1, x1)), f2(0.5f, 0.5f));
   return f2_mul(x, h);
+}
+
+// The same GELU on kN pairs at once, written stage by stage: every stage is kN INDEPENDENT packed instructions, so the
+// dependent chain of one element (1 mul, 6 fma, 4 mul, rcp, 1 fma, 1 mul ~ 100+ clocks of latency) is overlapped kN-fold
+// whatever the instruction scheduler makes of it.  tools/gemm_trace.py, round 2: with the per-pair form above a 32-column
+// GEGLU chunk took 2400-2800 clocks — 16 pairs executed almost back to back, two warps per scheduler cannot hide that.
+template <int kN>
+__device__ __forceinline__ void gelu_erf2_batch(F2 (&x)[kN]) {
+  F2 z[kN], q[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float x0, x1;
+    f2_get(x[i], x0, x1);
+    z[i] = f2_mul(f2(fabsf(x0), fabsf(x1)), f2(0.70710678118654752440f, 0.70710678118654752440f));
+  }
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(f2(0.0000430638f, 0.0000430638f), z[i], f2(0.0002765672f, 0.0002765672f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(q[i], z[i], f2(0.0001520143f, 0.0001520143f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(q[i], z[i], f2(0.0092705272f, 0.0092705272f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(q[i], z[i], f2(0.0422820123f, 0.0422820123f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(q[i], z[i], f2(0.0705230784f, 0.0705230784f));
+#pragma unroll
+  for (int i = 0; i < kN; ++i) q[i] = f2_fma(q[i], z[i], f2(1.0f, 1.0f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < kN; ++i) q[i] = f2_mul(q[i], q[i]);
+  }
+  float e0[kN], e1[kN];
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float q0, q1;
+    f2_get(q[i], q0, q1);
+    e0[i] = rcp_approx(q0);
+    e1[i] = rcp_approx(q1);
+  }
+#pragma unroll
+  for (int i = 0; i < kN; ++i) {
+    float x0, x1;
+    f2_get(x[i], x0, x1);
+    const F2 h = f2_fma(f2(0.5f, 0.5f), f2(copysignf(1.0f - e0[i], x0), copysignf(1.0f - e1[i], x1)), f2(0.5f, 0.5f));
+    x[i] = f2_mul(x[i], h);
+  }
 }
 
 template <bool kBf16>
@@ -201,6 +251,88 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int m
 // group has staged since the kernel started: the two staging buffers alternate ACROSS tiles, never per tile — the TMA
 // store of a tile's last chunk may still be reading its buffer when the next tile's first chunk is written, and only
 // the buffer of the store before that is known to be drained (bulk_wait_read precedes every store).
+// What one epilogue group needs to turn 32 fp32 accumulator columns into a stored output chunk.
+struct EpiCtx {
+  const GemmKernelParams* p;
+  const CUtensorMap* tmD;
+  const CUtensorMap* tmR;
+  GemmBarriers* bars;
+  uint8_t* my_d;   // this group's output staging buffers
+  uint8_t* my_r;   // this group's residual staging buffers
+  TileCoord tc;
+  int n_tile, out_bn, nchunks, group, r;
+  bool leader;
+  uint32_t base;   // chunks this group had staged before this tile (residual buffer parity)
+};
+
+__device__ __forceinline__ void load_residual(const EpiCtx& e, int buf, int c) {  // leader only
+  const GemmKernelParams& p = *e.p;
+  mbar_arrive_expect_tx(&e.bars->res_full[e.group][buf], p.d_bytes);
+  const int col = e.n_tile * e.out_bn + c * kChunkCols;
+  if (p.mode == 0) tma_load_2d(e.my_r + buf * kStageTileBytes, e.tmR, &e.bars->res_full[e.group][buf], col, e.tc.c1);
+  else tma_load_4d(e.my_r + buf * kStageTileBytes, e.tmR, &e.bars->res_full[e.group][buf], col, e.tc.c1, e.tc.c2, e.tc.c3);
+}
+
+// f[32] (bias / GEGLU already applied) -> + residual -> SiLU -> fp16 -> swizzled staging tile -> TMA store of chunk c
+template <bool kBf16>
+__device__ __forceinline__ void finish_chunk(const EpiCtx& e, float (&f)[32], int c, uint32_t ci, uint32_t (&uses)[2],
+                                             uint32_t& d_slot) {
+  const GemmKernelParams& p = *e.p;
+  const int buf = static_cast<int>((e.base + ci) & 1u);
+  const int r = e.r;
+  if (p.has_residual) {
+    mbar_wait(&e.bars->res_full[e.group][buf], uses[buf] & 1u, 5);
+    uses[buf]++;
+    const uint8_t* rt = e.my_r + buf * kStageTileBytes;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(rt + sw64_offset(r, q));
+      const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = unpack2<kBf16>(w[k]);
+        f[q * 8 + k * 2] += t.x;
+        f[q * 8 + k * 2 + 1] += t.y;
+      }
+    }
+  }
+  if (p.flags & B200SD_EPI_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+  }
+  uint8_t* dt = e.my_d + d_slot * kStageTileBytes;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    o.x = pack2<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
+    o.y = pack2<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
+    o.z = pack2<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
+    o.w = pack2<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(dt + sw64_offset(r, q)) = o;
+  }
+  fence_proxy_async_smem();          // my staging writes (and residual reads) -> visible / ordered for the async proxy
+  // before chunk i+1 is staged into the buffer after this one, the store that last read THAT buffer must be done:
+  // with two buffers that is the previous store (wait for all), with three the one before it (one may stay in flight)
+  if (e.leader) {
+    if (p.d_bufs == 3) bulk_wait_read<1>();
+    else bulk_wait_read<0>();
+  }
+  group_bar_sync(e.group);
+  if (e.leader) {
+    const int col = e.n_tile * e.out_bn + c * kChunkCols;
+    if (p.mode == 0) tma_store_2d(e.tmD, dt, col, e.tc.c1);
+    else tma_store_4d(e.tmD, dt, col, e.tc.c1, e.tc.c2, e.tc.c3);
+    bulk_commit();
+    if (p.has_residual && c + 4 < e.nchunks) load_residual(e, buf, c + 4);  // everyone is past reading this buffer
+  }
+  if (++d_slot == static_cast<uint32_t>(p.d_bufs)) d_slot = 0;
+}
+
+// One epilogue group's share of a tile.  `uses` counts how often each residual buffer of this group has been
+// filled so far (mbarrier phase bookkeeping, identical in all 128 threads).  `chunk_count` is the number of chunks this
+// group has staged since the kernel started: the two staging buffers alternate ACROSS tiles, never per tile — the TMA
+// store of a tile's last chunk may still be reading its buffer when the next tile's first chunk is written, and only
+// the buffer of the store before that is known to be drained (bulk_wait_read precedes every store).
 template <bool kBf16>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const CUtensorMap* tmD, const CUtensorMap* tmR,
                                               GemmBarriers* bars, uint8_t* stage_d, uint8_t* stage_r,
@@ -208,21 +340,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
                                               int m_tile, int n_tile, int quarter, int group, int lane,
                                               uint32_t (&uses)[2], uint32_t& chunk_count, uint32_t& d_slot, int tile_it) {
   const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
-  const bool leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
-  const TileCoord tc = tile_coord(p, m_tile);
   const bool geglu = (p.flags & B200SD_EPI_GEGLU) != 0;
-  const int out_bn = geglu ? p.block_n / 2 : p.block_n;
-  const int nchunks = out_bn / kChunkCols;
+  EpiCtx e;
+  e.p = &p; e.tmD = tmD; e.tmR = tmR; e.bars = bars;
+  e.my_d = stage_d + group * p.d_bufs * kStageTileBytes;
+  e.my_r = stage_r + group * 2 * kStageTileBytes;
+  e.tc = tile_coord(p, m_tile);
+  e.n_tile = n_tile;
+  e.out_bn = geglu ? p.block_n / 2 : p.block_n;
+  e.nchunks = e.out_bn / kChunkCols;
+  e.group = group; e.r = r;
+  e.leader = (quarter == ((2 + 4 * group) & 3)) && lane == 0;  // lane 0 of the group's first warp
+  e.base = chunk_count;
+  const int out_bn = e.out_bn, nchunks = e.nchunks;
   const uint32_t taddr_row = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-  uint8_t* my_d = stage_d + group * p.d_bufs * kStageTileBytes;
-  uint8_t* my_r = stage_r + group * 2 * kStageTileBytes;
-
-  auto load_residual = [&](int buf, int c) {  // leader only
-    mbar_arrive_expect_tx(&bars->res_full[group][buf], p.d_bytes);
-    const int col = n_tile * out_bn + c * kChunkCols;
-    if (p.mode == 0) tma_load_2d(my_r + buf * kStageTileBytes, tmR, &bars->res_full[group][buf], col, tc.c1);
-    else tma_load_4d(my_r + buf * kStageTileBytes, tmR, &bars->res_full[group][buf], col, tc.c1, tc.c2, tc.c3);
-  };
 
   // per-row bias group (per-image bias): needs the global output row of this thread
   const float* bias_row = p.bias;
@@ -232,16 +363,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
       row = static_cast<long long>(m_tile) * kBlockM + r;
       if (row >= p.M) row = 0;
     } else {
-      const int x = tc.c1 + r % p.bw, y = tc.c2 + (r / p.bw) % p.bh, n = tc.c3 + r / (p.bw * p.bh);
+      const int x = e.tc.c1 + r % p.bw, y = e.tc.c2 + (r / p.bw) % p.bh, n = e.tc.c3 + r / (p.bw * p.bh);
       row = (x < p.W && y < p.H && n < p.NB && r < p.bw * p.bh * p.bn) ? (static_cast<long long>(n) * p.H + y) * p.W + x : 0;
     }
     bias_row = p.bias + (row / p.bias_group_rows) * p.N;
   }
 
-  const uint32_t base = chunk_count;
-  if (p.has_residual && leader) {  // two chunks ahead; the buffers are free (last tile's barriers passed)
-    if (group < nchunks) load_residual(base & 1u, group);
-    if (group + 2 < nchunks) load_residual((base + 1u) & 1u, group + 2);
+  if (p.has_residual && e.leader) {  // two chunks ahead; the buffers are free (last tile's barriers passed)
+    if (group < nchunks) load_residual(e, e.base & 1u, group);
+    if (group + 2 < nchunks) load_residual(e, (e.base + 1u) & 1u, group + 2);
   }
   // One bias row for the whole tile (everything but the per-image conv1 biases): the group's 128 threads fetch the <= 128
   // floats its chunks need with ONE coalesced load each while the tile's MMAs are still running, and the chunk loop reads
@@ -260,25 +390,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
     }
     group_bar_sync(group);
   }
-  const bool tracer = leader;                     // one thread per epilogue group; events 8.. (group 0), 20.. (group 1)
-  const int ev0 = 8 + 12 * group;
+  [[maybe_unused]] const bool tracer = e.leader;  // one thread per epilogue group; events 8.. (group 0), 20.. (group 1)
+  [[maybe_unused]] const int ev0 = 8 + 12 * group;
   GEMM_TRACE(tracer, ev0 + 0, tile_it);           // epilogue: waiting for the accumulator
   mbar_wait(tmem_full_bar, full_parity, 4);
   tc_fence_after();
   GEMM_TRACE(tracer, ev0 + 1, tile_it);           // epilogue: accumulator complete
 
-  uint32_t ci = 0;
-  for (int c = group; c < nchunks; c += 2, ++ci) {
-    const int buf = static_cast<int>((base + ci) & 1u);
-    uint32_t v[32], g[32];
-    tmem_ld_x32(taddr_row + c * kChunkCols, v);
-    if (geglu) tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);  // both loads in flight, one wait
-    tmem_ld_wait();
-    GEMM_TRACE(tracer && ci < 4, ev0 + 2 + 2 * ci, tile_it);   // chunk ci: accumulator columns in registers
-    float f[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    const int col_in = n_tile * p.block_n + c * kChunkCols;  // column in the [N] space of the GEMM (bias index)
+  // f += this tile's bias for the 32 columns of chunk (c, ordinal ci)
+  auto add_bias = [&](float (&f)[32], int c, uint32_t ci) {
     if (bias_staged) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -286,76 +406,69 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const C
         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
     } else if (bias_row) {
+      const int col_in = n_tile * p.block_n + c * kChunkCols;  // column in the [N] space of the GEMM (bias index)
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + col_in + j));
         f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
     }
-    if (geglu) {
-      const int gcol = col_in + out_bn;
+  };
+
+  uint32_t ci = 0;
+  if (geglu) {
+    // value and gate columns of a chunk are loaded together (one wait); the chunk is bound by the GELU arithmetic
+    for (int c = group; c < nchunks; c += 2, ++ci) {
+      uint32_t v[32], g[32];
+      tmem_ld_x32(taddr_row + c * kChunkCols, v);
+      tmem_ld_x32(taddr_row + out_bn + c * kChunkCols, g);
+      tmem_ld_wait();
+      GEMM_TRACE(tracer && ci < 4, ev0 + 2 + 2 * ci, tile_it);   // chunk ci: accumulator columns in registers
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias_staged) b = *reinterpret_cast<const float4*>(bs_g + ci * 32 + j);
-        else if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + j));
-        const F2 y01 = f2_mul(f2(f[j], f[j + 1]),
-                              gelu_erf2(f2_add(f2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), f2(b.x, b.y))));
-        const F2 y23 = f2_mul(f2(f[j + 2], f[j + 3]),
-                              gelu_erf2(f2_add(f2(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), f2(b.z, b.w))));
-        f2_get(y01, f[j], f[j + 1]);
-        f2_get(y23, f[j + 2], f[j + 3]);
-      }
-    }
-    if (p.has_residual) {
-      mbar_wait(&bars->res_full[group][buf], uses[buf] & 1u, 5);
-      uses[buf]++;
-      const uint8_t* rt = my_r + buf * kStageTileBytes;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      add_bias(f, c, ci);
+      const int gcol = n_tile * p.block_n + c * kChunkCols + out_bn;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(rt + sw64_offset(r, q));
-        const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+      for (int hb = 0; hb < 32; hb += 16) {   // two batches of 8 pairs: gate + bias -> gelu -> * value
+        F2 x[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t = unpack2<kBf16>(w[e]);
-          f[q * 8 + e * 2] += t.x;
-          f[q * 8 + e * 2 + 1] += t.y;
+        for (int j = 0; j < 16; j += 4) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias_staged) b = *reinterpret_cast<const float4*>(bs_g + ci * 32 + hb + j);
+          else if (bias_row) b = __ldg(reinterpret_cast<const float4*>(bias_row + gcol + hb + j));
+          x[j / 2] = f2_add(f2(__uint_as_float(g[hb + j]), __uint_as_float(g[hb + j + 1])), f2(b.x, b.y));
+          x[j / 2 + 1] = f2_add(f2(__uint_as_float(g[hb + j + 2]), __uint_as_float(g[hb + j + 3])), f2(b.z, b.w));
+        }
+        gelu_erf2_batch<8>(x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const F2 y = f2_mul(f2(f[hb + 2 * i], f[hb + 2 * i + 1]), x[i]);
+          f2_get(y, f[hb + 2 * i], f[hb + 2 * i + 1]);
         }
       }
+      finish_chunk<kBf16>(e, f, c, ci, uses, d_slot);
+      GEMM_TRACE(tracer && ci < 4, ev0 + 3 + 2 * ci, tile_it);   // chunk ci: staged, group barrier passed
     }
-    if (p.flags & B200SD_EPI_SILU) {
+  } else {
+    // (A software-pipelined form — the next chunk's TMEM load in flight while this one is processed, which would hide ~420
+    // of a chunk's ~1050 clocks on K = 320 tiles, tools/gemm_trace.py — needs two 32-register arrays alive across the
+    // chunk body; at this kernel's 168-register ceiling (10 warps: three share one sub-partition's file) ptxas spills
+    // them, and a spilled in-flight tcgen05.ld destination is a correctness hazard, not just a slow-down.  Not shipped.)
+    for (int c = group; c < nchunks; c += 2, ++ci) {
+      uint32_t v[32];
+      tmem_ld_x32(taddr_row + c * kChunkCols, v);
+      tmem_ld_wait();
+      GEMM_TRACE(tracer && ci < 4, ev0 + 2 + 2 * ci, tile_it);   // chunk ci: accumulator columns in registers
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      add_bias(f, c, ci);
+      finish_chunk<kBf16>(e, f, c, ci, uses, d_slot);
+      GEMM_TRACE(tracer && ci < 4, ev0 + 3 + 2 * ci, tile_it);   // chunk ci: staged, group barrier passed
     }
-    uint8_t* dt = my_d + d_slot * kStageTileBytes;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 o;
-      o.x = pack2<kBf16>(f[q * 8 + 0], f[q * 8 + 1]);
-      o.y = pack2<kBf16>(f[q * 8 + 2], f[q * 8 + 3]);
-      o.z = pack2<kBf16>(f[q * 8 + 4], f[q * 8 + 5]);
-      o.w = pack2<kBf16>(f[q * 8 + 6], f[q * 8 + 7]);
-      *reinterpret_cast<uint4*>(dt + sw64_offset(r, q)) = o;
-    }
-    fence_proxy_async_smem();          // my staging writes (and residual reads) -> visible / ordered for the async proxy
-    // before chunk i+1 is staged into the buffer after this one, the store that last read THAT buffer must be done:
-    // with two buffers that is the previous store (wait for all), with three the one before it (one may stay in flight)
-    if (leader) {
-      if (p.d_bufs == 3) bulk_wait_read<1>();
-      else bulk_wait_read<0>();
-    }
-    group_bar_sync(group);
-    GEMM_TRACE(tracer && ci < 4, ev0 + 3 + 2 * ci, tile_it);   // chunk ci: staged, group barrier passed
-    if (leader) {
-      const int col = n_tile * out_bn + c * kChunkCols;
-      if (p.mode == 0) tma_store_2d(tmD, dt, col, tc.c1);
-      else tma_store_4d(tmD, dt, col, tc.c1, tc.c2, tc.c3);
-      bulk_commit();
-      if (p.has_residual && c + 4 < nchunks) load_residual(buf, c + 4);  // everyone is past reading this buffer
-    }
-    if (++d_slot == static_cast<uint32_t>(p.d_bufs)) d_slot = 0;
   }
-  chunk_count = base + ci;
+  chunk_count = e.base + ci;
 }
 
 // kPair = false: one CTA per tile (M = 128).
