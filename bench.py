@@ -393,7 +393,8 @@ def plugin_request(script, batch, tokens, seed0, workload, init_images=None):
         p = processing.StableDiffusionProcessingImg2Img(init_images=init_images, denoising_strength=DENOISE, **kw)
     else:
         p = processing.StableDiffusionProcessingTxt2Img(**kw)
-    p.prompt_tokens = tokens.tolist()       # host token ids ride along in the payload (p.__dict__)
+    p.prompt_tokens = tokens                # host token ids ride along in the payload (p.__dict__); a tensor: the per-job
+                                            # deepcopy of the payload (reference distributed.py:288-290) is then a memcpy
     return processing.process_images(p)
 
 

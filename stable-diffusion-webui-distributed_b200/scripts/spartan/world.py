@@ -400,7 +400,18 @@ class World:
             processed.all_subseeds, processed.all_negative_prompts = p.subseeds, p.negative_prompts
             processed.infotexts = [""] * world.num_requested()
             to_pil = ToPILImage()
-            processed.images = [to_pil(im) for im in pp.images]
+
+            def as_pil(im):
+                # local-GPU fast lane: the uint8 HWC bytes came along with the float tensor (scripts/distributed.py
+                # api_to_internal); a script that replaced pp.images[i] in postprocess_batch_list loses the attribute and
+                # takes the reference's ToPILImage path
+                u8 = getattr(im, "b200sd_u8", None)
+                if u8 is not None:
+                    from PIL import Image
+                    return Image.fromarray(u8.numpy())
+                return to_pil(im)
+
+            processed.images = [as_pil(im) for im in pp.images]
             world.p.scripts.postprocess(p, processed)
             if shared.opts.return_grid and len(processed.images) > 1:
                 processed.images.insert(0, image_grid(processed.images, len(processed.images)))
