@@ -119,15 +119,38 @@ class Conditioner:
         else:
             self.t0 = ClipText(sd, cfg, device, dtype)
 
+    CHUNK = 8   # sequences per text-tower call, always exactly this many
+
+    def _chunked(self, fn, tokens: torch.Tensor):
+        """Run a text tower batch-invariantly: the towers are library GEMMs (cuBLAS picks kernels — split-K included — by
+        the M = sequences x 77 of the call, so the same prompt encoded inside a batch of 17 or of 2 differed in the last
+        bit, which broke "a sharded batch equals the whole batch" at 8 GPUs).  Unique token rows only (a request normally
+        carries ONE prompt for all its images), always in calls of exactly CHUNK sequences (the tail padded by repetition):
+        every sequence then goes through the same kernels whatever the batch it arrived in."""
+        uniq, inverse = torch.unique(tokens.cpu(), dim=0, return_inverse=True)
+        outs = None
+        for i in range(0, uniq.shape[0], self.CHUNK):
+            part = uniq[i:i + self.CHUNK]
+            n = part.shape[0]
+            if n < self.CHUNK:
+                part = torch.cat([part, part[-1:].expand(self.CHUNK - n, -1)])
+            res = fn(part)
+            res = res if isinstance(res, tuple) else (res,)
+            outs = [[] for _ in res] if outs is None else outs
+            for o, r in zip(outs, res):
+                o.append(r[:n])
+        inverse = inverse.to(self.device)
+        return tuple(torch.cat(o)[inverse] for o in outs)
+
     @torch.no_grad()
     def __call__(self, tokens: torch.Tensor, width: int = 512, height: int = 512, zero_txt: bool = False) -> Cond:
         """zero_txt (SDXL): sdwui's force_zero_embeddings=['txt'] for an all-empty negative prompt"""
         if not self.xl:
-            return Cond(self.t0(tokens))
+            return Cond(self._chunked(self.t0, tokens)[0])
         cfg = self.cfg
         b = tokens.shape[0]
-        h0 = self.t0.hidden(tokens, cfg.layers - 1)
-        h1, pooled = self.t1(tokens)
+        (h0,) = self._chunked(lambda t: self.t0.hidden(t, cfg.layers - 1), tokens)
+        h1, pooled = self._chunked(self.t1, tokens)
         ctx = torch.cat([h0, h1], dim=-1)
         if zero_txt:
             ctx, pooled = torch.zeros_like(ctx), torch.zeros_like(pooled)
