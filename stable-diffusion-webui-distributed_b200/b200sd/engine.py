@@ -15,7 +15,7 @@ import torch
 
 from . import ops
 from . import samplers as S
-from .clip_text import Cond, Conditioner
+from .clip_text import CAPTURE_LOCK as _CAPTURE_LOCK, Cond, Conditioner
 from .config import CLIPConfig, UNetConfig, VAEConfig
 from .unet_exec import TimeEmbedding, UNetProgram, UNetWeights
 from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, VAEEncoderWeights
@@ -23,7 +23,7 @@ from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, V
 MAX_STEPS = 256
 MAX_PLANS = 6        # distinct (batch, latent h, w) kept per engine; the least recently used one is dropped beyond that
 NOISE_SAMPLERS = ("Euler a", "stage")   # graph-name prefixes of the step graphs that may read Plan.noise
-_CAPTURE_LOCK = threading.Lock()  # CUDA graph captures are serialised across the per-device worker threads
+# _CAPTURE_LOCK (imported): CUDA graph captures are serialised across the per-device worker threads
 
 
 # ------------------------------------------------------------------------------------------------ schedules
@@ -350,7 +350,7 @@ class SDEngine:
             self.unet_w = UNetWeights(sd, unet_cfg, self.device, dtype)
             self.vae_w = VAEDecoderWeights(sd, vae_cfg, self.device, dtype)
             self.vae_enc_w = VAEEncoderWeights(sd, vae_cfg, self.device, dtype)
-            self.clip = Conditioner(sd, clip_cfg, self.device, dtype)
+            self.clip = Conditioner(sd, clip_cfg, self.device, dtype, use_graphs=use_graphs)
             self.temb = TimeEmbedding(self.unet_w)
         self.plans: Dict[Tuple[int, int, int], Plan] = {}
         self.encoders: Dict[Tuple[int, int, int], VAEEncoderProgram] = {}

@@ -408,7 +408,7 @@ class World:
                 u8 = getattr(im, "b200sd_u8", None)
                 if u8 is not None:
                     from PIL import Image
-                    return Image.fromarray(u8.numpy())
+                    return Image.fromarray(u8.numpy())   # ("RGB" cannot be memory-mapped by PIL: one 0.75 ms copy per image)
                 return to_pil(im)
 
             processed.images = [as_pil(im) for im in pp.images]
