@@ -598,7 +598,8 @@ def main():
         e2e = {"value": world * b * args.steps / dt, "unit": "images/s",
                "h2d_bytes_per_step": int(tokens.numel() * 8 + neg.numel() * 8 + x_T.numel() * 4
                                          + (init_u8.numel() if img2img else 0)),
-               "d2h_bytes_per_step": int(b * HW * 8 * HW * 8 * 3),
+               # the uint8 images and their CHW float copies for sdwui's postprocess hooks (made on the device)
+               "d2h_bytes_per_step": int(b * HW * 8 * HW * 8 * 3 * (1 + 4)),
                "path": "hoststub process_images -> DistributedScript.before_process -> LocalGPUWorker.request -> "
                        "postprocess_batch_list -> postprocess (thin-client world, 1 local GPU per rank)"}
 

@@ -46,6 +46,7 @@ class LocalGPUWorker(Worker):
         self._factory = engine_factory
         self._engine = None
         self.png_images = png_images  # also fill response["images"] with base64 PNGs (API-exact, slower)
+        self.make_pil = False         # set by World when the thin-client collector will want PIL images
         self.queried = True
 
     # ------------------------------------------------------------------ engine access
@@ -247,16 +248,29 @@ class LocalGPUWorker(Worker):
             if eng.interrupted:
                 break
         images = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
+        host_chw = None
         if images.device.type == "cuda":
             with torch.cuda.device(images.device):  # this thread's current device is cuda:0 whatever the worker drives
                 host = torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)
                 host.copy_(images, non_blocking=True)
+                if inpaint is None:
+                    # what the collector needs per image — CHW float in [0, 1] for `pp.images` (reference
+                    # distributed.py:102-106) — is made on the device and copied out next to the bytes: the conversion
+                    # of a 32-image job cost the ONE collector thread 60 ms, times the number of jobs.  +0.5: sdwui's
+                    # later `(255 * x).astype(uint8)` then returns exactly these bytes.
+                    chw = images.permute(0, 3, 1, 2).float().add_(0.5).div_(255.0)
+                    host_chw = torch.empty(chw.shape, dtype=torch.float32, pin_memory=True)
+                    host_chw.copy_(chw, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
         else:  # an engine double in the host-logic tests; the real engine refuses non-CUDA devices
             host = images.to(torch.uint8).contiguous()
         if inpaint is not None:   # sdwui apply_overlay: the original pixels come back through the blurred mask
             from b200sd import inpaint as inp
             host = inp.apply_overlays(host, inpaint_overlays, inpaint.paste_to)
+        pil = None
+        if self.make_pil:   # thin-client collector (World._bypass_local_generation): PIL objects built here, per job thread
+            from PIL import Image
+            pil = [Image.fromarray(host[i].numpy()) for i in range(host.shape[0])]
         n = host.shape[0]
         seeds = [seed + (i if strength == 0 else 0) for i in range(n)]
         subseeds = [subseed + i for i in range(n)]
@@ -266,7 +280,7 @@ class LocalGPUWorker(Worker):
                 "all_negative_prompts": [negative] * n, "infotexts": infotexts, "seed": seeds[0], "subseed": subseeds[0],
                 "prompt": prompt, "negative_prompt": negative}
         return {"images": [self._png_b64(host[i]) for i in range(n)] if self.png_images else [None] * n,
-                "tensors": host,
+                "tensors": host, "tensors_chw": host_chw, "pil": pil,
                 "parameters": {"batch_size": batch, "n_iter": n_iter, "steps": steps, "width": width, "height": height,
                                "sampler_name": sampler, "cfg_scale": cfg_scale, "seed": seed},
                 "info": json.dumps(info)}

@@ -389,6 +389,9 @@ class World:
         """thin client / master got no images: the host's inner loop is replaced by one that only collects"""
         logger.debug("bypassing local generation completely")
         world = self
+        for w in self._workers:   # local-GPU workers build the PIL images this collector returns in their own job threads
+            if getattr(w, "is_local_gpu", False):
+                w.make_pil = True
 
         def process_images_inner_bypass(p) -> processing.Processed:
             from torchvision.transforms import ToPILImage
@@ -405,6 +408,9 @@ class World:
                 # local-GPU fast lane: the uint8 HWC bytes came along with the float tensor (scripts/distributed.py
                 # api_to_internal); a script that replaced pp.images[i] in postprocess_batch_list loses the attribute and
                 # takes the reference's ToPILImage path
+                ready = getattr(im, "b200sd_pil", None)
+                if ready is not None:
+                    return ready
                 u8 = getattr(im, "b200sd_u8", None)
                 if u8 is not None:
                     from PIL import Image
