@@ -1,7 +1,7 @@
 """Representative hot-path launches for Nsight Compute (run under `ncu --profile-from-start off ...`).
 
     python tools/ncu_cases.py unet            # one eager SD1.5 UNet evaluation at UNet batch 16 (launch list)
-    python tools/ncu_cases.py conv|geglu|proj|attn|gn|ln   # a single op at its UNet-batch-16 shape (--set full capture)
+    python tools/ncu_cases.py conv|geglu|proj|qkv|attn|gn|ln   # a single op at its UNet-batch-16 shape (--set full capture)
 """
 import os
 import sys
@@ -48,13 +48,18 @@ def main():
         b = torch.randn(320, device="cuda")
         fn = lambda: ops.linear(x, w, o, bias=b, residual=r)  # noqa: E731
     elif case == "attn":
-        qkv = torch.zeros((nb, 4096, 3, 8, 64), device="cuda", dtype=torch.half)
+        dp = 48  # head pitch round16(40 + 1), as the UNet's fused q|k|v buffer has it since round 2
+        qkv = torch.zeros((nb, 4096, 3, 8, dp), device="cuda", dtype=torch.half)
         qkv[..., :40] = rnd(nb, 4096, 3, 8, 40)
         qkv[:, :, 2, :, 40] = 1.0  # ones column of V, as the UNet's qkv bias produces it
-        flat = qkv.reshape(nb, 4096, 1536)
-        q, k, v = flat[..., :512], flat[..., 512:1024], flat[..., 1024:]
+        flat = qkv.reshape(nb, 4096, 3 * 8 * dp)
+        q, k, v = flat[..., :8 * dp], flat[..., 8 * dp:16 * dp], flat[..., 16 * dp:]
         o = torch.empty((nb, 4096, 320), device="cuda", dtype=torch.half)
-        fn = lambda: ops.attention(q, k, v, o, 8, 40, 64, 40 ** -0.5, v_ones_col=True)  # noqa: E731
+        fn = lambda: ops.attention(q, k, v, o, 8, 40, dp, 40 ** -0.5, v_ones_col=True)  # noqa: E731
+    elif case == "qkv":
+        x, w, o = rnd(nb * 4096, 320), rnd(1152, 320, scale=0.05), torch.empty((nb * 4096, 1152), device="cuda", dtype=torch.half)
+        b = torch.zeros(1152, device="cuda")
+        fn = lambda: ops.linear(x, w, o, bias=b)  # noqa: E731
     elif case == "gn":
         x, o = rnd(nb, 4096, 320), torch.empty((nb, 4096, 320), device="cuda", dtype=torch.half)
         st = torch.zeros((ops.groupnorm_stats_floats(nb, 4096, 320, 32),), device="cuda")
