@@ -618,13 +618,20 @@ def main():
         # rank 0 is about to drive from this process
         barrier()
         if rank == 0:
-            world_e2e, strong = world_level(args, world, b, tokens, seed0, init_pil, eng, local)
+            try:
+                world_e2e, strong = world_level(args, world, b, tokens, seed0, init_pil, eng, local)
+            except Exception as e:   # a secondary measurement must never take the headline line down
+                world_e2e = strong = {"value": None, "error": f"{type(e).__name__}: {str(e)[:300]}"}
         if world > 1:
             dist.barrier(group=cpu_group)
         barrier()
 
     # ---------------- roofline of the dominant kernel: per-launch CUDA-event timing of one eager UNet evaluation
-    roof, roof_attn, breakdown = kernel_rooflines(eng, b, peaks(), clk)
+    try:
+        roof, roof_attn, breakdown = kernel_rooflines(eng, b, peaks(), clk)
+    except Exception as e:
+        roof = roof_attn = {"frac": None, "error": f"{type(e).__name__}: {str(e)[:300]}"}
+        breakdown = None
 
     if rank != 0:
         if world > 1:
