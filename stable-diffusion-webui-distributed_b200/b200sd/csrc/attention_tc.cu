@@ -225,6 +225,35 @@ __device__ __forceinline__ void exp2_poly2(float& ea, float& eb, float xa, float
   eb = __uint_as_float(pb + (rb << 23));
 }
 
+// exp2 of a pair on the half-precision FMA pipe, straight to the packed fp16 P value (no MUFU, no separate pack):
+//   x -> half2, clamped to >= -13;  r = x + 1551 (fp16 ulp is 1 there: the low mantissa bits of r are round(x) + 527);
+//   n = r - 1551, f = x - n in [-0.5, 0.5];  2^f by a degree-3 polynomial (3 HFMA2);  2^n by adding n to the exponent field:
+//   bits = p + ((r & 0x3f) << 10) - (15 << 10) per 16-bit lane ((527 + n) & 0x3f == n + 15; no lane carries: p < 0x3dff).
+// The MUFU unit (16 ex2 / clock / SM) is this kernel's busiest pipe at 66-69 %; B200SD_ATTN_H2POLY_MASK says which of a
+// thread's 16 pairs per tile take this path instead (bit i = pair i; 0 = none).  fp16 only: bf16's 7 mantissa bits cannot
+// carry x.  Accuracy (numpy emulation): rms relative error 2.7e-4 for x in [-2, 0] (MUFU + pack: 2.1e-4), up to 0.3 % where
+// |x| > 8 (x itself is rounded to half there).
+// Measured (round 2, batch-64 self-attention shape, S = 4096, d = 40; tools/gpu_attn_exp.sh): none 2.811 ms; 2 of 16 pairs
+// 2.549; 3 of 16 2.503; 4 of 16 2.453 (pairs 3, 7, 11, 15) .. 2.501 (pairs 0, 4, 8, 12); 6 of 16 2.583; 8 of 16 2.623;
+// 12 of 16 2.866 — the first few offloaded pairs relieve the MUFU queue (ncu: mio_throttle was the second largest stall),
+// beyond a quarter the extra issue slots cost more.  Parity with 4 of 16: one SD1.5 UNet evaluation rel-rms 1.45e-3 (1.44e-3
+// without), images of whole sampler runs unchanged (max 1 LSB, mean 0.09-0.12, 88-91 % identical).
+#ifndef B200SD_ATTN_H2POLY_MASK
+#define B200SD_ATTN_H2POLY_MASK 0x8888
+#endif
+__device__ __forceinline__ uint32_t exp2_h2_poly(float xa, float xb) {
+  uint32_t x, r, n, f, p;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(xb), "f"(xa));           // low half = xa
+  asm("max.f16x2 %0, %1, %2;" : "=r"(x) : "r"(x), "r"(0xCA80CA80u));            // >= -13
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(0x660F660Fu));         // + 1551
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(n) : "r"(r), "r"(0xE60FE60Fu));         // - 1551 = round(x)
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(f) : "r"(x), "r"(n));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(0x2B102B10u), "r"(f), "r"(0x33C333C3u));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(f), "r"(0x398C398Cu));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(f), "r"(0x3C003C00u));
+  return p + ((r & 0x003F003Fu) << 10) - 0x3C003C00u;
+}
+
 // P values above this mean the tile's maximum exceeds the running maximum by more than 2^8: redo with a new maximum
 constexpr float kPRedo = 256.0f;
 
@@ -256,6 +285,17 @@ __device__ __forceinline__ bool softmax32(const uint32_t (&v)[32], uint32_t (&pk
   for (int i = 0; i < 32; i += 2) {
     float xa, xb;
     ffma2(xa, xb, v[i], v[i + 1], scale2, negm2);
+    if constexpr (!kBf16 && !kSum && B200SD_ATTN_H2POLY_MASK != 0) {
+      if ((B200SD_ATTN_H2POLY_MASK >> (i >> 1)) & 1) {   // compile-time after unrolling
+        uint32_t e2 = exp2_h2_poly(xa, xb);
+        if (!kFull) {
+          if (col0 + i >= nvalid) e2 &= 0xFFFF0000u;
+          if (col0 + i + 1 >= nvalid) e2 &= 0x0000FFFFu;
+        }
+        pk[i >> 1] = e2;
+        continue;
+      }
+    }
     float ea, eb;
     if (B200SD_ATTN_POLY_STRIDE > 0 && ((i >> 1) % (B200SD_ATTN_POLY_STRIDE > 0 ? B200SD_ATTN_POLY_STRIDE : 1)) ==
                                            (B200SD_ATTN_POLY_STRIDE > 0 ? B200SD_ATTN_POLY_STRIDE : 1) - 1) {
