@@ -788,11 +788,16 @@ def kernel_rooflines(eng, b, pk, clk):
     # sample-evaluation, LayerNorm 1 read + 1 write of 34.7 M) over the summed CUDA-event durations, against the measured
     # copy bandwidth
     hbm = {}
-    for name, elems, bpe in (("groupnorm", plan.unet.gn_elems, 6), ("layernorm", plan.unet.ln_elems, 4)):
+    gn_fused = getattr(plan.unet, "gn_fused_elems", 0)
+    for name, elems, nbytes in (("groupnorm", plan.unet.gn_elems, gn_fused * 4 + (plan.unet.gn_elems - gn_fused) * 6),
+                                ("layernorm", plan.unet.ln_elems, plan.unet.ln_elems * 4)):
         if name in agg and agg[name][1] > 0:
-            gbs = elems * bpe / (agg[name][1] * 1e-3) / 1e9
+            gbs = nbytes / (agg[name][1] * 1e-3) / 1e9
             hbm[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                         "launches": agg[name][0], "algorithmic_bytes": elems * bpe, "elements": elems}
+                         "launches": agg[name][0], "algorithmic_bytes": nbytes, "elements": elems, "ms": agg[name][1]}
+            if name == "groupnorm":   # bytes the kernels actually move: 1 read + 1 write through the one-pass kernel, 2 + 1 else
+                hbm[name]["one_pass_elements"] = gn_fused
+                hbm[name]["frac_at_4_bytes_per_element"] = elems * 4 / (agg[name][1] * 1e-3) / 1e9 / pk["hbm_gbs"]
     roof["hbm_kernels"] = hbm
     return roof, roof_attn, breakdown
 

@@ -15,6 +15,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "../../../include/b200sd.h"
 #include "tc_common.cuh"
 
@@ -106,15 +109,20 @@ constexpr int kGnUnroll = 4;
 // atomicAdd per (group, stat) and block lands in stats[n][g][2].
 template <bool kBf16>
 __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long pitch, int HW, int C, int G,
-                                       int pix_per_cta, float* __restrict__ stats) {
+                                       int pix_per_cta, float* __restrict__ stats, int reverse) {
   extern __shared__ float sh[];  // [PY][2C] partials, then [2C] channel totals reuse row 0
   pdl_trigger();
   pdl_wait();  // X is the previous kernel's output; the shared stats / ticket buffer is reused from GroupNorm to GroupNorm
-  const int n = blockIdx.y;
+  // `reverse`: the grid walks the tensor from its END.  The producer wrote it front to back and the apply kernel reads it
+  // front to back, so of a tensor larger than the L2 the statistics pass finds the producer's last ~L2-size bytes still
+  // cached, and leaves the FIRST ones cached for the apply pass (front-to-back twice evicts everything before its reuse).
+  // Which CTA owns which slab is unchanged — only the order in which they are scheduled — so every bit of the result is.
+  const int n = reverse ? static_cast<int>(gridDim.y - 1 - blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int bx = reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int v = threadIdx.x;
   const int py = threadIdx.y;
   const int PY = blockDim.y;
-  const int p0 = blockIdx.x * pix_per_cta;
+  const int p0 = bx * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
   F2 s2[4], q2[4];  // packed fp32 pairs: channel pairs (8v+2i, 8v+2i+1)
 #pragma unroll
@@ -168,14 +176,14 @@ __global__ void groupnorm_stats_kernel(const uint8_t* __restrict__ X, long long 
   const int parts = gridDim.x;
   float* out_stats = stats + static_cast<long long>(n) * G * 2;
   unsigned int* tickets = reinterpret_cast<unsigned int*>(stats + static_cast<long long>(gridDim.y) * G * 2);
-  float* partials = stats + static_cast<long long>(gridDim.y) * G * 2 + gridDim.y +
+  float* partials = stats + static_cast<long long>(gridDim.y) * G * 2 + gridDim.y + 1 +  // +1: the fused kernel's work counter
                     static_cast<long long>(n) * parts * 2 * G;
   for (int g = tid; g < 2 * G; g += nthreads) {
     const int grp = g >> 1, st = g & 1;
     float a = 0.f;
     for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) a += sh[st * C + c];
     if (parts == 1) out_stats[g] = a;
-    else __stcg(&partials[static_cast<long long>(blockIdx.x) * 2 * G + g], a);
+    else __stcg(&partials[static_cast<long long>(bx) * 2 * G + g], a);
   }
   if (parts == 1) return;
   __shared__ unsigned int s_last;
@@ -270,6 +278,223 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
     for (int k = 0; k < kGnUnroll; ++k) emit(u[k], p + k * PY);
   }
   for (; p < p1; p += PY) emit(__ldg(reinterpret_cast<const uint4*>(xb + p * rx)), p);
+}
+
+// ---- one-pass GroupNorm ------------------------------------------------------------------------------------------
+// stats + apply read the tensor twice (6 bytes per element with the write).  Here a CTA keeps its slab of one image
+// (~48 KB: `ppc` pixels x C channels) in shared memory while the image's statistics are agreed on across CTAs, then
+// normalises from shared memory: 1 read + 1 write (4 bytes per element).
+//
+// Cross-CTA protocol per image n (one 32-bit word, tickets[n], zero at rest):
+//   arrive  : a CTA publishes its 2G group partials, fences, adds 1.  The CTA that brings the word to `parts` adds all
+//             partials in slab order (the same sliced, fixed-order sum as groupnorm_stats_kernel), writes stats[n], fences,
+//             adds 1 more (parts + 1 = "statistics ready");
+//   wait    : the other CTAs spin (ld.acquire) until the word is >= parts + 1, then read stats[n];
+//   depart  : every CTA adds 1 after it has read them; the one that sees 2 * parts resets the word to 0.
+// A waiting CTA needs its siblings to RUN: slabs are handed out through an atomic work counter (not blockIdx), so the
+// slabs started so far always form a prefix of the (image-major) order and every image whose first slab is running has
+// all its slabs running or startable as long as `parts` CTAs fit on the device at once — the launcher checks that and
+// falls back to the two-kernel path otherwise (huge VAE tensors).  The spin is bounded: a protocol failure traps instead
+// of hanging the device.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+#ifndef B200SD_GN_FUSED_DEFAULT
+#define B200SD_GN_FUSED_DEFAULT 0
+#endif
+constexpr int kGnFusedThreads = 256;
+constexpr int kGnMaxGroups = 64;
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kGnFusedThreads, 3)
+groupnorm_fused_kernel(const uint8_t* __restrict__ X, long long pitch_x, uint8_t* __restrict__ Y, long long pitch_y,
+                       int NB, int HW, int C, int G, int ppc, int parts, float* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  __shared__ float g_mean[kGnMaxGroups], g_rstd[kGnMaxGroups];
+  __shared__ unsigned int s_item, s_last;
+  pdl_trigger();
+  pdl_wait();  // X is the previous kernel's output; the counters are left at zero by the previous GroupNorm
+  const int v = threadIdx.x;
+  const int py = threadIdx.y;
+  const int vx = blockDim.x;
+  const int PY = blockDim.y;
+  const int tid = py * vx + v;
+  const int nthreads = vx * PY;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(stats + static_cast<long long>(NB) * G * 2);
+  unsigned int* work = tickets + NB;
+  if (tid == 0) {
+    const unsigned int it = atomicAdd(work, 1u);
+    if (it == gridDim.x - 1) atomicExch(work, 0u);  // the last slab handed out: nobody else touches the counter
+    s_item = it;
+  }
+  __syncthreads();
+  const int item = static_cast<int>(s_item);
+  const int n = item / parts;
+  const int part = item - n * parts;
+  const int p0 = part * ppc;
+  const int p1 = min(HW, p0 + ppc);
+  uint4* slab = reinterpret_cast<uint4*>(gn_smem);                                            // [ppc][vx]
+  float* sh = reinterpret_cast<float*>(gn_smem + static_cast<size_t>(ppc) * vx * 16);        // [PY][2C]
+
+  // ---- pass over global memory: accumulate and keep
+  F2 s2[4], q2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s2[i] = f2_make(0.f, 0.f); q2[i] = s2[i]; }
+  const uint8_t* xb = X + (static_cast<long long>(n) * HW) * pitch_x * 2 + static_cast<long long>(v) * 16;
+  const long long rx = pitch_x * 2;
+  int p = p0 + py;
+  for (; p + (kGnUnroll - 1) * PY < p1; p += kGnUnroll * PY) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xb + (p + k * PY) * rx));
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      F2 f[4];
+      unpack4x2<kBf16>(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s2[i] = f2_add(s2[i], f[i]); q2[i] = f2_fma(f[i], f[i], q2[i]); }
+      slab[static_cast<size_t>(p + k * PY - p0) * vx + v] = u[k];
+    }
+  }
+  for (; p < p1; p += PY) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + p * rx));
+    F2 f[4];
+    unpack4x2<kBf16>(u, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s2[i] = f2_add(s2[i], f[i]); q2[i] = f2_fma(f[i], f[i], q2[i]); }
+    slab[static_cast<size_t>(p - p0) * vx + v] = u;
+  }
+  {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f2_get(s2[i], s[2 * i], s[2 * i + 1]);
+      f2_get(q2[i], q[2 * i], q[2 * i + 1]);
+    }
+    float* mine = sh + static_cast<size_t>(py) * 2 * C;
+    *reinterpret_cast<float4*>(mine + v * 8) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(mine + v * 8 + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(mine + C + v * 8) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(mine + C + v * 8 + 4) = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nthreads) {
+    float a = 0.f;
+    for (int k = 0; k < PY; ++k) a += sh[static_cast<size_t>(k) * 2 * C + i];
+    sh[i] = a;  // row 0, index i: written by the only thread that reads it
+  }
+  __syncthreads();
+
+  // ---- agree on the image's statistics
+  const int cpg = C / G;
+  const int items = 2 * G;
+  float* out_stats = stats + static_cast<long long>(n) * items;
+  float* partials = stats + static_cast<long long>(NB) * items + NB + 1 + static_cast<long long>(n) * parts * items;
+  float* fin = sh + max(PY * 2 * C, 8 * items);  // [items] final sums, behind the scratch (the launcher sizes both)
+  for (int g = tid; g < items; g += nthreads) {
+    const int grp = g >> 1, st = g & 1;
+    float a = 0.f;
+    for (int c = grp * cpg; c < (grp + 1) * cpg; ++c) a += sh[st * C + c];
+    if (parts == 1) { fin[g] = a; out_stats[g] = a; }
+    else __stcg(&partials[static_cast<long long>(part) * items + g], a);
+  }
+  if (parts > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[n], 1u) == static_cast<unsigned int>(parts - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (s_last != 0u) {
+      __threadfence();
+      const int slices = max(1, min(nthreads / items, 8));
+      float* red = sh;  // [slices][items] <= 2C floats: the channel totals are dead by now
+      for (int idx = tid; idx < slices * items; idx += nthreads) {
+        const int it = idx % items, sl = idx / items;
+        const int per = (parts + slices - 1) / slices;
+        const int lo = sl * per, hi = min(parts, lo + per);
+        float a = 0.f;
+#pragma unroll 8
+        for (int k = lo; k < hi; ++k) a += __ldcg(&partials[static_cast<long long>(k) * items + it]);
+        red[sl * items + it] = a;
+      }
+      __syncthreads();
+      for (int g = tid; g < items; g += nthreads) {
+        float a = 0.f;
+        for (int sl = 0; sl < slices; ++sl) a += red[sl * items + g];
+        fin[g] = a;
+        __stcg(&out_stats[g], a);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(&tickets[n], 1u);  // parts + 1: statistics ready
+    } else {
+      if (tid == 0) {
+        const unsigned int ready = static_cast<unsigned int>(parts) + 1u;
+        unsigned int spins = 0;
+        while (ld_acquire_u32(&tickets[n]) < ready) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) __trap();  // seconds: a sibling slab never ran — fail loudly, never hang
+        }
+      }
+      __syncthreads();
+      for (int g = tid; g < items; g += nthreads) fin[g] = __ldcg(&out_stats[g]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (atomicAdd(&tickets[n], 1u) == 2u * static_cast<unsigned int>(parts)) atomicExch(&tickets[n], 0u);
+    }
+  } else {
+    __syncthreads();
+  }
+  const float inv_cnt = 1.0f / (static_cast<float>(cpg) * static_cast<float>(HW));
+  for (int g = tid; g < G; g += nthreads) {
+    const float mean = fin[2 * g] * inv_cnt;
+    const float var = fmaxf(fin[2 * g + 1] * inv_cnt - mean * mean, 0.f);
+    g_mean[g] = mean;
+    g_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+
+  // ---- normalise from shared memory
+  F2 a2[4], b2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a[2], b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = v * 8 + 2 * i + j;
+      const int g = c / cpg;
+      a[j] = g_rstd[g] * gamma[c];
+      b[j] = beta[c] - g_mean[g] * a[j];
+    }
+    a2[i] = f2_make(a[0], a[1]);
+    b2[i] = f2_make(b[0], b[1]);
+  }
+  uint8_t* yb = Y + (static_cast<long long>(n) * HW) * pitch_y * 2 + static_cast<long long>(v) * 16;
+  const long long ry = pitch_y * 2;
+  const F2 nlog2e = f2_make(-1.4426950408889634f, -1.4426950408889634f), one2 = f2_make(1.0f, 1.0f);
+  for (p = p0 + py; p < p1; p += PY) {
+    const uint4 u = slab[static_cast<size_t>(p - p0) * vx + v];
+    F2 f[4];
+    unpack4x2<kBf16>(u, f);
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      F2 t = f2_fma(f[i], a2[i], b2[i]);
+      if (silu) {
+        float ex, ey;
+        f2_get(f2_mul(t, nlog2e), ex, ey);
+        float dx, dy;
+        f2_get(f2_add(f2_make(fast_exp2(ex), fast_exp2(ey)), one2), dx, dy);
+        t = f2_mul(t, f2_make(__frcp_rn_fast(dx), __frcp_rn_fast(dy)));
+      }
+      w[i] = pack2<kBf16>(t);
+    }
+    *reinterpret_cast<uint4*>(yb + p * ry) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 // LPR lanes (a power of two, 4..32) share one row and 32/LPR rows share a warp, so every lane carries data whatever C is
@@ -521,6 +746,15 @@ static int gn_stats_kb() {
   return kb;
 }
 
+static int g_gn_stats_reverse = -1;  // B200SD_GN_REVERSE (default 1): the statistics grid walks the tensor back to front
+static int gn_stats_reverse() {
+  if (g_gn_stats_reverse < 0) {
+    const char* e = std::getenv("B200SD_GN_REVERSE");
+    g_gn_stats_reverse = e ? (std::atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return g_gn_stats_reverse;
+}
+
 static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_per_cta, int chunk_kb = 48) {
   if (C % 8 != 0 || C / 8 > 1024) return B200SD_ERR_INVALID;
   const int vx = C / 8;
@@ -538,6 +772,86 @@ static int gn_geometry(int NB, int HW, int C, dim3& block, dim3& grid, int& pix_
   pix_per_cta = ppc;
   grid = dim3((HW + ppc - 1) / ppc, NB, 1);
   return B200SD_OK;
+}
+
+// One-pass GroupNorm geometry: 256 threads as (C/8, PY); a slab of ~B200SD_GN_FUSED_KB (default 48) KB per CTA, rounded DOWN
+// to whole unrolled rounds so that slab + scratch stay below 1/3 of an SM's shared memory (3 CTAs per SM).  Like
+// gn_geometry it depends on the image's shape only — never on the batch — so an image's bits do not depend on how a
+// request was sharded.
+struct GnFused {
+  dim3 block;
+  int ppc, parts;
+  size_t smem;
+};
+static int g_gn_fused_kb = 0;  // 0 = not read yet
+static int gn_fused_kb() {
+  if (g_gn_fused_kb == 0) {
+    const char* e = std::getenv("B200SD_GN_FUSED_KB");
+    int kb = e ? std::atoi(e) : 48;
+    if (kb < 8 || kb > 160) kb = 48;
+    g_gn_fused_kb = kb;
+  }
+  return g_gn_fused_kb;
+}
+static int gn_fused_mode() {  // B200SD_GN_FUSED: 0 never, 1 (default) where eligible
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("B200SD_GN_FUSED");
+    mode = e ? (std::atoi(e) != 0 ? 1 : 0) : B200SD_GN_FUSED_DEFAULT;
+  }
+  return mode;
+}
+static bool gn_fused_geometry(int HW, int C, int G, GnFused& f) {
+  if (C % 8 != 0 || G <= 0 || G > kGnMaxGroups || C % G != 0) return false;
+  const int vx = C / 8;
+  if (vx > kGnFusedThreads) return false;
+  int py = kGnFusedThreads / vx;
+  if (py > HW) py = HW;
+  const int quantum = py * kGnUnroll;
+  int ppc = (gn_fused_kb() * 1024 / (2 * C)) / quantum * quantum;
+  if (ppc < quantum) ppc = quantum;
+  f.block = dim3(vx, py, 1);
+  f.ppc = ppc;
+  f.parts = (HW + ppc - 1) / ppc;
+  const size_t scratch = static_cast<size_t>(py) * 2 * C > static_cast<size_t>(16 * G) ? static_cast<size_t>(py) * 2 * C : 16 * G;
+  f.smem = static_cast<size_t>(ppc) * C * 2 + (scratch + 2 * G) * sizeof(float);
+  return f.smem <= 72 * 1024;
+}
+// CTAs of the fused kernel that are resident at once on the current device (occupancy x SMs), cached per device and
+// shared-memory size class; 0 = unknown (treated as "not eligible")
+template <bool kBf16>
+static int gn_fused_capacity(const GnFused& f) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, size_t, unsigned>, int> cache;  // (device, smem, threads) -> resident CTAs
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  const unsigned threads = f.block.x * f.block.y;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(dev, f.smem, threads);
+  auto hit = cache.find(key);
+  if (hit != cache.end()) return hit->second;  // in particular: no CUDA API calls while a stream is being captured
+  if (sms[dev] == 0) {
+    if (cudaFuncSetAttribute(groupnorm_fused_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024) != cudaSuccess)
+      return 0;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 0;
+    sms[dev] = n;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, groupnorm_fused_kernel<kBf16>, static_cast<int>(threads),
+                                                    f.smem) != cudaSuccess)
+    return 0;
+  cache[key] = per_sm * sms[dev];
+  return per_sm * sms[dev];
+}
+template <bool kBf16>
+static int launch_gn_fused(const GnFused& f, cudaStream_t st, const uint8_t* X, long long pitch_x, uint8_t* Y, long long pitch_y,
+                           int NB, int HW, int C, int G, float* stats, const float* gamma, const float* beta, float eps,
+                           int silu) {
+  launch_pdl(groupnorm_fused_kernel<kBf16>, dim3(static_cast<unsigned>(NB) * f.parts), f.block, f.smem, st, X, pitch_x, Y,
+             pitch_y, NB, HW, C, G, f.ppc, f.parts, stats, gamma, beta, eps, silu);
+  return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 
 template <bool kBf16, int V>
@@ -589,8 +903,12 @@ extern "C" long long b200sd_groupnorm_stats_floats(int NB, int HW, int C, int G)
   dim3 block, grid;
   int ppc;
   if (gn_geometry(NB, HW, C, block, grid, ppc, gn_stats_kb()) != B200SD_OK) return -1;
-  // [NB][G][2] results | NB arrival tickets | [NB][CTAs per image][2G] partial sums
-  return static_cast<long long>(NB) * G * 2 + NB + static_cast<long long>(NB) * grid.x * 2 * G;
+  // [NB][G][2] results | NB arrival tickets + 1 work counter | [NB][CTAs per image][2G] partial sums (the larger of the
+  // two-kernel and the one-pass geometry)
+  long long parts = grid.x;
+  GnFused f;
+  if (gn_fused_geometry(HW, C, G, f) && f.parts > parts) parts = f.parts;
+  return static_cast<long long>(NB) * G * 2 + NB + 1 + static_cast<long long>(NB) * parts * 2 * G;
 }
 
 extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, int HW, int C, int G, float* stats,
@@ -604,10 +922,11 @@ extern "C" int b200sd_groupnorm_stats(const void* X, long long pitch, int NB, in
   const size_t sh = static_cast<size_t>(block.y) * 2 * C * sizeof(float);
   if (sh > 48 * 1024) return B200SD_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rev = gn_stats_reverse();
   if (dtype == B200SD_BF16)
-    launch_pdl(groupnorm_stats_kernel<true>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+    launch_pdl(groupnorm_stats_kernel<true>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats, rev);
   else
-    launch_pdl(groupnorm_stats_kernel<false>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats);
+    launch_pdl(groupnorm_stats_kernel<false>, grid, block, sh, st, static_cast<const uint8_t*>(X), pitch, HW, C, G, ppc, stats, rev);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
 }
 
@@ -630,6 +949,55 @@ extern "C" int b200sd_groupnorm_apply(const void* X, long long pitch_x, void* Y,
     launch_pdl(groupnorm_apply_kernel<false>, grid, block, 0, st, static_cast<const uint8_t*>(X), pitch_x,
                static_cast<uint8_t*>(Y), pitch_y, HW, C, G, ppc, stats, gamma, beta, eps, silu);
   return cudaGetLastError() == cudaSuccess ? B200SD_OK : B200SD_ERR_CUDA;
+}
+
+extern "C" int b200sd_groupnorm(const void* X, long long pitch_x, void* Y, long long pitch_y, int NB, int HW, int C, int G,
+                                float* stats, const float* gamma, const float* beta, float eps, int silu, int mode,
+                                int dtype, void* stream) {
+  if (NB <= 0 || HW <= 0) return B200SD_OK;
+  if (G <= 0 || C % G != 0 || pitch_x % 8 != 0 || pitch_y % 8 != 0 ||
+      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15))
+    return B200SD_ERR_INVALID;
+  if (mode < 0 || mode > 2) return B200SD_ERR_INVALID;
+  GnFused f;
+  bool fused = mode == 2 || (mode == 0 && gn_fused_mode() == 1);
+  if (fused) {
+    fused = gn_fused_geometry(HW, C, G, f);
+    if (fused) {
+      // every slab of one image must be able to run at the same time (the kernel's header explains why)
+      const int cap = dtype == B200SD_BF16 ? gn_fused_capacity<true>(f) : gn_fused_capacity<false>(f);
+      fused = f.parts <= cap && static_cast<long long>(NB) * f.parts < (1ll << 31);
+    }
+    if (!fused && mode == 2) return B200SD_ERR_UNSUPPORTED;
+  }
+  if (fused) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dtype == B200SD_BF16
+               ? launch_gn_fused<true>(f, st, static_cast<const uint8_t*>(X), pitch_x, static_cast<uint8_t*>(Y), pitch_y, NB, HW, C,
+                                       G, stats, gamma, beta, eps, silu)
+               : launch_gn_fused<false>(f, st, static_cast<const uint8_t*>(X), pitch_x, static_cast<uint8_t*>(Y), pitch_y, NB, HW,
+                                        C, G, stats, gamma, beta, eps, silu);
+  }
+  int rc = b200sd_groupnorm_stats(X, pitch_x, NB, HW, C, G, stats, dtype, stream);
+  if (rc != B200SD_OK) return rc;
+  return b200sd_groupnorm_apply(X, pitch_x, Y, pitch_y, NB, HW, C, G, stats, gamma, beta, eps, silu, dtype, stream);
+}
+
+/* tools/norm_sweep.py: slab size of the one-pass kernel (0 = keep) and scheduling order of the statistics kernel
+ * (-1 = keep) for the calls that follow; scratch sizes change with the slab size */
+extern "C" int b200sd_debug_gn_config(int slab_kb, int reverse_stats) {
+  if (slab_kb != 0 && (slab_kb < 8 || slab_kb > 160)) return B200SD_ERR_INVALID;
+  if (slab_kb != 0) g_gn_fused_kb = slab_kb;
+  if (reverse_stats >= 0) g_gn_stats_reverse = reverse_stats != 0 ? 1 : 0;
+  return B200SD_OK;
+}
+
+/* 1 when b200sd_groupnorm(mode 0 / 2) would take the one-pass kernel for this shape on the current device */
+extern "C" int b200sd_groupnorm_is_fused(int NB, int HW, int C, int G, int dtype) {
+  GnFused f;
+  if (NB <= 0 || !gn_fused_geometry(HW, C, G, f)) return 0;
+  const int cap = dtype == B200SD_BF16 ? gn_fused_capacity<true>(f) : gn_fused_capacity<false>(f);
+  return f.parts <= cap ? 1 : 0;
 }
 
 extern "C" int b200sd_layernorm(const void* X, long long ldx, void* Y, long long ldy, int rows, int C,

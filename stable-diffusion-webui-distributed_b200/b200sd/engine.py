@@ -22,6 +22,7 @@ from .vae_exec import VAEDecoderProgram, VAEDecoderWeights, VAEEncoderProgram, V
 
 MAX_STEPS = 256
 MAX_PLANS = 6        # distinct (batch, latent h, w) kept per engine; the least recently used one is dropped beyond that
+MAX_GRAPHS = 48      # step graphs kept per plan (one per sampler stage structure x cfg scale): oldest dropped beyond that
 NOISE_SAMPLERS = ("Euler a", "stage")   # graph-name prefixes of the step graphs that may read Plan.noise
 # _CAPTURE_LOCK (imported): CUDA graph captures are serialised across the per-device worker threads
 
@@ -266,6 +267,7 @@ class Plan:
         self.noise = None            # [rows, b, h*w, 4] fp32, persistent: captured graphs bake its address
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.graph_launches: Dict[str, int] = {}
+        self.stage_ids: Dict[tuple, int] = {}   # (lincomb structure, evaluated latent) of a generic stage -> graph-name id
 
     def noise_rows(self, rows: int) -> torch.Tensor:
         """the request's per-step noises live in ONE buffer per plan (the step graphs hold its raw address); it grows in
@@ -433,9 +435,16 @@ class SDEngine:
                 with torch.cuda.graph(g, stream=self._capture_stream(), capture_error_mode="thread_local"):
                     fn()
                 plan.graph_launches[name] = ops.LAUNCHES - l0   # b200sd kernels inside one replay
+            # a client walking through cfg scales / samplers must not accumulate graphs without bound ("vae" stays)
+            while len(plan.graphs) >= MAX_GRAPHS:
+                victim = next(n for n in plan.graphs if n != "vae")
+                del plan.graphs[victim]
+                plan.graph_launches.pop(victim, None)
             plan.graphs[name] = g
             for t, v in zip(state, saved):
                 t.copy_(v)
+        else:
+            plan.graphs[name] = plan.graphs.pop(name)   # most recently used last
         return plan.graphs[name]
 
     # ------------------------------------------------------------------------------------------ sampler programs
@@ -500,7 +509,8 @@ class SDEngine:
         return pr
 
     def _stage_graph(self, plan: Plan, st, cfg_scale: float, masked: bool, ts_sampler: bool):
-        name = f"stage:{hash((st.lcs, st.ev))}:{cfg_scale}:{int(masked)}{int(ts_sampler)}"
+        sid = plan.stage_ids.setdefault((st.lcs, st.ev), len(plan.stage_ids))   # exact structure -> id (no hash collisions)
+        name = f"stage:{sid}:{cfg_scale}:{int(masked)}{int(ts_sampler)}"
         fn = lambda: plan.stage(st.lcs, st.ev, cfg_scale, masked, ts_sampler)  # noqa: E731
         return name, fn, self._graph(plan, name, fn)
 

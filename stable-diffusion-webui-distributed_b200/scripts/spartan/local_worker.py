@@ -150,6 +150,8 @@ class LocalGPUWorker(Worker):
         n_iter = int(payload.get("n_iter", 1))
         steps = int(payload["steps"])
         width, height = int(payload["width"]), int(payload["height"])
+        if batch < 1 or n_iter < 1 or steps < 1:
+            raise ValueError(f"batch_size {batch}, n_iter {n_iter}, steps {steps}: all must be at least 1")
         sampler = payload.get("sampler_name") or payload.get("sampler_index") or "Euler a"
         if sampler not in supported_samplers():
             logger.warning(f"falling back to Euler a sampler for worker {self.label} ('{sampler}' is not implemented)")

@@ -64,6 +64,12 @@ class DevicePool:
             if w._engine is not None:
                 w._engine.interrupted = True
 
+    def restart(self):
+        """drop every device's engine — after the generation it is serving, never under it"""
+        for w, lock in zip(self.workers, self.locks):
+            with lock:
+                w.restart()
+
 
 MAX_BATCH = 64      # images per call and device
 MAX_SIDE = 2048     # pixels
@@ -191,8 +197,7 @@ def create_app(engine_factory: Callable, devices: Optional[List[int]] = None, ap
 
     @app.post(f"{API}/server-restart", dependencies=[Depends(auth)])
     def server_restart():
-        for w in pool.workers:
-            w.restart()
+        pool.restart()
         return {}
 
     return app

@@ -429,6 +429,29 @@ def test_euler_a_graph_reads_this_requests_noise(mods):
     assert not torch.equal(with_graphs[0], with_graphs[3])
 
 
+def test_step_graphs_per_plan_are_bounded(mods, monkeypatch):
+    """every (sampler stage structure, cfg scale) captures a step graph: a client walking through cfg scales must not grow
+    a plan without bound — the least recently used graphs are dropped and rebuilt on demand, with unchanged results"""
+    C, E, S, O = mods
+    cfgs, sd, dsd, eng, vocab_hi = _get(mods, "tiny")
+    monkeypatch.setattr(E, "MAX_GRAPHS", 4)
+    b, hw = 2, 16
+    tok, neg = O.random_prompt_tokens(b, vocab_hi=vocab_hi), O.empty_prompt_tokens(b, vocab_hi=vocab_hi)
+    run = lambda cfg, name: eng.txt2img(tok, neg, seed=31, steps=5, cfg_scale=cfg, height=hw * 8, width=hw * 8,  # noqa: E731
+                                        sampler=name).clone()
+    eng.use_graphs = True
+    try:
+        first = {(cfg, name): run(cfg, name) for name in ("Euler", "Heun") for cfg in (3.0, 4.5, 6.0, 7.5)}
+        plan = eng.plan(b, hw, hw)
+        assert len(plan.graphs) <= 4 and set(plan.graph_launches) <= set(plan.graphs)
+        again = {k: run(*k) for k in first}     # most of these graphs were evicted in the meantime
+    finally:
+        eng.use_graphs = False
+    for k in first:
+        assert torch.equal(first[k], again[k]), k
+    assert torch.equal(first[(7.5, "Heun")], run(7.5, "Heun"))   # and equal to the eager run
+
+
 def test_sd15_hires_fix_parity(mods):
     """hires fix at SD1.5 size: 256x256 first pass, Latent upscale x2, Euler a second pass from t_enc at 512x512"""
     C, E, S, O = mods

@@ -286,17 +286,26 @@ def test_attention_fused_qkv_buffer(ops):
 
 
 # ----------------------------------------------------------------------------------------------- norms
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("nb,hw,c,silu,eps", [(2, 4096, 320, True, 1e-5), (3, 64, 1280, True, 1e-5),
                                               (2, 1024, 1920, True, 1e-5), (1, 16384, 128, True, 1e-6),
                                               (2, 256, 2560, False, 1e-6), (2, 1024, 960, True, 1e-5)])
-def test_groupnorm(ops, nb, hw, c, silu, eps):
+def test_groupnorm(ops, nb, hw, c, silu, eps, mode):
+    """mode 1: statistics + apply kernels; mode 2: the one-pass kernel (slab kept in shared memory while the image's CTAs
+    agree on the statistics)"""
     g = _gen(hw + c)
     x = _rand((nb, hw, c), g, 2.0) + 0.5
     gamma = torch.randn(c, generator=g, device="cuda")
     beta = torch.randn(c, generator=g, device="cuda")
     out = torch.empty_like(x)
     stats = torch.zeros((ops.groupnorm_stats_floats(nb, hw, c, 32),), device="cuda")
-    ops.groupnorm(x, out, stats, gamma, beta, 32, eps, silu)
+    if mode == 2 and not ops.groupnorm_is_fused(nb, hw, c, 32, x.dtype):
+        assert c > 2048   # the only ineligible shape of this list: 320 vectors per pixel do not fit a 256-thread row
+        with pytest.raises(Exception):
+            ops.groupnorm(x, out, stats, gamma, beta, 32, eps, silu, mode=2)
+        return
+    ops.groupnorm(x, out, stats, gamma, beta, 32, eps, silu, mode=mode)
     torch.cuda.synchronize()
     # statistics: exact sums in fp32 order-of-magnitude, and bit-identical on a second run over the same (reused,
     # never re-zeroed) buffer — the cross-CTA reduction is ordered, not atomic
@@ -304,14 +313,99 @@ def test_groupnorm(ops, nb, hw, c, silu, eps):
     xs = x.float().reshape(nb, hw, 32, c // 32)
     ref_stats = torch.stack([xs.sum(dim=(1, 3)), (xs * xs).sum(dim=(1, 3))], dim=-1).reshape(-1)
     assert torch.allclose(first, ref_stats, rtol=2e-4, atol=1e-2)
+    # the arrival / work counters behind the results are back at zero
+    assert int(stats[nb * 64:nb * 64 + nb + 1].view(torch.int32).abs().sum()) == 0
     out2 = torch.empty_like(x)
-    ops.groupnorm(x, out2, stats, gamma, beta, 32, eps, silu)
+    ops.groupnorm(x, out2, stats, gamma, beta, 32, eps, silu, mode=mode)
     torch.cuda.synchronize()
     assert torch.equal(stats[:nb * 64], first) and torch.equal(out, out2)
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps).permute(0, 2, 1)
     if silu:
         ref = F.silu(ref)
-    assert_close(f"groupnorm nb{nb} hw{hw} c{c}", out, ref, atol=1e-2, rtol=4e-3)
+    assert_close(f"groupnorm mode{mode} nb{nb} hw{hw} c{c}", out, ref, atol=1e-2, rtol=4e-3)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("nb,hw,c,pitch,dt", [(64, 4096, 320, 320, torch.half), (5, 1024, 640, 1280, torch.half),
+                                              (3, 4096, 960, 960, torch.bfloat16), (7, 100, 64, 64, torch.half),
+                                              (2, 16384, 320, 320, torch.bfloat16), (33, 64, 1280, 2560, torch.half)])
+def test_groupnorm_one_pass(ops, nb, hw, c, pitch, dt):
+    """the one-pass kernel at the bench's largest site (64 images x 64x64x320: eight times more slabs than fit on the
+    device at once, so slabs are handed out while earlier images are still being agreed on), on channel slices of a wider
+    tensor (the UNet's concat buffers), bf16, a ragged last slab, and: an image's result does not depend on the batch it
+    is in, nor on the run"""
+    g = _gen(nb * 31 + c)
+    xw = (_rand((nb, hw, pitch), g, 1.5) + 0.25).to(dt)
+    ow = torch.full((nb, hw, pitch), 3.0, device="cuda", dtype=dt)
+    x, out = xw[:, :, pitch - c:], ow[:, :, :c]
+    gamma = torch.randn(c, generator=g, device="cuda")
+    beta = torch.randn(c, generator=g, device="cuda")
+    assert ops.groupnorm_is_fused(nb, hw, c, 32, dt)
+    stats = torch.zeros((ops.groupnorm_stats_floats(nb, hw, c, 32),), device="cuda")
+    ops.groupnorm(x, out, stats, gamma, beta, 32, 1e-5, True, mode=2)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1))
+    tol = dict(atol=1e-2, rtol=4e-3) if dt == torch.half else dict(atol=6e-2, rtol=2e-2)
+    assert_close(f"groupnorm one-pass nb{nb} hw{hw} c{c}/{pitch}", out, ref, **tol)
+    if pitch > c:
+        assert float((ow[:, :, c:].float() - 3.0).abs().max()) == 0.0   # nothing written outside the slice
+    assert int(stats[nb * 64:nb * 64 + nb + 1].view(torch.int32).abs().sum()) == 0
+    # against the two-kernel path: same statistics up to summation order, outputs within one rounding of the result
+    out1 = torch.empty((nb, hw, c), device="cuda", dtype=dt)
+    stats1 = torch.zeros_like(stats)
+    ops.groupnorm(x, out1, stats1, gamma, beta, 32, 1e-5, True, mode=1)
+    torch.cuda.synchronize()
+    assert torch.allclose(stats[:nb * 64], stats1[:nb * 64], rtol=1e-5, atol=1e-3)
+    ulp = 2.0 ** -10 if dt == torch.half else 2.0 ** -7
+    assert float(((out.float() - out1.float()).abs() / out1.float().abs().clamp_min(1.0)).max()) <= 2 * ulp
+    # run to run, and image by image (batch of one, fresh scratch): identical bits
+    for _ in range(3):
+        again = torch.empty((nb, hw, c), device="cuda", dtype=dt)
+        ops.groupnorm(x, again, stats, gamma, beta, 32, 1e-5, True, mode=2)
+        assert torch.equal(again, out)
+    for k in (0, nb - 1):
+        alone = torch.empty((1, hw, c), device="cuda", dtype=dt)
+        st1 = torch.zeros((ops.groupnorm_stats_floats(1, hw, c, 32),), device="cuda")
+        ops.groupnorm(x[k:k + 1], alone, st1, gamma, beta, 32, 1e-5, True, mode=2)
+        assert torch.equal(alone[0], out[k])
+
+
+@pytest.mark.timeout(300)
+def test_groupnorm_one_pass_under_graph_replay(ops):
+    """the step graphs replay GroupNorms back to back on one shared scratch buffer: a chain of one-pass and two-kernel
+    launches of different shapes, captured once and replayed, must leave the counters at zero and reproduce itself"""
+    g = _gen(77)
+    shapes = [(8, 4096, 320), (8, 1024, 640), (8, 256, 2560), (8, 64, 1280), (8, 4096, 320)]
+    xs = [_rand(s, g, 2.0) + 0.5 for s in shapes]
+    outs = [torch.empty_like(x) for x in xs]
+    gam = [torch.randn(s[2], generator=g, device="cuda") for s in shapes]
+    bet = [torch.randn(s[2], generator=g, device="cuda") for s in shapes]
+    need = max(ops.groupnorm_stats_floats(*s, 32) for s in shapes)
+    stats = torch.zeros((need,), device="cuda")
+
+    modes = [2 if ops.groupnorm_is_fused(*s, 32, torch.float16) else 1 for s in shapes]
+    modes[-1] = 1   # the first shape again, through the two kernels
+    assert modes == [2, 2, 1, 2, 1]
+
+    def chain():
+        for x, o, ga, be, mode in zip(xs, outs, gam, bet, modes):
+            ops.groupnorm(x, o, stats, ga, be, 32, 1e-5, True, mode=mode)
+    chain()
+    torch.cuda.synchronize()
+    want = [o.clone() for o in outs]
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        chain()
+    for _ in range(5):
+        for o in outs:
+            o.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for o, w in zip(outs, want):
+            assert torch.equal(o, w)
+    for x, w, ga, be in zip(xs, want, gam, bet):
+        ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, ga, be, 1e-5).permute(0, 2, 1))
+        assert_close("groupnorm chain", w, ref, atol=1e-2, rtol=4e-3)
 
 
 @pytest.mark.parametrize("rows,c,pitch,dt", [(100003, 320, 320, torch.half), (40000, 640, 704, torch.half),
