@@ -3,17 +3,25 @@
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` leg — never by the product path (stable-diffusion-webui-distributed_b200/).
 
-PARITY UNPINNED: the reference (papuSpartan/stable-diffusion-webui-distributed @ 8fd65ebd) contains none of this
-arithmetic and ships no tests or golden vectors.  Its call sites into the numeric path are
+PARITY PARTLY PINNED (UNet as a whole and the samplers: UNPINNED): the reference
+(papuSpartan/stable-diffusion-webui-distributed @ 8fd65ebd) contains none of this arithmetic and ships no tests or golden
+vectors.  Its call sites into the numeric path are
   scripts/spartan/world.py:196   process_images(p)                     (master's share / sample_master)
   scripts/spartan/worker.py:432  session.post(.../sdapi/v1/txt2img|img2img)  (remote sdwui: UNet x steps, VAE)
 The arithmetic lives in un-vendored third parties (AUTOMATIC1111 sdwui -> CompVis `ldm` openaimodel / model.py /
 attention.py, k-diffusion sampling.py); none is installable offline and the extension pins no version.  This file
 restates their published algorithms with ldm state_dict key names so a real checkpoint loads.
-Partial pins that ARE possible in this image (tests/test_oracle_pins_cpu.py): the CLIP text tower equals
-`transformers.CLIPTextModel` — the class ldm's FrozenCLIPEmbedder wraps — on shared random weights (2e-5), the schedule
-tables equal their closed forms, and the k-diffusion sampler restatements reproduce analytic solutions for synthetic
-denoisers.  The UNet and VAE restatements have no independent counterpart offline and stay unpinned.
+Pins against implementations that are NOT ours and exist in this image (tests/test_oracle_pins_cpu.py, 2e-5 on shared
+random weights): the CLIP text tower equals `transformers.CLIPTextModel` — the class ldm's FrozenCLIPEmbedder wraps; the
+VAE decoder and encoder equal the `Decoder` / `Encoder` classes of Black Forest Labs' FLUX autoencoder as shipped in
+torchtitan (torchtitan/experiments/flux/model/autoencoder.py: the ldm / taming autoencoder with ldm's own module names —
+loaded with strict=True, so every key name and shape of `first_stage_model.{encoder,decoder}.*` is the third party's);
+the UNet's attention equals `torch.nn.MultiheadAttention` with separate projection weights; the ResBlock's main path equals FLUX's
+`ResnetBlock` at eps 1e-5; the timestep embedding equals FLUX's; the schedule tables equal their closed forms and the k-diffusion sampler restatements reproduce analytic
+solutions for synthetic denoisers.  The UNet as a whole (ResBlock with its embedding path, SpatialTransformer wiring, skip
+concatenations, SDXL label_emb) and the sampler update rules have no independent counterpart offline (diffusers, ldm, sgm,
+k-diffusion are not installed): they stay unpinned restatements, cross-checked only by the product's independent
+derivation of the same samplers (tests/test_samplers_cpu.py).
 
 Everything here is NCHW fp32 (or whatever dtype/device the caller's tensors have), functional over a dict of
 parameters.  Function docstrings name the upstream symbol they follow.

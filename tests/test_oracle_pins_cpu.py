@@ -4,8 +4,11 @@ implementation that is NOT ours exists in this image).
 * CLIP text tower: `oracle.sd_oracle.clip_text_encode` vs `transformers.CLIPTextModel` (the very class ldm's
   FrozenCLIPEmbedder wraps as `cond_stage_model.transformer`) on the same random weights and tokens.
 * Schedules: the alphas / sigmas tables against their closed forms, DDIM / DPM++ 2M coefficient identities.
-The UNet and VAE restatements have no such counterpart offline (diffusers / ldm / k-diffusion are not installed): they stay
-"parity unpinned" (DESIGN.md §2).
+* Round 2: the VAE decoder / encoder vs the `Decoder` / `Encoder` of the FLUX autoencoder shipped in torchtitan (the ldm
+  autoencoder written by a third party, ldm's key names, strict load); the UNet's attention vs torch.nn.MultiheadAttention, its ResBlock's main path vs FLUX's ResnetBlock;
+  the timestep embedding vs FLUX's.
+The UNet as a whole and the sampler update rules have no such counterpart offline (diffusers / ldm / k-diffusion are not
+installed): they stay "parity unpinned" (DESIGN.md §2).
 """
 import math
 
@@ -74,3 +77,132 @@ def test_samplers_on_analytic_denoisers():
 
     assert float(O.sample_dpmpp_2m(to_zero, xT, c.expand(2, 1, 1), c.expand(2, 1, 1), 6, 3.0, karras=True).abs().max()) < 1e-4
     assert float(O.sample_euler(to_zero, xT, c.expand(2, 1, 1), c.expand(2, 1, 1), 6, 3.0).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ round 2: more pins
+def _flux_ae():
+    """torchtitan ships Black Forest Labs' FLUX autoencoder (torchtitan/experiments/flux/model/autoencoder.py): the ldm /
+    taming `Encoder` / `Decoder` (ResnetBlock, single-head AttnBlock, asymmetric-pad Downsample, nearest Upsample) written
+    by someone else, with ldm's own module names — i.e. ldm's state-dict keys."""
+    return pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+
+
+@pytest.mark.parametrize("cfg,hw", [(O.TINY_VAE, 8), (O.VAEConfig(ch=64, ch_mult=(1, 2, 4, 4), num_res_blocks=2), 4)])
+def test_vae_decoder_matches_independent_implementation(cfg, hw):
+    """oracle.vae_decode vs the FLUX / ldm `Decoder` class: strict state-dict load (every key name and shape of
+    `first_stage_model.decoder.*` is the third party's), same input, same output"""
+    A = _flux_ae()
+    from b200sd import synth
+    sd = synth.make_vae_state_dict(cfg, seed=3) if hasattr(synth, "make_vae_state_dict") else \
+        {k: v for k, v in synth.make_state_dict(O.TINY_UNET, cfg, O.TINY_CLIP, seed=3).items() if k.startswith("first_stage_model.")}
+    dec = A.Decoder(ch=cfg.ch, out_ch=3, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, in_channels=3,
+                    resolution=hw * 2 ** (len(cfg.ch_mult) - 1), z_channels=cfg.z_channels).eval().float()
+    weights = {k[len("first_stage_model.decoder."):]: v.float() for k, v in sd.items()
+               if k.startswith("first_stage_model.decoder.")}
+    dec.load_state_dict(weights, strict=True)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn((2, cfg.z_channels, hw, hw), generator=g)
+    with torch.no_grad():
+        got = O.vae_decode({k: v.float() for k, v in sd.items()}, cfg, z)
+        pq = torch.nn.functional.conv2d(z, sd["first_stage_model.post_quant_conv.weight"].float(),
+                                        sd["first_stage_model.post_quant_conv.bias"].float())
+        ref = dec(pq)
+    assert got.shape == ref.shape == (2, 3, hw * 2 ** (len(cfg.ch_mult) - 1), hw * 2 ** (len(cfg.ch_mult) - 1))
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("cfg,px", [(O.TINY_VAE, 64), (O.VAEConfig(ch=64, ch_mult=(1, 2, 4, 4), num_res_blocks=2), 32)])
+def test_vae_encoder_matches_independent_implementation(cfg, px):
+    """oracle.vae_encode_mean vs the FLUX / ldm `Encoder` class + quant_conv + the mean half of the moments"""
+    A = _flux_ae()
+    from b200sd import synth
+    sd = {k: v.float() for k, v in synth.make_state_dict(O.TINY_UNET, cfg, O.TINY_CLIP, seed=4).items()
+          if k.startswith("first_stage_model.")}
+    enc = A.Encoder(resolution=px, in_channels=3, ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks,
+                    z_channels=cfg.z_channels).eval().float()
+    enc.load_state_dict({k[len("first_stage_model.encoder."):]: v for k, v in sd.items()
+                         if k.startswith("first_stage_model.encoder.")}, strict=True)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand((2, 3, px, px), generator=g) * 2 - 1
+    with torch.no_grad():
+        got = O.vae_encode_mean(sd, cfg, x)
+        moments = torch.nn.functional.conv2d(enc(x), sd["first_stage_model.quant_conv.weight"],
+                                             sd["first_stage_model.quant_conv.bias"])
+        ref = moments.chunk(2, dim=1)[0]
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_timestep_embedding_matches_independent_implementation():
+    """ldm's timestep_embedding(t, dim) == FLUX's timestep_embedding(t, dim, time_factor=1) (cos | sin halves, max_period
+    10000; FLUX feeds t in [0, 1] and scales by 1000 inside)"""
+    L = pytest.importorskip("torchtitan.experiments.flux.model.layers")
+    t = torch.tensor([1.0, 51.0, 500.5, 999.0])
+    for dim in (320, 64):
+        ref = L.timestep_embedding(t, dim, max_period=10000, time_factor=1.0)
+        assert torch.allclose(O.timestep_embedding(t, dim), ref.float(), atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize("ctx_dim,n_ctx", [(None, None), (96, 77)])
+def test_unet_attention_matches_torch_multihead_attention(ctx_dim, n_ctx):
+    """ldm CrossAttention (to_q / to_k / to_v without bias, heads as contiguous channel chunks, scale d^-0.5, to_out with
+    bias) is torch.nn.MultiheadAttention with separate projection weights — an implementation that is not ours"""
+    c, heads, b, n = 64, 4, 2, 50
+    g = torch.Generator().manual_seed(8)
+    kd = c if ctx_dim is None else ctx_dim
+    sd = {"a.to_q.weight": torch.randn((c, c), generator=g) * 0.2, "a.to_k.weight": torch.randn((c, kd), generator=g) * 0.2,
+          "a.to_v.weight": torch.randn((c, kd), generator=g) * 0.2, "a.to_out.0.weight": torch.randn((c, c), generator=g) * 0.2,
+          "a.to_out.0.bias": torch.randn((c,), generator=g) * 0.2}
+    x = torch.randn((b, n, c), generator=g)
+    ctx = None if ctx_dim is None else torch.randn((b, n_ctx, ctx_dim), generator=g)
+    mha = torch.nn.MultiheadAttention(c, heads, bias=True, batch_first=True, kdim=kd, vdim=kd).eval()
+    with torch.no_grad():
+        if ctx_dim is None:   # same embed dims: one packed in-projection
+            mha.in_proj_weight.copy_(torch.cat([sd["a.to_q.weight"], sd["a.to_k.weight"], sd["a.to_v.weight"]]))
+        else:
+            mha.q_proj_weight.copy_(sd["a.to_q.weight"])
+            mha.k_proj_weight.copy_(sd["a.to_k.weight"])
+            mha.v_proj_weight.copy_(sd["a.to_v.weight"])
+        mha.in_proj_bias.zero_()
+        mha.out_proj.weight.copy_(sd["a.to_out.0.weight"])
+        mha.out_proj.bias.copy_(sd["a.to_out.0.bias"])
+        kv = x if ctx is None else ctx
+        ref, _ = mha(x, kv, kv, need_weights=False)
+        for sdpa in (False, True):
+            old, O.USE_SDPA = O.USE_SDPA, sdpa
+            try:
+                got = O.cross_attention(sd, "a", x, ctx, heads)
+            finally:
+                O.USE_SDPA = old
+            assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128)])
+def test_unet_resblock_main_path_matches_independent_resnet_block(cin, cout):
+    """openaimodel.ResBlock with a silent embedding path (emb_layers weight and bias zero) is the autoencoder's ResnetBlock
+    at eps 1e-5: GN32 - SiLU - conv3x3, GN32 - SiLU - conv3x3, 1x1 skip when the width changes.  The embedding path itself
+    (h + Linear(SiLU(emb)) broadcast over pixels, before the second GroupNorm) is checked as a shift of the first conv's
+    bias."""
+    A = _flux_ae()
+    g = torch.Generator().manual_seed(9)
+    blk = A.ResnetBlock(in_channels=cin, out_channels=cout).eval().float()
+    blk.norm1.eps = blk.norm2.eps = 1e-5
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    w = blk.state_dict()
+    names = {"norm1": "in_layers.0", "conv1": "in_layers.2", "norm2": "out_layers.0", "conv2": "out_layers.3",
+             "nin_shortcut": "skip_connection"}
+    sd = {"r." + names[k.split(".")[0]] + "." + k.split(".")[1]: v.clone() for k, v in w.items()}
+    emb_dim = 32
+    sd["r.emb_layers.1.weight"] = torch.zeros((cout, emb_dim))
+    sd["r.emb_layers.1.bias"] = torch.zeros((cout,))
+    x = torch.randn((2, cin, 8, 8), generator=g)
+    emb = torch.randn((2, emb_dim), generator=g)
+    with torch.no_grad():
+        assert float((O.res_block(sd, "r", x, emb) - blk(x)).abs().max()) <= 2e-5
+        # a per-channel embedding contribution equals the same shift of conv1's bias (same for every sample here)
+        shift = torch.randn((cout,), generator=g) * 0.3
+        sd["r.emb_layers.1.bias"] = shift.clone()
+        blk.conv1.bias.add_(shift)
+        assert float((O.res_block(sd, "r", x, emb) - blk(x)).abs().max()) <= 2e-5
