@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` leg — never by the product path (stable-diffusion-webui-distributed_b200/).
 
-PARITY PARTLY PINNED (UNet as a whole and the samplers: UNPINNED): the reference
+PARITY PARTLY PINNED (the UNet's top-level wiring and sdwui's step conventions: UNPINNED): the reference
 (papuSpartan/stable-diffusion-webui-distributed @ 8fd65ebd) contains none of this arithmetic and ships no tests or golden
 vectors.  Its call sites into the numeric path are
   scripts/spartan/world.py:196   process_images(p)                     (master's share / sample_master)
@@ -17,11 +17,14 @@ VAE decoder and encoder equal the `Decoder` / `Encoder` classes of Black Forest 
 torchtitan (torchtitan/experiments/flux/model/autoencoder.py: the ldm / taming autoencoder with ldm's own module names —
 loaded with strict=True, so every key name and shape of `first_stage_model.{encoder,decoder}.*` is the third party's);
 the UNet's attention equals `torch.nn.MultiheadAttention` with separate projection weights; the ResBlock's main path equals FLUX's
-`ResnetBlock` at eps 1e-5; the timestep embedding equals FLUX's; the schedule tables equal their closed forms and the k-diffusion sampler restatements reproduce analytic
-solutions for synthetic denoisers.  The UNet as a whole (ResBlock with its embedding path, SpatialTransformer wiring, skip
-concatenations, SDXL label_emb) and the sampler update rules have no independent counterpart offline (diffusers, ldm, sgm,
-k-diffusion are not installed): they stay unpinned restatements, cross-checked only by the product's independent
-derivation of the same samplers (tests/test_samplers_cpu.py).
+`ResnetBlock` at eps 1e-5; the timestep embedding equals FLUX's; BasicTransformerBlock's wiring equals torch.nn.TransformerDecoderLayer(norm_first=True); both SDXL text towers
+equal transformers (CLIP-L hidden_states[11], OpenCLIP bigG as CLIPTextModelWithProjection under the open_clip -> HF key
+mapping); the schedule tables equal their closed forms.  Samplers vs diffusion theory: on the closed-form optimal denoiser
+of Gaussian data every deterministic sampler (all names of the reference's table + DDIM) converges to the exact
+probability-flow solution with its order, and every ancestral / SDE sampler ends on the data distribution.  What has no
+independent counterpart offline (diffusers, ldm, sgm, k-diffusion are not installed) and stays an unpinned restatement:
+the UNet's top-level wiring (block lists, skip concatenations, SpatialTransformer reshapes, SDXL label_emb) and the
+conventions theory does not fix (sdwui's step counts, img2img t_enc, which noise draw feeds which step).
 
 Everything here is NCHW fp32 (or whatever dtype/device the caller's tensors have), functional over a dict of
 parameters.  Function docstrings name the upstream symbol they follow.

@@ -206,3 +206,175 @@ def test_unet_resblock_main_path_matches_independent_resnet_block(cin, cout):
         sd["r.emb_layers.1.bias"] = shift.clone()
         blk.conv1.bias.add_(shift)
         assert float((O.res_block(sd, "r", x, emb) - blk(x)).abs().max()) <= 2e-5
+
+
+def _hf_clip(transformers, vocab, width, layers, heads, act, proj=None):
+    cfg = transformers.CLIPTextConfig(vocab_size=vocab + 3, hidden_size=width, intermediate_size=4 * width,
+                                      num_hidden_layers=layers, num_attention_heads=heads, max_position_embeddings=77,
+                                      hidden_act=act, layer_norm_eps=1e-5, eos_token_id=vocab + 2, bos_token_id=vocab + 1,
+                                      pad_token_id=vocab + 2, **({} if proj is None else {"projection_dim": proj}))
+    torch.manual_seed(13)
+    model = (transformers.CLIPTextModel if proj is None else transformers.CLIPTextModelWithProjection)(cfg).eval().float()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    return model
+
+
+def test_sdxl_clip_l_hidden_layer_matches_transformers():
+    """sgm FrozenCLIPEmbedder(layer="hidden", layer_idx=11): hidden_states[11] of transformers.CLIPTextModel"""
+    transformers = pytest.importorskip("transformers")
+    cfg = O.CLIPConfig(vocab=1500, width=96, layers=4, heads=4)
+    model = _hf_clip(transformers, cfg.vocab, cfg.width, cfg.layers, cfg.heads, "quick_gelu")
+    sd = {"t." + k: v.detach().clone() for k, v in model.state_dict().items()}
+    tokens = O.random_prompt_tokens(3, seed=12, vocab_hi=cfg.vocab)
+    with torch.no_grad():
+        hs = model(input_ids=tokens, output_hidden_states=True).hidden_states
+        for idx in (cfg.layers - 1, 1):
+            got = O.clip_text_hidden(sd, cfg, tokens, idx, "t.text_model.")
+            assert float((got - hs[idx]).abs().max()) <= 2e-5 * max(1.0, float(hs[idx].abs().max()))
+
+
+def test_sdxl_open_clip_tower_matches_transformers_with_projection():
+    """sgm FrozenOpenCLIPEmbedder2 (open_clip text transformer: packed in_proj, GELU, penultimate layer, pooled =
+    ln_final(last)[EOS] @ text_projection) is transformers.CLIPTextModelWithProjection(hidden_act="gelu") under the
+    open_clip -> HF key mapping every SDXL checkpoint converter uses"""
+    transformers = pytest.importorskip("transformers")
+    cfg = O.CLIPConfig(vocab=1500, width=64, layers=2, heads=2, xl_width=96, xl_layers=4, xl_heads=4, xl_proj=80)
+    model = _hf_clip(transformers, cfg.vocab, cfg.xl_width, cfg.xl_layers, cfg.xl_heads, "gelu", proj=cfg.xl_proj)
+    hf = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = {"m.token_embedding.weight": hf["text_model.embeddings.token_embedding.weight"],
+          "m.positional_embedding": hf["text_model.embeddings.position_embedding.weight"],
+          "m.ln_final.weight": hf["text_model.final_layer_norm.weight"], "m.ln_final.bias": hf["text_model.final_layer_norm.bias"],
+          "m.text_projection": hf["text_projection.weight"].t().contiguous()}
+    for i in range(cfg.xl_layers):
+        h, o = f"text_model.encoder.layers.{i}.", f"m.transformer.resblocks.{i}."
+        sd[o + "attn.in_proj_weight"] = torch.cat([hf[h + f"self_attn.{n}_proj.weight"] for n in "qkv"])
+        sd[o + "attn.in_proj_bias"] = torch.cat([hf[h + f"self_attn.{n}_proj.bias"] for n in "qkv"])
+        for a, b_ in (("attn.out_proj", "self_attn.out_proj"), ("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"),
+                      ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            sd[o + a + ".weight"], sd[o + a + ".bias"] = hf[h + b_ + ".weight"], hf[h + b_ + ".bias"]
+    tokens = O.random_prompt_tokens(3, seed=14, vocab_hi=cfg.vocab)
+    with torch.no_grad():
+        out = model(input_ids=tokens, output_hidden_states=True)
+        pen, pooled = O.open_clip_text(sd, cfg, tokens, "m.")
+    assert float((pen - out.hidden_states[-2]).abs().max()) <= 2e-5 * max(1.0, float(out.hidden_states[-2].abs().max()))
+    assert float((pooled - out.text_embeds).abs().max()) <= 2e-5 * max(1.0, float(out.text_embeds.abs().max()))
+
+
+def test_unet_transformer_block_wiring_matches_torch_decoder_layer():
+    """BasicTransformerBlock = a pre-LN decoder layer: x + self_attn(LN1 x), x + cross_attn(LN2 x, context), x + FF(LN3 x).
+    torch.nn.TransformerDecoderLayer(norm_first=True) supplies the wiring, the LayerNorms and both attentions (cross
+    attention re-made with kdim = context width); the feed-forward is its linear1 -> activation -> linear2 with GEGLU
+    (value half times GELU of the gate half) as the activation."""
+    c, heads, ctx_dim, b, n, n_ctx = 64, 4, 96, 2, 40, 77
+    torch.manual_seed(21)
+    layer = torch.nn.TransformerDecoderLayer(c, heads, dim_feedforward=8 * c, dropout=0.0, batch_first=True, norm_first=True,
+                                             activation=lambda h: h.chunk(2, dim=-1)[0] * torch.nn.functional.gelu(h.chunk(2, dim=-1)[1]))
+    layer.multihead_attn = torch.nn.MultiheadAttention(c, heads, batch_first=True, kdim=ctx_dim, vdim=ctx_dim)
+    layer.linear2 = torch.nn.Linear(4 * c, c)
+    layer = layer.eval().float()
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_(torch.randn_like(p) * 0.15)
+        layer.self_attn.in_proj_bias.zero_()
+        layer.multihead_attn.in_proj_bias.zero_()
+    q, k, v = layer.self_attn.in_proj_weight.detach().chunk(3)
+    sd = {"b.attn1.to_q.weight": q, "b.attn1.to_k.weight": k, "b.attn1.to_v.weight": v,
+          "b.attn1.to_out.0.weight": layer.self_attn.out_proj.weight.detach(), "b.attn1.to_out.0.bias": layer.self_attn.out_proj.bias.detach(),
+          "b.attn2.to_q.weight": layer.multihead_attn.q_proj_weight.detach(), "b.attn2.to_k.weight": layer.multihead_attn.k_proj_weight.detach(),
+          "b.attn2.to_v.weight": layer.multihead_attn.v_proj_weight.detach(),
+          "b.attn2.to_out.0.weight": layer.multihead_attn.out_proj.weight.detach(), "b.attn2.to_out.0.bias": layer.multihead_attn.out_proj.bias.detach(),
+          "b.ff.net.0.proj.weight": layer.linear1.weight.detach(), "b.ff.net.0.proj.bias": layer.linear1.bias.detach(),
+          "b.ff.net.2.weight": layer.linear2.weight.detach(), "b.ff.net.2.bias": layer.linear2.bias.detach()}
+    for i in (1, 2, 3):
+        sd[f"b.norm{i}.weight"], sd[f"b.norm{i}.bias"] = getattr(layer, f"norm{i}").weight.detach(), getattr(layer, f"norm{i}").bias.detach()
+    x, ctx = torch.randn(b, n, c), torch.randn(b, n_ctx, ctx_dim)
+    with torch.no_grad():
+        ref = layer(x, ctx)
+        got = O.transformer_block(sd, "b", x, ctx, heads)
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------ samplers vs diffusion theory
+# For Gaussian data x ~ N(0, s^2) the optimal denoiser is known in closed form: eps(x_t, t) = x_t sqrt(1 - a) / (a s^2 + 1 - a)
+# (a = alphas_cumprod at t), i.e. denoised(x, sigma) = x s^2 / (s^2 + sigma^2) in k-diffusion's variables.  The probability-flow
+# ODE then has the exact solution x(sigma) = x(sigma_0) sqrt((s^2 + sigma^2) / (s^2 + sigma_0^2)), and every stochastic sampler
+# must end on samples of the data distribution (variance s^2).  No third-party code needed: a wrong coefficient anywhere in a
+# sampler restatement shows up as a wrong limit or a wrong convergence order.
+_S_DATA = 0.8
+
+
+def _gaussian_eps_model(x, t, ctx):
+    _, log_sig = O.model_sigmas()
+    tt = t.double().clamp(0, 999)
+    lo = tt.floor().long().clamp(max=998)
+    w = tt - lo
+    sg = ((1 - w) * log_sig[lo] + w * log_sig[lo + 1]).exp()
+    a = 1 / (1 + sg * sg)
+    k = (torch.sqrt(1 - a) / (a * _S_DATA ** 2 + 1 - a)).float()
+    return x * k[:, None, None, None]
+
+
+def _flow_error(name, steps, noise0):
+    c = torch.zeros(noise0.shape[0], 1, 1)
+    x = O.run_sampler(name, _gaussian_eps_model, c, c, 1.0, steps, noise0, None)
+    s = _S_DATA
+    if name == "PLMS":   # a timestep sampler: it stops at alphas_cumprod[0], not at sigma = 0
+        ac, ts = O.alphas_cumprod().double(), O.ddim_timesteps(steps)
+        a_T, a_0 = float(ac[ts[-1]]), float(ac[0])
+        exact = noise0 * math.sqrt((a_0 * s * s + 1 - a_0) / (a_T * s * s + 1 - a_T))
+    else:
+        karras = name.endswith("Karras") or name == "DPM++ 2M"
+        s0 = float((O.sigmas_karras(steps) if karras else O.karras_sigmas_compvis(steps))[0][0])
+        exact = noise0 * s0 * s / math.sqrt(s * s + s0 * s0)
+    return float((x - exact).norm() / exact.norm())
+
+
+@pytest.mark.parametrize("name,err40,order", [
+    ("Euler", 0.06, 1), ("Heun", 0.003, 2), ("DPM2", 0.012, 2), ("DPM2 Karras", 0.003, 2), ("DPM++ 2M", 0.006, 2),
+    ("DPM++ 2M Karras", 0.006, 2), ("LMS", 5e-4, 3), ("LMS Karras", 2e-3, 3), ("PLMS", 0.008, 1.2)])
+def test_deterministic_samplers_solve_the_probability_flow_ode(name, err40, order):
+    """error against the exact solution: small at 40 steps and falling with the sampler's order from 20 to 40 steps"""
+    noise0 = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(0))
+    e20, e40 = _flow_error(name, 20, noise0), _flow_error(name, 40, noise0)
+    assert e40 <= err40, (name, e20, e40)
+    assert e20 / e40 >= 0.8 * 2 ** order, (name, e20, e40)    # halving the step divides the error by ~2^order
+
+
+@pytest.mark.parametrize("name,tol", [("DPM fast", 0.01), ("DPM adaptive", 0.05)])
+def test_dpm_solver_samplers_solve_the_probability_flow_ode(name, tol):
+    """DPM fast (fixed n evaluations) and DPM adaptive (rtol 0.05 step control: the error is the tolerance's, whatever
+    `steps` says)"""
+    noise0 = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(0))
+    assert _flow_error(name, 20, noise0) <= tol
+
+
+@pytest.mark.parametrize("name,lo,hi", [("Euler a", 0.80, 1.02), ("DPM2 a", 0.93, 1.10), ("DPM++ 2S a", 0.92, 1.06),
+                                        ("DPM++ SDE", 0.90, 1.06), ("DPM2 a Karras", 0.93, 1.07),
+                                        ("DPM++ 2S a Karras", 0.93, 1.06), ("DPM++ SDE Karras", 0.93, 1.07)])
+def test_stochastic_samplers_end_on_the_data_distribution(name, lo, hi):
+    """40 steps of an ancestral / SDE sampler from pure noise: zero mean and the data's variance (Euler a, first order,
+    approaches it from below: 0.73 at 20 steps, 0.86 at 40)"""
+    g = torch.Generator().manual_seed(1)
+    shape = (4, 4, 32, 32)
+    noise0 = torch.randn(shape, generator=g)
+    draws = [torch.randn(shape, generator=g) for _ in range(160)]
+    c = torch.zeros(shape[0], 1, 1)
+    x = O.run_sampler(name, _gaussian_eps_model, c, c, 1.0, 40, noise0, draws)
+    ratio = float(x.var()) / _S_DATA ** 2
+    assert lo <= ratio <= hi and abs(float(x.mean())) <= 0.03, (name, ratio, float(x.mean()))
+
+
+def test_ddim_solves_the_probability_flow_ode():
+    """sdwui's DDIM (eta 0) on the same Gaussian-data denoiser: first order, ends at alphas_cumprod[timesteps[0]]"""
+    noise0 = torch.randn((2, 4, 16, 16), generator=torch.Generator().manual_seed(0))
+    c = torch.zeros(2, 1, 1)
+    errs = []
+    for steps in (20, 40):
+        x = O.sample_ddim(_gaussian_eps_model, noise0, c, c, steps, 1.0)
+        ac, ts = O.alphas_cumprod().double(), O.ddim_timesteps(steps)
+        a_T, a_0, s = float(ac[ts[-1]]), float(ac[ts[0]]), _S_DATA
+        exact = noise0 * math.sqrt((a_0 * s * s + 1 - a_0) / (a_T * s * s + 1 - a_T))
+        errs.append(float((x - exact).norm() / exact.norm()))
+    assert errs[1] <= 0.05 and errs[0] / errs[1] >= 1.6, errs
