@@ -37,6 +37,12 @@ import math
 import torch
 import torch.nn.functional as F
 
+# "fp32" has to mean fp32 when the oracle runs on a GPU (the -m gpu tests and smoke() put it next to the CUDA path): PyTorch
+# lets cuDNN run fp32 convolutions on TF32 tensor cores by default (10-bit mantissas — the precision class of the fp16 path
+# under test).  Importing the oracle turns that off for the process; matmuls are IEEE fp32 by default already.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 SD = Dict[str, torch.Tensor]
 # bench.py's stock-PyTorch comparator flips this: attention through F.scaled_dot_product_attention (the fused library
 # kernel a stock fp16 pipeline would use) instead of the explicit softmax(q k^T) v the parity checks run

@@ -13,6 +13,12 @@ for p in (ROOT, EXT_DIR, HOSTSTUB):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    try:   # fp32 references are IEEE fp32 on the GPU too (cuDNN's default lets fp32 convolutions use TF32 tensor cores)
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:  # pragma: no cover
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
