@@ -21,7 +21,9 @@ the UNet's attention equals `torch.nn.MultiheadAttention` with separate projecti
 equal transformers (CLIP-L hidden_states[11], OpenCLIP bigG as CLIPTextModelWithProjection under the open_clip -> HF key
 mapping); the schedule tables equal their closed forms.  Samplers vs diffusion theory: on the closed-form optimal denoiser
 of Gaussian data every deterministic sampler (all names of the reference's table + DDIM) converges to the exact
-probability-flow solution with its order, and every ancestral / SDE sampler ends on the data distribution.  What has no
+probability-flow solution with its order, and every ancestral / SDE sampler ends on the data distribution.  Known
+answers: the full-size state dicts have exactly the released models' parameter totals (SD1.5 UNet 859 520 964, VAE
+83 653 863, CLIP-L 123 060 480, SDXL UNet 2 567 463 684, bigG text 694 659 840).  What has no
 independent counterpart offline (diffusers, ldm, sgm, k-diffusion are not installed) and stays an unpinned restatement:
 the UNet's top-level wiring (block lists, skip concatenations, SpatialTransformer reshapes, SDXL label_emb) and the
 conventions theory does not fix (sdwui's step counts, img2img t_enc, which noise draw feeds which step).

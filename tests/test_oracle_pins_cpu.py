@@ -378,3 +378,44 @@ def test_ddim_solves_the_probability_flow_ode():
         exact = noise0 * math.sqrt((a_0 * s * s + 1 - a_0) / (a_T * s * s + 1 - a_T))
         errs.append(float((x - exact).norm() / exact.norm()))
     assert errs[1] <= 0.05 and errs[0] / errs[1] >= 1.6, errs
+
+
+# ------------------------------------------------------------------------------------------------ known-answer: parameter counts
+def _shape_only_state_dict(cfgs):
+    """b200sd.synth.make_state_dict with every random draw replaced by a meta tensor: shapes and key names, no storage"""
+    from unittest import mock
+    from b200sd import synth
+    real = torch.randn
+
+    def meta_randn(*shape, **kw):
+        shape = shape[0] if len(shape) == 1 and not isinstance(shape[0], int) else shape
+        return torch.empty(tuple(shape), device="meta")
+    with mock.patch.object(torch, "randn", meta_randn):
+        sd = synth.make_state_dict(*cfgs, seed=0)
+    assert torch.randn is real
+    return sd
+
+
+def _count(sd, prefix):
+    return sum(v.numel() for k, v in sd.items() if k.startswith(prefix))
+
+
+def test_parameter_counts_equal_the_published_models():
+    """Known answers the restatements cannot have been tuned to: the parameter totals of the released models.  The state
+    dict both the product and the oracle consume (same keys, same shapes; see test_*_program_matches_oracle) has, for the
+    full-size configurations, exactly
+      SD1.5  UNet 859 520 964 - kl-f8 VAE 83 653 863 - CLIP ViT-L/14 text model 123 060 480
+      SDXL   UNet 2 567 463 684 - OpenCLIP ViT-bigG/14 text tower 694 659 840 (+ the logit_scale scalar upstream keeps)
+    parameters.  Every block, its input width after the skip concatenations, every attention depth and head projection
+    enters these sums: a missing or extra layer, or a wrong channel count anywhere, changes them."""
+    from b200sd import config as C
+    sd = _shape_only_state_dict((C.SD15_UNET, C.SD15_VAE, C.SD15_CLIP))
+    assert _count(sd, C.UNET_PREFIX) == 859_520_964
+    assert _count(sd, C.VAE_PREFIX) == 83_653_863
+    assert _count(sd, C.CLIP_PREFIX) == 123_060_480
+    assert len(sd) == sum(1 for k in sd if k.startswith((C.UNET_PREFIX, C.VAE_PREFIX, C.CLIP_PREFIX)))
+    xl = _shape_only_state_dict((C.SDXL_UNET, C.SDXL_VAE, C.SDXL_CLIP))
+    assert _count(xl, C.UNET_PREFIX) == 2_567_463_684
+    assert _count(xl, C.VAE_PREFIX) == 83_653_863
+    assert _count(xl, C.XL_PREFIX0) == 123_060_480
+    assert _count(xl, C.XL_PREFIX1) == 694_659_840
