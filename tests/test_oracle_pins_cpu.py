@@ -419,3 +419,15 @@ def test_parameter_counts_equal_the_published_models():
     assert _count(xl, C.VAE_PREFIX) == 83_653_863
     assert _count(xl, C.XL_PREFIX0) == 123_060_480
     assert _count(xl, C.XL_PREFIX1) == 694_659_840
+
+
+def test_schedule_known_constants():
+    """numbers every SD1.x user has seen: k-diffusion reports sigma_min 0.0292 / sigma_max 14.6146 for this schedule, the
+    last alphas_cumprod is 0.00466, and sdwui's 20-step DDIM visits 1, 51, ..., 951"""
+    sig, _ = O.model_sigmas()
+    assert abs(float(sig[0]) - 0.0291675) < 2e-6 and abs(float(sig[-1]) - 14.614642) < 2e-5
+    ac = O.alphas_cumprod()
+    assert abs(float(ac[-1]) - 0.0046600) < 2e-6 and abs(float(ac[0]) - 0.99915) < 1e-6
+    assert O.ddim_timesteps(20).tolist() == list(range(1, 1000, 50))
+    assert O.SD15_VAE.scale_factor == 0.18215 and O.SDXL_VAE.scale_factor == 0.13025
+    assert O.SDXL_UNET.adm_in_channels == 1280 + 6 * 256
