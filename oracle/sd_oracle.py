@@ -31,7 +31,7 @@ conventions theory does not fix (sdwui's step counts, img2img t_enc, which noise
 Everything here is NCHW fp32 (or whatever dtype/device the caller's tensors have), functional over a dict of
 parameters.  Function docstrings name the upstream symbol they follow.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import math

@@ -7,7 +7,6 @@ exchange; results meet once, at the end (bench: one NCCL all-gather; plugin path
 """
 import contextlib
 import math
-import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 

@@ -19,7 +19,7 @@ algebra) and tests/ compare the two.
 """
 import math
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Sequence, Tuple
 
 COEF_LD = 32           # floats per coefficient row
 IDX_COL = COEF_LD - 1  # the row's last float = which tensor of the noise stack this stage reads

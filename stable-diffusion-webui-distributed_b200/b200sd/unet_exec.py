@@ -13,7 +13,7 @@ from the reference at scripts/spartan/world.py:196 and, remotely, worker.py:432)
   * q/k/v projection weights carry zero rows so each head is padded to a multiple of 64 columns — exactly one
     TMA SWIZZLE_128B box per head chunk in the attention kernel.
 """
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

@@ -19,7 +19,7 @@ import re
 import time
 from enum import Enum
 from threading import Thread
-from typing import List, Optional, Union
+from typing import List, Union
 
 import requests
 from modules.shared import cmd_opts

@@ -10,7 +10,6 @@ the local executor directly (it/s -> ipm) instead of timing HTTP round trips, so
 over the GPUs of the box with the reference's own arithmetic.
 """
 import concurrent.futures
-import copy
 import json
 import os
 import time

@@ -23,8 +23,6 @@ Images travel as base64 PNG (the API's wire format); the in-process fast lane (`
 over HTTP.  Optional HTTP basic auth mirrors sdwui's `--api-auth user:password`.
 """
 import argparse
-import base64
-import json
 import secrets
 import threading
 import time

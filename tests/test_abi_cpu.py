@@ -1,7 +1,4 @@
 """The C-ABI library loads without a GPU and exports every symbol include/b200sd.h declares (no compute calls)."""
-import ctypes
-import os
-
 
 def test_library_exports_every_declared_symbol():
     import __graft_entry__ as ge

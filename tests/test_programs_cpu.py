@@ -192,7 +192,6 @@ def test_variation_seeds(env):
     mid = E.per_image_noise(10, 3, shape, 2, 500, 0.3)
     assert torch.allclose(mid[0], O.per_image_noise(10, 3, shape, subseed=500, subseed_strength=0.3), atol=1e-6)
     assert not torch.allclose(mid[0], base[0]) and all(torch.equal(mid[1, k], base[1, 0]) for k in range(3))
-    import math
     s0 = E.slerp(0.3, base[0, 0], E.per_image_noise(501, 1, shape)[0, 0])   # image 1: noise(seed) with subnoise(subseed + 1)
     assert torch.allclose(mid[0, 1], s0, atol=1e-6)
     # through the request path: the engine's variation attribute changes the start noise only when set

@@ -31,7 +31,7 @@ def env(monkeypatch):
 
 def test_reference_table_is_covered():
     """no sampler name the reference's ETA model knows falls back any more"""
-    import importlib.util, os, re
+    import os, re
     from b200sd import engine as E
     src = open(os.path.join(os.path.dirname(__file__), "..", "stable-diffusion-webui-distributed_b200", "scripts", "spartan",
                             "worker.py")).read()
