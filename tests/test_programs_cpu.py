@@ -429,3 +429,32 @@ def test_only_masked_inpainting_geometry(size, box, proc):
     out = inp.apply_overlays(gen, ov, m.paste_to)
     assert out.shape == (1, h, w, 3) and torch.equal(out[0], torch.from_numpy(np.array(ref)))
     assert inp.prepare_mask_only_masked(Image.new("L", size, 0), pw, ph, ph // 8, pw // 8, mask_blur=0) is None
+
+
+def test_only_masked_crop_geometry_random():
+    """b200sd.inpaint.masked_region / grow_to_aspect (vectorised) against the oracle's loop-by-loop restatement of sdwui's
+    masking.get_crop_region / expand_crop_region on a few hundred random masks, paddings and aspect ratios — including
+    regions that touch the borders, single-pixel masks and boxes that must be shifted back inside the picture"""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+    from b200sd import inpaint as inp
+    from oracle import sd_oracle as O
+
+    @settings(max_examples=400, deadline=None)
+    @given(w=st.integers(8, 96), h=st.integers(8, 96), pad=st.integers(0, 40), pw=st.sampled_from([32, 64, 96, 128]),
+           ph=st.sampled_from([32, 64, 96, 128]), data=st.data())
+    def run(w, h, pad, pw, ph, data):
+        x1 = data.draw(st.integers(0, w - 1))
+        x2 = data.draw(st.integers(x1 + 1, w))
+        y1 = data.draw(st.integers(0, h - 1))
+        y2 = data.draw(st.integers(y1 + 1, h))
+        mask = np.zeros((h, w), dtype=np.uint8)
+        mask[y1:y2, x1:x2] = data.draw(st.sampled_from([1, 128, 255]))
+        if data.draw(st.booleans()):   # a second blob somewhere else
+            mask[data.draw(st.integers(0, h - 1)), data.draw(st.integers(0, w - 1))] = 255
+        region = inp.masked_region(mask, pad)
+        assert region == tuple(O.get_crop_region(mask, pad))
+        assert inp.grow_to_aspect(region, pw, ph, w, h) == tuple(O.expand_crop_region(region, pw, ph, w, h))
+
+    run()
+    assert inp.masked_region(np.zeros((5, 7), dtype=np.uint8), 3) is None

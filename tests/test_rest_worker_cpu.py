@@ -151,6 +151,60 @@ def test_api_auth():
     assert c.get("/sdapi/v1/memory", auth=("user", "secret")).status_code == 200
 
 
+def test_requests_are_bounded_and_restart_waits_for_the_running_generation():
+    """a client must not be able to walk the device out of memory by varying sizes (every distinct batch / size
+    builds buffers and graphs), and /server-restart must not pull the engine from under a generation in flight"""
+    from fastapi.testclient import TestClient
+    from server import sdapi
+    from server.sdapi import create_app
+
+    class Slow(EngineDouble):
+        def __init__(self):
+            super().__init__()
+            self.running = threading.Event()
+            self.release = threading.Event()
+
+        def txt2img(self, *a, **k):
+            self.running.set()
+            assert self.release.wait(10)
+            return super().txt2img(*a, **k)
+
+    eng = Slow()
+    built = []
+
+    def factory(device):
+        built.append(device)
+        return eng
+    app = create_app(factory, [0])
+    c = TestClient(app)
+    ok = dict(PAYLOAD, s_tmax=None)
+    for bad in ({"batch_size": 0}, {"batch_size": sdapi.MAX_BATCH + 1}, {"n_iter": 0}, {"steps": 0}, {"steps": 151},
+                {"width": sdapi.MAX_SIDE + 64}, {"height": 32}, {"width": 100}, {"batch_size": "many"}):
+        assert c.post("/sdapi/v1/txt2img", json=dict(ok, **bad)).status_code == 422, bad
+    assert eng.calls == [] and built == []     # nothing reached the executor, no engine was even built
+    # a generation in flight holds its device's lock: the restart waits for it, then drops the engine
+    import scripts.spartan.local_worker as lw
+    evicted = []
+    orig = lw.LocalGPUWorker.restart
+    lw.LocalGPUWorker.restart = lambda self: evicted.append(eng.release.is_set()) or True
+    try:
+        res = {}
+        t = threading.Thread(target=lambda: res.setdefault("gen", c.post("/sdapi/v1/txt2img", json=ok)))
+        t.start()
+        assert eng.running.wait(10)
+        r = threading.Thread(target=lambda: res.setdefault("restart", c.post("/sdapi/v1/server-restart")))
+        r.start()
+        time.sleep(0.3)
+        assert evicted == []            # still waiting for the generation
+        eng.release.set()
+        t.join(10)
+        r.join(10)
+    finally:
+        lw.LocalGPUWorker.restart = orig
+    assert res["gen"].status_code == 200 and res["restart"].status_code == 200
+    assert evicted == [True]            # the restart ran after the generation had been released
+
+
 @pytest.mark.skipif(not os.path.isdir(os.environ.get("REFERENCE_DIR", "/root/reference")),
                     reason="the unmodified reference exists in the build container only")
 def test_unmodified_reference_worker_drives_the_rest_server(server):
