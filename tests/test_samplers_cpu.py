@@ -139,3 +139,74 @@ def test_graph_warmup_must_not_shift_history():
     from b200sd import engine as E
     src = inspect.getsource(E.SDEngine._graph)
     assert "plan.lat.items()" in src and "plan.old" in src
+
+
+# ------------------------------------------------------------------------------------------------ the product vs diffusion theory
+# tests/test_oracle_pins_cpu.py pins the ORACLE's samplers to the exact probability-flow solution / data distribution of
+# Gaussian data.  Here the PRODUCT's sampler machinery (coefficient algebra of b200sd/samplers.py, the fused per-step kernels'
+# schedules, Program.start's scaling, the stage loop of the engine) meets the same theory directly, without the oracle in
+# between: the UNet program of the plan is replaced by the closed-form optimal eps-predictor, everything else runs as shipped.
+_S_DATA = 0.8
+
+
+def _theory_run(env, monkeypatch, name, steps, hw=16, seed=77):
+    E, O, eng, cond, unc, unet, b = env
+    _, log_sig = O.model_sigmas()
+    seen = {}
+    table = eng.temb.table
+
+    def recording_table(ts, y=None):
+        seen["ts"] = [float(v) for v in ts]
+        return table(ts, y)
+    monkeypatch.setattr(eng.temb, "table", recording_table)
+    plan = eng.plan(b, hw, hw)
+
+    def optimal_eps():   # eps(x_t, t) = x_t sqrt(1 - a) / (a s^2 + 1 - a), a = alphas_cumprod at (fractional) t
+        t = torch.tensor(seen["ts"][int(plan.step.item())], dtype=torch.float64).clamp(0, 999)
+        lo = t.floor().long().clamp(max=998)
+        w = t - lo
+        sg = ((1 - w) * log_sig[lo] + w * log_sig[lo + 1]).exp()
+        a = 1 / (1 + sg * sg)
+        k = float(torch.sqrt(1 - a) / (a * _S_DATA ** 2 + 1 - a))
+        plan.unet.eps[:, :, :4] = plan.unet.xin[:, :, :4].float() * k
+    monkeypatch.setattr(plan.unet, "run", optimal_eps)
+    pr = eng.program(name, None, steps)
+    nz = E.per_image_noise(seed, b, (4, hw, hw), 1 + pr.draws)
+    lat = eng.run_program(cond, unc, pr.start(nz[0]), pr, 1.0, noises=nz[1:] if pr.draws else None)
+    return pr, nz[0].permute(0, 2, 3, 1).reshape(b, hw * hw, 4), lat.clone()
+
+
+@pytest.mark.parametrize("name,err40,order", [
+    ("DDIM", 0.05, 0.75), ("Euler", 0.06, 1), ("Heun", 0.003, 2), ("DPM2", 0.012, 2), ("DPM2 Karras", 0.003, 2),
+    ("DPM++ 2M", 0.006, 2), ("DPM++ 2M Karras", 0.006, 2), ("LMS", 5e-4, 3), ("LMS Karras", 2e-3, 3), ("PLMS", 0.008, 1.2)])
+def test_product_deterministic_samplers_solve_the_probability_flow_ode(env, monkeypatch, name, err40, order):
+    E, O = env[0], env[1]
+    errs = []
+    for steps in (20, 40):
+        pr, noise0, lat = _theory_run(env, monkeypatch, name, steps)
+        s = _S_DATA
+        if name in ("DDIM", "PLMS"):    # timestep samplers stop at alphas_cumprod[timesteps[0]] (DDIM) / [0] (PLMS)
+            ac, ts = O.alphas_cumprod().double(), O.ddim_timesteps(steps)
+            a_T, a_0 = float(ac[ts[-1]]), float(ac[ts[0]] if name == "DDIM" else ac[0])
+            exact = noise0 * math.sqrt((a_0 * s * s + 1 - a_0) / (a_T * s * s + 1 - a_T))
+        else:
+            s0 = pr.noise_scale          # sigma_0 of the schedule the program was built on
+            exact = noise0 * s0 * s / math.sqrt(s * s + s0 * s0)
+        errs.append(float((lat - exact).norm() / exact.norm()))
+    assert errs[1] <= err40 and errs[0] / errs[1] >= 0.8 * 2 ** order, (name, errs)
+
+
+@pytest.mark.parametrize("name,tol", [("DPM fast", 0.01), ("DPM adaptive", 0.05)])
+def test_product_dpm_solver_samplers_solve_the_probability_flow_ode(env, monkeypatch, name, tol):
+    pr, noise0, lat = _theory_run(env, monkeypatch, name, 20)
+    s, s0 = _S_DATA, pr.noise_scale
+    exact = noise0 * s0 * s / math.sqrt(s * s + s0 * s0)
+    assert float((lat - exact).norm() / exact.norm()) <= tol
+
+
+@pytest.mark.parametrize("name,lo,hi", [("Euler a", 0.78, 1.04), ("DPM2 a", 0.90, 1.12), ("DPM++ 2S a", 0.90, 1.08),
+                                        ("DPM++ SDE", 0.88, 1.08), ("DPM++ SDE Karras", 0.90, 1.09)])
+def test_product_stochastic_samplers_end_on_the_data_distribution(env, monkeypatch, name, lo, hi):
+    pr, noise0, lat = _theory_run(env, monkeypatch, name, 40, hw=32)
+    ratio = float(lat.var()) / _S_DATA ** 2
+    assert lo <= ratio <= hi and abs(float(lat.mean())) <= 0.04, (name, ratio, float(lat.mean()))
