@@ -24,3 +24,13 @@ def test_engine_refuses_cpu_device():
     from b200sd import config as C, engine as E
     with pytest.raises(RuntimeError):
         E.SDEngine({}, C.TINY_UNET, C.TINY_VAE, C.TINY_CLIP, device="cpu")
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md's table names the upstream operation behind every exported symbol"""
+    import os
+    from b200sd import _lib
+    doc = open(os.path.join(os.path.dirname(__file__), "..", "INTEGRATION.md")).read()
+    for name in _lib.declared_symbols():
+        stem = name[:-len("_stats")] if name.endswith("_stats") else name[:-len("_apply")] if name.endswith("_apply") else name
+        assert name in doc or stem in doc, name
