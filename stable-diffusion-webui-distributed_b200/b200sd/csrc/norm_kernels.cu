@@ -295,7 +295,7 @@ __global__ void groupnorm_apply_kernel(const uint8_t* __restrict__ X, long long 
 // slabs started so far always form a prefix of the (image-major) order and every image whose first slab is running has
 // all its slabs running or startable as long as `parts` CTAs fit on the device at once — the launcher checks that and
 // falls back to the two-kernel path otherwise (huge VAE tensors).  The spin is bounded: a protocol failure traps instead
-// of hanging the device.
+// of hanging the device.  tests/test_gn_protocol_cpu.py model-checks exactly this protocol under random interleavings.
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
